@@ -1,0 +1,284 @@
+// C ABI of libvrt (include/vrt.h).  Thin: argument checks, device memory, kernel launches.
+// There is no CPU fallback — every compute entry point needs a CUDA device.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "host_util.h"
+#include "kernels.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(VRT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define VRT_CUDA(call)                                      \
+    do {                                                    \
+        cudaError_t e_ = (call);                            \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+
+// grow-only device scratch buffer
+struct DeviceBuffer {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t want) {
+        if (want <= bytes) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+};
+
+}  // namespace
+
+struct vrt_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    uint64_t launches = 0;
+    int sm_count = 0;
+    DeviceBuffer scratch_in, scratch_out;   // host-variant staging
+};
+
+struct vrt_scene {
+    vrt_context* ctx = nullptr;
+    int kind = 0;
+    uint32_t depth = 0;
+    int32_t guard = 0;
+    // LSVO
+    uint2* d_nodes = nullptr;
+    uint64_t n_nodes = 0;
+    uint64_t device_bytes = 0;
+    unsigned long long* d_counters = nullptr;   // [0] Σ complexity of the last cast
+};
+
+namespace {
+int use_device(const vrt_context* ctx) {
+    cudaError_t e = cudaSetDevice(ctx->device);
+    return e == cudaSuccess ? VRT_OK : cuda_fail(e, "cudaSetDevice");
+}
+}  // namespace
+
+extern "C" {
+
+int vrt_abi_version(void) { return VRT_ABI_VERSION; }
+const char* vrt_last_error(void) { return g_last_error.c_str(); }
+const char* vrt_build_info(void) {
+    return "libvrt sm_100a --fmad=false prec-div prec-sqrt; kernels: lsvo_cast_kernel<RefNodes>";
+}
+
+int vrt_context_create(int device, void* stream, vrt_context** out) {
+    if (!out) return fail(VRT_ERR_INVALID, "vrt_context_create: out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    if (device < 0 || device >= count) return fail(VRT_ERR_INVALID, "vrt_context_create: no such device");
+    vrt_context* ctx = new (std::nothrow) vrt_context();
+    if (!ctx) return fail(VRT_ERR_OOM, "vrt_context_create: host allocation failed");
+    ctx->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { delete ctx; return cuda_fail(e, "cudaSetDevice"); }
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (stream) {
+        ctx->stream = static_cast<cudaStream_t>(stream);
+    } else {
+        if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+            delete ctx;
+            return cuda_fail(e, "cudaStreamCreate");
+        }
+        ctx->owns_stream = true;
+    }
+    *out = ctx;
+    return VRT_OK;
+}
+
+int vrt_context_destroy(vrt_context* ctx) {
+    if (!ctx) return VRT_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->scratch_in.release();
+    ctx->scratch_out.release();
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return VRT_OK;
+}
+
+int vrt_context_synchronize(vrt_context* ctx) {
+    if (!ctx) return fail(VRT_ERR_INVALID, "vrt_context_synchronize: ctx is NULL");
+    if (int s = use_device(ctx)) return s;
+    VRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VRT_OK;
+}
+
+int vrt_context_set_stream(vrt_context* ctx, void* stream) {
+    if (!ctx) return fail(VRT_ERR_INVALID, "vrt_context_set_stream: ctx is NULL");
+    if (ctx->owns_stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+        ctx->owns_stream = false;
+    }
+    ctx->stream = static_cast<cudaStream_t>(stream);
+    return VRT_OK;
+}
+
+uint64_t vrt_context_launch_count(const vrt_context* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- host builders ---------------------------------------------------------------------------------
+int vrt_host_terrain_heights(int32_t size, int32_t* out) {
+    if (size <= 0 || !out) return fail(VRT_ERR_INVALID, "vrt_host_terrain_heights: bad arguments");
+    vrt::host_terrain_heights(size, out);
+    return VRT_OK;
+}
+
+int vrt_host_build_terrain_lsvo(uint32_t depth, const int32_t* heights, vrt_lnode* out, uint64_t cap, uint64_t* count) {
+    // the fill writes y + S/2 with y up to max(16, height): needs S/2 + 80 < S like the reference scene
+    if (depth < 8 || depth > 12 || !heights || !count)
+        return fail(VRT_ERR_INVALID, "vrt_host_build_terrain_lsvo: depth must be 8..12, heights/count non-NULL");
+    *count = vrt::host_build_terrain_lsvo(depth, heights, out, cap);
+    if (out && *count > cap) return fail(VRT_ERR_INVALID, "vrt_host_build_terrain_lsvo: buffer too small");
+    return VRT_OK;
+}
+
+int vrt_host_build_lsvo_from_voxels(uint32_t depth, const uint32_t* xyz, uint64_t n_voxels, vrt_lnode* out, uint64_t cap,
+                                    uint64_t* count) {
+    if (depth < 1 || depth > 12 || (!xyz && n_voxels) || !count)
+        return fail(VRT_ERR_INVALID, "vrt_host_build_lsvo_from_voxels: bad arguments");
+    const uint32_t S = 1u << depth;
+    for (uint64_t i = 0; i < 3 * n_voxels; ++i)
+        if (xyz[i] >= S) return fail(VRT_ERR_INVALID, "vrt_host_build_lsvo_from_voxels: voxel out of range");
+    *count = vrt::host_build_lsvo_from_voxels(depth, xyz, n_voxels, out, cap);
+    if (out && *count > cap) return fail(VRT_ERR_INVALID, "vrt_host_build_lsvo_from_voxels: buffer too small");
+    return VRT_OK;
+}
+
+int vrt_host_camera_rotation(const float view_angle[2], float rot_mat[9], float camera_vec[3]) {
+    if (!view_angle || !rot_mat || !camera_vec) return fail(VRT_ERR_INVALID, "vrt_host_camera_rotation: NULL argument");
+    vrt::host_camera_rotation(view_angle, rot_mat, camera_vec);
+    return VRT_OK;
+}
+
+// ---- scenes ----------------------------------------------------------------------------------------
+int vrt_lsvo_create(vrt_context* ctx, const vrt_lnode* nodes, uint64_t n_nodes, uint32_t depth, int32_t guard, vrt_scene** out) {
+    if (!ctx || !nodes || !n_nodes || !out) return fail(VRT_ERR_INVALID, "vrt_lsvo_create: NULL argument");
+    if (depth < 1 || depth > 12) return fail(VRT_ERR_INVALID, "vrt_lsvo_create: depth must be 1..12");
+    if (n_nodes > 0xffffffffull) return fail(VRT_ERR_UNSUPPORTED, "vrt_lsvo_create: more than 2^32 slots");
+    if (int s = use_device(ctx)) return s;
+    vrt_scene* sc = new (std::nothrow) vrt_scene();
+    if (!sc) return fail(VRT_ERR_OOM, "vrt_lsvo_create: host allocation failed");
+    sc->ctx = ctx;
+    sc->kind = VRT_SCENE_LSVO;
+    sc->depth = depth;
+    sc->guard = guard > 0 ? guard : (guard < 0 ? 0 : int32_t(depth));   // 0 = reference, <0 = lifted
+    sc->n_nodes = n_nodes;
+    cudaError_t e = cudaMalloc(&sc->d_nodes, n_nodes * sizeof(uint2));
+    if (e == cudaSuccess) e = cudaMalloc(&sc->d_counters, 16 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sc->d_nodes, nodes, n_nodes * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(sc->d_counters, 0, 16 * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        vrt_scene_destroy(sc);
+        return e == cudaErrorMemoryAllocation ? fail(VRT_ERR_OOM, "vrt_lsvo_create: device allocation failed")
+                                              : cuda_fail(e, "vrt_lsvo_create");
+    }
+    sc->device_bytes = n_nodes * sizeof(uint2);
+    *out = sc;
+    return VRT_OK;
+}
+
+int vrt_scene_destroy(vrt_scene* sc) {
+    if (!sc) return VRT_OK;
+    cudaSetDevice(sc->ctx->device);
+    cudaStreamSynchronize(sc->ctx->stream);
+    if (sc->d_nodes) cudaFree(sc->d_nodes);
+    if (sc->d_counters) cudaFree(sc->d_counters);
+    delete sc;
+    return VRT_OK;
+}
+
+int vrt_scene_info(const vrt_scene* sc, int32_t* kind, uint32_t* depth, uint64_t* device_bytes) {
+    if (!sc) return fail(VRT_ERR_INVALID, "vrt_scene_info: scene is NULL");
+    if (kind) *kind = sc->kind;
+    if (depth) *depth = sc->depth;
+    if (device_bytes) *device_bytes = sc->device_bytes;
+    return VRT_OK;
+}
+
+// ---- batched traversal -----------------------------------------------------------------------------
+int vrt_cast_rays_device(vrt_scene* sc, const float* d_origin, const float* d_dir, float coef, float bias, uint64_t n,
+                         vrt_hit* d_out) {
+    if (!sc) return fail(VRT_ERR_INVALID, "vrt_cast_rays_device: scene is NULL");
+    if (n && (!d_origin || !d_dir || !d_out)) return fail(VRT_ERR_INVALID, "vrt_cast_rays_device: NULL buffer");
+    if (n > (1ull << 31) * 128ull) return fail(VRT_ERR_UNSUPPORTED, "vrt_cast_rays_device: too many rays for one launch");
+    vrt_context* ctx = sc->ctx;
+    if (int s = use_device(ctx)) return s;
+    VRT_CUDA(cudaMemsetAsync(sc->d_counters, 0, sizeof(unsigned long long), ctx->stream));
+    if (n == 0) return VRT_OK;
+    switch (sc->kind) {
+        case VRT_SCENE_LSVO:
+            VRT_CUDA(vrt::launch_lsvo_cast_ref(sc->d_nodes, int(sc->depth), sc->guard, d_origin, d_dir, coef, bias, n, d_out,
+                                               sc->d_counters, ctx->stream));
+            ctx->launches += 1;
+            return VRT_OK;
+        default:
+            return fail(VRT_ERR_UNSUPPORTED, "vrt_cast_rays_device: scene kind not supported");
+    }
+}
+
+int vrt_cast_rays(vrt_scene* sc, const float* origin, const float* dir, float coef, float bias, uint64_t n, vrt_hit* out) {
+    if (!sc) return fail(VRT_ERR_INVALID, "vrt_cast_rays: scene is NULL");
+    if (n == 0) return VRT_OK;
+    if (!origin || !dir || !out) return fail(VRT_ERR_INVALID, "vrt_cast_rays: NULL buffer");
+    vrt_context* ctx = sc->ctx;
+    if (int s = use_device(ctx)) return s;
+    const size_t ray_bytes = size_t(n) * 3 * sizeof(float);
+    if (ctx->scratch_in.reserve(2 * ray_bytes) != cudaSuccess || ctx->scratch_out.reserve(size_t(n) * sizeof(vrt_hit)) != cudaSuccess)
+        return fail(VRT_ERR_OOM, "vrt_cast_rays: device staging allocation failed");
+    float* d_o = static_cast<float*>(ctx->scratch_in.ptr);
+    float* d_d = d_o + size_t(n) * 3;
+    vrt_hit* d_h = static_cast<vrt_hit*>(ctx->scratch_out.ptr);
+    VRT_CUDA(cudaMemcpyAsync(d_o, origin, ray_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    VRT_CUDA(cudaMemcpyAsync(d_d, dir, ray_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (int s = vrt_cast_rays_device(sc, d_o, d_d, coef, bias, n, d_h)) return s;
+    VRT_CUDA(cudaMemcpyAsync(out, d_h, size_t(n) * sizeof(vrt_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    VRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VRT_OK;
+}
+
+int vrt_scene_last_complexity(vrt_scene* sc, uint64_t* total) {
+    if (!sc || !total) return fail(VRT_ERR_INVALID, "vrt_scene_last_complexity: NULL argument");
+    if (int s = use_device(sc->ctx)) return s;
+    unsigned long long v = 0;
+    VRT_CUDA(cudaMemcpyAsync(&v, sc->d_counters, sizeof(v), cudaMemcpyDeviceToHost, sc->ctx->stream));
+    VRT_CUDA(cudaStreamSynchronize(sc->ctx->stream));
+    *total = v;
+    return VRT_OK;
+}
+
+// ---- not implemented yet (TODO: replaced as the kernels land) --------------------------------------
+int vrt_grid_create(vrt_context*, const uint8_t*, int32_t, int32_t, int32_t, int32_t, vrt_scene**) { return fail(VRT_ERR_UNSUPPORTED, "vrt_grid_create: not implemented"); }
+int vrt_svo_create(vrt_context*, const uint8_t*, uint32_t, vrt_scene**) { return fail(VRT_ERR_UNSUPPORTED, "vrt_svo_create: not implemented"); }
+int vrt_cast_rays_svo(vrt_scene*, const float*, const float*, uint32_t, uint64_t, vrt_hit*) { return fail(VRT_ERR_UNSUPPORTED, "vrt_cast_rays_svo: not implemented"); }
+int vrt_scene_set_textures(vrt_scene*, const uint8_t*, const uint8_t*) { return fail(VRT_ERR_UNSUPPORTED, "vrt_scene_set_textures: not implemented"); }
+int vrt_render_accumulate_device(vrt_scene*, const vrt_camera*, const vrt_render_params*, uint32_t*) { return fail(VRT_ERR_UNSUPPORTED, "not implemented"); }
+int vrt_render_resolve_device(vrt_scene*, const vrt_render_params*, const uint32_t*, uint8_t*) { return fail(VRT_ERR_UNSUPPORTED, "not implemented"); }
+int vrt_render(vrt_scene*, const vrt_camera*, const vrt_render_params*, uint8_t*, uint32_t*, vrt_render_stats*) { return fail(VRT_ERR_UNSUPPORTED, "not implemented"); }
+int vrt_scene_last_render_stats(vrt_scene*, vrt_render_stats*) { return fail(VRT_ERR_UNSUPPORTED, "not implemented"); }
+int vrt_autofocus(vrt_scene*, const vrt_camera*, float*) { return fail(VRT_ERR_UNSUPPORTED, "not implemented"); }
+
+}  // extern "C"

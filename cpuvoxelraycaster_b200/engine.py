@@ -1,0 +1,330 @@
+"""Host-side mirror of the reference's hot-path interface over libvrt's C ABI.
+
+Names follow the reference (file:line under the reference tree):
+  Volumetric.castRay        include/volumetric.hpp:55-61
+  LSVO                      include/lsvo.hpp:10-24, castRay :33
+  Grid3D / MipmapGrid3D     include/grid_3d.hpp:10-27, include/mipmap_grid3D.hpp:14-17
+  SVO                       include/svo.hpp:29, castRay :62, setCell :72
+  Camera                    include/camera_controller.hpp:16-61
+  RayCaster                 include/raycaster.hpp:43-282 (renderRay :67 → render(): whole frames)
+Batched entry points (cast_rays, render) are the additions: the reference casts one ray per call from
+a swarm worker (src/main.cpp:139-152); here one call is one kernel launch.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import HIT, LNODE, check, lib, ptr
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+# ---- host-side scene construction (src/main.cpp:59-86) ----------------------------------------------
+def host_terrain_heights(size):
+    out = np.zeros((size, size), np.int32)
+    check(lib().vrt_host_terrain_heights(size, ptr(out)))
+    return out
+
+
+def host_build_terrain_lsvo(depth, heights=None):
+    if heights is None:
+        heights = host_terrain_heights(1 << depth)
+    heights = np.ascontiguousarray(heights, np.int32)
+    n = C.c_uint64(0)
+    check(lib().vrt_host_build_terrain_lsvo(depth, ptr(heights), None, 0, C.byref(n)))
+    nodes = np.zeros(n.value, LNODE)
+    check(lib().vrt_host_build_terrain_lsvo(depth, ptr(heights), ptr(nodes), n.value, C.byref(n)))
+    return nodes
+
+
+def host_build_lsvo_from_voxels(depth, xyz):
+    xyz = np.ascontiguousarray(xyz, np.uint32).reshape(-1, 3)
+    n = C.c_uint64(0)
+    check(lib().vrt_host_build_lsvo_from_voxels(depth, ptr(xyz), len(xyz), None, 0, C.byref(n)))
+    nodes = np.zeros(n.value, LNODE)
+    check(lib().vrt_host_build_lsvo_from_voxels(depth, ptr(xyz), len(xyz), ptr(nodes), n.value, C.byref(n)))
+    return nodes
+
+
+# ---- execution resource -------------------------------------------------------------------------------
+class Context:
+    """One CUDA device + stream (replaces swrm::Swarm, src/main.cpp:90-92). Not thread-safe."""
+
+    def __init__(self, device=0, stream=None):
+        h = C.c_void_p()
+        check(lib().vrt_context_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.handle = h
+        self.device = int(device)
+
+    def synchronize(self):
+        check(lib().vrt_context_synchronize(self.handle))
+
+    def set_stream(self, stream):
+        check(lib().vrt_context_set_stream(self.handle, C.c_void_p(stream) if stream else None))
+
+    @property
+    def launch_count(self):
+        return int(lib().vrt_context_launch_count(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().vrt_context_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HitPoint:
+    """include/volumetric.hpp:7-22 for one ray; `cell` is truthy on a hit."""
+
+    __slots__ = ("position", "normal", "voxel_coord", "cell", "distance", "complexity")
+
+    def __init__(self, rec):
+        self.position = rec["position"].copy()
+        self.normal = rec["normal"].copy()
+        self.voxel_coord = rec["voxel_coord"].copy()
+        self.cell = bool(rec["flags"] & 1)
+        self.distance = float(rec["distance"])
+        self.complexity = int(rec["complexity"])
+
+
+class Volumetric:
+    """include/volumetric.hpp:55-61."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.handle = None
+
+    # -- batched: n rays, one launch --
+    def cast_rays(self, origin, direction, ray_size_coef=0.0, ray_size_bias=0.0):
+        o, d = _f32(origin, (-1, 3)), _f32(direction, (-1, 3))
+        if o.shape != d.shape:
+            raise ValueError("origin and direction must have the same shape")
+        out = np.zeros(len(o), HIT)
+        check(lib().vrt_cast_rays(self.handle, ptr(o), ptr(d), ray_size_coef, ray_size_bias, len(o), ptr(out)))
+        return out
+
+    def cast_rays_device(self, d_origin, d_dir, n, d_out, ray_size_coef=0.0, ray_size_bias=0.0):
+        """Device pointers (ints or torch tensors); enqueues on the context stream."""
+        check(lib().vrt_cast_rays_device(self.handle, ptr(d_origin), ptr(d_dir), ray_size_coef, ray_size_bias, int(n),
+                                         ptr(d_out)))
+
+    # -- reference signature: one ray --
+    def castRay(self, position, direction, ray_size_coef=0.0, ray_size_bias=0.0):
+        return HitPoint(self.cast_rays([position], [direction], ray_size_coef, ray_size_bias)[0])
+
+    def last_complexity(self):
+        v = C.c_uint64(0)
+        check(lib().vrt_scene_last_complexity(self.handle, C.byref(v)))
+        return v.value
+
+    def info(self):
+        k, d, b = C.c_int32(0), C.c_uint32(0), C.c_uint64(0)
+        check(lib().vrt_scene_info(self.handle, C.byref(k), C.byref(d), C.byref(b)))
+        return dict(kind=k.value, depth=d.value, device_bytes=b.value)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().vrt_scene_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class LSVO(Volumetric):
+    """LSVO<MAX_DEPTH> (include/lsvo.hpp:10). `nodes` is the reference's flattened layout (LNode[])."""
+
+    def __init__(self, ctx, nodes, depth, guard=0):
+        super().__init__(ctx)
+        nodes = np.ascontiguousarray(nodes)
+        if nodes.dtype.itemsize != 8:
+            raise ValueError("nodes must be 8-byte LNode records")
+        h = C.c_void_p()
+        check(lib().vrt_lsvo_create(ctx.handle, ptr(nodes), len(nodes), int(depth), int(guard), C.byref(h)))
+        self.handle = h
+        self.depth = int(depth)
+        self.n_nodes = len(nodes)
+
+    @classmethod
+    def from_terrain(cls, ctx, depth, guard=0):
+        """The demo scene T(D): src/main.cpp:59-83."""
+        return cls(ctx, host_build_terrain_lsvo(depth), depth, guard)
+
+    @classmethod
+    def from_voxels(cls, ctx, depth, xyz, guard=0):
+        """SVO::setCell for every voxel (svo.hpp:72) followed by LSVO(const SVO&) (lsvo.hpp:12)."""
+        return cls(ctx, host_build_lsvo_from_voxels(depth, xyz), depth, guard)
+
+    def setCell(self, *a):
+        """No-op, as in the reference (lsvo.hpp:26)."""
+
+    def set_textures(self, top_rgb, side_rgb):
+        t, s = np.ascontiguousarray(top_rgb, np.uint8), np.ascontiguousarray(side_rgb, np.uint8)
+        if t.size != 768 or s.size != 768:
+            raise ValueError("textures must be 16x16 RGB")
+        check(lib().vrt_scene_set_textures(self.handle, ptr(t), ptr(s)))
+
+
+class Grid3D(Volumetric):
+    """Grid3D<X,Y,Z> (include/grid_3d.hpp:10). cells[x,y,z] = Cell::Type (0 Empty, 1 Solid, 2 Mirror)."""
+
+    mip_levels = 0
+
+    def __init__(self, ctx, cells):
+        super().__init__(ctx)
+        cells = np.ascontiguousarray(cells, np.uint8)
+        X, Y, Z = cells.shape
+        h = C.c_void_p()
+        check(lib().vrt_grid_create(ctx.handle, ptr(cells), X, Y, Z, int(self.mip_levels), C.byref(h)))
+        self.handle = h
+        self.shape = (X, Y, Z)
+
+    def castRay(self, position, direction):  # grid_3d.hpp:16 takes no cone arguments
+        return HitPoint(self.cast_rays([position], [direction])[0])
+
+
+class MipmapGrid3D(Grid3D):
+    """MipmapGrid3D<X,Y,Z,MipmapDepth> (include/mipmap_grid3D.hpp:14-17; an empty stub in the reference).
+    Results are bit-identical to Grid3D; the occupancy pyramid only removes memory fetches."""
+
+    def __init__(self, ctx, cells, mip_levels=3):
+        self.mip_levels = int(mip_levels)
+        super().__init__(ctx, cells)
+
+
+class SVO(Volumetric):
+    """SVO<N> (include/svo.hpp:29) with the hit fill of svo.hpp:116-138 restored ("intended SVO")."""
+
+    def __init__(self, ctx, occ):
+        super().__init__(ctx)
+        occ = np.ascontiguousarray(occ, np.uint8)
+        S = occ.shape[0]
+        if occ.shape != (S, S, S) or S & (S - 1):
+            raise ValueError("occupancy must be a cube with a power-of-two edge")
+        h = C.c_void_p()
+        check(lib().vrt_svo_create(ctx.handle, ptr(occ), S.bit_length() - 1, C.byref(h)))
+        self.handle = h
+        self.depth = S.bit_length() - 1
+
+    def cast_rays(self, origin, direction, max_iter=1 << 30):
+        o, d = _f32(origin, (-1, 3)), _f32(direction, (-1, 3))
+        out = np.zeros(len(o), HIT)
+        check(lib().vrt_cast_rays_svo(self.handle, ptr(o), ptr(d), int(max_iter), len(o), ptr(out)))
+        return out
+
+    def castRay(self, position, direction, max_iter):  # svo.hpp:62
+        return HitPoint(self.cast_rays([position], [direction], max_iter)[0])
+
+
+# ---- camera -------------------------------------------------------------------------------------------
+class Camera:
+    """include/camera_controller.hpp:16-61."""
+
+    def __init__(self, position=(256.0, 200.0, 256.0), view_angle=(0.0, 0.0), fov=1.0, aperture=0.0, focal_length=1.0):
+        self.position = np.asarray(position, np.float32)
+        self.fov = float(fov)
+        self.aperture = float(aperture)
+        self.focal_length = float(focal_length)
+        self.setViewAngle(view_angle)
+
+    def setViewAngle(self, angle):
+        """camera_controller.hpp:27-32 + generateRotationMatrix (utils.cpp:94-100), computed by libvrt's host code
+        with the C library's cosf/sinf like the reference."""
+        self.view_angle = np.asarray(angle, np.float32)
+        m = np.zeros(9, np.float32)
+        v = np.zeros(3, np.float32)
+        check(lib().vrt_host_camera_rotation(ptr(self.view_angle), ptr(m), ptr(v)))
+        self.rot_mat = m
+        self.camera_vec = v
+
+    def as_struct(self):
+        c = capi.Camera()
+        c.position[:] = [float(x) for x in self.position]
+        c.rot_mat[:] = [float(x) for x in self.rot_mat]
+        c.fov, c.aperture, c.focal_length = self.fov, self.aperture, self.focal_length
+        return c
+
+    def getClosestPoint(self, volume):
+        """camera_controller.hpp:56-60 (the centre ray)."""
+        scale = np.float32(1.0) / np.float32(1 << volume.depth)
+        return volume.castRay(self.position * scale + np.float32(1.0), self.camera_vec, 0.0, 0.0)
+
+    def autofocus(self, volume):
+        """src/main.cpp:115-121, evaluated on the device."""
+        f = C.c_float(0)
+        check(lib().vrt_autofocus(volume.handle, C.byref(self.as_struct()), C.byref(f)))
+        self.focal_length = f.value
+        return f.value
+
+
+# ---- renderer -----------------------------------------------------------------------------------------
+class RayCaster:
+    """include/raycaster.hpp:43.  render() replaces the swarm lambda of src/main.cpp:139-154."""
+
+    def __init__(self, svo, render_size, tex_top=None, tex_side=None):
+        self.svo = svo
+        self.render_size = (int(render_size[0]), int(render_size[1]))
+        W, H = self.render_size
+        self.render_image = np.zeros((H, W, 4), np.uint8)     # sf::Image render_image (raycaster.hpp:261)
+        self.colors = np.zeros((H, W, 4), np.uint32)          # Sample accumulators r,g,b,count (raycaster.hpp:259)
+        self.light_position = np.zeros(3, np.float32)
+        self.use_gi = False
+        self.use_samples = False
+        self.gi_bounces = 1
+        self.seed = (0x5EED, 0)
+        self.sample_count = 0
+        self.last_stats = None
+        if tex_top is not None:
+            svo.set_textures(tex_top, tex_side)
+
+    def setLightPosition(self, position):                       # raycaster.hpp:62
+        self.light_position = np.asarray(position, np.float32)
+
+    def resetSamples(self):                                     # raycaster.hpp:105-116
+        self.colors[...] = 0
+        self.sample_count = 0
+
+    def params(self, spp=1, row_begin=0, row_end=0, sample_offset=None):
+        p = capi.RenderParams()
+        p.width, p.height = self.render_size
+        p.row_begin, p.row_end = int(row_begin), int(row_end) if row_end else self.render_size[1]
+        p.spp = int(spp)
+        p.sample_offset = self.sample_count if sample_offset is None else int(sample_offset)
+        p.seed_lo, p.seed_hi = self.seed
+        p.light_position[:] = [float(x) for x in self.light_position]
+        p.use_gi, p.gi_bounces, p.use_samples = int(self.use_gi), int(self.gi_bounces), int(self.use_samples)
+        return p
+
+    def render(self, camera, spp=1, row_begin=0, row_end=0):
+        """One frame (all pixels, no checkerboard): `spp` renderRay passes per pixel, then samples_to_image when
+        use_samples, else the 0.4/0.6 temporal blend into render_image (raycaster.hpp:77-91)."""
+        p = self.params(spp, row_begin, row_end)
+        stats = capi.RenderStats()
+        accum = np.zeros_like(self.colors)
+        check(lib().vrt_render(self.svo.handle, C.byref(camera.as_struct()), C.byref(p), ptr(self.render_image), ptr(accum),
+                               C.byref(stats)))
+        if self.use_samples:
+            self.colors += accum
+            self.sample_count += int(spp)
+        self.last_stats = dict(rays=list(stats.rays), complexity=list(stats.complexity))
+        return self.render_image
+
+    def samples_to_image(self):                                 # raycaster.hpp:94-103
+        cnt = np.maximum(self.colors[..., 3:4], 1)
+        self.render_image[..., :3] = (self.colors[..., :3] // cnt).astype(np.uint8)
+        self.render_image[..., 3] = 255
+        return self.render_image

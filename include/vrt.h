@@ -1,0 +1,186 @@
+/* vrt.h — C ABI of the B200-native voxel ray-traversal engine (libvrt.so).
+ *
+ * Drop-in boundary for the per-pixel hot path of johnBuffer/CpuVoxelRaycaster.  The reference has
+ * no FFI; its seam is C++-source-level.  Each entry point below names the reference
+ * interface it replaces (file:line under the reference tree).  The C++ drop-in classes in
+ * the headers under include/vrt/ (same names/signatures as the reference: Volumetric, HitPoint, LSVO<D>, SVO<N>,
+ * Grid3D, MipmapGrid3D, RayCaster, Camera) and the Python mirror (cpuvoxelraycaster_b200/) are thin
+ * callers of this ABI.
+ *
+ * Conventions
+ *   - every function returns vrt_status (0 = ok, negative = error); vrt_last_error() gives the text
+ *     of the last failure on the calling thread.  The reference reports no errors at all
+ *     (out-of-range setCell is UB); here bad arguments are VRT_ERR_INVALID.
+ *   - the caller owns every host buffer; handles are opaque; a context is bound to one CUDA device
+ *     and one stream and is NOT thread-safe (one context per host thread, or external locking).
+ *   - no C++ or torch types cross the ABI: plain pointers and sizes only.
+ *   - "*_device" variants take device pointers and only enqueue work on the context's stream.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     VRT_ERR_CUDA.  The vrt_host_* scene-construction helpers are pure host code by design
+ *     (the reference builds its scene once on the CPU, src/main.cpp:59-86).
+ */
+#ifndef VRT_H
+#define VRT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VRT_ABI_VERSION 1
+
+typedef enum vrt_status {
+    VRT_OK = 0,
+    VRT_ERR_INVALID = -1,   /* bad argument */
+    VRT_ERR_CUDA = -2,      /* CUDA runtime failure (no device, launch error, ...) */
+    VRT_ERR_OOM = -3,       /* host or device allocation failed */
+    VRT_ERR_UNSUPPORTED = -4
+} vrt_status;
+
+typedef struct vrt_context vrt_context;
+typedef struct vrt_scene vrt_scene;
+
+/* LNode, include/lsvo_utils.hpp:5-18 — the reference's flattened octree slot, accepted verbatim. */
+typedef struct vrt_lnode {
+    uint8_t color;
+    uint8_t child_mask;
+    uint8_t leaf_mask;
+    uint8_t pad;
+    uint32_t child_offset;
+} vrt_lnode;
+
+/* Superset of HitPoint (include/volumetric.hpp:7-22), 64 bytes, so that the C++ wrapper can rebuild
+ * a HitPoint exactly.  On a miss only `flags` (bit 0 clear) and `complexity` are defined — as in the
+ * reference, where a miss leaves position/normal/voxel_coord/distance uninitialised — and the other
+ * fields are written as zero. */
+typedef struct vrt_hit {
+    float position[3];    /* HitPoint::position */
+    float distance;       /* HitPoint::distance */
+    float normal[3];      /* HitPoint::normal (LSVO: ±1, ±2, ±4 per axis, lsvo.hpp:149) */
+    uint32_t complexity;  /* HitPoint::complexity (loop iterations) */
+    float voxel_coord[2]; /* HitPoint::voxel_coord */
+    uint32_t flags;       /* bit 0: hit (HitPoint::cell != nullptr) */
+    int32_t scale;        /* LSVO: octree scale of the hit cell (23 - depth for a leaf voxel) */
+    int32_t voxel[3];     /* integer coordinate of the hit cell's low corner, voxel units */
+    uint32_t face;        /* axis mask that entered the cell: bit0 x, bit1 y, bit2 z */
+} vrt_hit;
+#define VRT_HIT_FLAG_HIT 1u
+
+typedef enum vrt_scene_kind {
+    VRT_SCENE_LSVO = 1,   /* include/lsvo.hpp */
+    VRT_SCENE_GRID = 2,   /* include/grid_3d.hpp */
+    VRT_SCENE_MIPGRID = 3,/* include/mipmap_grid3D.hpp (stub in the reference; results == Grid3D) */
+    VRT_SCENE_SVO = 4     /* include/svo.hpp, intended semantics (fillHitResult restored) */
+} vrt_scene_kind;
+
+/* ---- library / context --------------------------------------------------------------------- */
+int vrt_abi_version(void);
+const char* vrt_last_error(void);
+const char* vrt_build_info(void);                   /* compile flags, arch, kernel variants */
+
+/* Replaces swrm::Swarm(thread_count) (src/main.cpp:90-92): the execution resource. `stream` is a
+ * cudaStream_t (NULL = the context creates its own non-blocking stream). */
+int vrt_context_create(int device, void* stream, vrt_context** out);
+int vrt_context_destroy(vrt_context* ctx);
+int vrt_context_synchronize(vrt_context* ctx);
+int vrt_context_set_stream(vrt_context* ctx, void* stream);
+/* number of kernel launches this context has enqueued so far (bench.py's gpu_launches) */
+uint64_t vrt_context_launch_count(const vrt_context* ctx);
+
+/* ---- host-side scene construction (pure host code, no GPU needed) ---------------------------- */
+/* FastNoise SimplexFractal heights of the demo terrain, src/main.cpp:61-68; out[x*size+z]. */
+int vrt_host_terrain_heights(int32_t size, int32_t* out);
+/* SVO::setCell fill (main.cpp:70-76, 256 → size/2) + compileSVO (lsvo_utils.hpp:45-55,
+ * lsvo_utils.cpp:4-49) in one pass, without the 80-byte pointer nodes.  Two-call protocol:
+ * out == NULL → *count only. */
+int vrt_host_build_terrain_lsvo(uint32_t depth, const int32_t* heights, vrt_lnode* out, uint64_t cap, uint64_t* count);
+/* Same flattening for an explicit voxel list (xyz triples in SVO::setCell coordinates, svo.hpp:72). */
+int vrt_host_build_lsvo_from_voxels(uint32_t depth, const uint32_t* xyz, uint64_t n_voxels, vrt_lnode* out,
+                                    uint64_t cap, uint64_t* count);
+
+/* Camera::setViewAngle (camera_controller.hpp:27-32) + generateRotationMatrix (utils.cpp:94-100,
+ * glm::rotate about -y then -x): rot_mat column major, camera_vec = (0,0,1) * rot_mat. */
+int vrt_host_camera_rotation(const float view_angle[2], float rot_mat[9], float camera_vec[3]);
+
+/* ---- scenes ---------------------------------------------------------------------------------- */
+/* LSVO<D>::LSVO(const SVO<D>&) (lsvo.hpp:12-24): upload a flattened octree in the reference layout.
+ * `guard` = lower bound of the traversal loop `scale > MAX_DEPTH` (lsvo.hpp:72); pass 0 for the
+ * reference expression (= depth). */
+int vrt_lsvo_create(vrt_context* ctx, const vrt_lnode* nodes, uint64_t n_nodes, uint32_t depth, int32_t guard,
+                    vrt_scene** out);
+/* Grid3D<X,Y,Z> (grid_3d.hpp:10-27): cell_types[(x*Y+y)*Z+z] = Cell::Type (0 = Empty).
+ * mip_levels > 0 builds the MipmapGrid3D occupancy pyramid (results identical to Grid3D). */
+int vrt_grid_create(vrt_context* ctx, const uint8_t* cell_types, int32_t X, int32_t Y, int32_t Z, int32_t mip_levels,
+                    vrt_scene** out);
+/* SVO<N> (svo.hpp:29) from a dense occupancy occ[(x*S+y)*S+z], S = 2^depth. */
+int vrt_svo_create(vrt_context* ctx, const uint8_t* occ, uint32_t depth, vrt_scene** out);
+int vrt_scene_destroy(vrt_scene* scene);
+int vrt_scene_info(const vrt_scene* scene, int32_t* kind, uint32_t* depth, uint64_t* device_bytes);
+
+/* ---- batched traversal ------------------------------------------------------------------------
+ * Volumetric::castRay (volumetric.hpp:58) for n rays at once:
+ *   LSVO<D>::castRay(position, d, ray_size_coef, ray_size_bias)  lsvo.hpp:33
+ *   Grid3D::castRay(position, direction)                          grid_3d.hpp:35   (coef/bias ignored)
+ *   SVO<N>::castRay(position, direction, max_iter)                svo.hpp:62       (vrt_cast_rays_svo)
+ * origin/dir are xyz triples (n*3 floats).  Host variant copies in, runs, copies out, synchronises. */
+int vrt_cast_rays(vrt_scene* scene, const float* origin, const float* dir, float ray_size_coef, float ray_size_bias,
+                  uint64_t n, vrt_hit* out);
+int vrt_cast_rays_device(vrt_scene* scene, const float* d_origin, const float* d_dir, float ray_size_coef,
+                         float ray_size_bias, uint64_t n, vrt_hit* d_out);
+int vrt_cast_rays_svo(vrt_scene* scene, const float* origin, const float* dir, uint32_t max_iter, uint64_t n,
+                      vrt_hit* out);
+/* Σ complexity over the rays of the most recent cast on this scene (valid after synchronisation). */
+int vrt_scene_last_complexity(vrt_scene* scene, uint64_t* total);
+
+/* ---- rendering ---------------------------------------------------------------------------------
+ * Replaces the swarm lambda src/main.cpp:139-154 + RayCaster::renderRay (raycaster.hpp:67-92) +
+ * Camera::getRay (camera_controller.hpp:34-49) + samples_to_image (raycaster.hpp:94-103). */
+typedef struct vrt_camera {
+    float position[3];     /* Camera::position, voxel units */
+    float rot_mat[9];      /* Camera::rot_mat, column major */
+    float fov;             /* Camera::fov */
+    float aperture;        /* Camera::aperture */
+    float focal_length;    /* Camera::focal_length */
+} vrt_camera;
+
+typedef struct vrt_render_params {
+    int32_t width, height;       /* RayCaster::render_size */
+    int32_t row_begin, row_end;  /* rows [begin,end) rendered by this call (multi-GPU slabs) */
+    int32_t spp;                 /* renderRay passes per pixel in this call */
+    int32_t sample_offset;       /* index of the first sample (spp batches) */
+    uint32_t seed_lo, seed_hi;   /* Philox4x32-10 key (replaces the racy global xorshf96, utils.cpp:11-25) */
+    float light_position[3];     /* RayCaster::light_position (normalised, main.cpp:126) */
+    int32_t use_gi;              /* RayCaster::use_gi */
+    int32_t gi_bounces;          /* 1 = reference; 2 = extension */
+    int32_t use_samples;         /* RayCaster::use_samples */
+    int32_t reserved[3];
+} vrt_render_params;
+
+typedef struct vrt_render_stats {
+    uint64_t rays[6];            /* primary, shadow, gi, gi-shadow, gi2, gi2-shadow */
+    uint64_t complexity[6];      /* Σ HitPoint::complexity per class */
+} vrt_render_stats;
+
+/* 16x16 RGB albedo textures, top-down rows: RayCaster::image_top / image_side (raycaster.hpp:53-54). */
+int vrt_scene_set_textures(vrt_scene* scene, const uint8_t* top_rgb, const uint8_t* side_rgb);
+
+/* d_accum: device uint32 [height*width*4] r,g,b,count sums (RayCaster::colors, raycaster.hpp:259; the
+ * integer sums equal the reference's double accumulators exactly).  Rows outside [row_begin,row_end)
+ * are not touched.  Enqueues on the context stream. */
+int vrt_render_accumulate_device(vrt_scene* scene, const vrt_camera* cam, const vrt_render_params* p, uint32_t* d_accum);
+/* samples_to_image (use_samples) or the 0.4/0.6 temporal blend against d_rgba's previous content. */
+int vrt_render_resolve_device(vrt_scene* scene, const vrt_render_params* p, const uint32_t* d_accum, uint8_t* d_rgba);
+/* Convenience host-buffer frame: clears the accumulator, renders rows, resolves, copies RGBA (and
+ * optionally the accumulator) back.  rgba: [height*width*4] uint8, in/out when !use_samples. */
+int vrt_render(vrt_scene* scene, const vrt_camera* cam, const vrt_render_params* p, uint8_t* rgba, uint32_t* accum,
+               vrt_render_stats* stats);
+int vrt_scene_last_render_stats(vrt_scene* scene, vrt_render_stats* stats);
+/* Camera::getClosestPoint + the focal-length rule of main.cpp:115-121. */
+int vrt_autofocus(vrt_scene* scene, const vrt_camera* cam, float* focal_length);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VRT_H */

@@ -1,0 +1,103 @@
+/* TEST INFRASTRUCTURE ONLY (oracle/): CPU restatement of the reference's per-pixel hot path.
+ *
+ * Plain C, scalar, -ffp-contract=off.  Every function cites the reference file:line it follows.
+ * Pinned against the reference's own compiled sources (oracle/_ref, built by oracle/Makefile) by
+ * tests/test_oracle_pinned.py and against the committed fixtures under tests/golden/.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load libvrt_oracle.so — as the checker, never as the thing measured or shipped.
+ */
+#ifndef VRT_ORACLE_PORT_H
+#define VRT_ORACLE_PORT_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* LNode, include/lsvo_utils.hpp:5-18 (8 bytes; `color` is always 1 and never read). */
+typedef struct vo_lnode {
+    uint8_t color, child_mask, leaf_mask, pad;
+    uint32_t child_offset;
+} vo_lnode;
+
+/* HitPoint, include/volumetric.hpp:7-22, plus the traversal state a checker wants to see. */
+typedef struct vo_hit {
+    float position[3];
+    float normal[3];
+    float voxel_coord[2];
+    float distance;
+    uint32_t complexity;
+    uint32_t hit;      /* 0 = miss (only complexity is defined, the rest is zeroed) */
+    int32_t scale;     /* octree scale of the hit cell (23-depth for a leaf voxel), 0 on a miss */
+    int32_t voxel[3];  /* integer cell coordinate of the hit cell's low corner, in voxel units */
+    uint32_t face;     /* step mask that entered the cell: bit0 x, bit1 y, bit2 z */
+} vo_hit;
+
+/* ---- scene construction ------------------------------------------------------------------ */
+/* FastNoise 0.4.1 SimplexFractal FBM heights as main.cpp:68; out[x*size+z]. */
+void vo_terrain_heights(int32_t size, int32_t* out);
+float vo_noise2d(float x, float y);
+/* compileSVO (lsvo_utils.hpp:45-55, lsvo_utils.cpp:4-49) of the terrain fill main.cpp:63-76 with
+ * 256 generalised to size/2, WITHOUT the pointer SVO.  Returns the slot count; if `out` is NULL only
+ * counts.  `cap` = capacity of out in nodes. */
+uint64_t vo_build_terrain_lsvo(int depth, const int32_t* heights, vo_lnode* out, uint64_t cap);
+/* Same flattening for an arbitrary dense occupancy grid occ[(x*S+y)*S+z] != 0 (setCell coordinates). */
+uint64_t vo_build_dense_lsvo(int depth, const uint8_t* occ, vo_lnode* out, uint64_t cap);
+
+/* ---- traversal ---------------------------------------------------------------------------- */
+/* LSVO<depth>::castRay, include/lsvo.hpp:33-172.  `guard` is the lower loop bound of lsvo.hpp:72
+ * (`scale > MAX_DEPTH`): pass `depth` for the reference expression. */
+void vo_lsvo_cast(const vo_lnode* nodes, int depth, int guard, const float* origin, const float* dir,
+                  float coef, float bias, uint64_t n, vo_hit* out, int threads);
+
+/* Grid3D<X,Y,Z>::castRay, include/grid_3d.hpp:35-132; cells[(x*Y+y)*Z+z] = Cell::Type. */
+void vo_grid_cast(const uint8_t* cells, int X, int Y, int Z, const float* origin, const float* dir,
+                  uint64_t n, vo_hit* out, uint32_t* steps, int threads);
+
+/* SVO<depth>::castRay with fillHitResult's commented body restored ("intended SVO"),
+ * include/svo.hpp:62-70,116-194, over a dense occupancy occ[(x*S+y)*S+z]. */
+void vo_svo_cast(const uint8_t* occ, int depth, const float* origin, const float* dir, uint32_t max_iter,
+                 uint64_t n, vo_hit* out, int threads);
+
+/* ---- shading ------------------------------------------------------------------------------ */
+typedef struct vo_render_params {
+    int32_t width, height;
+    int32_t depth;            /* octree depth D; scale = 1/2^D replaces the literal 1/512 */
+    int32_t guard;            /* loop guard, see vo_lsvo_cast */
+    float cam_position[3];    /* voxel units (main.cpp:51) */
+    float rot_mat[9];         /* Camera::rot_mat, column major (camera_controller.hpp:21) */
+    float fov, aperture, focal_length;
+    float light_position[3];  /* normalised: light/2^D + 1 (main.cpp:126) */
+    int32_t use_gi;
+    int32_t gi_bounces;       /* 1 = reference (raycaster.hpp:169-207); 2 = extension, see DESIGN.md */
+    int32_t use_samples;      /* accumulate (raycaster.hpp:87-90) vs 0.4/0.6 temporal blend (:79-85) */
+    int32_t spp;
+    uint32_t seed_lo, seed_hi;  /* Philox4x32-10 key */
+    int32_t sample_offset;      /* first sample index (spp batches) */
+    int32_t row_begin, row_end; /* rows [begin,end) */
+    int32_t threads;
+} vo_render_params;
+
+typedef struct vo_render_stats {
+    uint64_t rays[6];        /* primary, shadow, gi, gi-shadow, gi2, gi2-shadow (distinct castRay calls) */
+    uint64_t complexity[6];  /* summed HitPoint::complexity per class */
+} vo_render_stats;
+
+/* tex_top / tex_side: 16x16 RGB, top-down rows (res/grass_top_16x16.bmp, res/grass_side_16x16.bmp as
+ * sf::Image presents them).  accum: [H*W*4] uint32 r,g,b,count sums (exact integer image of the
+ * reference's double accumulators raycaster.hpp:87-90).  rgba: resolved image (samples_to_image
+ * raycaster.hpp:94-103, or the temporal blend against `rgba` as previous frame when !use_samples). */
+void vo_render(const vo_lnode* nodes, const vo_render_params* p, const uint8_t* tex_top, const uint8_t* tex_side,
+               uint32_t* accum, uint8_t* rgba, vo_render_stats* stats);
+
+/* Camera::getRay + main.cpp:145-149 for one pixel/sample with the Philox lattice RNG. */
+void vo_camera_ray(const vo_render_params* p, int32_t x, int32_t y, int32_t sample, float origin[3], float dir[3]);
+
+/* Philox4x32-10 (Salmon et al. 2011), exposed for the RNG parity test. */
+void vo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

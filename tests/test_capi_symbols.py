@@ -1,0 +1,53 @@
+"""The C-ABI library loads and exports every symbol include/vrt.h declares (no compute calls)."""
+import os
+import re
+
+from conftest import ROOT
+
+
+def declared_in_header():
+    text = open(os.path.join(ROOT, "include", "vrt.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vrt_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree(vrt):
+    assert declared_in_header() == vrt.capi.declared_symbols()
+
+
+def test_library_exports_every_symbol(vrt):
+    lib = vrt.capi.lib()
+    for name in declared_in_header():
+        assert getattr(lib, name) is not None
+    assert lib.vrt_abi_version() == 1
+    assert b"sm_100a" in lib.vrt_build_info()
+
+
+def test_struct_sizes(vrt):
+    import ctypes as C
+    assert vrt.HIT.itemsize == 64 and vrt.LNODE.itemsize == 8
+    assert C.sizeof(vrt.capi.Camera) == 15 * 4
+    assert C.sizeof(vrt.capi.RenderParams) == 17 * 4
+    assert C.sizeof(vrt.capi.RenderStats) == 12 * 8
+
+
+def test_no_cpu_fallback_without_device(vrt):
+    """On a box without a GPU the compute entry points must fail loudly, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    import pytest
+    with pytest.raises(vrt.VrtError) as e:
+        vrt.Context(0)
+    assert e.value.code == -2   # VRT_ERR_CUDA
+
+
+def test_bad_arguments_are_errors(vrt):
+    import ctypes as C
+    import pytest
+    lib = vrt.capi.lib()
+    n = C.c_uint64(0)
+    assert lib.vrt_host_build_terrain_lsvo(5, None, None, 0, C.byref(n)) == -1
+    assert b"depth" in lib.vrt_last_error()
+    with pytest.raises(vrt.VrtError):
+        vrt.host_build_lsvo_from_voxels(4, [[16, 0, 0]])       # out of range: UB in the reference, an error here

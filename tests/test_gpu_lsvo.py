@@ -1,0 +1,81 @@
+"""K1 parity: LSVO<D>::castRay on the B200 through the C ABI, bit-exact against the reference's golden
+vectors and against the oracle on seeded inputs (hit flag, position, normal, uv, distance, complexity)."""
+import numpy as np
+import pytest
+
+from conftest import assert_hits_equal, bits, golden
+
+pytestmark = pytest.mark.gpu
+
+
+def hit_flag(h):
+    return (h["flags"] & 1) != 0
+
+
+def test_single_voxel_known_answers(vrt, ctx):
+    g = golden("lsvo_kat.npz")
+    s = vrt.LSVO.from_voxels(ctx, 9, g["voxels"])
+    hits = s.cast_rays(g["origin"], g["dir"])
+    assert_hits_equal(hits, g["hits"], hit_flag(hits), "kat")
+    assert list(hits["voxel"][0]) == [411, 311, 211]
+    h = s.castRay(g["origin"][0], g["dir"][0])                  # reference signature, one ray
+    assert h.cell and h.complexity == 14 and list(h.normal) == [0.0, 0.0, -4.0]
+
+
+def test_golden_terrain(vrt, ctx, terrain9_nodes):
+    g = golden("lsvo_terrain9.npz")
+    s = vrt.LSVO(ctx, terrain9_nodes, 9)
+    for key, coef, bias in (("hits_coef0", 0.0, 0.0), ("hits_coef05", 0.5, 0.0), ("hits_bias", 0.25, 0.001)):
+        hits = s.cast_rays(g["origin"], g["dir"], coef, bias)
+        assert_hits_equal(hits, g[key], hit_flag(hits), key)
+        assert s.last_complexity() == int(g[key]["complexity"].sum())
+
+
+def test_golden_random_scene(vrt, ctx):
+    g = golden("lsvo_random6.npz")
+    s = vrt.LSVO(ctx, g["nodes"], 6)
+    for key, coef in (("hits_coef0", 0.0), ("hits_coef05", 0.5)):
+        hits = s.cast_rays(g["origin"], g["dir"], coef, 0.0)
+        assert_hits_equal(hits, g[key], hit_flag(hits), key)
+
+
+def test_oracle_large_seeded(vrt, ctx, port, terrain9_nodes):
+    rng = np.random.default_rng(7)
+    n = 1 << 20
+    o = rng.uniform(1, 2, (n, 3)).astype(np.float32)
+    o[:, 1] = rng.uniform(1.0, 1.45, n)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    s = vrt.LSVO(ctx, terrain9_nodes, 9)
+    got = s.cast_rays(o, d)
+    want = port.lsvo_cast(terrain9_nodes, 9, o, d, threads=8)
+    assert_hits_equal(got, want, hit_flag(got), "1M random rays")
+    m = hit_flag(got)
+    assert np.array_equal(got["voxel"][m], want["voxel"][m]) and np.array_equal(got["face"][m], want["face"][m])
+    assert np.array_equal(got["scale"][m], want["scale"][m])
+
+
+def test_edge_cases(vrt, ctx, port):
+    g = golden("lsvo_random6.npz")
+    s = vrt.LSVO(ctx, g["nodes"], 6)
+    assert len(s.cast_rays(np.zeros((0, 3)), np.zeros((0, 3)))) == 0             # empty batch
+    # ragged sizes around the block size, origins outside the cube, zero / denormal direction components
+    rng = np.random.default_rng(3)
+    for n in (1, 31, 33, 127, 129, 1000):
+        o = rng.uniform(-0.5, 3.5, (n, 3)).astype(np.float32)
+        d = rng.normal(size=(n, 3)).astype(np.float32)
+        d[rng.random((n, 3)) < 0.2] = 0.0
+        d[rng.random((n, 3)) < 0.05] = np.float32(1e-40)
+        d[rng.random((n, 3)) < 0.05] = np.float32(-0.0)
+        got = s.cast_rays(o, d)
+        want = port.lsvo_cast(g["nodes"], 6, o, d)
+        assert_hits_equal(got, want, hit_flag(got), "ragged n=%d" % n)
+    # empty octree (root only)
+    e = vrt.LSVO.from_voxels(ctx, 4, np.zeros((0, 3), np.uint32))
+    got = e.cast_rays([[1.5, 1.5, 1.1]], [[0, 0, 1]])
+    assert not hit_flag(got)[0]
+    # full octree: every ray that enters the cube hits at the entry face
+    full = np.stack(np.meshgrid(*[np.arange(8)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    f = vrt.LSVO.from_voxels(ctx, 3, full)
+    got = f.cast_rays([[1.5, 1.5, 0.5]], [[0, 0, 1]])
+    assert hit_flag(got)[0] and got["distance"][0] == 0.5 and list(got["normal"][0]) == [0.0, 0.0, -4.0]
