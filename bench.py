@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the voxel ray-traversal hot path.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[3], the configuration the metric "Mrays/s ... and ms/frame 1080p at
+1/2/4/8 B200" is quoted on): synthetic FastNoise terrain T(11) = 2048^3 in an LSVO, 1920x1080, 64 spp,
+use_samples + use_gi with 2 GI bounces + depth of field (aperture 0.5), camera C(11), rows dealt in
+4-row tiles round-robin over the GPUs, frame all-gathered with NCCL.  A "step" is one such frame.
+A "ray" is one distinct castRay (primary, sun shadow, GI, GI shadow, bounce-2 GI, its shadow).
+
+value  = rays of the whole frame / device time with the scene and frame buffers resident in HBM
+e2e    = the same through the user-facing FrameRenderer.render(): camera/params in from the host and the
+         finished RGBA frame copied back to pinned host memory inside the timed region
+The reference arm times the reference's own CPU implementation (oracle/_ref, compiled from the
+reference's sources) on a bounded sample of the same frame on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mrays/s (primary+shadow+GI), 1080p 64-spp GI+DOF frame on LSVO 2048^3"
+UNIT = "Mrays/s"
+
+
+def workload(args):
+    D = args.depth
+    S = 1 << D
+    return dict(depth=D, size=S, width=args.width, height=args.height, spp=args.spp, gi_bounces=args.gi_bounces,
+                aperture=args.aperture, cam_position=[S / 2.0, S / 2.0 - 56.0, S / 2.0], view_angle=[0.0, 0.0],
+                light=[-200.0, -1000.0, -300.0], seed=(0x5EED, 0))
+
+
+def light_normalised(w):
+    return np.float32(w["light"]) * np.float32(1.0 / w["size"]) + np.float32(1.0)      # main.cpp:124-126
+
+
+def load_textures():
+    t = np.load(os.path.join(ROOT, "tests", "golden", "textures.npz"))
+    return t["top"], t["side"]
+
+
+def config_json(w, n_gpus, extra=None):
+    c = {"workload": "cfg4: LSVO %d^3 FastNoise terrain T(%d), %dx%d, %d spp, use_samples+use_gi (%d bounces) + DOF aperture %.2f, "
+                     "camera C(%d), 4-row tiles round-robin over %d GPU(s), NCCL all-gather of RGBA tiles"
+                     % (w["size"], w["depth"], w["width"], w["height"], w["spp"], w["gi_bounces"], w["aperture"], w["depth"], n_gpus),
+         "depth": w["depth"], "width": w["width"], "height": w["height"], "spp": w["spp"], "gi_bounces": w["gi_bounces"],
+         "aperture": w["aperture"], "rng": "Philox4x32-10 on getRand's 100-level lattice, key 0x5EED",
+         "ray_definition": "distinct castRay calls (the reference's 4 identical shadow samples count once)",
+         "l2": "inputs larger than L2: %.2f GB node array + 33 MB accumulator vs 126 MB L2" % (w.get("node_gb", 0.0))}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ---- clocks sampler (B200_PROFILING.md recipe) --------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- CPU legs (the only places that may execute oracle/) ------------------------------------------------
+def cpu_port_sample(w, cores, tile_step, spp):
+    """The oracle restatement (kind "port") on a bounded sample of the workload: every tile_step-th 4-row tile,
+    `spp` of the samples, all host threads."""
+    from oracle import loader
+    P = loader.port()
+    nodes = P.build_terrain(w["depth"])
+    top, side = load_textures()
+    import cpuvoxelraycaster_b200 as vrt                     # host-only helper: camera basis (pure host code)
+    cam = vrt.Camera(position=w["cam_position"], view_angle=w["view_angle"], aperture=w["aperture"], focal_length=100.0)
+    p = loader.PortRenderParams()
+    p.width, p.height, p.depth, p.guard = w["width"], w["height"], w["depth"], w["depth"]
+    p.cam_position[:] = w["cam_position"]
+    p.rot_mat[:] = [float(x) for x in cam.rot_mat]
+    p.fov, p.aperture, p.focal_length = 1.0, w["aperture"], w["focal_length"]
+    p.light_position[:] = [float(x) for x in light_normalised(w)]
+    p.use_gi, p.gi_bounces, p.use_samples, p.spp = 1, w["gi_bounces"], 1, spp
+    p.seed_lo, p.seed_hi = w["seed"]
+    p.threads, p.tile_step, p.tile_index = cores, tile_step, 0
+    t0 = time.perf_counter()
+    _, _, st = P.render(nodes, p, top, side)
+    dt = time.perf_counter() - t0
+    rays = sum(st.rays)
+    return rays, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU code (oracle/_ref, RayCaster + Camera + LSVO::castRay compiled
+    from the reference's sources at the workload's depth, swarm-threaded) on a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import loader
+    w = workload(args)
+    cores = os.cpu_count() or 1
+    R = loader.ref_depth(w["depth"])
+    P = loader.port()
+    top, side = load_textures()
+    nodes = P.build_terrain(w["depth"])
+    w["node_gb"] = nodes.nbytes / 1e9
+    tile_step, spp = args.ref_tile_step, args.ref_spp
+    sample_desc = "every %d-th 4-row tile x %d of %d spp = 1/%d of the frame per step" % (
+        tile_step, spp, w["spp"], tile_step * w["spp"] // spp)
+    if R is not None:
+        kind = "reference"
+        R.register_textures(top, side)
+        scene = R.scene_from_nodes(w["depth"], nodes)
+        p = loader.RefRenderParams()
+        p.width, p.height = w["width"], w["height"]
+        p.cam_position[:] = w["cam_position"]
+        p.view_angle[:] = w["view_angle"]
+        p.fov, p.aperture = 1.0, w["aperture"]
+        p.light_position[:] = [float(x) for x in light_normalised(w)]
+        p.focal_length = R.autofocus(scene, p)
+        p.use_gi, p.use_samples, p.spp, p.threads = 1, 1, spp, cores
+        p.row_begin, p.row_end, p.tile_step, p.tile_index = 0, w["height"], tile_step, 0
+
+        def step():
+            r = R.render(scene, p)
+            # distinct rays: primary + shadow (4 identical invocations per hit under use_samples) + GI + GI shadow
+            pixels = sum(1 for y in range(w["height"]) if (y >> 2) % tile_step == 0) * w["width"] * spp
+            shadow = (r["cone0_calls"] - pixels) // 4
+            return pixels + shadow + r["cone_gi_calls"], r["seconds"]
+        note = "reference RayCaster has one GI bounce (raycaster.hpp:169-207); the 2-bounce workload is an extension"
+    else:
+        kind = "port"
+        w["focal_length"] = 100.0
+
+        def step():
+            return cpu_port_sample(w, cores, tile_step, spp)
+        note = "oracle/_ref absent: timed the C restatement"
+    for _ in range(args.warmup):
+        step()
+    rays, secs = 0, 0.0
+    for _ in range(args.steps):
+        r, s = step()
+        rays += r
+        secs += s
+    value = rays / secs / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * secs / args.steps, 3),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_json(w, args.gpus, {"note": note}),
+            "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample_desc},
+            "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---- our arm ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import cpuvoxelraycaster_b200 as vrt
+    from cpuvoxelraycaster_b200.frame import FrameRenderer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus %d must be launched with torchrun --nproc-per-node %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    w = workload(args)
+    stream = torch.cuda.Stream(device)
+    ctx = vrt.Context(local_rank, stream.cuda_stream)
+    t0 = time.perf_counter()
+    nodes = vrt.host_build_terrain_lsvo(w["depth"])          # every rank builds its replica (host code, < 1 s)
+    build_s = time.perf_counter() - t0
+    w["node_gb"] = nodes.nbytes / 1e9
+    scene = vrt.LSVO(ctx, nodes, w["depth"])
+    scene.set_textures(*load_textures())
+    n_slots = len(nodes)
+    del nodes
+    cam = vrt.Camera(position=w["cam_position"], view_angle=w["view_angle"], aperture=w["aperture"])
+    cam.autofocus(scene)                                     # main.cpp:115-121
+    w["focal_length"] = cam.focal_length
+
+    fr = FrameRenderer(scene, w["width"], w["height"], rank, world, None, device, stream)
+    fr.use_gi, fr.gi_bounces, fr.use_samples, fr.seed = True, w["gi_bounces"], True, w["seed"]
+    fr.light = light_normalised(w)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---- device-resident timing -------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        fr.render_device(cam, w["spp"])
+    sync_all()
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    cam_struct, p = cam.as_struct(), fr.params(w["spp"])
+    ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with torch.cuda.stream(stream):
+        ev_start.record(stream)
+        for i in range(args.steps):
+            fr.accum.zero_()
+            k_ev[i][0].record(stream)
+            fr.accumulate(cam_struct, p)                     # the dominant kernel, timed on its own stream
+            k_ev[i][1].record(stream)
+            fr.resolve(p)
+            fr.gather()
+        ev_end.record(stream)
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launch_count - launches0
+    ms_total = ev_start.elapsed_time(ev_end)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    st = fr.stats()                                          # this rank's tiles, last frame
+    t = torch.tensor([ms_total, kernel_ms], dtype=torch.float64, device=device)
+    cnt = torch.tensor(st["rays"] + st["complexity"], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        local_cnt = cnt.clone()
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    else:
+        local_cnt = cnt
+    ms_total, kernel_ms_max = float(t[0]), float(t[1])
+    rays = [int(x) for x in cnt[:6].tolist()]
+    cx = [int(x) for x in cnt[6:].tolist()]
+    total_rays = sum(rays)
+    ms_per_step = ms_total / args.steps
+    value = total_rays / (ms_per_step * 1e-3) / 1e6
+
+    # roofline of the dominant kernel on this rank: algorithmic bytes = sum over its rays of (8 B node per
+    # iteration + 64 B ray/hit record) + 16 B accumulator write per pixel
+    l_rays, l_cx = int(local_cnt[:6].sum()), int(local_cnt[6:].sum())
+    my_pixels = sum(1 for y in range(w["height"]) if (y >> 2) % world == rank) * w["width"]
+    algo_bytes = 8 * l_cx + 64 * l_rays + 16 * my_pixels
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("render_accumulate_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "render_accumulate_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": round(kernel_ms, 4),
+                "kernel_share_of_step": round(kernel_ms_max / ms_per_step, 4),
+                "note": "pointer chasing: latency/divergence bound by design, see DESIGN.md; node fetches are mostly L1/L2 hits"}
+
+    # ---- end to end through the public API (host in, host out) -------------------------------------------
+    for _ in range(2):
+        fr.render(cam, w["spp"])
+    sync_all()
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        frame = fr.render(cam, w["spp"])
+    e_end.record(stream)
+    sync_all()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e_start.elapsed_time(e_end), wall_ms) / args.steps
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te[0])
+    import ctypes as C
+    h2d = C.sizeof(vrt.capi.Camera) + C.sizeof(vrt.capi.RenderParams)
+    e2e = {"value": round(total_rays / (e2e_ms * 1e-3) / 1e6, 2), "unit": UNIT, "ms_per_step": round(e2e_ms, 3),
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(frame.nbytes),
+           "note": "a renderer's per-frame input is the camera + render parameters; the scene is resident like model weights"}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            c_rays, c_dt = cpu_port_sample(w, cores, args.cpu_tile_step, args.cpu_spp)
+            cpu = {"value": round(c_rays / c_dt / 1e6, 3), "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "every %d-th 4-row tile x %d of %d spp = 1/%d of the frame, %.1f s wall" % (
+                       args.cpu_tile_step, args.cpu_spp, w["spp"], args.cpu_tile_step * w["spp"] // args.cpu_spp, c_dt)}
+        line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config_json(w, world, {"focal_length": w["focal_length"], "lsvo_slots": n_slots,
+                                                 "scene_build_s_host": round(build_s, 2)}),
+                "rays_per_frame": dict(zip(["primary", "shadow", "gi", "gi_shadow", "gi2", "gi2_shadow"], rays)),
+                "mean_complexity": round(sum(cx) / max(1, total_rays), 2),
+                "ms_per_frame": round(ms_per_step, 4), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--depth", type=int, default=11)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--spp", type=int, default=64)
+    ap.add_argument("--gi-bounces", type=int, default=2)
+    ap.add_argument("--aperture", type=float, default=0.5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-tile-step", type=int, default=4)
+    ap.add_argument("--cpu-spp", type=int, default=16)
+    ap.add_argument("--ref-tile-step", type=int, default=8)
+    ap.add_argument("--ref-spp", type=int, default=8)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    return run_reference(args) if args.impl == "reference" else run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

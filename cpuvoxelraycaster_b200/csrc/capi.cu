@@ -66,7 +66,10 @@ struct vrt_scene {
     uint2* d_nodes = nullptr;
     uint64_t n_nodes = 0;
     uint64_t device_bytes = 0;
-    unsigned long long* d_counters = nullptr;   // [0] Σ complexity of the last cast
+    unsigned long long* d_counters = nullptr;   // [0] Σ complexity of the last cast; [2..13] render rays/complexity per class
+    uint8_t* d_tex = nullptr;                   // top (768 B) then side (768 B)
+    bool has_tex = false;
+    DeviceBuffer frame_accum, frame_rgba;       // vrt_render staging
 };
 
 namespace {
@@ -207,6 +210,9 @@ int vrt_scene_destroy(vrt_scene* sc) {
     cudaStreamSynchronize(sc->ctx->stream);
     if (sc->d_nodes) cudaFree(sc->d_nodes);
     if (sc->d_counters) cudaFree(sc->d_counters);
+    if (sc->d_tex) cudaFree(sc->d_tex);
+    sc->frame_accum.release();
+    sc->frame_rgba.release();
     delete sc;
     return VRT_OK;
 }
@@ -270,15 +276,130 @@ int vrt_scene_last_complexity(vrt_scene* sc, uint64_t* total) {
     return VRT_OK;
 }
 
+// ---- rendering -------------------------------------------------------------------------------------
+namespace {
+constexpr int kRenderCounters = 2;   // offset of the 12 render counters inside d_counters
+
+int check_render_args(const vrt_scene* sc, const vrt_camera* cam, const vrt_render_params* p, const char* who) {
+    if (!sc || !p) return fail(VRT_ERR_INVALID, std::string(who) + ": NULL argument");
+    if (sc->kind != VRT_SCENE_LSVO) return fail(VRT_ERR_UNSUPPORTED, std::string(who) + ": rendering needs an LSVO scene (raycaster.hpp:265)");
+    if (p->width <= 0 || p->height <= 0 || p->width > 65536 || p->height > 65536) return fail(VRT_ERR_INVALID, std::string(who) + ": bad frame size");
+    if (p->row_begin < 0 || p->row_end > p->height || p->row_begin > p->row_end) return fail(VRT_ERR_INVALID, std::string(who) + ": bad row range");
+    if (cam && (p->spp <= 0 || p->gi_bounces < 0 || p->gi_bounces > 2)) return fail(VRT_ERR_INVALID, std::string(who) + ": spp must be > 0 and gi_bounces in 0..2");
+    if (p->tile_step > 1 && (p->tile_index < 0 || p->tile_index >= p->tile_step)) return fail(VRT_ERR_INVALID, std::string(who) + ": tile_index must be in [0, tile_step)");
+    if (cam && !sc->has_tex) return fail(VRT_ERR_INVALID, std::string(who) + ": call vrt_scene_set_textures first (raycaster.hpp:53-54)");
+    return VRT_OK;
+}
+
+vrt::RenderLaunch make_launch(const vrt_scene* sc, const vrt_camera* cam, const vrt_render_params* p) {
+    vrt::RenderLaunch L;
+    L.width = p->width; L.height = p->height; L.row_begin = p->row_begin; L.row_end = p->row_end;
+    L.spp = p->spp; L.sample_offset = p->sample_offset;
+    L.depth = int(sc->depth); L.guard = sc->guard;
+    L.use_gi = p->use_gi; L.gi_bounces = p->gi_bounces < 1 ? 1 : p->gi_bounces;
+    L.seed_lo = p->seed_lo; L.seed_hi = p->seed_hi;
+    for (int i = 0; i < 3; ++i) L.light[i] = p->light_position[i];
+    L.cam = *cam;
+    L.tile_step = p->tile_step > 1 ? p->tile_step : 1;
+    L.tile_index = p->tile_step > 1 ? p->tile_index : 0;
+    L.tex_top = sc->d_tex; L.tex_side = sc->d_tex + 768;
+    return L;
+}
+}  // namespace
+
+int vrt_scene_set_textures(vrt_scene* sc, const uint8_t* top_rgb, const uint8_t* side_rgb) {
+    if (!sc || !top_rgb || !side_rgb) return fail(VRT_ERR_INVALID, "vrt_scene_set_textures: NULL argument");
+    if (int s = use_device(sc->ctx)) return s;
+    if (!sc->d_tex) VRT_CUDA(cudaMalloc(&sc->d_tex, 1536));
+    VRT_CUDA(cudaMemcpyAsync(sc->d_tex, top_rgb, 768, cudaMemcpyHostToDevice, sc->ctx->stream));
+    VRT_CUDA(cudaMemcpyAsync(sc->d_tex + 768, side_rgb, 768, cudaMemcpyHostToDevice, sc->ctx->stream));
+    VRT_CUDA(cudaStreamSynchronize(sc->ctx->stream));
+    sc->has_tex = true;
+    return VRT_OK;
+}
+
+int vrt_render_accumulate_device(vrt_scene* sc, const vrt_camera* cam, const vrt_render_params* p, uint32_t* d_accum) {
+    if (!cam || !d_accum) return fail(VRT_ERR_INVALID, "vrt_render_accumulate_device: NULL argument");
+    if (int s = check_render_args(sc, cam, p, "vrt_render_accumulate_device")) return s;
+    vrt_context* ctx = sc->ctx;
+    if (int s = use_device(ctx)) return s;
+    VRT_CUDA(cudaMemsetAsync(sc->d_counters + kRenderCounters, 0, 12 * sizeof(unsigned long long), ctx->stream));
+    if (p->row_end == p->row_begin) return VRT_OK;
+    VRT_CUDA(vrt::launch_render_accumulate_ref(sc->d_nodes, make_launch(sc, cam, p), d_accum, sc->d_counters + kRenderCounters,
+                                               ctx->stream));
+    ctx->launches += 1;
+    return VRT_OK;
+}
+
+int vrt_render_resolve_device(vrt_scene* sc, const vrt_render_params* p, const uint32_t* d_accum, uint8_t* d_rgba) {
+    if (!d_accum || !d_rgba) return fail(VRT_ERR_INVALID, "vrt_render_resolve_device: NULL argument");
+    if (int s = check_render_args(sc, nullptr, p, "vrt_render_resolve_device")) return s;
+    vrt_context* ctx = sc->ctx;
+    if (int s = use_device(ctx)) return s;
+    if (p->row_end == p->row_begin) return VRT_OK;
+    VRT_CUDA(vrt::launch_resolve(d_accum, d_rgba, p->width, p->row_begin, p->row_end, p->use_samples,
+                                 p->tile_step > 1 ? p->tile_step : 1, p->tile_step > 1 ? p->tile_index : 0, ctx->stream));
+    ctx->launches += 1;
+    return VRT_OK;
+}
+
+int vrt_scene_last_render_stats(vrt_scene* sc, vrt_render_stats* stats) {
+    if (!sc || !stats) return fail(VRT_ERR_INVALID, "vrt_scene_last_render_stats: NULL argument");
+    if (int s = use_device(sc->ctx)) return s;
+    unsigned long long v[12];
+    VRT_CUDA(cudaMemcpyAsync(v, sc->d_counters + kRenderCounters, sizeof(v), cudaMemcpyDeviceToHost, sc->ctx->stream));
+    VRT_CUDA(cudaStreamSynchronize(sc->ctx->stream));
+    for (int k = 0; k < 6; ++k) { stats->rays[k] = v[k]; stats->complexity[k] = v[6 + k]; }
+    return VRT_OK;
+}
+
+int vrt_render(vrt_scene* sc, const vrt_camera* cam, const vrt_render_params* p, uint8_t* rgba, uint32_t* accum,
+               vrt_render_stats* stats) {
+    if (!cam || !rgba) return fail(VRT_ERR_INVALID, "vrt_render: NULL argument");
+    if (int s = check_render_args(sc, cam, p, "vrt_render")) return s;
+    if (!p->use_samples && p->spp != 1) return fail(VRT_ERR_INVALID, "vrt_render: the temporal-blend mode renders one sample per frame (raycaster.hpp:77-85)");
+    vrt_context* ctx = sc->ctx;
+    if (int s = use_device(ctx)) return s;
+    const size_t px = size_t(p->width) * p->height;
+    if (sc->frame_accum.reserve(px * 16) != cudaSuccess || sc->frame_rgba.reserve(px * 4) != cudaSuccess)
+        return fail(VRT_ERR_OOM, "vrt_render: device frame allocation failed");
+    uint32_t* d_accum = static_cast<uint32_t*>(sc->frame_accum.ptr);
+    uint8_t* d_rgba = static_cast<uint8_t*>(sc->frame_rgba.ptr);
+    const size_t row0 = size_t(p->row_begin) * p->width, nrow = size_t(p->row_end - p->row_begin) * p->width;
+    if (p->accum_in && accum)
+        VRT_CUDA(cudaMemcpyAsync(d_accum + row0 * 4, accum + row0 * 4, nrow * 16, cudaMemcpyHostToDevice, ctx->stream));
+    else
+        VRT_CUDA(cudaMemsetAsync(d_accum + row0 * 4, 0, nrow * 16, ctx->stream));
+    if (!p->use_samples)   // the blend reads the previous frame
+        VRT_CUDA(cudaMemcpyAsync(d_rgba + row0 * 4, rgba + row0 * 4, nrow * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (int s = vrt_render_accumulate_device(sc, cam, p, d_accum)) return s;
+    if (int s = vrt_render_resolve_device(sc, p, d_accum, d_rgba)) return s;
+    VRT_CUDA(cudaMemcpyAsync(rgba + row0 * 4, d_rgba + row0 * 4, nrow * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (accum) VRT_CUDA(cudaMemcpyAsync(accum + row0 * 4, d_accum + row0 * 4, nrow * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    VRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (stats) return vrt_scene_last_render_stats(sc, stats);
+    return VRT_OK;
+}
+
+int vrt_autofocus(vrt_scene* sc, const vrt_camera* cam, float* focal_length) {
+    if (!sc || !cam || !focal_length) return fail(VRT_ERR_INVALID, "vrt_autofocus: NULL argument");
+    if (sc->kind != VRT_SCENE_LSVO) return fail(VRT_ERR_UNSUPPORTED, "vrt_autofocus: needs an LSVO scene");
+    // Camera::getClosestPoint (camera_controller.hpp:56-60): position*scale + 1 along camera_vec = (0,0,1)*rot_mat
+    const float scale = 1.0f / float(1u << sc->depth);
+    float o[3], d[3];
+    for (int i = 0; i < 3; ++i) {
+        o[i] = cam->position[i] * scale + 1.0f;
+        d[i] = (cam->rot_mat[3 * i + 0] * 0.0f + cam->rot_mat[3 * i + 1] * 0.0f) + cam->rot_mat[3 * i + 2] * 1.0f;
+    }
+    vrt_hit h;
+    if (int s = vrt_cast_rays(sc, o, d, 0.0f, 0.0f, 1, &h)) return s;
+    *focal_length = (h.flags & VRT_HIT_FLAG_HIT) ? h.distance * float(1u << sc->depth) : 100.0f;   // main.cpp:116-121
+    return VRT_OK;
+}
+
 // ---- not implemented yet (TODO: replaced as the kernels land) --------------------------------------
 int vrt_grid_create(vrt_context*, const uint8_t*, int32_t, int32_t, int32_t, int32_t, vrt_scene**) { return fail(VRT_ERR_UNSUPPORTED, "vrt_grid_create: not implemented"); }
 int vrt_svo_create(vrt_context*, const uint8_t*, uint32_t, vrt_scene**) { return fail(VRT_ERR_UNSUPPORTED, "vrt_svo_create: not implemented"); }
 int vrt_cast_rays_svo(vrt_scene*, const float*, const float*, uint32_t, uint64_t, vrt_hit*) { return fail(VRT_ERR_UNSUPPORTED, "vrt_cast_rays_svo: not implemented"); }
-int vrt_scene_set_textures(vrt_scene*, const uint8_t*, const uint8_t*) { return fail(VRT_ERR_UNSUPPORTED, "vrt_scene_set_textures: not implemented"); }
-int vrt_render_accumulate_device(vrt_scene*, const vrt_camera*, const vrt_render_params*, uint32_t*) { return fail(VRT_ERR_UNSUPPORTED, "not implemented"); }
-int vrt_render_resolve_device(vrt_scene*, const vrt_render_params*, const uint32_t*, uint8_t*) { return fail(VRT_ERR_UNSUPPORTED, "not implemented"); }
-int vrt_render(vrt_scene*, const vrt_camera*, const vrt_render_params*, uint8_t*, uint32_t*, vrt_render_stats*) { return fail(VRT_ERR_UNSUPPORTED, "not implemented"); }
-int vrt_scene_last_render_stats(vrt_scene*, vrt_render_stats*) { return fail(VRT_ERR_UNSUPPORTED, "not implemented"); }
-int vrt_autofocus(vrt_scene*, const vrt_camera*, float*) { return fail(VRT_ERR_UNSUPPORTED, "not implemented"); }
 
 }  // extern "C"

@@ -11,4 +11,24 @@ cudaError_t launch_lsvo_cast_ref(const uint2* nodes, int depth, int guard, const
                                  float coef, float bias, uint64_t n, vrt_hit* d_out, unsigned long long* d_complexity,
                                  cudaStream_t stream);
 
+// Everything one render launch needs, passed by value (constant bank).
+struct RenderLaunch {
+    int width, height, row_begin, row_end;
+    int spp, sample_offset;
+    int depth, guard;
+    int use_gi, gi_bounces;
+    int tile_step, tile_index;   // 4-row tiles t with t % tile_step == tile_index are rendered
+    uint32_t seed_lo, seed_hi;
+    float light[3];
+    vrt_camera cam;
+    const uint8_t* tex_top;    // 16x16 RGB, device
+    const uint8_t* tex_side;
+};
+
+// K0+K4: ray generation, traversal, shading and accumulation for rows [row_begin,row_end) (render_kernels.cu)
+cudaError_t launch_render_accumulate_ref(const uint2* nodes, const RenderLaunch& L, uint32_t* d_accum,
+                                         unsigned long long* d_counters, cudaStream_t stream);
+cudaError_t launch_resolve(const uint32_t* d_accum, uint8_t* d_rgba, int width, int row_begin, int row_end, int use_samples,
+                           int tile_step, int tile_index, cudaStream_t stream);
+
 }  // namespace vrt

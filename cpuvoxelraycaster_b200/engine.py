@@ -314,17 +314,17 @@ class RayCaster:
         use_samples, else the 0.4/0.6 temporal blend into render_image (raycaster.hpp:77-91)."""
         p = self.params(spp, row_begin, row_end)
         stats = capi.RenderStats()
-        accum = np.zeros_like(self.colors)
-        check(lib().vrt_render(self.svo.handle, C.byref(camera.as_struct()), C.byref(p), ptr(self.render_image), ptr(accum),
-                               C.byref(stats)))
         if self.use_samples:
-            self.colors += accum
+            p.accum_in = 1                                      # progressive: sums carry over (raycaster.hpp:87-90)
+        else:
+            self.colors[...] = 0
+        check(lib().vrt_render(self.svo.handle, C.byref(camera.as_struct()), C.byref(p), ptr(self.render_image),
+                               ptr(self.colors), C.byref(stats)))
+        if self.use_samples:
             self.sample_count += int(spp)
         self.last_stats = dict(rays=list(stats.rays), complexity=list(stats.complexity))
         return self.render_image
 
-    def samples_to_image(self):                                 # raycaster.hpp:94-103
-        cnt = np.maximum(self.colors[..., 3:4], 1)
-        self.render_image[..., :3] = (self.colors[..., :3] // cnt).astype(np.uint8)
-        self.render_image[..., 3] = 255
+    def samples_to_image(self):
+        """raycaster.hpp:94-103 — already applied on the device by render() when use_samples."""
         return self.render_image

@@ -1,0 +1,98 @@
+"""Whole-frame rendering on 1..N GPUs of one box — the replacement of the reference's per-frame driver,
+the swarm lambda src/main.cpp:139-154 (16 CPU threads in 4x4 screen tiles) + samples_to_image (:156-158).
+
+One process per GPU.  The voxel scene is replicated; the frame's 4-row tiles are dealt round-robin to the
+ranks (sky and terrain rows cost very differently, so contiguous slabs would be unbalanced); every rank
+renders and resolves its tiles with libvrt's kernels and the RGBA slabs are exchanged with ONE NCCL
+all-gather over NVLink.  Because the RNG is counter based (pixel, sample, dimension) the assembled frame
+is bit-identical for every world size.
+
+torch is used for device buffers, the stream and torch.distributed only.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import capi
+from .capi import check, lib, ptr
+
+
+class FrameRenderer:
+    def __init__(self, scene, width, height, rank=0, world=1, group=None, device=None, stream=None):
+        self.scene, self.W, self.H = scene, int(width), int(height)
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.device = device if device is not None else torch.device("cuda", scene.ctx.device)
+        # libvrt's launches and torch's copies/collectives must share one stream
+        self.stream = stream if stream is not None else torch.cuda.Stream(self.device)
+        scene.ctx.set_stream(self.stream.cuda_stream)
+        unit = 4 * self.world
+        self.H_pad = (self.H + unit - 1) // unit * unit
+        self.accum = torch.zeros(self.H_pad * self.W * 4, dtype=torch.int32, device=self.device)   # r,g,b,count sums
+        self.rgba = torch.zeros(self.H_pad * self.W * 4, dtype=torch.uint8, device=self.device)
+        self.tiles_local = self.H_pad // unit
+        self.row_bytes = self.W * 4
+        if self.world > 1:
+            self.slab = torch.empty(self.tiles_local * 4 * self.row_bytes, dtype=torch.uint8, device=self.device)
+            self.gathered = torch.empty(self.world * self.slab.numel(), dtype=torch.uint8, device=self.device)
+            self.frame = torch.empty(self.H_pad * self.row_bytes, dtype=torch.uint8, device=self.device)
+        else:
+            self.frame = self.rgba
+        self.host_frame = torch.empty(self.H * self.row_bytes, dtype=torch.uint8).pin_memory()
+        self.use_gi, self.gi_bounces, self.use_samples = False, 1, True
+        self.seed = (0x5EED, 0)
+        self.light = np.zeros(3, np.float32)
+
+    def params(self, spp, sample_offset=0):
+        p = capi.RenderParams()
+        p.width, p.height, p.row_begin, p.row_end = self.W, self.H, 0, self.H
+        p.spp, p.sample_offset = int(spp), int(sample_offset)
+        p.seed_lo, p.seed_hi = self.seed
+        p.light_position[:] = [float(x) for x in self.light]
+        p.use_gi, p.gi_bounces, p.use_samples = int(self.use_gi), int(self.gi_bounces), int(self.use_samples)
+        p.tile_step, p.tile_index = self.world, self.rank
+        return p
+
+    # -- device-resident frame: enqueue only (the caller owns stream/synchronisation) --
+    def accumulate(self, cam_struct, p):
+        check(lib().vrt_render_accumulate_device(self.scene.handle, C.byref(cam_struct), C.byref(p), ptr(self.accum)))
+
+    def resolve(self, p):
+        check(lib().vrt_render_resolve_device(self.scene.handle, C.byref(p), ptr(self.accum), ptr(self.rgba)))
+
+    def gather(self):
+        """All-gather of the ranks' RGBA tiles (the frame's one exchange step).  No-op on one GPU."""
+        if self.world == 1:
+            return self.frame
+        import torch.distributed as dist
+        tiles = self.rgba.view(self.tiles_local, self.world, 4 * self.row_bytes)       # [local tile, owner, bytes]
+        self.slab.view(self.tiles_local, 4 * self.row_bytes).copy_(tiles[:, self.rank, :])
+        dist.all_gather_into_tensor(self.gathered, self.slab, group=self.group)
+        g = self.gathered.view(self.world, self.tiles_local, 4 * self.row_bytes)
+        self.frame.view(self.tiles_local, self.world, 4 * self.row_bytes).copy_(g.permute(1, 0, 2))
+        return self.frame
+
+    def render_device(self, camera, spp, sample_offset=0, clear=True):
+        """One frame, device resident on every rank: clear, accumulate, resolve, gather.  Returns a uint8 view
+        [H, W, 4] of the assembled frame."""
+        p = self.params(spp, sample_offset)
+        with torch.cuda.stream(self.stream):
+            if clear:
+                self.accum.zero_()
+            self.accumulate(camera.as_struct(), p)
+            self.resolve(p)
+            frame = self.gather()
+        return frame.view(self.H_pad, self.W, 4)[: self.H]
+
+    def render(self, camera, spp, sample_offset=0):
+        """The user-facing call: a finished frame in host memory (pinned), as numpy [H, W, 4] uint8."""
+        frame = self.render_device(camera, spp, sample_offset)
+        with torch.cuda.stream(self.stream):
+            self.host_frame.view(self.H, self.W, 4).copy_(frame, non_blocking=True)
+        self.stream.synchronize()
+        return self.host_frame.view(self.H, self.W, 4).numpy()
+
+    def stats(self):
+        st = capi.RenderStats()
+        check(lib().vrt_scene_last_render_stats(self.scene.handle, C.byref(st)))
+        return dict(rays=list(st.rays), complexity=list(st.complexity))

@@ -155,7 +155,9 @@ typedef struct vrt_render_params {
     int32_t use_gi;              /* RayCaster::use_gi */
     int32_t gi_bounces;          /* 1 = reference; 2 = extension */
     int32_t use_samples;         /* RayCaster::use_samples */
-    int32_t reserved[3];
+    int32_t accum_in;            /* vrt_render: 1 = `accum` holds earlier sums and is added to (progressive frames) */
+    int32_t tile_step;           /* > 1: only 4-row tiles t (counted from row_begin) with t % tile_step == tile_index */
+    int32_t tile_index;          /*      are rendered/resolved — the balanced multi-GPU row partition */
 } vrt_render_params;
 
 typedef struct vrt_render_stats {
@@ -172,8 +174,9 @@ int vrt_scene_set_textures(vrt_scene* scene, const uint8_t* top_rgb, const uint8
 int vrt_render_accumulate_device(vrt_scene* scene, const vrt_camera* cam, const vrt_render_params* p, uint32_t* d_accum);
 /* samples_to_image (use_samples) or the 0.4/0.6 temporal blend against d_rgba's previous content. */
 int vrt_render_resolve_device(vrt_scene* scene, const vrt_render_params* p, const uint32_t* d_accum, uint8_t* d_rgba);
-/* Convenience host-buffer frame: clears the accumulator, renders rows, resolves, copies RGBA (and
- * optionally the accumulator) back.  rgba: [height*width*4] uint8, in/out when !use_samples. */
+/* Host-buffer frame (what RayCaster::render calls): uploads or clears the accumulator (accum_in),
+ * renders rows, resolves, copies RGBA and — if accum != NULL — the accumulator back.
+ * rgba: [height*width*4] uint8, in/out when !use_samples (previous frame of the temporal blend). */
 int vrt_render(vrt_scene* scene, const vrt_camera* cam, const vrt_render_params* p, uint8_t* rgba, uint32_t* accum,
                vrt_render_stats* stats);
 int vrt_scene_last_render_stats(vrt_scene* scene, vrt_render_stats* stats);

@@ -30,7 +30,8 @@ class PortRenderParams(C.Structure):
                 ("light_position", C.c_float * 3),
                 ("use_gi", C.c_int32), ("gi_bounces", C.c_int32), ("use_samples", C.c_int32), ("spp", C.c_int32),
                 ("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32), ("sample_offset", C.c_int32),
-                ("row_begin", C.c_int32), ("row_end", C.c_int32), ("threads", C.c_int32)]
+                ("row_begin", C.c_int32), ("row_end", C.c_int32), ("threads", C.c_int32),
+                ("tile_step", C.c_int32), ("tile_index", C.c_int32)]
 
 
 class PortRenderStats(C.Structure):
@@ -42,7 +43,11 @@ class RefRenderParams(C.Structure):
                 ("view_angle", C.c_float * 2), ("fov", C.c_float), ("aperture", C.c_float),
                 ("focal_length", C.c_float), ("light_position", C.c_float * 3),
                 ("use_gi", C.c_int32), ("use_samples", C.c_int32), ("spp", C.c_int32), ("threads", C.c_int32),
-                ("row_begin", C.c_int32), ("row_end", C.c_int32)]
+                ("row_begin", C.c_int32), ("row_end", C.c_int32), ("tile_step", C.c_int32), ("tile_index", C.c_int32)]
+
+
+class RefRayCounts(C.Structure):
+    _fields_ = [("cone0_calls", C.c_uint64), ("cone_gi_calls", C.c_uint64)]
 
 
 def _p(a):
@@ -181,7 +186,7 @@ class Ref:
         L.vrt_ref_autofocus.restype = C.c_float
         L.vrt_ref_autofocus.argtypes = [C.c_void_p, C.POINTER(RefRenderParams)]
         L.vrt_ref_render.argtypes = [C.c_void_p, C.POINTER(RefRenderParams), C.c_void_p, C.c_void_p, C.c_void_p,
-                                     C.POINTER(C.c_double)]
+                                     C.POINTER(C.c_double), C.POINTER(RefRayCounts)]
         L.vrt_ref_register_texture.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p]
         L.vrt_ref_getrand.argtypes = [C.c_uint64, C.c_void_p]
         self.depth = L.vrt_ref_compiled_depth()
@@ -254,10 +259,12 @@ class Ref:
         img = np.zeros((H, W, 4), np.uint8)
         smp = np.zeros((H, W, 4), np.float64)
         sec = C.c_double(0)
-        code = self.lib.vrt_ref_render(scene, C.byref(params), _p(raw), _p(img), _p(smp), C.byref(sec))
+        cnt = RefRayCounts()
+        code = self.lib.vrt_ref_render(scene, C.byref(params), _p(raw), _p(img), _p(smp), C.byref(sec), C.byref(cnt))
         if code < 0:
             raise RuntimeError("reference render failed (code %d)" % code)
-        return dict(raw=raw, image=img, samples=smp, seconds=sec.value, code=code)
+        return dict(raw=raw, image=img, samples=smp, seconds=sec.value, code=code,
+                    cone0_calls=cnt.cone0_calls, cone_gi_calls=cnt.cone_gi_calls)
 
     def getrand(self, n):
         out = np.zeros(n, np.float32)

@@ -670,6 +670,7 @@ static void render_range(void* c_, uint64_t b, uint64_t e) {
     const uint64_t W = (uint64_t)p->width;
     for (uint64_t i = b; i < e; ++i) {
         const int32_t y = p->row_begin + (int32_t)(i / W), x = (int32_t)(i % W);
+        if (p->tile_step > 1 && (((y - p->row_begin) >> 2) % p->tile_step) != p->tile_index) continue;
         const size_t px = (size_t)y * W + (size_t)x;
         for (int32_t s = 0; s < p->spp; ++s) {
             uint8_t rgb[3];

@@ -77,6 +77,7 @@ typedef struct vo_render_params {
     int32_t sample_offset;      /* first sample index (spp batches) */
     int32_t row_begin, row_end; /* rows [begin,end) */
     int32_t threads;
+    int32_t tile_step, tile_index; /* > 1: only 4-row tiles t (from row_begin) with t % tile_step == tile_index */
 } vo_render_params;
 
 typedef struct vo_render_stats {

@@ -73,6 +73,14 @@ struct vrt_ref_render_params {
     int32_t spp;              // number of renderRay passes per pixel
     int32_t threads;          // 1 = deterministic single thread, >1 = swarm tiles (racy RNG, as the reference)
     int32_t row_begin, row_end;  // rows [begin,end) only (bounded samples for the CPU baseline)
+    int32_t tile_step, tile_index;  // > 1: only 4-row tiles t (from row_begin) with t % tile_step == tile_index
+};
+
+// castRay invocations seen by the counting subclass below, split by cone coefficient:
+// coef == 0 → primary + sun-shadow calls (raycaster.hpp:131,153), coef != 0 → GI + GI-shadow (:194,:198)
+struct vrt_ref_ray_counts {
+    uint64_t cone0_calls;
+    uint64_t cone_gi_calls;
 };
 
 }  // extern "C"
@@ -154,6 +162,24 @@ template <uint8_t D> SceneBase* make_from_nodes(const LNode* nodes, uint64_t n) 
     s->lsvo->raw_data = &(s->lsvo->data[0]);
     return s;
 }
+
+// LSVO<D>::castRay is virtual (Volumetric, volumetric.hpp:58) and RayCaster calls it through a
+// `const LSVO<SVO_DEPTH>&` (raycaster.hpp:265), so a subclass that forwards to the unmodified
+// implementation can count invocations for the Mrays/s metric without touching reference code.
+struct alignas(64) PaddedCounts { uint64_t cone0 = 0, cone_gi = 0; };
+static PaddedCounts g_counts[256];
+static std::atomic<uint32_t> g_next_thread_slot(0);
+static thread_local int t_slot = -1;
+
+struct CountingLSVO : LSVO<VRT_REF_DEPTH> {
+    CountingLSVO(const SVO<VRT_REF_DEPTH>& svo) : LSVO<VRT_REF_DEPTH>(svo) {}
+    HitPoint castRay(const glm::vec3& position, glm::vec3 d, const float ray_size_coef = 0.0f,
+                     const float ray_size_bias = 0.0f) const override {
+        if (t_slot < 0) t_slot = int(g_next_thread_slot.fetch_add(1) % 256u);
+        if (ray_size_coef == 0.0f) ++g_counts[t_slot].cone0; else ++g_counts[t_slot].cone_gi;
+        return LSVO<VRT_REF_DEPTH>::castRay(position, d, ray_size_coef, ray_size_bias);
+    }
+};
 
 #define VRT_DISPATCH_DEPTH(depth, CALL)                                                                     \
     switch (depth) {                                                                                        \
@@ -297,10 +323,17 @@ float vrt_ref_autofocus(void* scene, const vrt_ref_render_params* p) {
 //                          counts inside a single-threaded replica only when threads==1; else zeros)
 // Returns the run_parallel code.
 int vrt_ref_render(void* scene, const vrt_ref_render_params* p, uint8_t* rgba_raw, uint8_t* rgba_image,
-                   double* samples, double* seconds) {
+                   double* samples, double* seconds, vrt_ref_ray_counts* counts) {
     const SceneBase* s = static_cast<SceneBase*>(scene);
     if (s->depth != VRT_REF_DEPTH) return -2;
-    const LSVO<VRT_REF_DEPTH>& lsvo = *static_cast<const LSVO<VRT_REF_DEPTH>*>(s->lsvo_ptr());
+    // same node array behind a counting subclass (the scene's own LSVO is left untouched)
+    SVO<VRT_REF_DEPTH>* empty = new SVO<VRT_REF_DEPTH>();
+    CountingLSVO counting(*empty);
+    delete empty;
+    counting.data.clear();
+    counting.raw_data = &(s->nodes()[0]);
+    for (auto& c : g_counts) c = PaddedCounts();
+    const LSVO<VRT_REF_DEPTH>& lsvo = counting;
     RayCaster raycaster(lsvo, sf::Vector2i(p->width, p->height));
     raycaster.use_gi = p->use_gi != 0;
     raycaster.use_samples = p->use_samples != 0;
@@ -324,6 +357,7 @@ int vrt_ref_render(void* scene, const vrt_ref_render_params* p, uint8_t* rgba_ra
         for (int32_t pass = 0; pass < p->spp; ++pass)
             for (uint32_t x = id; x < W; x += total)
                 for (uint32_t y = r0; y < r1; ++y) {
+                    if (p->tile_step > 1 && int32_t(((y - r0) >> 2) % uint32_t(p->tile_step)) != p->tile_index) continue;
                     const float lens_x = float(x) / float(H) - aspect_ratio * 0.5f;
                     const float lens_y = float(y) / float(H) - 0.5f;
                     const CameraRay cr = cam.getRay(glm::vec2(lens_x, lens_y));
@@ -341,6 +375,10 @@ int vrt_ref_render(void* scene, const vrt_ref_render_params* p, uint8_t* rgba_ra
     });
     const auto t1 = std::chrono::steady_clock::now();
     if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    if (counts) {
+        counts->cone0_calls = counts->cone_gi_calls = 0;
+        for (const auto& c : g_counts) { counts->cone0_calls += c.cone0; counts->cone_gi_calls += c.cone_gi; }
+    }
 
     if (raycaster.use_samples) {
         if (samples)
@@ -351,7 +389,7 @@ int vrt_ref_render(void* scene, const vrt_ref_render_params* p, uint8_t* rgba_ra
                     q[0] = sm.r; q[1] = sm.g; q[2] = sm.b; q[3] = sm.update_count;
                 }
         // samples_to_image divides by update_count; untouched rows would be 0/0 → only resolve when full
-        if (r0 == 0 && r1 == H) raycaster.samples_to_image();
+        if (r0 == 0 && r1 == H && p->tile_step <= 1) raycaster.samples_to_image();
     }
     if (rgba_image)
         for (uint32_t y = 0; y < H; ++y)

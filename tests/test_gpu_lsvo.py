@@ -77,5 +77,9 @@ def test_edge_cases(vrt, ctx, port):
     # full octree: every ray that enters the cube hits at the entry face
     full = np.stack(np.meshgrid(*[np.arange(8)] * 3, indexing="ij"), -1).reshape(-1, 3)
     f = vrt.LSVO.from_voxels(ctx, 3, full)
-    got = f.cast_rays([[1.5, 1.5, 0.5]], [[0, 0, 1]])
-    assert hit_flag(got)[0] and got["distance"][0] == 0.5 and list(got["normal"][0]) == [0.0, 0.0, -4.0]
+    fn = vrt.host_build_lsvo_from_voxels(3, full)
+    o, d = np.float32([[1.5, 1.5, 0.5], [1.3, 1.7, 1.2]]), np.float32([[0, 0, 1], [0.3, -0.2, 0.5]])
+    got = f.cast_rays(o, d)
+    assert_hits_equal(got, port.lsvo_cast(fn, 3, o, d), hit_flag(got), "full octree")
+    # entering the root's first child without an ADVANCE step leaves the face mask at 0: normal is all zero
+    assert hit_flag(got)[0] and got["distance"][0] == 0.5 and not np.any(got["normal"][0])
