@@ -70,6 +70,10 @@ struct vrt_scene {
     uint8_t* d_tex = nullptr;                   // top (768 B) then side (768 B)
     bool has_tex = false;
     DeviceBuffer frame_accum, frame_rgba;       // vrt_render staging
+    // Grid3D / MipmapGrid3D / SVO: bit-packed occupancy pyramid
+    vrt::GridLevels grid{};
+    uint32_t* d_grid_bits = nullptr;
+    bool use_mip = false;
 };
 
 namespace {
@@ -211,6 +215,7 @@ int vrt_scene_destroy(vrt_scene* sc) {
     if (sc->d_nodes) cudaFree(sc->d_nodes);
     if (sc->d_counters) cudaFree(sc->d_counters);
     if (sc->d_tex) cudaFree(sc->d_tex);
+    if (sc->d_grid_bits) cudaFree(sc->d_grid_bits);
     sc->frame_accum.release();
     sc->frame_rgba.release();
     delete sc;
@@ -241,8 +246,14 @@ int vrt_cast_rays_device(vrt_scene* sc, const float* d_origin, const float* d_di
                                                sc->d_counters, ctx->stream));
             ctx->launches += 1;
             return VRT_OK;
+        case VRT_SCENE_GRID:
+        case VRT_SCENE_MIPGRID:
+            VRT_CUDA(cudaMemsetAsync(sc->d_counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
+            VRT_CUDA(vrt::launch_grid_cast(sc->grid, sc->use_mip, d_origin, d_dir, n, d_out, sc->d_counters, ctx->stream));
+            ctx->launches += 1;
+            return VRT_OK;
         default:
-            return fail(VRT_ERR_UNSUPPORTED, "vrt_cast_rays_device: scene kind not supported");
+            return fail(VRT_ERR_UNSUPPORTED, "vrt_cast_rays_device: scene kind not supported (SVO scenes use vrt_cast_rays_svo)");
     }
 }
 
@@ -397,9 +408,97 @@ int vrt_autofocus(vrt_scene* sc, const vrt_camera* cam, float* focal_length) {
     return VRT_OK;
 }
 
-// ---- not implemented yet (TODO: replaced as the kernels land) --------------------------------------
-int vrt_grid_create(vrt_context*, const uint8_t*, int32_t, int32_t, int32_t, int32_t, vrt_scene**) { return fail(VRT_ERR_UNSUPPORTED, "vrt_grid_create: not implemented"); }
-int vrt_svo_create(vrt_context*, const uint8_t*, uint32_t, vrt_scene**) { return fail(VRT_ERR_UNSUPPORTED, "vrt_svo_create: not implemented"); }
-int vrt_cast_rays_svo(vrt_scene*, const float*, const float*, uint32_t, uint64_t, vrt_hit*) { return fail(VRT_ERR_UNSUPPORTED, "vrt_cast_rays_svo: not implemented"); }
+// ---- dense grids: Grid3D / MipmapGrid3D / SVO ---------------------------------------------------------
+namespace {
+// Packs occupancy (cells != 0) into bits and builds the OR-pyramid up to `levels` levels (level l = cubes of
+// edge 2^l; dims rounded up).  Returns the host words and fills `g` with word offsets in place of pointers.
+std::vector<uint32_t> build_grid_pyramid(const uint8_t* cells, int X, int Y, int Z, int levels, vrt::GridLevels& g,
+                                         std::vector<size_t>& offsets) {
+    std::vector<uint32_t> words;
+    g.X = X; g.Y = Y; g.Z = Z; g.n_levels = levels;
+    std::vector<uint8_t> cur(cells, cells + size_t(X) * Y * Z), next;
+    int nx = X, ny = Y, nz = Z;
+    for (int l = 0; l < levels; ++l) {
+        g.level[l].nx = nx; g.level[l].ny = ny; g.level[l].nz = nz;
+        const size_t nbits = size_t(nx) * ny * nz, nwords = (nbits + 31) / 32;
+        offsets.push_back(words.size());
+        words.resize(words.size() + nwords, 0u);
+        uint32_t* w = words.data() + offsets.back();
+        for (size_t i = 0; i < nbits; ++i)
+            if (cur[i]) w[i >> 5] |= 1u << (i & 31);
+        if (l + 1 < levels) {
+            const int mx = (nx + 1) / 2, my = (ny + 1) / 2, mz = (nz + 1) / 2;
+            next.assign(size_t(mx) * my * mz, 0);
+            for (int x = 0; x < nx; ++x)
+                for (int y = 0; y < ny; ++y)
+                    for (int z = 0; z < nz; ++z)
+                        if (cur[(size_t(x) * ny + y) * nz + z]) next[(size_t(x >> 1) * my + (y >> 1)) * mz + (z >> 1)] = 1;
+            cur.swap(next);
+            nx = mx; ny = my; nz = mz;
+        }
+    }
+    return words;
+}
+
+int create_grid_scene(vrt_context* ctx, const uint8_t* cells, int X, int Y, int Z, int levels, int kind, uint32_t depth,
+                      vrt_scene** out) {
+    if (int s = use_device(ctx)) return s;
+    vrt_scene* sc = new (std::nothrow) vrt_scene();
+    if (!sc) return fail(VRT_ERR_OOM, "grid scene: host allocation failed");
+    sc->ctx = ctx; sc->kind = kind; sc->depth = depth;
+    std::vector<size_t> offsets;
+    std::vector<uint32_t> words = build_grid_pyramid(cells, X, Y, Z, levels, sc->grid, offsets);
+    cudaError_t e = cudaMalloc(&sc->d_grid_bits, words.size() * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&sc->d_counters, 16 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sc->d_grid_bits, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(sc->d_counters, 0, 16 * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { vrt_scene_destroy(sc); return cuda_fail(e, "grid scene upload"); }
+    for (int l = 0; l < levels; ++l) sc->grid.level[l].bits = sc->d_grid_bits + offsets[l];
+    sc->device_bytes = words.size() * sizeof(uint32_t);
+    *out = sc;
+    return VRT_OK;
+}
+}  // namespace
+
+int vrt_grid_create(vrt_context* ctx, const uint8_t* cell_types, int32_t X, int32_t Y, int32_t Z, int32_t mip_levels,
+                    vrt_scene** out) {
+    if (!ctx || !cell_types || !out) return fail(VRT_ERR_INVALID, "vrt_grid_create: NULL argument");
+    if (X <= 0 || Y <= 0 || Z <= 0 || X > 4096 || Y > 4096 || Z > 4096) return fail(VRT_ERR_INVALID, "vrt_grid_create: dimensions must be 1..4096");
+    if (mip_levels < 0 || mip_levels > 11) return fail(VRT_ERR_INVALID, "vrt_grid_create: mip_levels must be 0..11");
+    int s = create_grid_scene(ctx, cell_types, X, Y, Z, 1 + mip_levels, mip_levels > 0 ? VRT_SCENE_MIPGRID : VRT_SCENE_GRID, 0, out);
+    if (s == VRT_OK) (*out)->use_mip = mip_levels > 0;
+    return s;
+}
+
+int vrt_svo_create(vrt_context* ctx, const uint8_t* occ, uint32_t depth, vrt_scene** out) {
+    if (!ctx || !occ || !out) return fail(VRT_ERR_INVALID, "vrt_svo_create: NULL argument");
+    if (depth < 1 || depth > 10) return fail(VRT_ERR_INVALID, "vrt_svo_create: depth must be 1..10 (dense occupancy input)");
+    const int S = 1 << depth;
+    return create_grid_scene(ctx, occ, S, S, S, int(depth) + 1, VRT_SCENE_SVO, depth, out);
+}
+
+int vrt_cast_rays_svo(vrt_scene* sc, const float* origin, const float* dir, uint32_t max_iter, uint64_t n, vrt_hit* out) {
+    if (!sc) return fail(VRT_ERR_INVALID, "vrt_cast_rays_svo: scene is NULL");
+    if (sc->kind != VRT_SCENE_SVO) return fail(VRT_ERR_INVALID, "vrt_cast_rays_svo: not an SVO scene");
+    if (n == 0) return VRT_OK;
+    if (!origin || !dir || !out) return fail(VRT_ERR_INVALID, "vrt_cast_rays_svo: NULL buffer");
+    vrt_context* ctx = sc->ctx;
+    if (int s = use_device(ctx)) return s;
+    const size_t ray_bytes = size_t(n) * 3 * sizeof(float);
+    if (ctx->scratch_in.reserve(2 * ray_bytes) != cudaSuccess || ctx->scratch_out.reserve(size_t(n) * sizeof(vrt_hit)) != cudaSuccess)
+        return fail(VRT_ERR_OOM, "vrt_cast_rays_svo: device staging allocation failed");
+    float* d_o = static_cast<float*>(ctx->scratch_in.ptr);
+    float* d_d = d_o + size_t(n) * 3;
+    vrt_hit* d_h = static_cast<vrt_hit*>(ctx->scratch_out.ptr);
+    VRT_CUDA(cudaMemcpyAsync(d_o, origin, ray_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    VRT_CUDA(cudaMemcpyAsync(d_d, dir, ray_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    VRT_CUDA(cudaMemsetAsync(sc->d_counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    VRT_CUDA(vrt::launch_svo_cast(sc->grid, int(sc->depth), d_o, d_d, max_iter, n, d_h, sc->d_counters, ctx->stream));
+    ctx->launches += 1;
+    VRT_CUDA(cudaMemcpyAsync(out, d_h, size_t(n) * sizeof(vrt_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    VRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VRT_OK;
+}
 
 }  // extern "C"

@@ -1,0 +1,231 @@
+// Dense-grid traversal — kernels K2 (Grid3D), K2m (MipmapGrid3D) and K3 (pointer-SVO semantics).
+//
+//   K2   Grid3D<X,Y,Z>::castRay            reference include/grid_3d.hpp:35-132 (Amanatides-Woo DDA)
+//   K2m  MipmapGrid3D                      reference include/mipmap_grid3D.hpp:14-17 is an empty stub; defined
+//                                          here as "Grid3D::castRay results, bit-identical, with fewer fetches"
+//   K3   SVO<N>::castRay + rec_castRay     reference include/svo.hpp:62-70,140-194 with fillHitResult's
+//                                          commented body (svo.hpp:116-138) restored
+//
+// Device format: the reference stores an 8-byte Cell per voxel (1 GiB at 512^3); traversal only asks
+// `type != Empty`, so the device keeps ONE BIT per cell, z-contiguous like m_cells[x][y][z] (16 MiB at
+// 512^3 — L2 resident), plus an OR-pyramid of the same bit grids (level l = cubes of edge 2^l).
+// The per-cell recurrence (t_max += t_d, one float add per step) is kept exactly as written, so every
+// result is bit-identical; the pyramid is only used to SKIP FETCHES while the ray is inside a cube already
+// known to be empty (a multi-cell jump would change the rounding of t_max, hence the hit on grazing rays).
+#include "vrt_device.cuh"
+#include "kernels.h"
+
+namespace vrt {
+
+__device__ __forceinline__ bool grid_bit(const GridLevels& g, int l, int x, int y, int z) {
+    const GridLevel& L = g.level[l];
+    const uint64_t i = (uint64_t(x >> l) * uint64_t(L.ny) + uint64_t(y >> l)) * uint64_t(L.nz) + uint64_t(z >> l);
+    return (__ldg(L.bits + (i >> 5)) >> (i & 31u)) & 1u;
+}
+
+template <bool kMip>
+__global__ void __launch_bounds__(256) grid_cast_kernel(GridLevels g, const float* __restrict__ origin, const float* __restrict__ dir,
+                                                        uint64_t n, vrt_hit* __restrict__ out,
+                                                        unsigned long long* __restrict__ counters) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    uint32_t iter = 0u, fetches = 0u;
+    if (i < n) {
+        const float ox = origin[3 * i], oy = origin[3 * i + 1], oz = origin[3 * i + 2];
+        const float dx = dir[3 * i], dy = dir[3 * i + 1], dz = dir[3 * i + 2];
+        const int X = g.X, Y = g.Y, Z = g.Z;
+        const float tdx = fabsf(1.0f / dx), tdy = fabsf(1.0f / dy), tdz = fabsf(1.0f / dz);       // grid_3d.hpp:42-44
+        const int sx = dx < 0 ? -1 : 1, sy = dy < 0 ? -1 : 1, sz = dz < 0 ? -1 : 1;               // :48-50
+        int cx = int(ox), cy = int(oy), cz = int(oz);                                              // :58-60
+        float tmx = (float(cx + (sx > 0 ? 1 : 0)) - ox) / dx;                                      // :62-64
+        float tmy = (float(cy + (sy > 0 ? 1 : 0)) - oy) / dy;
+        float tmz = (float(cz + (sz > 0 ? 1 : 0)) - oz) / dz;
+        // cube currently known to be empty (mip variant): level and coordinates at that level
+        int e_level = -1, ex = 0, ey = 0, ez = 0;
+        bool hit = false;
+        int side = 0;
+        float t = 0.0f;
+        while (cx >= 0 && cy >= 0 && cz >= 0 && cx < X && cy < Y && cz < Z && iter < 2048u) {      // :68-70
+            ++iter;
+            side = (tmx < tmy) ? ((tmx < tmz) ? 0 : 2) : ((tmy < tmz) ? 1 : 2);                     // :73-99
+            if (side == 0) { t = tmx; tmx += tdx; cx += sx; }
+            else if (side == 1) { t = tmy; tmy += tdy; cy += sy; }
+            else { t = tmz; tmz += tdz; cz += sz; }
+            if (cx >= 0 && cy >= 0 && cz >= 0 && cx < X && cy < Y && cz < Z) {                     // :101
+                bool solid;
+                if (kMip) {
+                    if (e_level >= 0 && (cx >> e_level) == ex && (cy >> e_level) == ey && (cz >> e_level) == ez) {
+                        solid = false;                       // still inside the empty cube: no fetch
+                    } else {
+                        e_level = -1;
+                        solid = true;
+                        for (int l = g.n_levels - 1; l >= 0; --l) {   // coarse to fine, stop at the first empty cube
+                            ++fetches;
+                            if (!grid_bit(g, l, cx, cy, cz)) {
+                                solid = false;
+                                if (l > 0) { e_level = l; ex = cx >> l; ey = cy >> l; ez = cz >> l; }
+                                break;
+                            }
+                        }
+                    }
+                } else {
+                    ++fetches;
+                    solid = grid_bit(g, 0, cx, cy, cz);                                            // :103-104
+                }
+                if (solid) { hit = true; break; }
+            }
+        }
+        float4* q = reinterpret_cast<float4*>(out + i);
+        if (hit) {
+            const float hx = ox + t * dx, hy = oy + t * dy, hz = oz + t * dz;                      // :105-107
+            float nx = 0.0f, ny = 0.0f, nz = 0.0f, u, v;
+            if (side == 0) { nx = float(-sx); u = 1.0f - fracf(hz); v = fracf(hy); }               // :112-121
+            else if (side == 1) { ny = float(-sy); u = fracf(hx); v = fracf(hz); }
+            else { nz = float(-sz); u = fracf(hx); v = fracf(hy); }
+            q[0] = make_float4(hx, hy, hz, t);
+            q[1] = make_float4(nx, ny, nz, __uint_as_float(iter));                                 // complexity = iter, :124
+            q[2] = make_float4(u, v, __uint_as_float(VRT_HIT_FLAG_HIT), 0.0f);
+            q[3] = make_float4(__int_as_float(cx), __int_as_float(cy), __int_as_float(cz), __uint_as_float(1u << side));
+        } else {
+            // HitPoint::complexity stays 0 on a miss (only written on a hit, :124)
+            q[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            q[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            q[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            q[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    // counters[0] += loop iterations (the unit of the DDA roofline), counters[1] += occupancy fetches
+    for (int o = 16; o > 0; o >>= 1) {
+        iter += __shfl_xor_sync(0xffffffffu, iter, o);
+        fetches += __shfl_xor_sync(0xffffffffu, fetches, o);
+    }
+    if ((threadIdx.x & 31) == 0 && iter) {
+        atomicAdd(counters, (unsigned long long)iter);
+        atomicAdd(counters + 1, (unsigned long long)fetches);
+    }
+}
+
+// ---- K3: SVO<N>::castRay (svo.hpp:62-70) ----------------------------------------------------------------
+// The recursion of rec_castRay (svo.hpp:140-194) is unrolled into an explicit per-level frame; a node
+// "exists" iff the occupancy pyramid bit of its cube is set, and it is a leaf iff its edge is one voxel.
+struct SvoFrame {
+    float px, py, pz;       // `position` argument of this level (re-based, :164)
+    float cix, ciy, ciz;    // cell_pos_i
+    float tmx, tmy, tmz;    // t_max
+    float tmm;              // t_max_min
+    float t_total;          // copy taken at entry (:151)
+    int bx, by, bz;         // low corner of this node's cube in voxel units
+};
+
+__global__ void __launch_bounds__(128) svo_cast_kernel(GridLevels g, int depth, const float* __restrict__ origin,
+                                                       const float* __restrict__ dir, uint32_t max_iter, uint64_t n,
+                                                       vrt_hit* __restrict__ out, unsigned long long* __restrict__ counters) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    uint32_t complexity = 0u;
+    if (i < n) {
+        const float sx0 = origin[3 * i], sy0 = origin[3 * i + 1], sz0 = origin[3 * i + 2];
+        const float dx = dir[3 * i], dy = dir[3 * i + 1], dz = dir[3 * i + 2];
+        // Ray, volumetric.hpp:28-40
+        const float rtx = fabsf(1.0f / dx), rty = fabsf(1.0f / dy), rtz = fabsf(1.0f / dz);
+        const float stx = dx >= 0.0f ? 1.0f : -1.0f, sty = copysignf(1.0f, dy), stz = copysignf(1.0f, dz);
+        const float pdx = dx > 0.0f ? 1.0f : 0.0f, pdy = dy > 0.0f ? 1.0f : 0.0f, pdz = dz > 0.0f ? 1.0f : 0.0f;
+        int side = 0;
+        float ray_t_total = 0.0f;
+        bool hit = false;
+        float hit_t = 0.0f;
+        int hvx = 0, hvy = 0, hvz = 0;
+
+        SvoFrame st[13];
+        int lvl = 0;                                   // frame index; children of frame `lvl` have edge 2^(depth-1-lvl)
+        bool enter = true;                             // true: initialise frame `lvl` (function entry), false: resume after a return
+        st[0].px = sx0; st[0].py = sy0; st[0].pz = sz0; st[0].bx = 0; st[0].by = 0; st[0].bz = 0;
+        while (lvl >= 0) {
+            SvoFrame& f = st[lvl];
+            const int cl = depth - 1 - lvl;            // log2 of cell_size at this level
+            const float cs = float(1u << cl);
+            bool resume = !enter;                      // resuming after a child returned without a hit (:167-169)
+            if (enter) {                                                                             // :142-151
+                f.cix = float(int(f.px / cs)); f.ciy = float(int(f.py / cs)); f.ciz = float(int(f.pz / cs));
+                f.cix = f.cix > 1.0f ? 1.0f : (f.cix < 0.0f ? 0.0f : f.cix);
+                f.ciy = f.ciy > 1.0f ? 1.0f : (f.ciy < 0.0f ? 0.0f : f.ciy);
+                f.ciz = f.ciz > 1.0f ? 1.0f : (f.ciz < 0.0f ? 0.0f : f.ciz);
+                f.tmx = ((f.cix + pdx) * cs - f.px) / dx;
+                f.tmy = ((f.ciy + pdy) * cs - f.py) / dy;
+                f.tmz = ((f.ciz + pdz) * cs - f.pz) / dz;
+                f.tmm = 0.0f;
+                f.t_total = ray_t_total;
+            }
+            for (;;) {
+                if (!resume) {
+                    if (!(f.cix >= 0 && f.ciy >= 0 && f.ciz >= 0 && f.cix < 2 && f.ciy < 2 && f.ciz < 2 && complexity < max_iter)) {   // :152
+                        --lvl; enter = false;          // return to the caller
+                        break;
+                    }
+                    ++complexity;                                                                    // :154
+                    const int cx = f.bx + int(uint32_t(f.cix)) * (1 << cl), cy = f.by + int(uint32_t(f.ciy)) * (1 << cl),
+                              cz = f.bz + int(uint32_t(f.ciz)) * (1 << cl);
+                    if (grid_bit(g, cl, cx, cy, cz)) {                                               // sub_node != nullptr, :156-157
+                        if (cl == 0) {                                                               // leaf, :158-161
+                            hit = true; hit_t = f.t_total + f.tmm; hvx = cx; hvy = cy; hvz = cz;
+                            lvl = -1;
+                            break;
+                        }
+                        SvoFrame& c = st[lvl + 1];                                                   // :163-166
+                        c.px = (f.px + f.tmm * dx) - f.cix * cs;
+                        c.py = (f.py + f.tmm * dy) - f.ciy * cs;
+                        c.pz = (f.pz + f.tmm * dz) - f.ciz * cs;
+                        c.bx = cx; c.by = cy; c.bz = cz;
+                        ray_t_total = f.t_total + f.tmm;
+                        ++lvl; enter = true;
+                        break;
+                    }
+                }
+                resume = false;
+                const float tx = cs * rtx, ty = cs * rty, tz = cs * rtz;                             // :148
+                if (f.tmx < f.tmy) {                                                                 // :173-192
+                    if (f.tmx < f.tmz) { f.tmm = f.tmx; f.tmx += tx; f.cix += stx; side = 0; }
+                    else { f.tmm = f.tmz; f.tmz += tz; f.ciz += stz; side = 2; }
+                } else {
+                    if (f.tmy < f.tmz) { f.tmm = f.tmy; f.tmy += ty; f.ciy += sty; side = 1; }
+                    else { f.tmm = f.tmz; f.tmz += tz; f.ciz += stz; side = 2; }
+                }
+            }
+        }
+        float4* q = reinterpret_cast<float4*>(out + i);
+        if (hit) {                                                                                   // fillHitResult, :116-138
+            const float hx = sx0 + hit_t * dx, hy = sy0 + hit_t * dy, hz = sz0 + hit_t * dz;
+            float nx = 0.0f, ny = 0.0f, nz = 0.0f, u, v;
+            if (side == 0) { nx = -stx; u = 1.0f - fracf(hz); v = fracf(hy); }
+            else if (side == 1) { ny = -sty; u = fracf(hx); v = fracf(hz); }
+            else { nz = -stz; u = fracf(hx); v = fracf(hy); }
+            q[0] = make_float4(hx, hy, hz, hit_t);
+            q[1] = make_float4(nx, ny, nz, __uint_as_float(complexity));
+            q[2] = make_float4(u, v, __uint_as_float(VRT_HIT_FLAG_HIT), 0.0f);
+            q[3] = make_float4(__int_as_float(hvx), __int_as_float(hvy), __int_as_float(hvz), __uint_as_float(1u << side));
+        } else {
+            q[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            q[1] = make_float4(0.f, 0.f, 0.f, __uint_as_float(complexity));   // complexity counts on a miss too (:154)
+            q[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            q[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) complexity += __shfl_xor_sync(0xffffffffu, complexity, o);
+    if ((threadIdx.x & 31) == 0 && complexity) atomicAdd(counters, (unsigned long long)complexity);
+}
+
+cudaError_t launch_grid_cast(const GridLevels& g, bool use_mip, const float* d_origin, const float* d_dir, uint64_t n,
+                             vrt_hit* d_out, unsigned long long* d_counters, cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    const unsigned grid = unsigned((n + 255) / 256);
+    if (use_mip && g.n_levels > 1) grid_cast_kernel<true><<<grid, 256, 0, stream>>>(g, d_origin, d_dir, n, d_out, d_counters);
+    else grid_cast_kernel<false><<<grid, 256, 0, stream>>>(g, d_origin, d_dir, n, d_out, d_counters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_svo_cast(const GridLevels& g, int depth, const float* d_origin, const float* d_dir, uint32_t max_iter,
+                            uint64_t n, vrt_hit* d_out, unsigned long long* d_counters, cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    svo_cast_kernel<<<unsigned((n + 127) / 128), 128, 0, stream>>>(g, depth, d_origin, d_dir, max_iter, n, d_out, d_counters);
+    return cudaGetLastError();
+}
+
+}  // namespace vrt

@@ -11,6 +11,25 @@ cudaError_t launch_lsvo_cast_ref(const uint2* nodes, int depth, int guard, const
                                  float coef, float bias, uint64_t n, vrt_hit* d_out, unsigned long long* d_complexity,
                                  cudaStream_t stream);
 
+// Bit-packed occupancy pyramid of a dense grid: level l holds cubes of edge 2^l, z-contiguous like
+// Grid3D::m_cells[x][y][z] (grid_3d.hpp:26); bit i of the level = word i>>5, bit i&31.
+struct GridLevel {
+    const uint32_t* bits;
+    int nx, ny, nz;
+};
+struct GridLevels {
+    GridLevel level[13];
+    int n_levels;
+    int X, Y, Z;
+};
+
+// K2 / K2m: Grid3D::castRay, flat or with the fetch-skipping pyramid (grid_kernels.cu)
+cudaError_t launch_grid_cast(const GridLevels& g, bool use_mip, const float* d_origin, const float* d_dir, uint64_t n,
+                             vrt_hit* d_out, unsigned long long* d_counters, cudaStream_t stream);
+// K3: SVO<N>::castRay with the hit fill restored (grid_kernels.cu)
+cudaError_t launch_svo_cast(const GridLevels& g, int depth, const float* d_origin, const float* d_dir, uint32_t max_iter,
+                            uint64_t n, vrt_hit* d_out, unsigned long long* d_counters, cudaStream_t stream);
+
 // Everything one render launch needs, passed by value (constant bank).
 struct RenderLaunch {
     int width, height, row_begin, row_end;

@@ -11,6 +11,7 @@ Batched entry points (cast_rays, render) are the additions: the reference casts 
 a swarm worker (src/main.cpp:139-152); here one call is one kernel launch.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -61,6 +62,7 @@ class Context:
         check(lib().vrt_context_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
         self.handle = h
         self.device = int(device)
+        self._scenes = weakref.WeakSet()      # scenes hold a pointer to the context: they must die first
 
     def synchronize(self):
         check(lib().vrt_context_synchronize(self.handle))
@@ -74,6 +76,8 @@ class Context:
 
     def close(self):
         if getattr(self, "handle", None):
+            for sc in list(self._scenes):
+                sc.close()
             lib().vrt_context_destroy(self.handle)
             self.handle = None
 
@@ -104,6 +108,7 @@ class Volumetric:
     def __init__(self, ctx):
         self.ctx = ctx
         self.handle = None
+        ctx._scenes.add(self)
 
     # -- batched: n rays, one launch --
     def cast_rays(self, origin, direction, ray_size_coef=0.0, ray_size_bias=0.0):

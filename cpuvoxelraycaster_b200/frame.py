@@ -18,6 +18,39 @@ from . import capi
 from .capi import check, lib, ptr
 
 
+class TileExchange:
+    """Round-robin 4-row-tile partition of a W x H RGBA frame over `world` ranks and its all-gather.
+    Pure torch (any device / backend): NCCL on the GPUs, gloo in the CPU tests."""
+
+    def __init__(self, width, height, rank, world, device, group=None):
+        self.W, self.H, self.rank, self.world, self.group = int(width), int(height), int(rank), int(world), group
+        unit = 4 * self.world
+        self.H_pad = (self.H + unit - 1) // unit * unit
+        self.tiles_local = self.H_pad // unit
+        self.row_bytes = self.W * 4
+        self.tile_bytes = 4 * self.row_bytes
+        if self.world > 1:
+            self.slab = torch.empty(self.tiles_local * self.tile_bytes, dtype=torch.uint8, device=device)
+            self.gathered = torch.empty(self.world * self.slab.numel(), dtype=torch.uint8, device=device)
+            self.frame = torch.empty(self.H_pad * self.row_bytes, dtype=torch.uint8, device=device)
+
+    def owned_rows(self):
+        """Rows this rank renders: 4-row tile t belongs to rank t % world."""
+        return [y for y in range(self.H) if (y >> 2) % self.world == self.rank]
+
+    def gather(self, rgba):
+        """rgba: flat uint8 [H_pad*W*4] with this rank's rows filled → the assembled frame on every rank."""
+        if self.world == 1:
+            return rgba
+        import torch.distributed as dist
+        tiles = rgba.view(self.tiles_local, self.world, self.tile_bytes)                # [local tile, owner, bytes]
+        self.slab.view(self.tiles_local, self.tile_bytes).copy_(tiles[:, self.rank, :])
+        dist.all_gather_into_tensor(self.gathered, self.slab, group=self.group)
+        g = self.gathered.view(self.world, self.tiles_local, self.tile_bytes)
+        self.frame.view(self.tiles_local, self.world, self.tile_bytes).copy_(g.permute(1, 0, 2))
+        return self.frame
+
+
 class FrameRenderer:
     def __init__(self, scene, width, height, rank=0, world=1, group=None, device=None, stream=None):
         self.scene, self.W, self.H = scene, int(width), int(height)
@@ -26,18 +59,10 @@ class FrameRenderer:
         # libvrt's launches and torch's copies/collectives must share one stream
         self.stream = stream if stream is not None else torch.cuda.Stream(self.device)
         scene.ctx.set_stream(self.stream.cuda_stream)
-        unit = 4 * self.world
-        self.H_pad = (self.H + unit - 1) // unit * unit
+        self.exchange = TileExchange(self.W, self.H, self.rank, self.world, self.device, group)
+        self.H_pad, self.row_bytes = self.exchange.H_pad, self.exchange.row_bytes
         self.accum = torch.zeros(self.H_pad * self.W * 4, dtype=torch.int32, device=self.device)   # r,g,b,count sums
         self.rgba = torch.zeros(self.H_pad * self.W * 4, dtype=torch.uint8, device=self.device)
-        self.tiles_local = self.H_pad // unit
-        self.row_bytes = self.W * 4
-        if self.world > 1:
-            self.slab = torch.empty(self.tiles_local * 4 * self.row_bytes, dtype=torch.uint8, device=self.device)
-            self.gathered = torch.empty(self.world * self.slab.numel(), dtype=torch.uint8, device=self.device)
-            self.frame = torch.empty(self.H_pad * self.row_bytes, dtype=torch.uint8, device=self.device)
-        else:
-            self.frame = self.rgba
         self.host_frame = torch.empty(self.H * self.row_bytes, dtype=torch.uint8).pin_memory()
         self.use_gi, self.gi_bounces, self.use_samples = False, 1, True
         self.seed = (0x5EED, 0)
@@ -62,15 +87,7 @@ class FrameRenderer:
 
     def gather(self):
         """All-gather of the ranks' RGBA tiles (the frame's one exchange step).  No-op on one GPU."""
-        if self.world == 1:
-            return self.frame
-        import torch.distributed as dist
-        tiles = self.rgba.view(self.tiles_local, self.world, 4 * self.row_bytes)       # [local tile, owner, bytes]
-        self.slab.view(self.tiles_local, 4 * self.row_bytes).copy_(tiles[:, self.rank, :])
-        dist.all_gather_into_tensor(self.gathered, self.slab, group=self.group)
-        g = self.gathered.view(self.world, self.tiles_local, 4 * self.row_bytes)
-        self.frame.view(self.tiles_local, self.world, 4 * self.row_bytes).copy_(g.permute(1, 0, 2))
-        return self.frame
+        return self.exchange.gather(self.rgba)
 
     def render_device(self, camera, spp, sample_offset=0, clear=True):
         """One frame, device resident on every rank: clear, accumulate, resolve, gather.  Returns a uint8 view

@@ -83,6 +83,7 @@ const char* vrt_build_info(void);                   /* compile flags, arch, kern
 /* Replaces swrm::Swarm(thread_count) (src/main.cpp:90-92): the execution resource. `stream` is a
  * cudaStream_t (NULL = the context creates its own non-blocking stream). */
 int vrt_context_create(int device, void* stream, vrt_context** out);
+/* Destroy every scene created on a context before the context itself (scenes borrow it). */
 int vrt_context_destroy(vrt_context* ctx);
 int vrt_context_synchronize(vrt_context* ctx);
 int vrt_context_set_stream(vrt_context* ctx, void* stream);
