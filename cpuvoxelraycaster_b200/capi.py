@@ -49,6 +49,7 @@ _SIGNATURES = {
     "vrt_context_synchronize": (C.c_int, [_vp]),
     "vrt_context_set_stream": (C.c_int, [_vp, _vp]),
     "vrt_context_launch_count": (_u64, [_vp]),
+    "vrt_context_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "vrt_host_terrain_heights": (C.c_int, [_i32, _vp]),
     "vrt_host_build_terrain_lsvo": (C.c_int, [_u32, _vp, _vp, _u64, C.POINTER(_u64)]),
     "vrt_host_build_lsvo_from_voxels": (C.c_int, [_u32, _vp, _u64, _vp, _u64, C.POINTER(_u64)]),

@@ -54,6 +54,10 @@ struct vrt_context {
     bool owns_stream = false;
     uint64_t launches = 0;
     int sm_count = 0;
+    // 1 = persistent threads with per-lane ray regeneration (default); 0 = one thread per ray / pixel (the
+    // first kernels, kept for A/B measurements: profiles/r01_summary.md)
+    int kernel_variant = 1;
+    int refill_cast = 8, refill_render = 8;   // parked lanes that trigger a refill (1..32)
     DeviceBuffer scratch_in, scratch_out;   // host-variant staging
 };
 
@@ -145,6 +149,16 @@ int vrt_context_set_stream(vrt_context* ctx, void* stream) {
 }
 
 uint64_t vrt_context_launch_count(const vrt_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int vrt_context_set_option(vrt_context* ctx, const char* key, int value) {
+    if (!ctx || !key) return fail(VRT_ERR_INVALID, "vrt_context_set_option: NULL argument");
+    const std::string k(key);
+    if (k == "kernel_variant" && (value == 0 || value == 1)) ctx->kernel_variant = value;
+    else if (k == "refill_cast" && value >= 1 && value <= 32) ctx->refill_cast = value;
+    else if (k == "refill_render" && value >= 1 && value <= 32) ctx->refill_render = value;
+    else return fail(VRT_ERR_INVALID, "vrt_context_set_option: unknown key or value out of range: " + k);
+    return VRT_OK;
+}
 
 // ---- host builders ---------------------------------------------------------------------------------
 int vrt_host_terrain_heights(int32_t size, int32_t* out) {
@@ -238,12 +252,16 @@ int vrt_cast_rays_device(vrt_scene* sc, const float* d_origin, const float* d_di
     if (n > (1ull << 31) * 128ull) return fail(VRT_ERR_UNSUPPORTED, "vrt_cast_rays_device: too many rays for one launch");
     vrt_context* ctx = sc->ctx;
     if (int s = use_device(ctx)) return s;
-    VRT_CUDA(cudaMemsetAsync(sc->d_counters, 0, sizeof(unsigned long long), ctx->stream));
+    VRT_CUDA(cudaMemsetAsync(sc->d_counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
     if (n == 0) return VRT_OK;
     switch (sc->kind) {
         case VRT_SCENE_LSVO:
-            VRT_CUDA(vrt::launch_lsvo_cast_ref(sc->d_nodes, int(sc->depth), sc->guard, d_origin, d_dir, coef, bias, n, d_out,
-                                               sc->d_counters, ctx->stream));
+            if (ctx->kernel_variant == 0)
+                VRT_CUDA(vrt::launch_lsvo_cast_ref(sc->d_nodes, int(sc->depth), sc->guard, d_origin, d_dir, coef, bias, n, d_out,
+                                                   sc->d_counters, ctx->stream));
+            else
+                VRT_CUDA(vrt::launch_lsvo_cast_persistent(sc->d_nodes, int(sc->depth), sc->guard, d_origin, d_dir, coef, bias, n,
+                                                          d_out, sc->d_counters, ctx->refill_cast, ctx->stream));
             ctx->launches += 1;
             return VRT_OK;
         case VRT_SCENE_GRID:
@@ -334,10 +352,14 @@ int vrt_render_accumulate_device(vrt_scene* sc, const vrt_camera* cam, const vrt
     if (int s = check_render_args(sc, cam, p, "vrt_render_accumulate_device")) return s;
     vrt_context* ctx = sc->ctx;
     if (int s = use_device(ctx)) return s;
-    VRT_CUDA(cudaMemsetAsync(sc->d_counters + kRenderCounters, 0, 12 * sizeof(unsigned long long), ctx->stream));
+    VRT_CUDA(cudaMemsetAsync(sc->d_counters + kRenderCounters, 0, 13 * sizeof(unsigned long long), ctx->stream));
     if (p->row_end == p->row_begin) return VRT_OK;
-    VRT_CUDA(vrt::launch_render_accumulate_ref(sc->d_nodes, make_launch(sc, cam, p), d_accum, sc->d_counters + kRenderCounters,
-                                               ctx->stream));
+    if (ctx->kernel_variant == 0)
+        VRT_CUDA(vrt::launch_render_accumulate_ref(sc->d_nodes, make_launch(sc, cam, p), d_accum, sc->d_counters + kRenderCounters,
+                                                   ctx->stream));
+    else
+        VRT_CUDA(vrt::launch_render_persistent(sc->d_nodes, make_launch(sc, cam, p), d_accum, sc->d_counters + kRenderCounters,
+                                               ctx->refill_render, ctx->stream));
     ctx->launches += 1;
     return VRT_OK;
 }

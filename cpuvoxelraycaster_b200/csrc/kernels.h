@@ -51,3 +51,14 @@ cudaError_t launch_resolve(const uint32_t* d_accum, uint8_t* d_rgba, int width, 
                            int tile_step, int tile_index, cudaStream_t stream);
 
 }  // namespace vrt
+
+namespace vrt {
+// K1p / K4p: persistent-thread variants with per-lane ray regeneration (persistent_kernels.cu).
+// `refill` = number of parked lanes that makes a warp leave the traversal loop (1..32).
+// d_counters: cast: [0] Σ complexity, [1] work counter; render: [0..11] stats, [12] work counter — zeroed by the caller.
+cudaError_t launch_lsvo_cast_persistent(const uint2* nodes, int depth, int guard, const float* d_origin, const float* d_dir,
+                                        float coef, float bias, uint64_t n, vrt_hit* d_out, unsigned long long* d_counters,
+                                        int refill, cudaStream_t stream);
+cudaError_t launch_render_persistent(const uint2* nodes, const RenderLaunch& L, uint32_t* d_accum, unsigned long long* d_counters,
+                                     int refill, cudaStream_t stream);
+}  // namespace vrt

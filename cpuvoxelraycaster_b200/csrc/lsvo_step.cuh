@@ -1,0 +1,118 @@
+// LSVO traversal as a resumable per-lane state machine: init() = prologue of LSVO<D>::castRay
+// (reference include/lsvo.hpp:44-70), step() = exactly one trip of its while loop (:72-146),
+// finish() = the hit epilogue (:148-169, in lsvo_traverse.cuh).
+//
+// Same fp32 operations in the same order as lsvo_cast() — the split only lets a persistent warp keep
+// every lane busy: a lane whose ray has terminated parks its result and is handed a new ray while its
+// neighbours keep stepping (ncu on the one-thread-per-ray kernels: 15 of 32 lanes active per instruction
+// on GI frames, 4.7 of 32 on incoherent rays — profiles/r01_summary.md).
+#pragma once
+#include "lsvo_traverse.cuh"
+
+namespace vrt {
+
+struct Trav {
+    // ray (direction after the |d| >= 2^-23 clamp) and cone
+    float ox, oy, oz, dx, dy, dz, coef, bias;
+    // traversal state
+    float tcx, tcy, tcz, tox, toy, toz;
+    float px, py, pz;
+    float t_min, t_max, h;
+    uint32_t parent;
+    uint32_t child, mirror, face;
+    int scale;
+    uint32_t iters;
+    bool hit;
+
+    __device__ __forceinline__ float scale_f() const { return __uint_as_float(uint32_t(scale - kSvoMaxDepth + 127) << 23); }
+
+    __device__ __forceinline__ void init(float ox_, float oy_, float oz_, float dx_, float dy_, float dz_, float coef_, float bias_) {
+        ox = ox_; oy = oy_; oz = oz_; coef = coef_; bias = bias_;
+        if (fabsf(dx_) < kEps) dx_ = copysignf(kEps, dx_);                 // lsvo.hpp:44-46
+        if (fabsf(dy_) < kEps) dy_ = copysignf(kEps, dy_);
+        if (fabsf(dz_) < kEps) dz_ = copysignf(kEps, dz_);
+        dx = dx_; dy = dy_; dz = dz_;
+        tcx = -1.0f / fabsf(dx); tcy = -1.0f / fabsf(dy); tcz = -1.0f / fabsf(dz);   // :47
+        tox = ox * tcx; toy = oy * tcy; toz = oz * tcz;                     // :48
+        mirror = 7u;
+        if (dx > 0.0f) { mirror ^= 1u; tox = 3.0f * tcx - tox; }           // :50-52
+        if (dy > 0.0f) { mirror ^= 2u; toy = 3.0f * tcy - toy; }
+        if (dz > 0.0f) { mirror ^= 4u; toz = 3.0f * tcz - toz; }
+        t_min = fmaxf(2.0f * tcx - tox, fmaxf(2.0f * tcy - toy, 2.0f * tcz - toz));   // :54
+        t_max = fminf(tcx - tox, fminf(tcy - toy, tcz - toz));                         // :55
+        h = t_max;
+        t_min = fmaxf(0.0f, t_min);
+        t_max = fminf(1.0f, t_max);
+        parent = 0u; child = 0u; face = 0u;
+        scale = kSvoMaxDepth - 1;
+        px = 1.0f; py = 1.0f; pz = 1.0f;
+        if (1.5f * tcx - tox > t_min) { child ^= 1u; px = 1.5f; }          // :66-68
+        if (1.5f * tcy - toy > t_min) { child ^= 2u; py = 1.5f; }
+        if (1.5f * tcz - toz > t_min) { child ^= 4u; pz = 1.5f; }
+        iters = 0u;
+        hit = false;
+    }
+
+    // One trip of the loop.  Returns true while the ray is alive (the loop condition :72 still holds and no hit).
+    template <typename Nodes, typename Stack>
+    __device__ __forceinline__ bool step(const Nodes& nodes, Stack& stack, int depth_offset, int guard) {
+        ++iters;
+        const float sf = scale_f();
+        const NodeView nd = nodes.fetch(parent);                             // :74
+        const float cx = px * tcx - tox, cy = py * tcy - toy, cz = pz * tcz - toz;   // :76
+        const float tc_max = fminf(cx, fminf(cy, cz));
+        const uint32_t shift = child ^ mirror;                               // :79
+        if (((nd.child_mask >> shift) & 1u) && t_min <= t_max) {             // :80-81
+            if (tc_max * coef + bias >= sf) { hit = true; return false; }    // :82-85
+            const float tv_max = fminf(t_max, tc_max);
+            const float half = sf * 0.5f;
+            if (t_min <= tv_max) {                                           // :89
+                if ((nd.leaf_mask >> shift) & 1u) { hit = true; return false; }   // :90-95
+                if (tc_max < h) stack.push(scale - depth_offset, parent, t_max);  // :97-100
+                h = tc_max;
+                parent = nodes.child(nd, shift);                             // :103
+                child = 0u;
+                --scale;
+                if (half * tcx + cx > t_min) { child ^= 1u; px += half; }    // :88,107-109
+                if (half * tcy + cy > t_min) { child ^= 2u; py += half; }
+                if (half * tcz + cz > t_min) { child ^= 4u; pz += half; }
+                t_max = tv_max;
+                return scale > guard;                                        // :72 (scale < 23 holds after a descent)
+            }
+        }
+        uint32_t step_mask = 0u;                                             // :115-118
+        if (cx <= tc_max) { step_mask ^= 1u; px -= sf; }
+        if (cy <= tc_max) { step_mask ^= 2u; py -= sf; }
+        if (cz <= tc_max) { step_mask ^= 4u; pz -= sf; }
+        t_min = tc_max;
+        child ^= step_mask;
+        face = step_mask;
+        if (child & step_mask) {                                             // :124-145
+            const uint32_t ix = __float_as_uint(px), iy = __float_as_uint(py), iz = __float_as_uint(pz);
+            uint32_t diff = 0u;
+            if (step_mask & 1u) diff |= ix ^ __float_as_uint(px + sf);
+            if (step_mask & 2u) diff |= iy ^ __float_as_uint(py + sf);
+            if (step_mask & 4u) diff |= iz ^ __float_as_uint(pz + sf);
+            scale = int((__float_as_uint(__uint2float_rn(diff)) >> 23) - 127u);   // :132
+            if (scale >= kSvoMaxDepth) return false;                         // left the root cube: miss
+            stack.pop(scale - depth_offset, parent, t_max);                  // :134-136
+            const uint32_t sx = ix >> scale, sy = iy >> scale, sz = iz >> scale;
+            px = __uint_as_float(sx << scale);
+            py = __uint_as_float(sy << scale);
+            pz = __uint_as_float(sz << scale);
+            child = (sx & 1u) | ((sy & 1u) << 1) | ((sz & 1u) << 2);
+            h = 0.0f;
+            return scale > guard;
+        }
+        return true;
+    }
+
+    __device__ __forceinline__ void result(LsvoResult& r) const {
+        r.px = px; r.py = py; r.pz = pz;
+        r.t_min = t_min; r.scale_f = scale_f(); r.scale = scale; r.face = face; r.mirror = mirror;
+        r.complexity = iters; r.hit = hit;
+        r.dx = dx; r.dy = dy; r.dz = dz;
+    }
+};
+
+}  // namespace vrt

@@ -11,6 +11,7 @@ Batched entry points (cast_rays, render) are the additions: the reference casts 
 a swarm worker (src/main.cpp:139-152); here one call is one kernel launch.
 """
 import ctypes as C
+import os
 import weakref
 
 import numpy as np
@@ -63,6 +64,14 @@ class Context:
         self.handle = h
         self.device = int(device)
         self._scenes = weakref.WeakSet()      # scenes hold a pointer to the context: they must die first
+
+        for key in ("kernel_variant", "refill_cast", "refill_render"):      # measurement overrides (tools/, profiles/)
+            v = os.environ.get("VRT_" + key.upper())
+            if v is not None:
+                self.set_option(key, int(v))
+
+    def set_option(self, key, value):
+        check(lib().vrt_context_set_option(self.handle, key.encode(), int(value)))
 
     def synchronize(self):
         check(lib().vrt_context_synchronize(self.handle))

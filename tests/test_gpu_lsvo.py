@@ -83,3 +83,23 @@ def test_edge_cases(vrt, ctx, port):
     assert_hits_equal(got, port.lsvo_cast(fn, 3, o, d), hit_flag(got), "full octree")
     # entering the root's first child without an ADVANCE step leaves the face mask at 0: normal is all zero
     assert hit_flag(got)[0] and got["distance"][0] == 0.5 and not np.any(got["normal"][0])
+
+
+@pytest.mark.parametrize("variant,refill", [(0, 8), (1, 1), (1, 8), (1, 20), (1, 32)])
+def test_kernel_variants_agree(vrt, port, terrain9_nodes, variant, refill):
+    """One-thread-per-ray and persistent/regenerating kernels give byte-identical hit records for every refill
+    threshold (scheduling must not change results)."""
+    c = vrt.Context(0)
+    c.set_option("kernel_variant", variant)
+    c.set_option("refill_cast", refill)
+    s = vrt.LSVO(c, terrain9_nodes, 9)
+    rng = np.random.default_rng(11)
+    for n in (1, 77, 4097, 300001):
+        o = rng.uniform(1, 2, (n, 3)).astype(np.float32)
+        o[:, 1] = rng.uniform(1.0, 1.45, n)
+        d = rng.normal(size=(n, 3)).astype(np.float32)
+        got = s.cast_rays(o, d, 0.0 if n % 2 else 0.5, 0.0)
+        want = port.lsvo_cast(terrain9_nodes, 9, o, d, 0.0 if n % 2 else 0.5, 0.0, threads=8)
+        assert_hits_equal(got, want, hit_flag(got), "variant %d refill %d n=%d" % (variant, refill, n))
+        assert s.last_complexity() == int(want["complexity"].sum())
+    c.close()

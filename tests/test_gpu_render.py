@@ -107,3 +107,23 @@ def test_autofocus(vrt, scene9, port, terrain9_nodes):
     want = port.lsvo_cast(terrain9_nodes, 9, [o], [cam.camera_vec])[0]
     assert want["hit"] and f == np.float32(want["distance"]) * np.float32(512.0)
     assert vrt.Camera(position=(256, 200, 256), view_angle=(0.0, 0.0)).autofocus(scene9) == 100.0   # centre ray misses
+
+
+@pytest.mark.parametrize("variant,refill", [(0, 8), (1, 1), (1, 12), (1, 32)])
+def test_render_kernel_variants_agree(vrt, port, terrain9_nodes, textures, variant, refill):
+    c = vrt.Context(0)
+    c.set_option("kernel_variant", variant)
+    c.set_option("refill_render", refill)
+    s = vrt.LSVO(c, terrain9_nodes, 9)
+    s.set_textures(*textures)
+    W, H = 203, 77                                   # ragged: not a multiple of the 8x4 tile
+    cam = vrt.Camera(position=(256, 200, 256), view_angle=(0.3, -0.35), aperture=0.5, focal_length=60.0)
+    rc = vrt.RayCaster(s, (W, H))
+    rc.setLightPosition(default_light())
+    rc.use_samples, rc.use_gi, rc.gi_bounces = True, True, 2
+    img = rc.render(cam, spp=3)
+    p = port_params(W, H, 9, cam, default_light(), 1, 2, True, 3)
+    accum, rgba, stats = port.render(terrain9_nodes, p, *textures)
+    assert np.array_equal(rc.colors, accum) and np.array_equal(img, rgba)
+    assert rc.last_stats["rays"] == list(stats.rays) and rc.last_stats["complexity"] == list(stats.complexity)
+    c.close()
