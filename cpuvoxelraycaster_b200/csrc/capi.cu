@@ -54,10 +54,11 @@ struct vrt_context {
     bool owns_stream = false;
     uint64_t launches = 0;
     int sm_count = 0;
-    // 1 = persistent threads with per-lane ray regeneration (default); 0 = one thread per ray / pixel (the
-    // first kernels, kept for A/B measurements: profiles/r01_summary.md)
-    int kernel_variant = 1;
-    int refill_cast = 8, refill_render = 8;   // parked lanes that trigger a refill (1..32)
+    // 1 = persistent threads with per-lane ray regeneration; 0 = one thread per ray / pixel.
+    // Defaults follow the measurements in profiles/r01_summary.md: batched casts regenerate (warp-adaptive),
+    // frames keep one lane per pixel (coherent primary/shadow rays lose more from de-phasing than GI rays gain).
+    int cast_variant = 1, render_variant = 0;
+    int refill_cast = 0, refill_render = 16;   // parked lanes that trigger a refill (1..32); cast: 0 = warp-adaptive
     DeviceBuffer scratch_in, scratch_out;   // host-variant staging
 };
 
@@ -153,8 +154,9 @@ uint64_t vrt_context_launch_count(const vrt_context* ctx) { return ctx ? ctx->la
 int vrt_context_set_option(vrt_context* ctx, const char* key, int value) {
     if (!ctx || !key) return fail(VRT_ERR_INVALID, "vrt_context_set_option: NULL argument");
     const std::string k(key);
-    if (k == "kernel_variant" && (value == 0 || value == 1)) ctx->kernel_variant = value;
-    else if (k == "refill_cast" && value >= 1 && value <= 32) ctx->refill_cast = value;
+    if (k == "cast_variant" && (value == 0 || value == 1)) ctx->cast_variant = value;
+    else if (k == "render_variant" && (value == 0 || value == 1)) ctx->render_variant = value;
+    else if (k == "refill_cast" && value >= 0 && value <= 32) ctx->refill_cast = value;
     else if (k == "refill_render" && value >= 1 && value <= 32) ctx->refill_render = value;
     else return fail(VRT_ERR_INVALID, "vrt_context_set_option: unknown key or value out of range: " + k);
     return VRT_OK;
@@ -256,7 +258,7 @@ int vrt_cast_rays_device(vrt_scene* sc, const float* d_origin, const float* d_di
     if (n == 0) return VRT_OK;
     switch (sc->kind) {
         case VRT_SCENE_LSVO:
-            if (ctx->kernel_variant == 0)
+            if (ctx->cast_variant == 0)
                 VRT_CUDA(vrt::launch_lsvo_cast_ref(sc->d_nodes, int(sc->depth), sc->guard, d_origin, d_dir, coef, bias, n, d_out,
                                                    sc->d_counters, ctx->stream));
             else
@@ -354,7 +356,7 @@ int vrt_render_accumulate_device(vrt_scene* sc, const vrt_camera* cam, const vrt
     if (int s = use_device(ctx)) return s;
     VRT_CUDA(cudaMemsetAsync(sc->d_counters + kRenderCounters, 0, 13 * sizeof(unsigned long long), ctx->stream));
     if (p->row_end == p->row_begin) return VRT_OK;
-    if (ctx->kernel_variant == 0)
+    if (ctx->render_variant == 0)
         VRT_CUDA(vrt::launch_render_accumulate_ref(sc->d_nodes, make_launch(sc, cam, p), d_accum, sc->d_counters + kRenderCounters,
                                                    ctx->stream));
     else

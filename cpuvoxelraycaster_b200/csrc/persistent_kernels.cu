@@ -38,7 +38,13 @@ __device__ __forceinline__ void store_hit_record(vrt_hit* out, const LsvoResult&
 }
 
 // ---- K1p: LSVO<D>::castRay over a ray buffer ---------------------------------------------------------------
-constexpr int kRayChunk = 256;
+// Work is fetched 64 rays at a time (one atomic per fetch) so that the tail stays balanced.
+// refill > 0: fixed regeneration threshold.  refill == 0 (default): warp-adaptive — a warp starts in
+// "coherent" mode (threshold 32: 32 rays walk in lock-step like the reference's pixel neighbours, which keeps
+// the push/advance/pop branches uniform); after every synchronous batch it measures the batch's SIMT
+// efficiency sum(iters) / (32 * max(iters)) and drops to threshold 8 when rays turn out incoherent
+// (ncu: 4.7 of 32 lanes active on random rays without regeneration), probing coherent mode again now and then.
+constexpr int kRayChunk = 64;
 
 template <typename Nodes>
 __global__ void __launch_bounds__(128, 4) lsvo_cast_persistent_kernel(Nodes nodes, int depth, int guard,
@@ -54,6 +60,10 @@ __global__ void __launch_bounds__(128, 4) lsvo_cast_persistent_kernel(Nodes node
     const int depth_offset = kSvoMaxDepth - depth;
     const int lane = threadIdx.x & 31;
     const unsigned lt = lanemask_lt();
+    const bool adaptive = refill <= 0;
+    int threshold = adaptive ? 32 : refill;                // warp-uniform
+    int refills_since_probe = 0;
+    bool sync_batch = false;                               // all 32 lanes were started in the same refill phase
 
     Trav t;
     bool alive = false, has_result = false, exhausted = false;
@@ -62,7 +72,22 @@ __global__ void __launch_bounds__(128, 4) lsvo_cast_persistent_kernel(Nodes node
 
     for (;;) {
         // ---- refill phase: retire parked lanes, hand out new rays ----
-        if (!alive && has_result) {
+        const bool retiring = !alive && has_result;
+        if (adaptive) {
+            const unsigned rmask = __ballot_sync(kFull, retiring);
+            if (threshold == 32 && sync_batch && rmask == kFull) {
+                uint32_t sum = t.iters, mx = t.iters;
+                for (int o = 16; o > 0; o >>= 1) {
+                    sum += __shfl_xor_sync(kFull, sum, o);
+                    mx = max(mx, __shfl_xor_sync(kFull, mx, o));
+                }
+                if (sum * 100u < 55u * 32u * mx) threshold = 8;      // < 55 % of the lanes did useful work
+            } else if (threshold != 32 && ++refills_since_probe >= 256) {
+                threshold = 32;                                      // drain, then measure one synchronous batch
+                refills_since_probe = 0;
+            }
+        }
+        if (retiring) {
             LsvoResult r;
             t.result(r);
             LsvoHit h;
@@ -72,6 +97,7 @@ __global__ void __launch_bounds__(128, 4) lsvo_cast_persistent_kernel(Nodes node
             has_result = false;
         }
         unsigned want = __ballot_sync(kFull, !alive);
+        sync_batch = want == kFull;
         while (want && !exhausted) {
             if (chunk_next == chunk_end) {
                 unsigned long long base = 0;
@@ -94,12 +120,19 @@ __global__ void __launch_bounds__(128, 4) lsvo_cast_persistent_kernel(Nodes node
             chunk_next += __popc(took);
             want &= ~took;
         }
+        if (want) sync_batch = false;                      // the buffer ran dry: not a full batch
         if (!__ballot_sync(kFull, alive)) break;
-        // ---- traversal phase: step until `refill` lanes are parked (or, at the tail, until all are) ----
-        const int min_alive = exhausted ? 1 : 32 - refill + 1;
-        do {
-            if (alive) alive = t.step(nodes, stack, depth_offset, guard);
-        } while (__popc(__ballot_sync(kFull, alive)) >= min_alive);
+        // ---- traversal phase: step until `threshold` lanes are parked (or, at the tail, until all are) ----
+        if (exhausted || threshold == 32) {
+            // lock-step batch (or tail): every lane runs its ray to the end, no per-trip vote needed
+            while (alive) alive = t.step(nodes, stack, depth_offset, guard);
+            __syncwarp();
+        } else {
+            const int min_alive = 32 - threshold + 1;
+            do {
+                if (alive) alive = t.step(nodes, stack, depth_offset, guard);
+            } while (__popc(__ballot_sync(kFull, alive)) >= min_alive);
+        }
     }
     for (int o = 16; o > 0; o >>= 1) iter_sum += __shfl_xor_sync(kFull, iter_sum, o);
     if (lane == 0 && iter_sum) atomicAdd(counters, iter_sum);

@@ -85,12 +85,12 @@ def test_edge_cases(vrt, ctx, port):
     assert hit_flag(got)[0] and got["distance"][0] == 0.5 and not np.any(got["normal"][0])
 
 
-@pytest.mark.parametrize("variant,refill", [(0, 8), (1, 1), (1, 8), (1, 20), (1, 32)])
+@pytest.mark.parametrize("variant,refill", [(0, 8), (1, 0), (1, 1), (1, 8), (1, 20), (1, 32)])
 def test_kernel_variants_agree(vrt, port, terrain9_nodes, variant, refill):
     """One-thread-per-ray and persistent/regenerating kernels give byte-identical hit records for every refill
     threshold (scheduling must not change results)."""
     c = vrt.Context(0)
-    c.set_option("kernel_variant", variant)
+    c.set_option("cast_variant", variant)
     c.set_option("refill_cast", refill)
     s = vrt.LSVO(c, terrain9_nodes, 9)
     rng = np.random.default_rng(11)

@@ -112,7 +112,7 @@ def test_autofocus(vrt, scene9, port, terrain9_nodes):
 @pytest.mark.parametrize("variant,refill", [(0, 8), (1, 1), (1, 12), (1, 32)])
 def test_render_kernel_variants_agree(vrt, port, terrain9_nodes, textures, variant, refill):
     c = vrt.Context(0)
-    c.set_option("kernel_variant", variant)
+    c.set_option("render_variant", variant)
     c.set_option("refill_render", refill)
     s = vrt.LSVO(c, terrain9_nodes, 9)
     s.set_textures(*textures)
