@@ -1,0 +1,411 @@
+// vrt.hpp — C++ drop-in classes for the reference's per-pixel hot path, implemented on libvrt's C ABI.
+//
+// Same class names, member names and call signatures as johnBuffer/CpuVoxelRaycaster so that the
+// reference's main.cpp keeps compiling with `#include <vrt/vrt.hpp>` in place of its own headers:
+//
+//   Cell                     include/cell.hpp:3-24
+//   HitPoint, Volumetric     include/volumetric.hpp:7-22,55-61
+//   SVO<N>                   include/svo.hpp:29         (setCell :72, castRay :62 — hit fill restored)
+//   LSVO<D>                  include/lsvo.hpp:10        (ctor from SVO :12, castRay :33, setCell no-op :26)
+//   Grid3D<X,Y,Z>            include/grid_3d.hpp:10     (castRay :16, setCell :18, getCellAt :20)
+//   MipmapGrid3D<X,Y,Z,L>    include/mipmap_grid3D.hpp:14 (a stub in the reference; Grid3D results here)
+//   Camera                   include/camera_controller.hpp:16-61
+//   RayCaster                include/raycaster.hpp:43   (setLightPosition :62, samples_to_image :94,
+//                                                        resetSamples :105, use_gi/use_samples/... :269-282)
+//
+// What changes for the caller: a single-ray castRay() is one tiny kernel launch, so hot loops should use
+// the batched castRays(); and the swarm lambda of src/main.cpp:139-154 (one renderRay per pixel from
+// 16 threads) becomes ONE call, RayCaster::render(camera).  There is no CPU fallback: every cast needs a
+// CUDA device and throws vrt::Error otherwise.
+//
+// glm: the reference passes glm::vec3; if <glm/glm.hpp> is on the include path it is used, otherwise a
+// minimal glm::vec2/vec3/mat3 with the same layout is provided so this header is self-contained.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../vrt.h"
+
+#if defined(__has_include)
+#if __has_include(<glm/glm.hpp>)
+#include <glm/glm.hpp>
+#define VRT_HAVE_GLM 1
+#endif
+#endif
+#ifndef VRT_HAVE_GLM
+namespace glm {
+struct vec2 { float x = 0, y = 0; vec2() {} vec2(float a, float b) : x(a), y(b) {} };
+struct vec3 {
+    float x = 0, y = 0, z = 0;
+    vec3() {}
+    explicit vec3(float s) : x(s), y(s), z(s) {}
+    vec3(float a, float b, float c) : x(a), y(b), z(c) {}
+};
+inline vec3 operator+(const vec3& a, const vec3& b) { return vec3(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline vec3 operator-(const vec3& a, const vec3& b) { return vec3(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline vec3 operator*(const vec3& a, float s) { return vec3(a.x * s, a.y * s, a.z * s); }
+inline vec3 operator*(float s, const vec3& a) { return vec3(s * a.x, s * a.y, s * a.z); }
+struct mat3 { vec3 c[3]; vec3& operator[](int i) { return c[i]; } const vec3& operator[](int i) const { return c[i]; } };
+}  // namespace glm
+#endif
+
+namespace vrt {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error("libvrt error " + std::to_string(c) + ": " + m), code(c) {}
+};
+inline void check(int status) {
+    if (status != VRT_OK) throw Error(status, vrt_last_error());
+}
+
+// One device + stream shared by every drop-in object of the process (replaces swrm::Swarm, main.cpp:90-92).
+inline vrt_context* default_context(int device = 0) {
+    struct Holder {
+        vrt_context* ctx = nullptr;
+        ~Holder() { /* scenes may outlive static destruction order: leave the context to process exit */ }
+    };
+    static Holder h;
+    if (!h.ctx) check(vrt_context_create(device, nullptr, &h.ctx));
+    return h.ctx;
+}
+
+struct SceneHandle {
+    vrt_scene* s = nullptr;
+    SceneHandle() {}
+    SceneHandle(const SceneHandle&) = delete;
+    SceneHandle& operator=(const SceneHandle&) = delete;
+    ~SceneHandle() { if (s) vrt_scene_destroy(s); }
+};
+
+}  // namespace vrt
+
+// ---- include/cell.hpp -----------------------------------------------------------------------------------
+struct Cell {
+    enum Type { Empty, Solid, Mirror };
+    enum Texture { None, Grass, Red, White };
+    Cell() : type(Type::Empty), texture(Texture::None) {}
+    Type type;
+    Texture texture;
+};
+
+// ---- include/volumetric.hpp ---------------------------------------------------------------------------
+struct HitPoint {
+    HitPoint() : cell(nullptr), distance(0.0f), complexity(0u) {}
+    glm::vec3 position;
+    glm::vec3 normal;
+    glm::vec2 voxel_coord;
+    const Cell* cell;
+    float distance;
+    uint32_t complexity;
+};
+
+class Volumetric {
+public:
+    virtual ~Volumetric() {}
+    virtual HitPoint castRay(const glm::vec3& position, glm::vec3 direction, const float ray_size_coef,
+                             const float ray_size_bias) const = 0;
+    virtual void setCell(Cell::Type type, Cell::Texture texture, uint32_t x, uint32_t y, uint32_t z) = 0;
+    // batched form (addition): n rays in, n HitPoints out, one kernel launch
+    virtual std::vector<HitPoint> castRays(const std::vector<glm::vec3>& positions, const std::vector<glm::vec3>& directions,
+                                           float ray_size_coef = 0.0f, float ray_size_bias = 0.0f) const = 0;
+    virtual vrt_scene* scene() const = 0;
+};
+
+namespace vrt {
+inline HitPoint to_hitpoint(const vrt_hit& h, const Cell* cell) {
+    HitPoint p;
+    p.complexity = h.complexity;
+    if (h.flags & VRT_HIT_FLAG_HIT) {
+        p.cell = cell;
+        p.position = glm::vec3(h.position[0], h.position[1], h.position[2]);
+        p.normal = glm::vec3(h.normal[0], h.normal[1], h.normal[2]);
+        p.voxel_coord = glm::vec2(h.voxel_coord[0], h.voxel_coord[1]);
+        p.distance = h.distance;
+    }
+    return p;
+}
+inline void flatten(const std::vector<glm::vec3>& v, std::vector<float>& out) {
+    out.resize(v.size() * 3);
+    for (size_t i = 0; i < v.size(); ++i) { out[3 * i] = v[i].x; out[3 * i + 1] = v[i].y; out[3 * i + 2] = v[i].z; }
+}
+}  // namespace vrt
+
+// ---- include/svo.hpp --------------------------------------------------------------------------------------
+// The reference grows a pointer octree voxel by voxel (80-byte nodes).  Here setCell only records the voxel;
+// the octree is flattened when an LSVO is constructed from it, or packed to bits for SVO::castRay.
+template <uint8_t N>
+class SVO {
+public:
+    SVO() {}
+    void setCell(Cell::Type type, Cell::Texture texture, uint32_t x, uint32_t y, uint32_t z) {
+        if (x >= (1u << N) || y >= (1u << N) || z >= (1u << N)) throw vrt::Error(VRT_ERR_INVALID, "SVO::setCell: voxel out of range");
+        (void)type; (void)texture;                     // every leaf of the demo is Solid/Grass (main.cpp:73)
+        voxels.push_back(x); voxels.push_back(y); voxels.push_back(z);
+        m_dirty = true;
+    }
+    // svo.hpp:62 — position in voxel units
+    HitPoint castRay(const glm::vec3& position, const glm::vec3& direction, const uint32_t max_iter) const {
+        static_assert(N <= 10, "SVO::castRay packs a dense occupancy: depth <= 10");
+        ensure_scene();
+        const float o[3] = {position.x, position.y, position.z}, d[3] = {direction.x, direction.y, direction.z};
+        vrt_hit h;
+        vrt::check(vrt_cast_rays_svo(m_scene->s, o, d, max_iter, 1, &h));
+        return vrt::to_hitpoint(h, &m_cell);
+    }
+    std::vector<uint32_t> voxels;                      // xyz triples in setCell order
+
+private:
+    void ensure_scene() const {
+        if (m_scene && !m_dirty) return;
+        const size_t S = size_t(1) << N;
+        std::vector<uint8_t> occ(S * S * S, 0);
+        for (size_t i = 0; i + 2 < voxels.size(); i += 3) occ[(size_t(voxels[i]) * S + voxels[i + 1]) * S + voxels[i + 2]] = 1;
+        m_scene.reset(new vrt::SceneHandle());
+        vrt::check(vrt_svo_create(vrt::default_context(), occ.data(), N, &m_scene->s));
+        m_dirty = false;
+    }
+    mutable std::unique_ptr<vrt::SceneHandle> m_scene;
+    mutable bool m_dirty = true;
+    Cell m_cell = solid_grass();
+    static Cell solid_grass() { Cell c; c.type = Cell::Solid; c.texture = Cell::Grass; return c; }
+};
+
+// ---- include/lsvo.hpp -------------------------------------------------------------------------------------
+template <uint8_t MAX_DEPTH>
+struct LSVO : public Volumetric {
+    LSVO(const SVO<MAX_DEPTH>& svo) { importFromSVO(svo); }
+    // extension: adopt an already flattened octree (e.g. vrt_host_build_terrain_lsvo for 2048^3 and up)
+    explicit LSVO(std::vector<vrt_lnode> nodes, int32_t guard = 0) : data(std::move(nodes)) { upload(guard); }
+
+    void importFromSVO(const SVO<MAX_DEPTH>& svo) {                       // lsvo.hpp:18-24
+        uint64_t n = 0;
+        const uint64_t nv = svo.voxels.size() / 3;
+        vrt::check(vrt_host_build_lsvo_from_voxels(MAX_DEPTH, svo.voxels.data(), nv, nullptr, 0, &n));
+        data.resize(n);
+        vrt::check(vrt_host_build_lsvo_from_voxels(MAX_DEPTH, svo.voxels.data(), nv, data.data(), n, &n));
+        upload(0);
+    }
+    void setCell(Cell::Type, Cell::Texture, uint32_t, uint32_t, uint32_t) override {}   // lsvo.hpp:26
+
+    HitPoint castRay(const glm::vec3& position, glm::vec3 d, const float ray_size_coef = 0.0f,
+                     const float ray_size_bias = 0.0f) const override {          // lsvo.hpp:33
+        const float o[3] = {position.x, position.y, position.z}, dir[3] = {d.x, d.y, d.z};
+        vrt_hit h;
+        vrt::check(vrt_cast_rays(m_scene.s, o, dir, ray_size_coef, ray_size_bias, 1, &h));
+        return vrt::to_hitpoint(h, cell);
+    }
+    std::vector<HitPoint> castRays(const std::vector<glm::vec3>& positions, const std::vector<glm::vec3>& directions,
+                                   float ray_size_coef = 0.0f, float ray_size_bias = 0.0f) const override {
+        if (positions.size() != directions.size()) throw vrt::Error(VRT_ERR_INVALID, "castRays: size mismatch");
+        std::vector<float> o, d;
+        vrt::flatten(positions, o);
+        vrt::flatten(directions, d);
+        std::vector<vrt_hit> h(positions.size());
+        vrt::check(vrt_cast_rays(m_scene.s, o.data(), d.data(), ray_size_coef, ray_size_bias, h.size(), h.data()));
+        std::vector<HitPoint> out(h.size());
+        for (size_t i = 0; i < h.size(); ++i) out[i] = vrt::to_hitpoint(h[i], cell);
+        return out;
+    }
+    vrt_scene* scene() const override { return m_scene.s; }
+
+    std::vector<vrt_lnode> data;                        // LNode[] in the reference layout (lsvo.hpp:287)
+    const vrt_lnode* raw_data = nullptr;                // lsvo.hpp:288
+    Cell* cell = nullptr;                               // the one shared Solid/Grass cell (lsvo.hpp:21-23,289)
+
+private:
+    void upload(int32_t guard) {
+        raw_data = data.data();
+        m_cell.type = Cell::Solid;
+        m_cell.texture = Cell::Grass;
+        cell = &m_cell;
+        vrt::check(vrt_lsvo_create(vrt::default_context(), data.data(), data.size(), MAX_DEPTH, guard, &m_scene.s));
+    }
+    Cell m_cell;
+    vrt::SceneHandle m_scene;
+};
+
+// ---- include/grid_3d.hpp / include/mipmap_grid3D.hpp ------------------------------------------------
+template <int32_t X, int32_t Y, int32_t Z, int32_t MipLevels = 0>
+class Grid3DBase : public Volumetric {
+public:
+    Grid3DBase() : m_types(size_t(X) * Y * Z, 0), m_cells(1) {}
+    // grid_3d.hpp:16 (2-argument form; the 4-argument Volumetric form ignores the cone)
+    HitPoint castRay(const glm::vec3& position, const glm::vec3& direction) const { return castRay(position, direction, 0.0f, 0.0f); }
+    HitPoint castRay(const glm::vec3& position, glm::vec3 direction, const float, const float) const override {
+        ensure_scene();
+        const float o[3] = {position.x, position.y, position.z}, d[3] = {direction.x, direction.y, direction.z};
+        vrt_hit h;
+        vrt::check(vrt_cast_rays(m_scene->s, o, d, 0.0f, 0.0f, 1, &h));
+        return hit(h);
+    }
+    std::vector<HitPoint> castRays(const std::vector<glm::vec3>& positions, const std::vector<glm::vec3>& directions, float = 0.0f,
+                                   float = 0.0f) const override {
+        ensure_scene();
+        std::vector<float> o, d;
+        vrt::flatten(positions, o);
+        vrt::flatten(directions, d);
+        std::vector<vrt_hit> h(positions.size());
+        vrt::check(vrt_cast_rays(m_scene->s, o.data(), d.data(), 0.0f, 0.0f, h.size(), h.data()));
+        std::vector<HitPoint> out(h.size());
+        for (size_t i = 0; i < h.size(); ++i) out[i] = hit(h[i]);
+        return out;
+    }
+    void setCell(Cell::Type type, uint32_t x, uint32_t y, uint32_t z) {   // grid_3d.hpp:18
+        if (x >= uint32_t(X) || y >= uint32_t(Y) || z >= uint32_t(Z)) throw vrt::Error(VRT_ERR_INVALID, "Grid3D::setCell: out of range");
+        m_types[(size_t(x) * Y + y) * Z + z] = uint8_t(type);
+        m_dirty = true;
+    }
+    void setCell(Cell::Type type, Cell::Texture, uint32_t x, uint32_t y, uint32_t z) override { setCell(type, x, y, z); }
+    Cell getCellAt(const glm::vec3& position) const {                     // grid_3d.hpp:20
+        Cell c;
+        c.type = Cell::Type(m_types[(size_t(int(position.x)) * Y + size_t(int(position.y))) * Z + size_t(int(position.z))]);
+        return c;
+    }
+    vrt_scene* scene() const override { ensure_scene(); return m_scene->s; }
+
+private:
+    HitPoint hit(const vrt_hit& h) const {
+        if (!(h.flags & VRT_HIT_FLAG_HIT)) return vrt::to_hitpoint(h, nullptr);
+        // the reference returns a pointer into m_cells; one Cell per distinct type is enough to carry it
+        const uint8_t t = m_types[(size_t(h.voxel[0]) * Y + size_t(h.voxel[1])) * Z + size_t(h.voxel[2])];
+        if (m_cells.size() < 3) { m_cells.resize(3); for (int i = 0; i < 3; ++i) m_cells[i].type = Cell::Type(i); }
+        return vrt::to_hitpoint(h, &m_cells[t < 3 ? t : 1]);
+    }
+    void ensure_scene() const {
+        if (m_scene && !m_dirty) return;
+        m_scene.reset(new vrt::SceneHandle());
+        vrt::check(vrt_grid_create(vrt::default_context(), m_types.data(), X, Y, Z, MipLevels, &m_scene->s));
+        m_dirty = false;
+    }
+    std::vector<uint8_t> m_types;                       // Cell::Type per cell (the reference keeps 8-byte Cells)
+    mutable std::vector<Cell> m_cells;
+    mutable std::unique_ptr<vrt::SceneHandle> m_scene;
+    mutable bool m_dirty = true;
+};
+template <int32_t X, int32_t Y, int32_t Z> using Grid3D = Grid3DBase<X, Y, Z, 0>;
+template <int32_t X, int32_t Y, int32_t Z, uint32_t MipmapDepth> using MipmapGrid3D = Grid3DBase<X, Y, Z, int32_t(MipmapDepth)>;
+
+// ---- include/camera_controller.hpp ------------------------------------------------------------------
+struct Camera {
+    glm::vec3 position;
+    glm::vec2 view_angle;
+    glm::vec3 camera_vec;
+    glm::mat3 rot_mat;
+    float aperture = 0.0f;
+    float focal_length = 1.0f;
+    float fov = 1.0f;
+
+    void setViewAngle(const glm::vec2& angle) {                           // camera_controller.hpp:27-32
+        view_angle = angle;
+        const float a[2] = {angle.x, angle.y};
+        float m[9], v[3];
+        vrt::check(vrt_host_camera_rotation(a, m, v));
+        for (int c = 0; c < 3; ++c) rot_mat[c] = glm::vec3(m[3 * c], m[3 * c + 1], m[3 * c + 2]);
+        camera_vec = glm::vec3(v[0], v[1], v[2]);
+    }
+    vrt_camera as_struct() const {
+        vrt_camera c;
+        c.position[0] = position.x; c.position[1] = position.y; c.position[2] = position.z;
+        for (int k = 0; k < 3; ++k) { c.rot_mat[3 * k] = rot_mat[k].x; c.rot_mat[3 * k + 1] = rot_mat[k].y; c.rot_mat[3 * k + 2] = rot_mat[k].z; }
+        c.fov = fov; c.aperture = aperture; c.focal_length = focal_length;
+        return c;
+    }
+    // camera_controller.hpp:56-60 + main.cpp:115-121: returns the focal length the demo would use
+    float autofocus(const Volumetric& volume) {
+        const vrt_camera c = as_struct();
+        vrt::check(vrt_autofocus(volume.scene(), &c, &focal_length));
+        return focal_length;
+    }
+};
+
+// ---- include/raycaster.hpp --------------------------------------------------------------------------------
+namespace vrt {
+struct Vector2i { int x = 0, y = 0; Vector2i() {} Vector2i(int a, int b) : x(a), y(b) {} };   // sf::Vector2i stand-in
+struct Color { uint8_t r = 0, g = 0, b = 0, a = 255; };                                       // sf::Color stand-in
+
+// 24-bit uncompressed BMP → 16x16 RGB, top-down rows (what sf::Image::loadFromFile yields)
+inline bool load_bmp16(const std::string& path, uint8_t out[768]) {
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    uint8_t hdr[54];
+    bool ok = std::fread(hdr, 1, 54, f) == 54 && hdr[0] == 'B' && hdr[1] == 'M';
+    uint32_t off = 0; int32_t w = 0, h = 0; uint16_t bpp = 0;
+    if (ok) { std::memcpy(&off, hdr + 10, 4); std::memcpy(&w, hdr + 18, 4); std::memcpy(&h, hdr + 22, 4); std::memcpy(&bpp, hdr + 28, 2); }
+    ok = ok && w == 16 && (h == 16 || h == -16) && bpp == 24 && std::fseek(f, long(off), SEEK_SET) == 0;
+    for (int row = 0; ok && row < 16; ++row) {
+        uint8_t line[48];
+        ok = std::fread(line, 1, 48, f) == 48;
+        const int y = h > 0 ? 15 - row : row;
+        for (int x = 0; ok && x < 16; ++x) { out[3 * (y * 16 + x)] = line[3 * x + 2]; out[3 * (y * 16 + x) + 1] = line[3 * x + 1]; out[3 * (y * 16 + x) + 2] = line[3 * x]; }
+    }
+    std::fclose(f);
+    return ok;
+}
+}  // namespace vrt
+
+template <uint8_t SVO_DEPTH_>
+struct RayCasterT {
+    // raycaster.hpp:48 — loads res/grass_side_16x16.bmp and res/grass_top_16x16.bmp relative to the CWD like the
+    // reference; pass explicit textures (16x16 RGB, top-down) to skip the files.
+    RayCasterT(const LSVO<SVO_DEPTH_>& svo_, const vrt::Vector2i& render_size_, const uint8_t* top_rgb = nullptr,
+               const uint8_t* side_rgb = nullptr)
+        : svo(svo_), render_size(render_size_) {
+        uint8_t top[768], side[768];
+        if (top_rgb && side_rgb) { std::memcpy(top, top_rgb, 768); std::memcpy(side, side_rgb, 768); }
+        else if (!vrt::load_bmp16("res/grass_top_16x16.bmp", top) || !vrt::load_bmp16("res/grass_side_16x16.bmp", side))
+            throw vrt::Error(VRT_ERR_INVALID, "RayCaster: cannot read res/grass_{top,side}_16x16.bmp");
+        vrt::check(vrt_scene_set_textures(svo.scene(), top, side));
+        render_image.assign(size_t(render_size.x) * render_size.y * 4, 0);
+        colors.assign(size_t(render_size.x) * render_size.y * 4, 0u);
+    }
+    void setLightPosition(const glm::vec3& position) { light_position = position; }          // raycaster.hpp:62
+
+    // Replaces the swarm lambda main.cpp:139-154 (+ samples_to_image when use_samples): every pixel, `spp` passes.
+    void render(const Camera& camera, int spp = 1) {
+        vrt_render_params p;
+        std::memset(&p, 0, sizeof(p));
+        p.width = render_size.x; p.height = render_size.y; p.row_begin = 0; p.row_end = render_size.y;
+        p.spp = use_samples ? spp : 1;
+        p.sample_offset = int32_t(sample_count);
+        p.seed_lo = seed_lo; p.seed_hi = seed_hi;
+        p.light_position[0] = light_position.x; p.light_position[1] = light_position.y; p.light_position[2] = light_position.z;
+        p.use_gi = use_gi; p.gi_bounces = gi_bounces; p.use_samples = use_samples;
+        p.accum_in = use_samples ? 1 : 0;
+        if (!use_samples) std::fill(colors.begin(), colors.end(), 0u);
+        const vrt_camera c = camera.as_struct();
+        vrt::check(vrt_render(svo.scene(), &c, &p, render_image.data(), colors.data(), &last_stats));
+        if (use_samples) sample_count += uint32_t(p.spp);
+    }
+    void samples_to_image() {}                          // raycaster.hpp:94-103: done on the device by render()
+    void resetSamples() {                               // raycaster.hpp:105-116
+        std::fill(colors.begin(), colors.end(), 0u);
+        sample_count = 0;
+    }
+    vrt::Color getPixel(int x, int y) const {
+        const uint8_t* q = &render_image[4 * (size_t(y) * render_size.x + x)];
+        vrt::Color c; c.r = q[0]; c.g = q[1]; c.b = q[2]; c.a = q[3];
+        return c;
+    }
+
+    std::vector<uint32_t> colors;                       // Sample accumulators r,g,b,count per pixel (raycaster.hpp:259)
+    std::vector<uint8_t> render_image;                  // RGBA8, row major (sf::Image render_image, raycaster.hpp:261)
+    const LSVO<SVO_DEPTH_>& svo;
+    const vrt::Vector2i render_size;
+    glm::vec3 light_position;
+    bool use_ao = false;                                // toggles without effect, as in the reference (:273,:276)
+    bool use_gi = false;
+    bool use_samples = false;
+    bool use_god_rays = false;
+    int gi_bounces = 1;                                 // 2 = extension
+    uint32_t seed_lo = 0x5EED, seed_hi = 0, sample_count = 0;
+    vrt_render_stats last_stats{};
+};
+constexpr uint8_t SVO_DEPTH = 9u;                       // raycaster.hpp:42
+using RayCaster = RayCasterT<SVO_DEPTH>;
