@@ -1,5 +1,5 @@
 // Batched LSVO<D>::castRay (reference include/lsvo.hpp:33-172) — kernel K1.
-#include "lsvo_traverse.cuh"
+#include "lsvo_step.cuh"
 #include "kernels.h"
 
 namespace vrt {
@@ -26,12 +26,11 @@ template <typename Nodes>
 __global__ void __launch_bounds__(128) lsvo_cast_kernel(Nodes nodes, int depth, int guard, const float* __restrict__ origin,
                                                         const float* __restrict__ dir, float coef, float bias, uint64_t n,
                                                         vrt_hit* __restrict__ out, unsigned long long* __restrict__ total_complexity) {
-    extern __shared__ uint32_t smem[];
-    const int entries = depth + 1;
-    SharedStack stack;
-    stack.stride = blockDim.x;
-    stack.parent = smem + threadIdx.x;
-    stack.t_max = reinterpret_cast<float*>(smem + entries * blockDim.x) + threadIdx.x;
+    extern __shared__ uint2 smem[];
+    Stack64<128> stack{smem + threadIdx.x};
+    nodes.slots = pin(nodes.slots);
+    guard = pin(guard);
+    const int depth_offset = pin(kSvoMaxDepth - depth);
 
     const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     uint32_t iters = 0u;
@@ -39,7 +38,7 @@ __global__ void __launch_bounds__(128) lsvo_cast_kernel(Nodes nodes, int depth, 
         const float ox = origin[3 * i], oy = origin[3 * i + 1], oz = origin[3 * i + 2];
         const float dx = dir[3 * i], dy = dir[3 * i + 1], dz = dir[3 * i + 2];
         LsvoResult r;
-        lsvo_cast(nodes, stack, depth, guard, ox, oy, oz, dx, dy, dz, coef, bias, r);
+        lsvo_cast_ray(nodes, stack, depth_offset, guard, ox, oy, oz, dx, dy, dz, coef, bias, r);
         LsvoHit h;
         if (r.hit) lsvo_finish(r, ox, oy, oz, depth, h);
         store_hit(out + i, r, h, depth);

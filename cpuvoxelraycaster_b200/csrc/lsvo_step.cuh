@@ -1,15 +1,39 @@
 // LSVO traversal as a resumable per-lane state machine: init() = prologue of LSVO<D>::castRay
 // (reference include/lsvo.hpp:44-70), step() = exactly one trip of its while loop (:72-146),
-// finish() = the hit epilogue (:148-169, in lsvo_traverse.cuh).
+// lsvo_finish() = the hit epilogue (:148-169, in lsvo_traverse.cuh).
 //
-// Same fp32 operations in the same order as lsvo_cast() — the split only lets a persistent warp keep
-// every lane busy: a lane whose ray has terminated parks its result and is handed a new ray while its
-// neighbours keep stepping (ncu on the one-thread-per-ray kernels: 15 of 32 lanes active per instruction
-// on GI frames, 4.7 of 32 on incoherent rays — profiles/r01_summary.md).
+// Same fp32 operations in the same order as the reference, so results are bit-identical.  What is NOT
+// copied is the integer bookkeeping around them, which the first ncu source-level capture showed to be
+// a quarter of all issued instructions (profiles/r01_summary.md):
+//   * POP (lsvo.hpp:124-145): the reference finds the highest differing bit by converting the XOR of two
+//     float bit patterns to float and reading its exponent (:132).  The operand always has < 24
+//     significant bits (positions are multiples of 2^-12 in [0.5, 2], so its low 10 bits are zero), the
+//     conversion is exact and the exponent is the index of the highest set bit: one FLO (31 - clz).
+//     Truncating the position to the new scale ((x >> s) << s, :137-142) is one AND with a mask.
+//   * PUSH/POP use ONE 8-byte shared-memory access per stack entry ({parent, t_max} interleaved, entry-major,
+//     compile-time stride), instead of two 4-byte accesses with run-time address arithmetic.
+//   * the node base pointer and the loop guard are pinned in registers (they were re-read from the constant
+//     bank on every trip, in the dependent chain in front of the node fetch).
 #pragma once
 #include "lsvo_traverse.cuh"
 
 namespace vrt {
+
+// Stack in shared memory: entry i of thread t at base[i * kThreads + t] (uint2 = {parent index, t_max bits}).
+template <int kThreads>
+struct Stack64 {
+    uint2* base;   // already offset by the thread index
+    __device__ __forceinline__ void push(int i, uint32_t p, float t) { base[i * kThreads] = make_uint2(p, __float_as_uint(t)); }
+    __device__ __forceinline__ void pop(int i, uint32_t& p, float& t) const {
+        const uint2 e = base[i * kThreads];
+        p = e.x;
+        t = __uint_as_float(e.y);
+    }
+};
+
+// Keeps a kernel parameter in a register across the traversal loop (defeats re-materialisation from c[0x0]).
+__device__ __forceinline__ const uint2* pin(const uint2* p) { asm volatile("" : "+l"(p)); return p; }
+__device__ __forceinline__ int pin(int v) { asm volatile("" : "+r"(v)); return v; }
 
 struct Trav {
     // ray (direction after the |d| >= 2^-23 clamp) and cone
@@ -93,14 +117,14 @@ struct Trav {
             if (step_mask & 1u) diff |= ix ^ __float_as_uint(px + sf);
             if (step_mask & 2u) diff |= iy ^ __float_as_uint(py + sf);
             if (step_mask & 4u) diff |= iz ^ __float_as_uint(pz + sf);
-            scale = int((__float_as_uint(__uint2float_rn(diff)) >> 23) - 127u);   // :132
+            scale = 31 - __clz(int(diff));        // == (floatAsInt((float)diff) >> 23) - 127 (:132), see the header
             if (scale >= kSvoMaxDepth) return false;                         // left the root cube: miss
             stack.pop(scale - depth_offset, parent, t_max);                  // :134-136
-            const uint32_t sx = ix >> scale, sy = iy >> scale, sz = iz >> scale;
-            px = __uint_as_float(sx << scale);
-            py = __uint_as_float(sy << scale);
-            pz = __uint_as_float(sz << scale);
-            child = (sx & 1u) | ((sy & 1u) << 1) | ((sz & 1u) << 2);
+            const uint32_t keep = 0xffffffffu << scale;                      // (x >> s) << s == x & ~((1 << s) - 1)
+            px = __uint_as_float(ix & keep);                                 // :137-142
+            py = __uint_as_float(iy & keep);
+            pz = __uint_as_float(iz & keep);
+            child = ((ix >> scale) & 1u) | (((iy >> scale) & 1u) << 1) | (((iz >> scale) & 1u) << 2);   // :143
             h = 0.0f;
             return scale > guard;
         }
@@ -114,5 +138,15 @@ struct Trav {
         r.dx = dx; r.dy = dy; r.dz = dz;
     }
 };
+
+// Whole ray: LSVO<D>::castRay (lsvo.hpp:33-147).  The hit epilogue is lsvo_finish().
+template <typename Nodes, typename Stack>
+__device__ __forceinline__ void lsvo_cast_ray(const Nodes& nodes, Stack& stack, int depth_offset, int guard, float ox, float oy,
+                                              float oz, float dx, float dy, float dz, float coef, float bias, LsvoResult& r) {
+    Trav t;
+    t.init(ox, oy, oz, dx, dy, dz, coef, bias);
+    while (t.step(nodes, stack, depth_offset, guard)) {}
+    t.result(r);
+}
 
 }  // namespace vrt

@@ -52,12 +52,11 @@ __global__ void __launch_bounds__(128, 4) lsvo_cast_persistent_kernel(Nodes node
                                                                       const float* __restrict__ dir, float coef, float bias,
                                                                       uint64_t n, vrt_hit* __restrict__ out,
                                                                       unsigned long long* __restrict__ counters, int refill) {
-    extern __shared__ uint32_t smem[];
-    SharedStack stack;
-    stack.stride = blockDim.x;
-    stack.parent = smem + threadIdx.x;
-    stack.t_max = reinterpret_cast<float*>(smem + (depth + 1) * blockDim.x) + threadIdx.x;
-    const int depth_offset = kSvoMaxDepth - depth;
+    extern __shared__ uint2 smem[];
+    Stack64<128> stack{smem + threadIdx.x};
+    nodes.slots = pin(nodes.slots);
+    guard = pin(guard);
+    const int depth_offset = pin(kSvoMaxDepth - depth);
     const int lane = threadIdx.x & 31;
     const unsigned lt = lanemask_lt();
     const bool adaptive = refill <= 0;
@@ -152,15 +151,14 @@ __device__ __forceinline__ void view_to_world_p(const float* m, float vx, float 
 template <typename Nodes>
 __global__ void __launch_bounds__(128, 4) render_persistent_kernel(Nodes nodes, RenderLaunch L, uint32_t* __restrict__ accum,
                                                                    unsigned long long* __restrict__ counters, int refill) {
-    extern __shared__ uint32_t smem[];
+    extern __shared__ uint2 smem[];
     __shared__ uint32_t s_stats[12];                                        // rays / complexity per class, spilled to global at 2^31
-    SharedStack stack;
-    stack.stride = blockDim.x;
-    stack.parent = smem + threadIdx.x;
-    stack.t_max = reinterpret_cast<float*>(smem + (L.depth + 1) * blockDim.x) + threadIdx.x;
+    Stack64<128> stack{smem + threadIdx.x};
+    nodes.slots = pin(nodes.slots);
+    const int guard = pin(L.guard);
     if (threadIdx.x < 12) s_stats[threadIdx.x] = 0u;
     __syncthreads();
-    const int depth_offset = kSvoMaxDepth - L.depth;
+    const int depth_offset = pin(kSvoMaxDepth - L.depth);
     const int lane = threadIdx.x & 31;
     const unsigned lt = lanemask_lt();
 
@@ -374,7 +372,7 @@ __global__ void __launch_bounds__(128, 4) render_persistent_kernel(Nodes nodes, 
         // ================= traversal phase =================
         const int min_alive = exhausted ? 1 : 32 - refill + 1;
         do {
-            if (alive) alive = t.step(nodes, stack, depth_offset, L.guard);
+            if (alive) alive = t.step(nodes, stack, depth_offset, guard);
         } while (__popc(__ballot_sync(kFull, alive)) >= min_alive);
     }
     __syncthreads();

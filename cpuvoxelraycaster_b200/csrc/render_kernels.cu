@@ -11,7 +11,7 @@
 // (primary, sun shadow, GI, GI shadow, second bounce, its shadow).  The chain is a small state
 // machine around ONE inlined copy of the traversal loop, so lanes at different chain stages still
 // execute the traversal converged.
-#include "lsvo_traverse.cuh"
+#include "lsvo_step.cuh"
 #include "kernels.h"
 
 namespace vrt {
@@ -32,12 +32,11 @@ __device__ __forceinline__ void view_to_world(const float* m, float vx, float vy
 template <typename Nodes>
 __global__ void __launch_bounds__(128) render_accumulate_kernel(Nodes nodes, RenderLaunch L, uint32_t* __restrict__ accum,
                                                                 unsigned long long* __restrict__ counters) {
-    extern __shared__ uint32_t smem[];
-    const int entries = L.depth + 1;
-    SharedStack stack;
-    stack.stride = blockDim.x;
-    stack.parent = smem + threadIdx.x;
-    stack.t_max = reinterpret_cast<float*>(smem + entries * blockDim.x) + threadIdx.x;
+    extern __shared__ uint2 smem[];
+    Stack64<128> stack{smem + threadIdx.x};
+    nodes.slots = pin(nodes.slots);
+    const int guard = pin(L.guard);
+    const int depth_offset = pin(kSvoMaxDepth - L.depth);
 
     // 8x4 pixel tile per warp, 4 tiles side by side per block: coherent primary rays share nodes
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -95,7 +94,7 @@ __global__ void __launch_bounds__(128) render_accumulate_kernel(Nodes nodes, Ren
             int stage = kPrimary;
             while (stage != kDone) {
                 LsvoResult r;
-                lsvo_cast(nodes, stack, L.depth, L.guard, ox, oy, oz, dx, dy, dz, coef, 0.0f, r);
+                lsvo_cast_ray(nodes, stack, depth_offset, guard, ox, oy, oz, dx, dy, dz, coef, 0.0f, r);
 #pragma unroll
                 for (int k = 0; k < 6; ++k) {                                  // predicated: keeps the counters in registers
                     n_rays[k] += (stage == k) ? 1u : 0u;

@@ -35,7 +35,12 @@ def test_dropin_matches_python_api(vrt, ctx, terrain9_nodes, textures):
     build()
     r = subprocess.run([EXE, TEX], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
-    out = dict(line.split(" ", 1) for line in r.stdout.strip().splitlines())
+    out = {}
+    for line in r.stdout.strip().splitlines():
+        key, _, rest = line.partition(" ")
+        if "=" in key:                                   # "autofocus=100.000000"
+            key, _, rest = line.partition("=")
+        out[key] = rest
     assert out["kat"].startswith("nodes=73 hit=1 complexity=14 distance=0.41210938 normal=(-0,-0,-4)")
     assert out["batch"] == "hits=101"
     assert out["terrain"] == "nodes=10528393"
