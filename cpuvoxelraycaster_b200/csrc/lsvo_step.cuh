@@ -31,9 +31,13 @@ struct Stack64 {
     }
 };
 
-// Keeps a kernel parameter in a register across the traversal loop (defeats re-materialisation from c[0x0]).
-__device__ __forceinline__ const uint2* pin(const uint2* p) { asm volatile("" : "+l"(p)); return p; }
-__device__ __forceinline__ int pin(int v) { asm volatile("" : "+r"(v)); return v; }
+// Keeps a kernel parameter in a register across the traversal loop.  ptxas re-materialises parameters from the
+// constant bank (an LDC in front of every node fetch); adding blockIdx.y — always 0, every launch is 1-D, but
+// not provably so — makes the value a computed one that has to stay in a register.
+__device__ __forceinline__ const uint2* pin(const uint2* p) {
+    return reinterpret_cast<const uint2*>(reinterpret_cast<uintptr_t>(p) + blockIdx.y);
+}
+__device__ __forceinline__ int pin(int v) { return v + int(blockIdx.y); }
 
 struct Trav {
     // ray (direction after the |d| >= 2^-23 clamp) and cone
@@ -86,12 +90,13 @@ struct Trav {
         const float cx = px * tcx - tox, cy = py * tcy - toy, cz = pz * tcz - toz;   // :76
         const float tc_max = fminf(cx, fminf(cy, cz));
         const uint32_t shift = child ^ mirror;                               // :79
-        if (((nd.child_mask >> shift) & 1u) && t_min <= t_max) {             // :80-81
+        const uint32_t child_bit = 0x100u << shift;                          // child_mask lives in bits 8..15 of the word
+        if ((nd.raw & child_bit) && t_min <= t_max) {                        // :80-81
             if (tc_max * coef + bias >= sf) { hit = true; return false; }    // :82-85
             const float tv_max = fminf(t_max, tc_max);
             const float half = sf * 0.5f;
             if (t_min <= tv_max) {                                           // :89
-                if ((nd.leaf_mask >> shift) & 1u) { hit = true; return false; }   // :90-95
+                if (nd.raw & (child_bit << 8)) { hit = true; return false; }  // leaf_mask: bits 16..23, :90-95
                 if (tc_max < h) stack.push(scale - depth_offset, parent, t_max);  // :97-100
                 h = tc_max;
                 parent = nodes.child(nd, shift);                             // :103
@@ -104,6 +109,7 @@ struct Trav {
                 return scale > guard;                                        // :72 (scale < 23 holds after a descent)
             }
         }
+        const uint32_t ox_bits = __float_as_uint(px), oy_bits = __float_as_uint(py), oz_bits = __float_as_uint(pz);
         uint32_t step_mask = 0u;                                             // :115-118
         if (cx <= tc_max) { step_mask ^= 1u; px -= sf; }
         if (cy <= tc_max) { step_mask ^= 2u; py -= sf; }
@@ -113,10 +119,9 @@ struct Trav {
         face = step_mask;
         if (child & step_mask) {                                             // :124-145
             const uint32_t ix = __float_as_uint(px), iy = __float_as_uint(py), iz = __float_as_uint(pz);
-            uint32_t diff = 0u;
-            if (step_mask & 1u) diff |= ix ^ __float_as_uint(px + sf);
-            if (step_mask & 2u) diff |= iy ^ __float_as_uint(py + sf);
-            if (step_mask & 4u) diff |= iz ^ __float_as_uint(pz + sf);
+            // :126-131: on a stepped axis p + scale_f is exactly the position before the step (grid-aligned
+            // values, exact subtraction and addition); on the other axes the position did not change, XOR = 0
+            const uint32_t diff = (ix ^ ox_bits) | (iy ^ oy_bits) | (iz ^ oz_bits);
             scale = 31 - __clz(int(diff));        // == (floatAsInt((float)diff) >> 23) - 127 (:132), see the header
             if (scale >= kSvoMaxDepth) return false;                         // left the root cube: miss
             stack.pop(scale - depth_offset, parent, t_max);                  // :134-136

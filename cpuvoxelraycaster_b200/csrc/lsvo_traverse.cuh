@@ -11,6 +11,7 @@ namespace vrt {
 
 // One octree node as the traversal sees it, whatever the memory format.
 struct NodeView {
+    uint32_t raw;          // first word of the slot: color | child_mask << 8 | leaf_mask << 16
     uint32_t child_mask;   // LNode::child_mask
     uint32_t leaf_mask;    // LNode::leaf_mask
     uint32_t child_base;   // index such that child slot s lives at child_base + s
@@ -22,6 +23,7 @@ struct RefNodes {
     __device__ __forceinline__ NodeView fetch(uint32_t id) const {
         const uint2 w = __ldg(slots + id);                 // one coalescable 8-byte load (lsvo.hpp:74)
         NodeView v;
+        v.raw = w.x;
         v.child_mask = (w.x >> 8) & 0xffu;
         v.leaf_mask = (w.x >> 16) & 0xffu;
         v.child_base = id + w.y;
