@@ -155,7 +155,7 @@ int vrt_context_set_option(vrt_context* ctx, const char* key, int value) {
     if (!ctx || !key) return fail(VRT_ERR_INVALID, "vrt_context_set_option: NULL argument");
     const std::string k(key);
     if (k == "cast_variant" && (value == 0 || value == 1)) ctx->cast_variant = value;
-    else if (k == "render_variant" && (value == 0 || value == 1)) ctx->render_variant = value;
+    else if (k == "render_variant" && (value == 0 || value == 1 || (value >= 5 && value <= 8))) ctx->render_variant = value;
     else if (k == "refill_cast" && value >= 0 && value <= 32) ctx->refill_cast = value;
     else if (k == "refill_render" && value >= 1 && value <= 32) ctx->refill_render = value;
     else return fail(VRT_ERR_INVALID, "vrt_context_set_option: unknown key or value out of range: " + k);
@@ -356,7 +356,10 @@ int vrt_render_accumulate_device(vrt_scene* sc, const vrt_camera* cam, const vrt
     if (int s = use_device(ctx)) return s;
     VRT_CUDA(cudaMemsetAsync(sc->d_counters + kRenderCounters, 0, 13 * sizeof(unsigned long long), ctx->stream));
     if (p->row_end == p->row_begin) return VRT_OK;
-    if (ctx->render_variant == 0)
+    if (ctx->render_variant >= 5)
+        VRT_CUDA(vrt::launch_render_smem(sc->d_nodes, make_launch(sc, cam, p), d_accum, sc->d_counters + kRenderCounters,
+                                         ctx->render_variant, ctx->stream));
+    else if (ctx->render_variant == 0)
         VRT_CUDA(vrt::launch_render_accumulate_ref(sc->d_nodes, make_launch(sc, cam, p), d_accum, sc->d_counters + kRenderCounters,
                                                    ctx->stream));
     else
