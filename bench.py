@@ -265,7 +265,7 @@ def run_ours(args):
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
     st = fr.stats()                                          # this rank's tiles, last frame
     t = torch.tensor([ms_total, kernel_ms], dtype=torch.float64, device=device)
-    cnt = torch.tensor(st["rays"] + st["complexity"], dtype=torch.int64, device=device)
+    cnt = torch.tensor(st["rays"] + st["complexity"] + [launches], dtype=torch.int64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         local_cnt = cnt.clone()
@@ -274,14 +274,15 @@ def run_ours(args):
         local_cnt = cnt
     ms_total, kernel_ms_max = float(t[0]), float(t[1])
     rays = [int(x) for x in cnt[:6].tolist()]
-    cx = [int(x) for x in cnt[6:].tolist()]
+    cx = [int(x) for x in cnt[6:12].tolist()]
+    launches = int(cnt[12])                                  # libvrt kernels launched in the timed region, all ranks
     total_rays = sum(rays)
     ms_per_step = ms_total / args.steps
     value = total_rays / (ms_per_step * 1e-3) / 1e6
 
     # roofline of the dominant kernel on this rank: algorithmic bytes = sum over its rays of (8 B node per
     # iteration + 64 B ray/hit record) + 16 B accumulator write per pixel
-    l_rays, l_cx = int(local_cnt[:6].sum()), int(local_cnt[6:].sum())
+    l_rays, l_cx = int(local_cnt[:6].sum()), int(local_cnt[6:12].sum())
     my_pixels = sum(1 for y in range(w["height"]) if (y >> 2) % world == rank) * w["width"]
     algo_bytes = 8 * l_cx + 64 * l_rays + 16 * my_pixels
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -292,7 +293,7 @@ def run_ours(args):
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath):
+    if world == 1 and os.path.exists(tpath):      # the ncu capture is of the 1-GPU launch (whole frame)
         try:
             traffic = json.load(open(tpath)).get("render_accumulate_kernel_dram_bytes_per_launch")
         except Exception:
