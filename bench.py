@@ -363,8 +363,8 @@ def main():
     ap.add_argument("--gi-bounces", type=int, default=2)
     ap.add_argument("--aperture", type=float, default=0.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-tile-step", type=int, default=4)
-    ap.add_argument("--cpu-spp", type=int, default=16)
+    ap.add_argument("--cpu-tile-step", type=int, default=2)      # cpu_baseline sample: 1/2 of the tiles x 1/2 of the
+    ap.add_argument("--cpu-spp", type=int, default=32)           # samples = 1/4 frame, ~30-40 core-seconds
     ap.add_argument("--ref-tile-step", type=int, default=8)
     ap.add_argument("--ref-spp", type=int, default=8)
     args = ap.parse_args()
