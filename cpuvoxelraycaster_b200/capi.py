@@ -24,7 +24,8 @@ class RenderParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("row_begin", C.c_int32), ("row_end", C.c_int32),
                 ("spp", C.c_int32), ("sample_offset", C.c_int32), ("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32),
                 ("light_position", C.c_float * 3), ("use_gi", C.c_int32), ("gi_bounces", C.c_int32),
-                ("use_samples", C.c_int32), ("accum_in", C.c_int32), ("tile_step", C.c_int32), ("tile_index", C.c_int32)]
+                ("use_samples", C.c_int32), ("accum_in", C.c_int32), ("tile_step", C.c_int32), ("tile_index", C.c_int32),
+                ("roughness", C.c_float), ("max_bounds", C.c_int32)]
 
 
 class RenderStats(C.Structure):

@@ -93,7 +93,9 @@ extern "C" {
 int vrt_abi_version(void) { return VRT_ABI_VERSION; }
 const char* vrt_last_error(void) { return g_last_error.c_str(); }
 const char* vrt_build_info(void) {
-    return "libvrt sm_100a --fmad=false prec-div prec-sqrt; kernels: lsvo_cast_kernel<RefNodes>";
+    return "libvrt sm_100a --fmad=false -prec-div=true -prec-sqrt=true -ftz=false; kernels: lsvo_cast_kernel (K1), "
+           "lsvo_cast_persistent_kernel (K1p, default), render_accumulate_kernel (K4, default), render_persistent_kernel (K4p), "
+           "render_smem_kernel (K4s), resolve_kernel, grid_cast_kernel<mip> (K2/K2m), svo_cast_kernel (K3)";
 }
 
 int vrt_context_create(int device, void* stream, vrt_context** out) {
@@ -201,6 +203,15 @@ int vrt_lsvo_create(vrt_context* ctx, const vrt_lnode* nodes, uint64_t n_nodes, 
     if (!ctx || !nodes || !n_nodes || !out) return fail(VRT_ERR_INVALID, "vrt_lsvo_create: NULL argument");
     if (depth < 1 || depth > 12) return fail(VRT_ERR_INVALID, "vrt_lsvo_create: depth must be 1..12");
     if (n_nodes > 0xffffffffull) return fail(VRT_ERR_UNSUPPORTED, "vrt_lsvo_create: more than 2^32 slots");
+    // The traversal follows child_offset blindly; a malformed array would fault (or spin) on the device, so the
+    // structure is checked once here: every referenced child block must lie inside the array and in front of
+    // its parent (compileSVO emits children after their parent, lsvo_utils.cpp:7-10), leaves have no block.
+    for (uint64_t i = 0; i < n_nodes; ++i) {
+        const vrt_lnode& nd = nodes[i];
+        if (!nd.child_mask) continue;
+        if ((nd.leaf_mask & ~nd.child_mask) || nd.child_offset == 0 || i + nd.child_offset + 8 > n_nodes)
+            return fail(VRT_ERR_INVALID, "vrt_lsvo_create: malformed node array at slot " + std::to_string(i));
+    }
     if (int s = use_device(ctx)) return s;
     vrt_scene* sc = new (std::nothrow) vrt_scene();
     if (!sc) return fail(VRT_ERR_OOM, "vrt_lsvo_create: host allocation failed");
@@ -313,7 +324,10 @@ constexpr int kRenderCounters = 2;   // offset of the 12 render counters inside 
 
 int check_render_args(const vrt_scene* sc, const vrt_camera* cam, const vrt_render_params* p, const char* who) {
     if (!sc || !p) return fail(VRT_ERR_INVALID, std::string(who) + ": NULL argument");
-    if (sc->kind != VRT_SCENE_LSVO) return fail(VRT_ERR_UNSUPPORTED, std::string(who) + ": rendering needs an LSVO scene (raycaster.hpp:265)");
+    if (sc->kind != VRT_SCENE_LSVO && sc->kind != VRT_SCENE_GRID && sc->kind != VRT_SCENE_MIPGRID)
+        return fail(VRT_ERR_UNSUPPORTED, std::string(who) + ": rendering needs an LSVO or grid scene");
+    if (cam && sc->kind != VRT_SCENE_LSVO && (p->use_gi || p->max_bounds < 0 || p->max_bounds > 16))
+        return fail(VRT_ERR_INVALID, std::string(who) + ": grid frames have no GI pass; max_bounds must be 0..16");
     if (p->width <= 0 || p->height <= 0 || p->width > 65536 || p->height > 65536) return fail(VRT_ERR_INVALID, std::string(who) + ": bad frame size");
     if (p->row_begin < 0 || p->row_end > p->height || p->row_begin > p->row_end) return fail(VRT_ERR_INVALID, std::string(who) + ": bad row range");
     if (cam && (p->spp <= 0 || p->gi_bounces < 0 || p->gi_bounces > 2)) return fail(VRT_ERR_INVALID, std::string(who) + ": spp must be > 0 and gi_bounces in 0..2");
@@ -331,6 +345,8 @@ vrt::RenderLaunch make_launch(const vrt_scene* sc, const vrt_camera* cam, const 
     L.seed_lo = p->seed_lo; L.seed_hi = p->seed_hi;
     for (int i = 0; i < 3; ++i) L.light[i] = p->light_position[i];
     L.cam = *cam;
+    L.roughness = p->roughness;
+    L.max_bounds = p->max_bounds;
     L.tile_step = p->tile_step > 1 ? p->tile_step : 1;
     L.tile_index = p->tile_step > 1 ? p->tile_index : 0;
     L.tex_top = sc->d_tex; L.tex_side = sc->d_tex + 768;
@@ -356,7 +372,10 @@ int vrt_render_accumulate_device(vrt_scene* sc, const vrt_camera* cam, const vrt
     if (int s = use_device(ctx)) return s;
     VRT_CUDA(cudaMemsetAsync(sc->d_counters + kRenderCounters, 0, 13 * sizeof(unsigned long long), ctx->stream));
     if (p->row_end == p->row_begin) return VRT_OK;
-    if (ctx->render_variant >= 5)
+    if (sc->kind != VRT_SCENE_LSVO)
+        VRT_CUDA(vrt::launch_grid_render(sc->grid, sc->use_mip, make_launch(sc, cam, p), d_accum, sc->d_counters + kRenderCounters,
+                                         ctx->stream));
+    else if (ctx->render_variant >= 5)
         VRT_CUDA(vrt::launch_render_smem(sc->d_nodes, make_launch(sc, cam, p), d_accum, sc->d_counters + kRenderCounters,
                                          ctx->render_variant, ctx->stream));
     else if (ctx->render_variant == 0)
@@ -475,6 +494,17 @@ int create_grid_scene(vrt_context* ctx, const uint8_t* cells, int X, int Y, int 
     sc->ctx = ctx; sc->kind = kind; sc->depth = depth;
     std::vector<size_t> offsets;
     std::vector<uint32_t> words = build_grid_pyramid(cells, X, Y, Z, levels, sc->grid, offsets);
+    // Cell::Mirror (= 2, cell.hpp:8) bit plane for the reflection pass, only if the grid has mirrors
+    const size_t ncell = size_t(X) * Y * Z;
+    size_t mirror_off = 0;
+    bool any_mirror = false;
+    for (size_t i = 0; i < ncell && !any_mirror; ++i) any_mirror = cells[i] == 2;
+    if (any_mirror) {
+        mirror_off = words.size();
+        words.resize(words.size() + (ncell + 31) / 32, 0u);
+        for (size_t i = 0; i < ncell; ++i)
+            if (cells[i] == 2) words[mirror_off + (i >> 5)] |= 1u << (i & 31);
+    }
     cudaError_t e = cudaMalloc(&sc->d_grid_bits, words.size() * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&sc->d_counters, 16 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemcpyAsync(sc->d_grid_bits, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
@@ -482,6 +512,7 @@ int create_grid_scene(vrt_context* ctx, const uint8_t* cells, int X, int Y, int 
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { vrt_scene_destroy(sc); return cuda_fail(e, "grid scene upload"); }
     for (int l = 0; l < levels; ++l) sc->grid.level[l].bits = sc->d_grid_bits + offsets[l];
+    sc->grid.mirror = any_mirror ? sc->d_grid_bits + mirror_off : nullptr;
     sc->device_bytes = words.size() * sizeof(uint32_t);
     *out = sc;
     return VRT_OK;

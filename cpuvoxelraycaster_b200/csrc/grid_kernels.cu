@@ -212,6 +212,171 @@ __global__ void __launch_bounds__(128) svo_cast_kernel(GridLevels g, int depth, 
     if ((threadIdx.x & 31) == 0 && complexity) atomicAdd(counters, (unsigned long long)complexity);
 }
 
+// ---- grid frames: RayCaster semantics over a dense grid, with mirror reflections (extension) ----
+struct DdaHit {
+    bool hit;
+    int side, cx, cy, cz;
+    float t;
+    uint32_t steps;
+};
+
+// Grid3D::castRay (grid_3d.hpp:35-132) as a device function; same recurrence as grid_cast_kernel.
+template <bool kMip>
+__device__ __forceinline__ void grid_dda(const GridLevels& g, float ox, float oy, float oz, float dx, float dy, float dz, DdaHit& r) {
+    const int X = g.X, Y = g.Y, Z = g.Z;
+    const float tdx = fabsf(1.0f / dx), tdy = fabsf(1.0f / dy), tdz = fabsf(1.0f / dz);
+    const int sx = dx < 0 ? -1 : 1, sy = dy < 0 ? -1 : 1, sz = dz < 0 ? -1 : 1;
+    int cx = int(ox), cy = int(oy), cz = int(oz);
+    float tmx = (float(cx + (sx > 0 ? 1 : 0)) - ox) / dx;
+    float tmy = (float(cy + (sy > 0 ? 1 : 0)) - oy) / dy;
+    float tmz = (float(cz + (sz > 0 ? 1 : 0)) - oz) / dz;
+    int e_level = -1, ex = 0, ey = 0, ez = 0;
+    uint32_t iter = 0u;
+    int side = 0;
+    float t = 0.0f;
+    bool hit = false;
+    while (cx >= 0 && cy >= 0 && cz >= 0 && cx < X && cy < Y && cz < Z && iter < 2048u) {
+        ++iter;
+        side = (tmx < tmy) ? ((tmx < tmz) ? 0 : 2) : ((tmy < tmz) ? 1 : 2);
+        if (side == 0) { t = tmx; tmx += tdx; cx += sx; }
+        else if (side == 1) { t = tmy; tmy += tdy; cy += sy; }
+        else { t = tmz; tmz += tdz; cz += sz; }
+        if (cx >= 0 && cy >= 0 && cz >= 0 && cx < X && cy < Y && cz < Z) {
+            bool solid;
+            if (kMip) {
+                if (e_level >= 0 && (cx >> e_level) == ex && (cy >> e_level) == ey && (cz >> e_level) == ez) {
+                    solid = false;
+                } else {
+                    e_level = -1;
+                    solid = true;
+                    for (int l = g.n_levels - 1; l >= 0; --l)
+                        if (!grid_bit(g, l, cx, cy, cz)) {
+                            solid = false;
+                            if (l > 0) { e_level = l; ex = cx >> l; ey = cy >> l; ez = cz >> l; }
+                            break;
+                        }
+                }
+            } else {
+                solid = grid_bit(g, 0, cx, cy, cz);
+            }
+            if (solid) { hit = true; break; }
+        }
+    }
+    r.hit = hit; r.side = side; r.cx = cx; r.cy = cy; r.cz = cz; r.t = t; r.steps = iter;
+}
+
+__device__ __forceinline__ uint8_t mul_u8g(uint8_t c, float f) { return uint8_t(fminf(255.0f, float(c) * f)); }   // utils.cpp:43-48
+
+template <bool kMip>
+__global__ void __launch_bounds__(128) grid_render_kernel(GridLevels g, RenderLaunch L, uint32_t* __restrict__ accum,
+                                                          unsigned long long* __restrict__ counters) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tiles_x = (L.width + 31) / 32;
+    const int bx = blockIdx.x % tiles_x, by = blockIdx.x / tiles_x;
+    const int x = bx * 32 + warp * 8 + (lane & 7);
+    const int y = L.row_begin + (by * L.tile_step + L.tile_index) * 4 + (lane >> 3);
+    uint32_t n_rays[3] = {0, 0, 0}, n_steps[3] = {0, 0, 0};      // primary, shadow, reflection
+    if (x < L.width && y < L.row_end) {
+        const float aspect = float(L.width) / float(L.height);
+        const float lens_x = float(x) / float(L.height) - aspect * 0.5f, lens_y = float(y) / float(L.height) - 0.5f;
+        const uint32_t pixel = uint32_t(y) * uint32_t(L.width) + uint32_t(x);
+        uint32_t sum_r = 0, sum_g = 0, sum_b = 0;
+        for (int s = 0; s < L.spp; ++s) {
+            const uint32_t sample = uint32_t(L.sample_offset + s);
+            float ox, oy, oz, dx, dy, dz;
+            {   // Camera::getRay (camera_controller.hpp:34-49) in voxel units
+                const uint4 rnd0 = philox4x32_10(pixel, sample, 0u, 0u, L.seed_lo, L.seed_hi);
+                const float u0 = lattice(rnd0.x, -0.5f, 0.5f), u1 = lattice(rnd0.y, -0.5f, 0.5f);
+                float fx = lens_x, fy = lens_y, fz = L.cam.fov;
+                normalize3(fx, fy, fz);
+                fx *= L.cam.focal_length; fy *= L.cam.focal_length; fz *= L.cam.focal_length;
+                const float rx = L.cam.aperture * u0, ry = L.cam.aperture * u1, rz = L.cam.aperture * 0.0f;
+                float qx = fx - rx, qy = fy - ry, qz = fz - rz;
+                normalize3(qx, qy, qz);
+                const float* m = L.cam.rot_mat;
+                dx = (m[0] * qx + m[1] * qy) + m[2] * qz; dy = (m[3] * qx + m[4] * qy) + m[5] * qz; dz = (m[6] * qx + m[7] * qy) + m[8] * qz;
+                ox = L.cam.position[0] + ((m[0] * rx + m[1] * ry) + m[2] * rz);
+                oy = L.cam.position[1] + ((m[3] * rx + m[4] * ry) + m[5] * rz);
+                oz = L.cam.position[2] + ((m[6] * rx + m[7] * ry) + m[8] * rz);
+            }
+            float tint = 1.0f;
+            int bounds = 0;
+            for (;;) {
+                DdaHit h;
+                grid_dda<kMip>(g, ox, oy, oz, dx, dy, dz, h);
+                const int cls = bounds == 0 ? 0 : 2;
+                n_rays[0] += cls == 0; n_rays[2] += cls == 2;
+                n_steps[0] += cls == 0 ? h.steps : 0u; n_steps[2] += cls == 2 ? h.steps : 0u;
+                if (!h.hit) break;
+                const float hx = ox + h.t * dx, hy = oy + h.t * dy, hz = oz + h.t * dz;          // grid_3d.hpp:105-107
+                float nx = 0.0f, ny = 0.0f, nz = 0.0f, u, v;
+                if (h.side == 0) { nx = float(dx < 0 ? 1 : -1); u = 1.0f - fracf(hz); v = fracf(hy); }   // :112-121
+                else if (h.side == 1) { ny = float(dy < 0 ? 1 : -1); u = fracf(hx); v = fracf(hz); }
+                else { nz = float(dz < 0 ? 1 : -1); u = fracf(hx); v = fracf(hy); }
+                const uint64_t ci = (uint64_t(h.cx) * uint64_t(g.Y) + uint64_t(h.cy)) * uint64_t(g.Z) + uint64_t(h.cz);
+                const bool mirror = g.mirror && ((__ldg(g.mirror + (ci >> 5)) >> (ci & 31u)) & 1u);
+                if (mirror && bounds < L.max_bounds) {
+                    ox = hx + nx * 0.001f; oy = hy + ny * 0.001f; oz = hz + nz * 0.001f;
+                    if (h.side == 0) dx = -dx; else if (h.side == 1) dy = -dy; else dz = -dz;
+                    // dimensions 8+3b, 9+3b, 10+3b of the sample's Philox stream
+                    float r[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const uint32_t dim = 8u + 3u * uint32_t(bounds) + uint32_t(k);
+                        const uint4 w = philox4x32_10(pixel, sample, dim >> 2, 0u, L.seed_lo, L.seed_hi);
+                        const uint32_t word = (dim & 3u) == 0u ? w.x : ((dim & 3u) == 1u ? w.y : ((dim & 3u) == 2u ? w.z : w.w));
+                        r[k] = lattice(word, -0.5f, 0.5f);
+                    }
+                    dx = dx + L.roughness * r[0]; dy = dy + L.roughness * r[1]; dz = dz + L.roughness * r[2];
+                    normalize3(dx, dy, dz);
+                    tint = tint * 0.8f;
+                    ++bounds;
+                    continue;
+                }
+                const uint8_t* tex = (ny != 0.0f) ? L.tex_top : L.tex_side;
+                u = fminf(fmaxf(u, 0.0f), 1.0f); v = fminf(fmaxf(v, 0.0f), 1.0f);
+                const uint32_t tx = min(15u, uint32_t(16.0f * u)), ty = min(15u, uint32_t(16.0f * v));
+                const uint8_t* texel = tex + 3u * (ty * 16u + tx);
+                const float sox = hx + nx * 0.001f, soy = hy + ny * 0.001f, soz = hz + nz * 0.001f;
+                float tlx = L.light[0] - sox, tly = L.light[1] - soy, tlz = L.light[2] - soz;
+                normalize3(tlx, tly, tlz);
+                DdaHit sh;
+                grid_dda<kMip>(g, sox, soy, soz, tlx, tly, tlz, sh);
+                n_rays[1] += 1u; n_steps[1] += sh.steps;
+                float light = 0.0f;
+                if (!sh.hit) light = fmaxf(0.0f, dot3(tlx, tly, tlz, nx, ny, nz));
+                const float f = fminf(1.0f, fmaxf(0.0f, light));
+                sum_r += mul_u8g(mul_u8g(__ldg(texel), f), tint);
+                sum_g += mul_u8g(mul_u8g(__ldg(texel + 1), f), tint);
+                sum_b += mul_u8g(mul_u8g(__ldg(texel + 2), f), tint);
+                break;
+            }
+        }
+        uint4* a = reinterpret_cast<uint4*>(accum) + pixel;
+        uint4 v4 = *a;
+        v4.x += sum_r; v4.y += sum_g; v4.z += sum_b; v4.w += uint32_t(L.spp);
+        *a = v4;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        uint32_t a = n_rays[k], b = n_steps[k];
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+        if (lane == 0 && a) { atomicAdd(counters + k, (unsigned long long)a); atomicAdd(counters + 6 + k, (unsigned long long)b); }
+    }
+}
+
+cudaError_t launch_grid_render(const GridLevels& g, bool use_mip, const RenderLaunch& L, uint32_t* d_accum,
+                               unsigned long long* d_counters, cudaStream_t stream) {
+    const int rows = L.row_end - L.row_begin;
+    if (rows <= 0 || L.width <= 0 || L.spp <= 0) return cudaSuccess;
+    const int tiles_x = (L.width + 31) / 32, tiles_y = ((rows + 3) / 4 + L.tile_step - 1 - L.tile_index) / L.tile_step;
+    if (tiles_y <= 0) return cudaSuccess;
+    const unsigned grid = unsigned(tiles_x) * unsigned(tiles_y);
+    if (use_mip && g.n_levels > 1) grid_render_kernel<true><<<grid, 128, 0, stream>>>(g, L, d_accum, d_counters);
+    else grid_render_kernel<false><<<grid, 128, 0, stream>>>(g, L, d_accum, d_counters);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_grid_cast(const GridLevels& g, bool use_mip, const float* d_origin, const float* d_dir, uint64_t n,
                              vrt_hit* d_out, unsigned long long* d_counters, cudaStream_t stream) {
     if (!n) return cudaSuccess;

@@ -21,6 +21,7 @@ struct GridLevels {
     GridLevel level[13];
     int n_levels;
     int X, Y, Z;
+    const uint32_t* mirror;   // level-0 bit plane: Cell::type == Mirror (cell.hpp:8); may be null
 };
 
 // K2 / K2m: Grid3D::castRay, flat or with the fetch-skipping pyramid (grid_kernels.cu)
@@ -42,6 +43,8 @@ struct RenderLaunch {
     vrt_camera cam;
     const uint8_t* tex_top;    // 16x16 RGB, device
     const uint8_t* tex_side;
+    float roughness;           // grid frames: blur of mirror reflections
+    int max_bounds;            // grid frames: reflection depth (RayCaster::max_bounds, raycaster.hpp:277)
 };
 
 // K0+K4: ray generation, traversal, shading and accumulation for rows [row_begin,row_end) (render_kernels.cu)
@@ -64,4 +67,7 @@ cudaError_t launch_render_persistent(const uint2* nodes, const RenderLaunch& L, 
 // K4s: frame kernel with the chain state in shared memory (render_smem_kernel.cu); min_blocks = CTAs per SM (5..8)
 cudaError_t launch_render_smem(const uint2* nodes, const RenderLaunch& L, uint32_t* d_accum, unsigned long long* d_counters,
                                int min_blocks, cudaStream_t stream);
+// Grid frames: camera rays, DDA, mirror reflections, texture + sun shadow, accumulation (grid_kernels.cu)
+cudaError_t launch_grid_render(const GridLevels& g, bool use_mip, const RenderLaunch& L, uint32_t* d_accum,
+                               unsigned long long* d_counters, cudaStream_t stream);
 }  // namespace vrt

@@ -1,9 +1,6 @@
-// LSVO stack traversal on the device — the engine's restatement of LSVO<D>::castRay
-// (reference include/lsvo.hpp:33-172), op for op in fp32 without contraction so that the hit record
-// and the iteration count (HitPoint::complexity) are bit-identical to the CPU reference.
-//
-// The traversal state lives in registers; the per-ray stack (lsvo.hpp:42, OctreeStack
-// lsvo_utils.hpp:35-39) is addressed through a policy so that kernels can keep it in shared memory.
+// LSVO traversal on the device: node access and the hit epilogue of LSVO<D>::castRay
+// (reference include/lsvo.hpp:148-169).  The loop itself is in lsvo_step.cuh.
+// fp32 without contraction, op for op, so that the hit record is bit-identical to the CPU reference.
 #pragma once
 #include "vrt_device.cuh"
 
@@ -11,9 +8,7 @@ namespace vrt {
 
 // One octree node as the traversal sees it, whatever the memory format.
 struct NodeView {
-    uint32_t raw;          // first word of the slot: color | child_mask << 8 | leaf_mask << 16
-    uint32_t child_mask;   // LNode::child_mask
-    uint32_t leaf_mask;    // LNode::leaf_mask
+    uint32_t raw;          // first word of the slot: color | child_mask << 8 | leaf_mask << 16 (lsvo_utils.hpp:14-17)
     uint32_t child_base;   // index such that child slot s lives at child_base + s
 };
 
@@ -21,36 +16,18 @@ struct NodeView {
 struct RefNodes {
     const uint2* __restrict__ slots;
     __device__ __forceinline__ NodeView fetch(uint32_t id) const {
-        const uint2 w = __ldg(slots + id);                 // one coalescable 8-byte load (lsvo.hpp:74)
+        const uint2 w = __ldg(slots + id);                 // one 8-byte load per loop trip (lsvo.hpp:74)
         NodeView v;
         v.raw = w.x;
-        v.child_mask = (w.x >> 8) & 0xffu;
-        v.leaf_mask = (w.x >> 16) & 0xffu;
         v.child_base = id + w.y;
         return v;
     }
     __device__ __forceinline__ uint32_t child(const NodeView& v, uint32_t slot) const { return v.child_base + slot; }
 };
 
-// Per-thread stack in local memory (v0 policy).
-struct LocalStack {
-    uint32_t parent[kSvoMaxDepth + 1];
-    float t_max[kSvoMaxDepth + 1];
-    __device__ __forceinline__ void push(int i, uint32_t p, float t) { parent[i] = p; t_max[i] = t; }
-    __device__ __forceinline__ void pop(int i, uint32_t& p, float& t) const { p = parent[i]; t = t_max[i]; }
-};
-
-// Stack in shared memory, one column per thread: entry i of thread t at [i * blockDim + t] (conflict-free).
-struct SharedStack {
-    uint32_t* parent;   // already offset by threadIdx.x
-    float* t_max;
-    int stride;
-    __device__ __forceinline__ void push(int i, uint32_t p, float t) { parent[i * stride] = p; t_max[i * stride] = t; }
-    __device__ __forceinline__ void pop(int i, uint32_t& p, float& t) const { p = parent[i * stride]; t = t_max[i * stride]; }
-};
-
+// Traversal state at termination (what the epilogue needs).
 struct LsvoResult {
-    float px, py, pz;      // cell low corner in the mirrored frame (un-mirrored by finish())
+    float px, py, pz;      // cell low corner in the mirrored frame (un-mirrored by lsvo_finish)
     float t_min;
     float scale_f;
     int scale;
@@ -60,89 +37,6 @@ struct LsvoResult {
     bool hit;
     float dx, dy, dz;      // direction after the |d| >= 2^-23 clamp (lsvo.hpp:44-46)
 };
-
-template <typename Nodes, typename Stack>
-__device__ __forceinline__ void lsvo_cast(const Nodes& nodes, Stack& stack, int depth, int guard, float ox, float oy,
-                                          float oz, float dx, float dy, float dz, float coef, float bias, LsvoResult& r) {
-    const int depth_offset = kSvoMaxDepth - depth;                       // lsvo.hpp:38
-    if (fabsf(dx) < kEps) dx = copysignf(kEps, dx);                      // lsvo.hpp:44-46
-    if (fabsf(dy) < kEps) dy = copysignf(kEps, dy);
-    if (fabsf(dz) < kEps) dz = copysignf(kEps, dz);
-    const float tcx = -1.0f / fabsf(dx), tcy = -1.0f / fabsf(dy), tcz = -1.0f / fabsf(dz);   // :47
-    float tox = ox * tcx, toy = oy * tcy, toz = oz * tcz;                // :48
-    uint32_t mirror = 7u;
-    if (dx > 0.0f) { mirror ^= 1u; tox = 3.0f * tcx - tox; }             // :50-52
-    if (dy > 0.0f) { mirror ^= 2u; toy = 3.0f * tcy - toy; }
-    if (dz > 0.0f) { mirror ^= 4u; toz = 3.0f * tcz - toz; }
-    float t_min = fmaxf(2.0f * tcx - tox, fmaxf(2.0f * tcy - toy, 2.0f * tcz - toz));   // :54
-    float t_max = fminf(tcx - tox, fminf(tcy - toy, tcz - toz));                        // :55
-    float h = t_max;
-    t_min = fmaxf(0.0f, t_min);
-    t_max = fminf(1.0f, t_max);
-    uint32_t parent = 0u, child = 0u, face = 0u;
-    int scale = kSvoMaxDepth - 1;
-    float px = 1.0f, py = 1.0f, pz = 1.0f, scale_f = 0.5f;
-    if (1.5f * tcx - tox > t_min) { child ^= 1u; px = 1.5f; }           // :66-68
-    if (1.5f * tcy - toy > t_min) { child ^= 2u; py = 1.5f; }
-    if (1.5f * tcz - toz > t_min) { child ^= 4u; pz = 1.5f; }
-    bool hit = false;
-    uint32_t iters = 0u;
-
-    while (scale < kSvoMaxDepth && scale > guard) {                      // :72
-        ++iters;
-        const NodeView nd = nodes.fetch(parent);                         // :74
-        const float cx = px * tcx - tox, cy = py * tcy - toy, cz = pz * tcz - toz;   // :76
-        const float tc_max = fminf(cx, fminf(cy, cz));
-        const uint32_t shift = child ^ mirror;                           // :79
-        if (((nd.child_mask >> shift) & 1u) && t_min <= t_max) {         // :80-81
-            if (tc_max * coef + bias >= scale_f) { hit = true; break; }  // :82-85
-            const float tv_max = fminf(t_max, tc_max);
-            const float half = scale_f * 0.5f;
-            if (t_min <= tv_max) {                                       // :89
-                if ((nd.leaf_mask >> shift) & 1u) { hit = true; break; } // :90-95
-                if (tc_max < h) stack.push(scale - depth_offset, parent, t_max);   // :97-100
-                h = tc_max;
-                parent = nodes.child(nd, shift);                         // :103
-                child = 0u;
-                --scale;
-                scale_f = half;
-                if (half * tcx + cx > t_min) { child ^= 1u; px += scale_f; }   // :88,107-109
-                if (half * tcy + cy > t_min) { child ^= 2u; py += scale_f; }
-                if (half * tcz + cz > t_min) { child ^= 4u; pz += scale_f; }
-                t_max = tv_max;
-                continue;
-            }
-        }
-        uint32_t step = 0u;                                              // :115-118
-        if (cx <= tc_max) { step ^= 1u; px -= scale_f; }
-        if (cy <= tc_max) { step ^= 2u; py -= scale_f; }
-        if (cz <= tc_max) { step ^= 4u; pz -= scale_f; }
-        t_min = tc_max;
-        child ^= step;
-        face = step;
-        if (child & step) {                                              // :124-145
-            const uint32_t ix = __float_as_uint(px), iy = __float_as_uint(py), iz = __float_as_uint(pz);
-            uint32_t diff = 0u;
-            if (step & 1u) diff |= ix ^ __float_as_uint(px + scale_f);
-            if (step & 2u) diff |= iy ^ __float_as_uint(py + scale_f);
-            if (step & 4u) diff |= iz ^ __float_as_uint(pz + scale_f);
-            scale = int((__float_as_uint(__uint2float_rn(diff)) >> 23) - 127u);   // :132
-            scale_f = __uint_as_float(uint32_t(scale - kSvoMaxDepth + 127) << 23);  // :133
-            if (scale >= kSvoMaxDepth) break;   // left the root cube; the reference's stack read here is dead
-            stack.pop(scale - depth_offset, parent, t_max);              // :134-136
-            const uint32_t sx = ix >> scale, sy = iy >> scale, sz = iz >> scale;
-            px = __uint_as_float(sx << scale);
-            py = __uint_as_float(sy << scale);
-            pz = __uint_as_float(sz << scale);
-            child = (sx & 1u) | ((sy & 1u) << 1) | ((sz & 1u) << 2);
-            h = 0.0f;
-        }
-    }
-    r.px = px; r.py = py; r.pz = pz;
-    r.t_min = t_min; r.scale_f = scale_f; r.scale = scale; r.face = face; r.mirror = mirror;
-    r.complexity = iters; r.hit = hit;
-    r.dx = dx; r.dy = dy; r.dz = dz;
-}
 
 // Hit epilogue, lsvo.hpp:148-169.  Only valid when r.hit.
 struct LsvoHit {

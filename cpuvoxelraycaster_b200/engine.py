@@ -137,6 +137,13 @@ class Volumetric:
     def castRay(self, position, direction, ray_size_coef=0.0, ray_size_bias=0.0):
         return HitPoint(self.cast_rays([position], [direction], ray_size_coef, ray_size_bias)[0])
 
+    def set_textures(self, top_rgb, side_rgb):
+        """RayCaster::image_top / image_side (raycaster.hpp:53-54): 16x16 RGB, top-down rows."""
+        t, s = np.ascontiguousarray(top_rgb, np.uint8), np.ascontiguousarray(side_rgb, np.uint8)
+        if t.size != 768 or s.size != 768:
+            raise ValueError("textures must be 16x16 RGB")
+        check(lib().vrt_scene_set_textures(self.handle, ptr(t), ptr(s)))
+
     def last_complexity(self):
         v = C.c_uint64(0)
         check(lib().vrt_scene_last_complexity(self.handle, C.byref(v)))
@@ -185,12 +192,6 @@ class LSVO(Volumetric):
 
     def setCell(self, *a):
         """No-op, as in the reference (lsvo.hpp:26)."""
-
-    def set_textures(self, top_rgb, side_rgb):
-        t, s = np.ascontiguousarray(top_rgb, np.uint8), np.ascontiguousarray(side_rgb, np.uint8)
-        if t.size != 768 or s.size != 768:
-            raise ValueError("textures must be 16x16 RGB")
-        check(lib().vrt_scene_set_textures(self.handle, ptr(t), ptr(s)))
 
 
 class Grid3D(Volumetric):
@@ -299,6 +300,8 @@ class RayCaster:
         self.use_gi = False
         self.use_samples = False
         self.gi_bounces = 1
+        self.roughness = 0.0            # grid volumes: blur of Cell::Mirror reflections (extension)
+        self.max_bounds = 4             # raycaster.hpp:277
         self.seed = (0x5EED, 0)
         self.sample_count = 0
         self.last_stats = None
@@ -321,6 +324,7 @@ class RayCaster:
         p.seed_lo, p.seed_hi = self.seed
         p.light_position[:] = [float(x) for x in self.light_position]
         p.use_gi, p.gi_bounces, p.use_samples = int(self.use_gi), int(self.gi_bounces), int(self.use_samples)
+        p.roughness, p.max_bounds = float(self.roughness), int(self.max_bounds)
         return p
 
     def render(self, camera, spp=1, row_begin=0, row_end=0):

@@ -65,6 +65,7 @@ class FrameRenderer:
         self.rgba = torch.zeros(self.H_pad * self.W * 4, dtype=torch.uint8, device=self.device)
         self.host_frame = torch.empty(self.H * self.row_bytes, dtype=torch.uint8).pin_memory()
         self.use_gi, self.gi_bounces, self.use_samples = False, 1, True
+        self.roughness, self.max_bounds = 0.0, 4
         self.seed = (0x5EED, 0)
         self.light = np.zeros(3, np.float32)
 
@@ -76,6 +77,7 @@ class FrameRenderer:
         p.light_position[:] = [float(x) for x in self.light]
         p.use_gi, p.gi_bounces, p.use_samples = int(self.use_gi), int(self.gi_bounces), int(self.use_samples)
         p.tile_step, p.tile_index = self.world, self.rank
+        p.roughness, p.max_bounds = float(self.roughness), int(self.max_bounds)
         return p
 
     # -- device-resident frame: enqueue only (the caller owns stream/synchronisation) --

@@ -165,6 +165,8 @@ typedef struct vrt_render_params {
     int32_t accum_in;            /* vrt_render: 1 = `accum` holds earlier sums and is added to (progressive frames) */
     int32_t tile_step;           /* > 1: only 4-row tiles t (counted from row_begin) with t % tile_step == tile_index */
     int32_t tile_index;          /*      are rendered/resolved — the balanced multi-GPU row partition */
+    float roughness;             /* grid scenes: blur of Cell::Mirror reflections (0 = perfect mirror) */
+    int32_t max_bounds;          /* grid scenes: reflection depth, RayCaster::max_bounds = 4 (raycaster.hpp:277) */
 } vrt_render_params;
 
 typedef struct vrt_render_stats {
@@ -172,7 +174,11 @@ typedef struct vrt_render_stats {
     uint64_t complexity[6];      /* Σ HitPoint::complexity per class */
 } vrt_render_stats;
 
-/* 16x16 RGB albedo textures, top-down rows: RayCaster::image_top / image_side (raycaster.hpp:53-54). */
+/* Frames can be rendered from LSVO scenes (the reference's RayCaster: primary, sun shadow, GI, DOF) and from
+ * Grid3D / MipmapGrid3D scenes (extension: primary, sun shadow, DOF and blurry mirror reflections off Cell::Mirror
+ * cells; camera and light in voxel units; no GI).  See DESIGN.md §2.
+ *
+ * 16x16 RGB albedo textures, top-down rows: RayCaster::image_top / image_side (raycaster.hpp:53-54). */
 int vrt_scene_set_textures(vrt_scene* scene, const uint8_t* top_rgb, const uint8_t* side_rgb);
 
 /* d_accum: device uint32 [height*width*4] r,g,b,count sums (RayCaster::colors, raycaster.hpp:259; the

@@ -31,7 +31,7 @@ class PortRenderParams(C.Structure):
                 ("use_gi", C.c_int32), ("gi_bounces", C.c_int32), ("use_samples", C.c_int32), ("spp", C.c_int32),
                 ("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32), ("sample_offset", C.c_int32),
                 ("row_begin", C.c_int32), ("row_end", C.c_int32), ("threads", C.c_int32),
-                ("tile_step", C.c_int32), ("tile_index", C.c_int32)]
+                ("tile_step", C.c_int32), ("tile_index", C.c_int32), ("roughness", C.c_float), ("max_bounds", C.c_int32)]
 
 
 class PortRenderStats(C.Structure):
@@ -91,6 +91,8 @@ class Port:
                                   C.c_int]
         L.vo_render.argtypes = [C.c_void_p, C.POINTER(PortRenderParams), C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.POINTER(PortRenderStats)]
+        L.vo_grid_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(PortRenderParams), C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.POINTER(PortRenderStats)]
         L.vo_camera_ray.argtypes = [C.POINTER(PortRenderParams), C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                     C.c_void_p]
         L.vo_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -147,6 +149,18 @@ class Port:
         stats = PortRenderStats()
         tt, ts = np.ascontiguousarray(tex_top, np.uint8), np.ascontiguousarray(tex_side, np.uint8)
         self.lib.vo_render(_p(nodes), C.byref(params), _p(tt), _p(ts), _p(accum), _p(rgba), C.byref(stats))
+        return accum, rgba, stats
+
+    def grid_render(self, cells, params, tex_top, tex_side):
+        """Grid shading with mirror reflections (extension). Returns (accum, rgba, stats)."""
+        cells = np.ascontiguousarray(cells, np.uint8)
+        X, Y, Z = cells.shape
+        H, W = params.height, params.width
+        accum = np.zeros((H, W, 4), np.uint32)
+        rgba = np.zeros((H, W, 4), np.uint8)
+        stats = PortRenderStats()
+        tt, ts = np.ascontiguousarray(tex_top, np.uint8), np.ascontiguousarray(tex_side, np.uint8)
+        self.lib.vo_grid_render(_p(cells), X, Y, Z, C.byref(params), _p(tt), _p(ts), _p(accum), _p(rgba), C.byref(stats))
         return accum, rgba, stats
 
     def camera_ray(self, params, x, y, sample=0):

@@ -707,3 +707,113 @@ void vo_render(const vo_lnode* nodes, const vo_render_params* p, const uint8_t* 
     par_for(render_range, &c, n, 256, p->threads);
     pthread_mutex_destroy(&c.lock);
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Grid shading with mirror reflections — extension, specified in port.h / DESIGN.md §2         */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct grid_shade_ctx {
+    const uint8_t* cells; int X, Y, Z;
+    const vo_render_params* p; const uint8_t *tex_top, *tex_side;
+    uint32_t* accum; uint8_t* rgba; vo_render_stats* stats; pthread_mutex_t lock;
+} grid_shade_ctx;
+
+static void grid_shade_sample(const grid_shade_ctx* c, int32_t x, int32_t y, int32_t sample, uint8_t rgb[3], vo_render_stats* st) {
+    const vo_render_params* p = c->p;
+    const uint32_t pixel = (uint32_t)y * (uint32_t)p->width + (uint32_t)x;
+    float o[3], d[3];
+    {   /* Camera::getRay in voxel units */
+        const float aspect = (float)p->width / (float)p->height;
+        const float lens_x = (float)x / (float)p->height - aspect * 0.5f, lens_y = (float)y / (float)p->height - 0.5f;
+        const float u0 = lattice_rand(p, pixel, (uint32_t)sample, 0, -0.5f, 0.5f), u1 = lattice_rand(p, pixel, (uint32_t)sample, 1, -0.5f, 0.5f);
+        const v3 fn = norm3(v3_(lens_x, lens_y, p->fov));
+        const v3 focal = v3_(fn.x * p->focal_length, fn.y * p->focal_length, fn.z * p->focal_length);
+        const v3 rnd = v3_(p->aperture * u0, p->aperture * u1, p->aperture * 0.0f);
+        const v3 ray = norm3(v3_(focal.x - rnd.x, focal.y - rnd.y, focal.z - rnd.z));
+        const v3 wd = view_to_world(p->rot_mat, ray), wo = view_to_world(p->rot_mat, rnd);
+        o[0] = p->cam_position[0] + wo.x; o[1] = p->cam_position[1] + wo.y; o[2] = p->cam_position[2] + wo.z;
+        d[0] = wd.x; d[1] = wd.y; d[2] = wd.z;
+    }
+    rgb[0] = rgb[1] = rgb[2] = 0;
+    float tint = 1.0f;
+    int bounds = 0;
+    for (;;) {
+        vo_hit h; uint32_t steps;
+        grid_cast_one(c->cells, c->X, c->Y, c->Z, o, d, &h, &steps);
+        st->rays[bounds == 0 ? 0 : 2]++; st->complexity[bounds == 0 ? 0 : 2] += steps;
+        if (!h.hit) return;
+        const uint8_t type = c->cells[((size_t)h.voxel[0] * (size_t)c->Y + (size_t)h.voxel[1]) * (size_t)c->Z + (size_t)h.voxel[2]];
+        const int axis = h.face == 1u ? 0 : (h.face == 2u ? 1 : 2);
+        if (type == 2 && bounds < p->max_bounds) {                       /* Cell::Mirror */
+            for (int a = 0; a < 3; ++a) o[a] = h.position[a] + h.normal[a] * 0.001f;
+            d[axis] = -d[axis];
+            const float r0 = lattice_rand(p, pixel, (uint32_t)sample, 8u + 3u * (uint32_t)bounds, -0.5f, 0.5f);
+            const float r1 = lattice_rand(p, pixel, (uint32_t)sample, 9u + 3u * (uint32_t)bounds, -0.5f, 0.5f);
+            const float r2 = lattice_rand(p, pixel, (uint32_t)sample, 10u + 3u * (uint32_t)bounds, -0.5f, 0.5f);
+            const v3 nd = norm3(v3_(d[0] + p->roughness * r0, d[1] + p->roughness * r1, d[2] + p->roughness * r2));
+            d[0] = nd.x; d[1] = nd.y; d[2] = nd.z;
+            tint = tint * 0.8f;
+            ++bounds;
+            continue;
+        }
+        const uint8_t* tex = h.normal[1] != 0.0f ? c->tex_top : c->tex_side;
+        float u = h.voxel_coord[0], v = h.voxel_coord[1];
+        clampf_(&u, 0.0f, 1.0f); clampf_(&v, 0.0f, 1.0f);
+        uint32_t tx = (uint32_t)(16.0f * u), ty = (uint32_t)(16.0f * v);
+        if (tx > 15u) tx = 15u;                                          /* reference reads out of bounds at u == 1 (H6) */
+        if (ty > 15u) ty = 15u;
+        const uint8_t* texel = tex + 3 * ((size_t)ty * 16 + tx);
+        float so[3], sd[3];
+        for (int a = 0; a < 3; ++a) so[a] = h.position[a] + h.normal[a] * 0.001f;
+        const v3 tl = norm3(v3_(p->light_position[0] - so[0], p->light_position[1] - so[1], p->light_position[2] - so[2]));
+        sd[0] = tl.x; sd[1] = tl.y; sd[2] = tl.z;
+        vo_hit sh; uint32_t ssteps;
+        grid_cast_one(c->cells, c->X, c->Y, c->Z, so, sd, &sh, &ssteps);
+        st->rays[1]++; st->complexity[1] += ssteps;
+        float light = 0.0f;
+        if (!sh.hit) light = maxf_(0.0f, dot3(tl, v3_(h.normal[0], h.normal[1], h.normal[2])));
+        const float f = minf_(1.0f, maxf_(0.0f, light));
+        for (int k = 0; k < 3; ++k) rgb[k] = mulc(mulc(texel[k], f), tint);
+        return;
+    }
+}
+
+static void grid_render_range(void* c_, uint64_t b, uint64_t e) {
+    grid_shade_ctx* c = (grid_shade_ctx*)c_;
+    const vo_render_params* p = c->p;
+    vo_render_stats st; memset(&st, 0, sizeof(st));
+    const uint64_t W = (uint64_t)p->width;
+    for (uint64_t i = b; i < e; ++i) {
+        const int32_t y = p->row_begin + (int32_t)(i / W), x = (int32_t)(i % W);
+        if (p->tile_step > 1 && (((y - p->row_begin) >> 2) % p->tile_step) != p->tile_index) continue;
+        const size_t px = (size_t)y * W + (size_t)x;
+        uint32_t* a = c->accum + 4 * px;
+        for (int32_t s = 0; s < p->spp; ++s) {
+            uint8_t rgb[3];
+            grid_shade_sample(c, x, y, p->sample_offset + s, rgb, &st);
+            a[0] += rgb[0]; a[1] += rgb[1]; a[2] += rgb[2]; a[3] += 1u;
+        }
+        if (c->rgba) {
+            uint8_t* q = c->rgba + 4 * px;
+            for (int k = 0; k < 3; ++k) q[k] = (uint8_t)((double)a[k] / (double)a[3]);
+            q[3] = 255;
+        }
+    }
+    if (c->stats) {
+        pthread_mutex_lock(&c->lock);
+        for (int k = 0; k < 6; ++k) { c->stats->rays[k] += st.rays[k]; c->stats->complexity[k] += st.complexity[k]; }
+        pthread_mutex_unlock(&c->lock);
+    }
+}
+
+void vo_grid_render(const uint8_t* cells, int X, int Y, int Z, const vo_render_params* p, const uint8_t* tex_top,
+                    const uint8_t* tex_side, uint32_t* accum, uint8_t* rgba, vo_render_stats* stats) {
+    grid_shade_ctx c;
+    c.cells = cells; c.X = X; c.Y = Y; c.Z = Z; c.p = p; c.tex_top = tex_top; c.tex_side = tex_side;
+    c.accum = accum; c.rgba = rgba; c.stats = stats;
+    pthread_mutex_init(&c.lock, NULL);
+    if (stats) memset(stats, 0, sizeof(*stats));
+    const int32_t r1 = p->row_end > p->row_begin ? p->row_end : p->height;
+    par_for(grid_render_range, &c, (uint64_t)(r1 - p->row_begin) * (uint64_t)p->width, 256, p->threads);
+    pthread_mutex_destroy(&c.lock);
+}
+

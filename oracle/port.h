@@ -78,6 +78,8 @@ typedef struct vo_render_params {
     int32_t row_begin, row_end; /* rows [begin,end) */
     int32_t threads;
     int32_t tile_step, tile_index; /* > 1: only 4-row tiles t (from row_begin) with t % tile_step == tile_index */
+    float roughness;               /* vo_grid_render: blur of mirror reflections (0 = perfect mirror) */
+    int32_t max_bounds;            /* vo_grid_render: reflection depth, RayCaster::max_bounds = 4 (raycaster.hpp:277) */
 } vo_render_params;
 
 typedef struct vo_render_stats {
@@ -91,6 +93,21 @@ typedef struct vo_render_stats {
  * raycaster.hpp:94-103, or the temporal blend against `rgba` as previous frame when !use_samples). */
 void vo_render(const vo_lnode* nodes, const vo_render_params* p, const uint8_t* tex_top, const uint8_t* tex_side,
                uint32_t* accum, uint8_t* rgba, vo_render_stats* stats);
+
+/* Shading over a dense grid (Grid3D / MipmapGrid3D) with mirror reflections — an EXTENSION, "parity unpinned":
+ * the reference has Cell::Mirror (cell.hpp:8), RayContext::bounds and max_bounds = 4 (raycaster.hpp:13,127,277) but no
+ * code that reflects.  Specification:
+ *   positions are in voxel units (Grid3D::castRay, grid_3d.hpp:35); camera ray as Camera::getRay with
+ *   start = cam_position + world_rand_offset; light_position in voxel units;
+ *   loop: hit = Grid3D::castRay(o, d); miss → black.  Mirror cell and bounds < max_bounds → ++bounds,
+ *     o = hit + n * 0.001, d = d with the hit axis negated (reflection about the unit normal, exact),
+ *     d = normalize(d + roughness * (r0, r1, r2)), r_k = getRand() of dimensions 8+3*bounce+k, tint *= 0.8, repeat.
+ *   otherwise (Solid, or Mirror at max depth): albedo = texture (top iff n.y != 0; texel index min(15, uint(16*uv))),
+ *     shadow ray o = hit + n * 0.001 toward the light, light = unoccluded ? max(0, dot(to_light, n)) : 0,
+ *     colour = mult(mult(albedo, clamp01(light)), tint) (utils.cpp:43-48).
+ * cells[(x*Y+y)*Z+z] = Cell::Type.  stats->rays: [0] primary, [1] shadow, [2] reflection rays. */
+void vo_grid_render(const uint8_t* cells, int X, int Y, int Z, const vo_render_params* p, const uint8_t* tex_top,
+                    const uint8_t* tex_side, uint32_t* accum, uint8_t* rgba, vo_render_stats* stats);
 
 /* Camera::getRay + main.cpp:145-149 for one pixel/sample with the Philox lattice RNG. */
 void vo_camera_ray(const vo_render_params* p, int32_t x, int32_t y, int32_t sample, float origin[3], float dir[3]);

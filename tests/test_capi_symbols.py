@@ -27,7 +27,7 @@ def test_struct_sizes(vrt):
     import ctypes as C
     assert vrt.HIT.itemsize == 64 and vrt.LNODE.itemsize == 8
     assert C.sizeof(vrt.capi.Camera) == 15 * 4
-    assert C.sizeof(vrt.capi.RenderParams) == 17 * 4
+    assert C.sizeof(vrt.capi.RenderParams) == 19 * 4
     assert C.sizeof(vrt.capi.RenderStats) == 12 * 8
 
 
@@ -51,3 +51,20 @@ def test_bad_arguments_are_errors(vrt):
     assert b"depth" in lib.vrt_last_error()
     with pytest.raises(vrt.VrtError):
         vrt.host_build_lsvo_from_voxels(4, [[16, 0, 0]])       # out of range: UB in the reference, an error here
+
+
+def test_node_array_validation_is_host_side(vrt):
+    """vrt_lsvo_create rejects malformed arrays before touching the device (the traversal trusts child_offset)."""
+    import ctypes as C
+    import numpy as np
+    lib = vrt.capi.lib()
+    bad = np.zeros(9, vrt.LNODE)
+    bad["child_mask"][0] = 1
+    bad["child_offset"][0] = 5            # child block would end at slot 13 > 9
+    h = C.c_void_p()
+    fake_ctx = C.c_void_p(1)              # never dereferenced: validation comes first
+    assert lib.vrt_lsvo_create(fake_ctx, bad.ctypes.data_as(C.c_void_p), 9, 3, 0, C.byref(h)) == -1
+    assert b"malformed" in lib.vrt_last_error()
+    bad["child_offset"][0] = 1
+    bad["leaf_mask"][0] = 2               # leaf bit without child bit
+    assert lib.vrt_lsvo_create(fake_ctx, bad.ctypes.data_as(C.c_void_p), 9, 3, 0, C.byref(h)) == -1

@@ -101,3 +101,53 @@ def test_svo_terrain_vs_oracle(vrt, ctx, port):
     assert_hits_equal(got, want, hit_flag(got), "svo terrain")
     m = hit_flag(got)
     assert np.array_equal(got["voxel"][m], want["voxel"][m]) and m.mean() > 0.3
+
+
+def mirror_scene(vrt, size=128):
+    """Terrain columns over a flat lake of Cell::Mirror voxels (types: 0 empty, 1 solid, 2 mirror)."""
+    h = vrt.host_terrain_heights(256)[:size, :size]
+    top = 30 + np.clip(h, 0, 70)
+    y = np.arange(size)[None, :, None]
+    cells = (y <= top[:, None, :]).astype(np.uint8)
+    lake = h <= 18
+    xs, zs = np.nonzero(lake)
+    cells[xs, 30 + np.clip(h, 0, 70)[lake], zs] = 2
+    return cells
+
+
+@pytest.mark.parametrize("mip,roughness,aperture,spp", [(0, 0.0, 0.0, 1), (3, 0.15, 0.0, 2), (3, 0.3, 0.4, 3)])
+def test_grid_frame_with_reflections_matches_oracle(vrt, ctx, port, textures, mip, roughness, aperture, spp):
+    from oracle import loader
+    cells = mirror_scene(vrt)
+    assert (cells == 2).sum() > 100
+    scene = vrt.MipmapGrid3D(ctx, cells, mip) if mip else vrt.Grid3D(ctx, cells)
+    scene.set_textures(*textures)
+    W, H = 200, 120
+    cam = vrt.Camera(position=(64.0, 118.0, 20.0), view_angle=(0.0, 0.75), aperture=aperture, focal_length=40.0)
+    light = np.float32([300.0, 900.0, -200.0])
+    rc = vrt.RayCaster(scene, (W, H))
+    rc.setLightPosition(light)
+    rc.use_samples, rc.roughness, rc.max_bounds = True, roughness, 4
+    img = rc.render(cam, spp=spp)
+    p = loader.PortRenderParams()
+    p.width, p.height, p.depth, p.guard = W, H, 7, 7
+    p.cam_position[:] = [float(x) for x in cam.position]
+    p.rot_mat[:] = [float(x) for x in cam.rot_mat]
+    p.fov, p.aperture, p.focal_length = cam.fov, cam.aperture, cam.focal_length
+    p.light_position[:] = [float(x) for x in light]
+    p.use_gi, p.gi_bounces, p.use_samples, p.spp = 0, 1, 1, spp
+    p.seed_lo, p.seed_hi, p.threads = 0x5EED, 0, 8
+    p.roughness, p.max_bounds = roughness, 4
+    accum, rgba, stats = port.grid_render(cells, p, *textures)
+    assert np.array_equal(rc.colors, accum) and np.array_equal(img, rgba)
+    assert rc.last_stats["rays"][:3] == list(stats.rays)[:3] and rc.last_stats["complexity"][:3] == list(stats.complexity)[:3]
+    assert stats.rays[2] > 0 and img[..., :3].max() > 0, "the view must contain reflections and lit terrain"
+
+
+def test_grid_frame_rejects_gi(vrt, ctx, textures):
+    scene = vrt.Grid3D(ctx, np.ones((8, 8, 8), np.uint8))
+    scene.set_textures(*textures)
+    rc = vrt.RayCaster(scene, (16, 16))
+    rc.use_samples, rc.use_gi = True, True
+    with pytest.raises(vrt.VrtError):
+        rc.render(vrt.Camera(position=(4, 20, 4)), spp=1)
