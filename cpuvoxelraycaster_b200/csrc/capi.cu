@@ -237,6 +237,43 @@ int vrt_lsvo_create(vrt_context* ctx, const vrt_lnode* nodes, uint64_t n_nodes, 
     return VRT_OK;
 }
 
+int vrt_lsvo_create_terrain(vrt_context* ctx, uint32_t depth, int32_t guard, vrt_scene** out) {
+    if (!ctx || !out) return fail(VRT_ERR_INVALID, "vrt_lsvo_create_terrain: NULL argument");
+    if (depth < 8 || depth > 12) return fail(VRT_ERR_INVALID, "vrt_lsvo_create_terrain: depth must be 8..12");
+    if (int s = use_device(ctx)) return s;
+    vrt_scene* sc = new (std::nothrow) vrt_scene();
+    if (!sc) return fail(VRT_ERR_OOM, "vrt_lsvo_create_terrain: host allocation failed");
+    sc->ctx = ctx;
+    sc->kind = VRT_SCENE_LSVO;
+    sc->depth = depth;
+    sc->guard = guard > 0 ? guard : (guard < 0 ? 0 : int32_t(depth));
+    cudaError_t e = vrt::device_build_terrain_lsvo(int(depth), &sc->d_nodes, &sc->n_nodes, nullptr, ctx->stream);
+    ctx->launches += 7 + 9 * depth;      // heights, pyramid, count/scan (4 per level), size/place/emit per level, fill, root
+    if (e == cudaSuccess) e = cudaMalloc(&sc->d_counters, 16 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemsetAsync(sc->d_counters, 0, 16 * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        vrt_scene_destroy(sc);
+        return e == cudaErrorMemoryAllocation ? fail(VRT_ERR_OOM, "vrt_lsvo_create_terrain: device allocation failed")
+                                              : cuda_fail(e, "vrt_lsvo_create_terrain");
+    }
+    sc->device_bytes = sc->n_nodes * sizeof(uint2);
+    *out = sc;
+    return VRT_OK;
+}
+
+int vrt_scene_download_nodes(vrt_scene* sc, vrt_lnode* out, uint64_t cap, uint64_t* count) {
+    if (!sc || !count) return fail(VRT_ERR_INVALID, "vrt_scene_download_nodes: NULL argument");
+    if (sc->kind != VRT_SCENE_LSVO) return fail(VRT_ERR_INVALID, "vrt_scene_download_nodes: not an LSVO scene");
+    *count = sc->n_nodes;
+    if (!out) return VRT_OK;
+    if (cap < sc->n_nodes) return fail(VRT_ERR_INVALID, "vrt_scene_download_nodes: buffer too small");
+    if (int s = use_device(sc->ctx)) return s;
+    VRT_CUDA(cudaMemcpyAsync(out, sc->d_nodes, sc->n_nodes * sizeof(uint2), cudaMemcpyDeviceToHost, sc->ctx->stream));
+    VRT_CUDA(cudaStreamSynchronize(sc->ctx->stream));
+    return VRT_OK;
+}
+
 int vrt_scene_destroy(vrt_scene* sc) {
     if (!sc) return VRT_OK;
     cudaSetDevice(sc->ctx->device);

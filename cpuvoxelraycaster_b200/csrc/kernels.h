@@ -71,4 +71,7 @@ cudaError_t launch_render_smem(const uint2* nodes, const RenderLaunch& L, uint32
 // Grid frames: camera rays, DDA, mirror reflections, texture + sun shadow, accumulation (grid_kernels.cu)
 cudaError_t launch_grid_render(const GridLevels& g, bool use_mip, const RenderLaunch& L, uint32_t* d_accum,
                                unsigned long long* d_counters, cudaStream_t stream);
+// Scene construction on the device (scene_device.cu): T(depth) in the reference's LNode layout, nothing crosses PCIe.
+// *d_slots is cudaMalloc'ed (the caller frees it); d_heights_out may be null.
+cudaError_t device_build_terrain_lsvo(int depth, uint2** d_slots, uint64_t* n_slots, int32_t* d_heights_out, cudaStream_t stream);
 }  // namespace vrt

@@ -52,6 +52,12 @@ public:
         return sum * bounding_;
     }
 
+    void tables(uint8_t perm[512], uint8_t perm12[512], float* bounding) const {
+        std::memcpy(perm, perm_, 512);
+        std::memcpy(perm12, perm12_, 512);
+        *bounding = bounding_;
+    }
+
 private:
     static int floor_to_int(float f) { return f >= 0 ? int(f) : int(f) - 1; }
 
@@ -86,6 +92,9 @@ private:
     const int octaves_ = 3;
     float bounding_;
 };
+
+// permutation tables + fractal bounding for the device-side noise (scene_device.cu)
+void host_simplex_tables(uint8_t perm[512], uint8_t perm12[512], float* bounding) { SimplexFbm2D().tables(perm, perm12, bounding); }
 
 void host_terrain_heights(int32_t size, int32_t* out) {
     const SimplexFbm2D noise;

@@ -181,9 +181,31 @@ class LSVO(Volumetric):
         self.n_nodes = len(nodes)
 
     @classmethod
-    def from_terrain(cls, ctx, depth, guard=0):
-        """The demo scene T(D): src/main.cpp:59-83."""
-        return cls(ctx, host_build_terrain_lsvo(depth), depth, guard)
+    def from_terrain(cls, ctx, depth, guard=0, on_device=True):
+        """The demo scene T(D): src/main.cpp:59-83.  Built on the GPU by default (byte-identical to the host builder)."""
+        if not on_device:
+            return cls(ctx, host_build_terrain_lsvo(depth), depth, guard)
+        self = cls.__new__(cls)
+        Volumetric.__init__(self, ctx)
+        h = C.c_void_p()
+        check(lib().vrt_lsvo_create_terrain(ctx.handle, int(depth), int(guard), C.byref(h)))
+        self.handle = h
+        self.depth = int(depth)
+        self.n_nodes = len(self)
+        return self
+
+    def __len__(self):
+        n = C.c_uint64(0)
+        check(lib().vrt_scene_download_nodes(self.handle, None, 0, C.byref(n)))
+        return int(n.value)
+
+    def download_nodes(self):
+        """LSVO::data (lsvo.hpp:287)."""
+        n = C.c_uint64(0)
+        check(lib().vrt_scene_download_nodes(self.handle, None, 0, C.byref(n)))
+        nodes = np.zeros(n.value, LNODE)
+        check(lib().vrt_scene_download_nodes(self.handle, ptr(nodes), n.value, C.byref(n)))
+        return nodes
 
     @classmethod
     def from_voxels(cls, ctx, depth, xyz, guard=0):

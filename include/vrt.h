@@ -118,6 +118,12 @@ int vrt_host_camera_rotation(const float view_angle[2], float rot_mat[9], float 
  * reference expression (= depth). */
 int vrt_lsvo_create(vrt_context* ctx, const vrt_lnode* nodes, uint64_t n_nodes, uint32_t depth, int32_t guard,
                     vrt_scene** out);
+/* The demo scene T(depth), depth 8..12, built entirely on the device (FastNoise heights, the SVO::setCell fill
+ * main.cpp:61-76 and compileSVO lsvo_utils.cpp:4-49 in one pass; byte-identical to vrt_host_build_terrain_lsvo and to
+ * the reference's own array) — nothing crosses PCIe. */
+int vrt_lsvo_create_terrain(vrt_context* ctx, uint32_t depth, int32_t guard, vrt_scene** out);
+/* LSVO::data (lsvo.hpp:287): copy the scene's LNode array back to the host.  out == NULL → *count only. */
+int vrt_scene_download_nodes(vrt_scene* scene, vrt_lnode* out, uint64_t cap, uint64_t* count);
 /* Grid3D<X,Y,Z> (grid_3d.hpp:10-27): cell_types[(x*Y+y)*Z+z] = Cell::Type (0 = Empty).
  * mip_levels > 0 builds the MipmapGrid3D occupancy pyramid (results identical to Grid3D). */
 int vrt_grid_create(vrt_context* ctx, const uint8_t* cell_types, int32_t X, int32_t Y, int32_t Z, int32_t mip_levels,

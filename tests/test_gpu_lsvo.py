@@ -103,3 +103,34 @@ def test_kernel_variants_agree(vrt, port, terrain9_nodes, variant, refill):
         assert_hits_equal(got, want, hit_flag(got), "variant %d refill %d n=%d" % (variant, refill, n))
         assert s.last_complexity() == int(want["complexity"].sum())
     c.close()
+
+
+@pytest.mark.parametrize("depth", [8, 9, 10])
+def test_device_scene_construction_is_byte_identical(vrt, ctx, depth):
+    """vrt_lsvo_create_terrain builds T(D) on the GPU: the LNode array equals the host builder's (which equals the
+    reference's compileSVO, tests/test_host_logic.py) byte for byte."""
+    import hashlib
+    s = vrt.LSVO.from_terrain(ctx, depth)                     # on_device=True
+    got = s.download_nodes()
+    want = vrt.host_build_terrain_lsvo(depth)
+    assert len(got) == len(want)
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+    if depth == 9:
+        assert hashlib.sha256(got.tobytes()).hexdigest() == str(golden("terrain_heights.npz")["sha_nodes9"])
+    s.close()
+
+
+def test_device_scene_large_depths(vrt, ctx):
+    """2048^3 and 4096^3: slot counts match the host builder's closed-form count; a cast works on the result."""
+    import ctypes as C
+    for depth, guard in ((11, 0), (12, -1)):
+        s = vrt.LSVO.from_terrain(ctx, depth, guard)
+        n = C.c_uint64(0)
+        h = vrt.host_terrain_heights(1 << depth)
+        vrt.capi.check(vrt.capi.lib().vrt_host_build_terrain_lsvo(depth, vrt.capi.ptr(h), None, 0, C.byref(n)))
+        assert len(s) == n.value
+        S = float(1 << depth)
+        o = np.float32([[1.5, 1 + (S / 2 - 56) / S, 1.5]])
+        got = s.cast_rays(o, np.float32([[0.2, 0.5, 0.8]]))
+        assert hit_flag(got)[0] and got["complexity"][0] > depth
+        s.close()
