@@ -116,7 +116,7 @@ struct Emitter {
     vrt_lnode* at(uint64_t i) { return (out && i < cap) ? out + i : nullptr; }
 };
 
-// Occupancy oracle for the terrain: column (x,z) is solid for y in [S/2+1, top(x,z)].
+// Occupancy predicate for the terrain: column (x,z) is solid for y in [S/2+1, top(x,z)].
 struct TerrainOcc {
     int S, bottom;
     std::vector<std::vector<int32_t>> top;   // top[l][(x>>l)*(S>>l)+(z>>l)] = max column top over the square

@@ -1,0 +1,126 @@
+"""BASELINE.json configurations at (or near) their full sizes: bit-exact against the oracle where the oracle finishes
+in seconds, and size-independent properties (kernel variants agree byte for byte, ray-class bookkeeping, partitions)
+where it does not."""
+import numpy as np
+import pytest
+
+from conftest import assert_hits_equal, golden
+
+pytestmark = pytest.mark.gpu
+
+
+def hit_flag(h):
+    return (h["flags"] & 1) != 0
+
+
+def camera_rays(D, W, H, voxel_units=False):
+    S = float(1 << D)
+    cam = np.float32([S / 2, S / 2 - 56, S / 2])
+    x, y = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32))
+    d = np.stack([x / np.float32(H) - np.float32(W / H * 0.5), y / np.float32(H) - np.float32(0.5), np.ones_like(x)], -1).reshape(-1, 3)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    o = cam if voxel_units else cam / np.float32(S) + np.float32(1)
+    return np.broadcast_to(o, d.shape).astype(np.float32).copy(), d.astype(np.float32)
+
+
+def test_cfg2_grid512_1080p_bit_exact(vrt, ctx, port):
+    """configs[1]: dense Grid3D 512^3, coherent primary rays at 1920x1080, hit buffer bit-exact."""
+    size = 512
+    h = vrt.host_terrain_heights(size)
+    hm = np.maximum(16, np.minimum(size, h))
+    y = np.arange(size)[None, :, None]
+    cells = ((y >= size // 2 + 1) & (y <= (size // 2 + hm - 1)[:, None, :])).astype(np.uint8)
+    cells = np.ascontiguousarray(cells[::-1, ::-1, ::-1])          # the world the LSVO shows (point mirrored)
+    o, d = camera_rays(9, 1920, 1080, voxel_units=True)
+    got = vrt.Grid3D(ctx, cells).cast_rays(o, d)
+    want, steps = port.grid_cast(cells, o, d, threads=16)
+    assert_hits_equal(got, want, hit_flag(got), "cfg2")
+    assert 0.3 < hit_flag(got).mean() < 0.7
+    mip = vrt.MipmapGrid3D(ctx, cells, 4).cast_rays(o, d)
+    assert np.array_equal(got.view(np.uint8), mip.view(np.uint8))
+
+
+def test_cfg4_scene_2048_rays_and_variants(vrt, port):
+    """configs[3] scene (T(11), built on the GPU): 1080p primary rays — K1 and K1p byte-identical on all 2 M rays,
+    bit-exact against the oracle on a 200 k prefix (the oracle builds its own 1.35 GB node array)."""
+    c = vrt.Context(0)
+    s = vrt.LSVO.from_terrain(c, 11)
+    o, d = camera_rays(11, 1920, 1080)
+    c.set_option("cast_variant", 0)
+    a = s.cast_rays(o, d)
+    c.set_option("cast_variant", 1)
+    b = s.cast_rays(o, d)
+    assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    nodes = port.build_terrain(11)
+    assert len(nodes) == len(s)
+    sel = np.arange(0, len(o), len(o) // 200000)[:200000]
+    want = port.lsvo_cast(nodes, 11, o[sel], d[sel], threads=16)
+    assert_hits_equal(a[sel], want, hit_flag(a[sel]), "cfg4 primary")
+    c.close()
+
+
+def test_cfg4_frame_bookkeeping_and_partitions(vrt, ctx, textures):
+    """1080p GI + DOF frame at 2048^3 (8 spp): ray-class counts obey the chain's structure, and the frame is the same
+    whether it is rendered in one call, in sample batches, or in interleaved tile partitions."""
+    s = vrt.LSVO.from_terrain(ctx, 11)
+    s.set_textures(*textures)
+    W, H, spp = 1920, 1080, 8
+    S = 2048.0
+    cam = vrt.Camera(position=(S / 2, S / 2 - 56, S / 2), view_angle=(0, 0), aperture=0.5)
+    cam.autofocus(s)
+    light = np.float32([-200, -1000, -300]) * np.float32(1 / S) + np.float32(1)
+
+    def rc():
+        r = vrt.RayCaster(s, (W, H))
+        r.setLightPosition(light)
+        r.use_samples, r.use_gi, r.gi_bounces = True, True, 2
+        return r
+    one = rc()
+    one.render(cam, spp)
+    rays = one.last_stats["rays"]
+    assert rays[0] == W * H * spp                       # one primary ray per sample
+    assert rays[1] == rays[2]                           # every primary hit casts one shadow and one GI ray
+    assert rays[3] == rays[4] and rays[5] <= rays[4] <= rays[2]
+    assert int(one.colors[..., 3].min()) == spp == int(one.colors[..., 3].max())
+    parts = rc()
+    parts.render(cam, 3)
+    parts.render(cam, 5)                                # sample batches continue the Philox stream
+    assert np.array_equal(one.colors, parts.colors) and np.array_equal(one.render_image, parts.render_image)
+    from cpuvoxelraycaster_b200 import capi
+    import ctypes as C
+    tiled = rc()
+    for idx in range(3):                                # what 3 GPUs would each render
+        p = tiled.params(spp, 0, H, 0)
+        p.tile_step, p.tile_index, p.accum_in = 3, idx, 1
+        st = capi.RenderStats()
+        capi.check(capi.lib().vrt_render(s.handle, C.byref(cam.as_struct()), C.byref(p), capi.ptr(tiled.render_image),
+                                         capi.ptr(tiled.colors), C.byref(st)))
+    assert np.array_equal(one.colors, tiled.colors) and np.array_equal(one.render_image, tiled.render_image)
+    s.close()
+
+
+def test_cfg5_lsvo4096_random_rays(vrt, port):
+    """configs[4]: LSVO 4096^3 (built on the GPU, lsvo.hpp:72 guard lifted), incoherent random rays: the persistent
+    regenerating kernel and the one-thread-per-ray kernel agree byte for byte on 4 M rays; a 100 k prefix is bit-exact
+    against the oracle walking its own host-built 5.4 GB array."""
+    c = vrt.Context(0)
+    s = vrt.LSVO.from_terrain(c, 12, guard=-1)
+    rng = np.random.default_rng(0xD1CE)
+    n = 1 << 22
+    o = rng.uniform([1, 1, 1], [2, 1.5 - 96 / 4096.0, 2], (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    c.set_option("cast_variant", 1)
+    a = s.cast_rays(o, d)
+    c.set_option("cast_variant", 0)
+    b = s.cast_rays(o, d)
+    assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    assert 0.15 < hit_flag(a).mean() < 0.4
+    nodes = port.build_terrain(12)
+    assert len(nodes) == len(s)
+    want = port.lsvo_cast(nodes, 12, o[:100000], d[:100000], guard=0, threads=16)
+    assert_hits_equal(a[:100000], want, hit_flag(a[:100000]), "cfg5 prefix")
+    # with the reference's guard (scale > 12) nothing below level 10 is reachable: every ray misses
+    ref_guard = vrt.LSVO.from_terrain(c, 12, guard=0)
+    assert not hit_flag(ref_guard.cast_rays(o[:20000], d[:20000])).any()
+    c.close()
