@@ -96,7 +96,7 @@ const char* vrt_last_error(void) { return g_last_error.c_str(); }
 const char* vrt_build_info(void) {
     return "libvrt sm_100a --fmad=false -prec-div=true -prec-sqrt=true -ftz=false; kernels: lsvo_cast_kernel (K1), "
            "lsvo_cast_persistent_kernel (K1p, default), render_accumulate_kernel (K4, default), render_persistent_kernel (K4p), "
-           "render_smem_kernel (K4s), resolve_kernel, grid_cast_kernel<mip> (K2/K2m), svo_cast_kernel (K3)";
+           "resolve_kernel, grid_cast_kernel<mip> (K2/K2m), svo_cast_kernel (K3), grid_render_kernel<mip>, terrain builder";
 }
 
 int vrt_context_create(int device, void* stream, vrt_context** out) {
@@ -158,7 +158,7 @@ int vrt_context_set_option(vrt_context* ctx, const char* key, int value) {
     if (!ctx || !key) return fail(VRT_ERR_INVALID, "vrt_context_set_option: NULL argument");
     const std::string k(key);
     if (k == "cast_variant" && (value == 0 || value == 1)) ctx->cast_variant = value;
-    else if (k == "render_variant" && (value == 0 || value == 1 || (value >= 5 && value <= 8))) ctx->render_variant = value;
+    else if (k == "render_variant" && (value == 0 || value == 1)) ctx->render_variant = value;
     else if (k == "spp_chunks" && value >= 0 && value <= 4096) ctx->spp_chunks = value;
     else if (k == "refill_cast" && value >= 0 && value <= 32) ctx->refill_cast = value;
     else if (k == "refill_render" && value >= 1 && value <= 32) ctx->refill_render = value;
@@ -415,9 +415,6 @@ int vrt_render_accumulate_device(vrt_scene* sc, const vrt_camera* cam, const vrt
     if (sc->kind != VRT_SCENE_LSVO)
         VRT_CUDA(vrt::launch_grid_render(sc->grid, sc->use_mip, make_launch(sc, cam, p), d_accum, sc->d_counters + kRenderCounters,
                                          ctx->stream));
-    else if (ctx->render_variant >= 5)
-        VRT_CUDA(vrt::launch_render_smem(sc->d_nodes, make_launch(sc, cam, p), d_accum, sc->d_counters + kRenderCounters,
-                                         ctx->render_variant, ctx->stream));
     else if (ctx->render_variant == 0)
         VRT_CUDA(vrt::launch_render_accumulate_ref(sc->d_nodes, make_launch(sc, cam, p), d_accum, sc->d_counters + kRenderCounters,
                                                    ctx->stream));

@@ -65,9 +65,6 @@ cudaError_t launch_lsvo_cast_persistent(const uint2* nodes, int depth, int guard
                                         int refill, cudaStream_t stream);
 cudaError_t launch_render_persistent(const uint2* nodes, const RenderLaunch& L, uint32_t* d_accum, unsigned long long* d_counters,
                                      int refill, cudaStream_t stream);
-// K4s: frame kernel with the chain state in shared memory (render_smem_kernel.cu); min_blocks = CTAs per SM (5..8)
-cudaError_t launch_render_smem(const uint2* nodes, const RenderLaunch& L, uint32_t* d_accum, unsigned long long* d_counters,
-                               int min_blocks, cudaStream_t stream);
 // Grid frames: camera rays, DDA, mirror reflections, texture + sun shadow, accumulation (grid_kernels.cu)
 cudaError_t launch_grid_render(const GridLevels& g, bool use_mip, const RenderLaunch& L, uint32_t* d_accum,
                                unsigned long long* d_counters, cudaStream_t stream);

@@ -4,10 +4,10 @@
  *
  * Pinning status: every function below is checked against the reference's own compiled sources
  * (oracle/_ref/libvrt_ref*.so) in tests/test_oracle_pinned.py, except
- *   - gi_bounces == 2 and the Philox lattice RNG: extensions with no reference behaviour
- *     ("parity unpinned" for those, specified in DESIGN.md; gi_bounces == 1 IS pinned by feeding
- *     both sides the same random numbers is impossible with the reference's racy global RNG, so the
- *     pin is statistical: PSNR of images);
+ *   - gi_bounces == 2, vo_grid_render (mirror reflections) and the Philox lattice RNG: extensions with no
+ *     reference behaviour ("parity unpinned" for those, specified in DESIGN.md §2).  gi_bounces == 1 follows the
+ *     reference expression; feeding both sides the same random numbers is impossible with the reference's racy
+ *     global RNG, so that pin is statistical (PSNR of images, tests/test_oracle_pinned.py);
  *   - glm itself is un-vendored and unpinned in the reference; the shim restates its public
  *     definitions (oracle/shim/glm/glm.hpp).
  */
