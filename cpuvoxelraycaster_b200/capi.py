@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvrt.so")
+LIB_PATH = os.environ.get("VRT_LIBRARY", os.path.join(HERE, "libvrt.so"))    # override: A/B builds in tools/
 
 VRT_OK = 0
 

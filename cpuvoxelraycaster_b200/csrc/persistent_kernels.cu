@@ -8,7 +8,7 @@
 // Every lane's arithmetic is exactly that of LSVO<D>::castRay / RayCaster::castRay in the reference
 // (see lsvo_step.cuh, render_kernels.cu), so results do not depend on the scheduling.
 #include "lsvo_step.cuh"
-#include "kernels.h"
+#include "render_chain.cuh"
 
 namespace vrt {
 
@@ -138,16 +138,6 @@ __global__ void __launch_bounds__(128, 4) lsvo_cast_persistent_kernel(Nodes node
 }
 
 // ---- K4p: frame rendering ------------------------------------------------------------------------------------
-enum Stage : int { kPrimary = 0, kShadow = 1, kGi0 = 2, kGi0Shadow = 3, kGi1 = 4, kGi1Shadow = 5, kDone = 6 };
-
-__device__ __forceinline__ uint8_t mul_u8p(uint8_t c, float f) { return uint8_t(fminf(255.0f, float(c) * f)); }   // utils.cpp:43-48
-
-__device__ __forceinline__ void view_to_world_p(const float* m, float vx, float vy, float vz, float& x, float& y, float& z) {
-    x = (m[0] * vx + m[1] * vy) + m[2] * vz;                               // v * rot_mat, camera_controller.hpp:51-54
-    y = (m[3] * vx + m[4] * vy) + m[5] * vz;
-    z = (m[6] * vx + m[7] * vy) + m[8] * vz;
-}
-
 template <typename Nodes>
 __global__ void __launch_bounds__(128, 4) render_persistent_kernel(Nodes nodes, RenderLaunch L, uint32_t* __restrict__ accum,
                                                                    unsigned long long* __restrict__ counters, int refill) {
@@ -175,26 +165,18 @@ __global__ void __launch_bounds__(128, 4) render_persistent_kernel(Nodes nodes, 
     Trav t;
     bool alive = false, has_ray = false, have_pixel = false, exhausted = false;
     unsigned long long chunk_next = 0, chunk_end = 0;                       // warp-uniform
-    // pixel state
-    uint32_t pixel = 0, sum_r = 0, sum_g = 0, sum_b = 0;
+    uint32_t pixel = 0, sum_r = 0, sum_g = 0, sum_b = 0;                    // pixel state
     float lens_x = 0.f, lens_y = 0.f;
     int s = 0;
-    // chain state (one sample)
-    int stage = kPrimary;
-    uint4 rnd0 = make_uint4(0, 0, 0, 0);
-    float nx = 0.f, ny = 0.f, nz = 0.f, light = 0.f;
-    float dot_gi0 = 0.f, dot_gi1 = 0.f, irr0 = 0.f, irr1 = 0.f;
-    float gnx = 0.f, gny = 0.f, gnz = 0.f, gpx = 0.f, gpy = 0.f, gpz = 0.f;
-    float tlx = 0.f, tly = 0.f, tlz = 0.f;
-    uint8_t tex_r = 0, tex_g = 0, tex_b = 0;
-    bool have_hit = false, gi0_hit = false, gi1_hit = false;
+    int stage = kPrimary;                                                   // chain state (one sample)
+    ChainState c;
 
     for (;;) {
         // ================= refill phase =================
-        float rox = 0.f, roy = 0.f, roz = 0.f, rdx = 0.f, rdy = 0.f, rdz = 0.f, rcoef = 0.f;
+        NextRay nr;
         bool new_ray = false, want_primary = false;
         if (!alive && has_ray) {
-            // ---- A: the lane's ray has terminated: advance the sample's chain (raycaster.hpp:118-207) ----
+            // ---- A: the lane's ray has terminated: advance the sample's chain (render_chain.cuh) ----
             has_ray = false;
             LsvoResult r;
             t.result(r);
@@ -205,94 +187,12 @@ __global__ void __launch_bounds__(128, 4) render_persistent_kernel(Nodes nodes, 
                 atomicSub(&s_stats[6 + stage], 0x80000000u);
                 atomicAdd(counters + 6 + stage, 0x80000000ull);
             }
-            int next = kDone;
-            switch (stage) {
-                case kPrimary: {                                             // :131-145
-                    if (!r.hit) break;
-                    have_hit = true;
-                    nx = h.normal[0]; ny = h.normal[1]; nz = h.normal[2];
-                    const uint8_t* tex = (ny != 0.0f) ? L.tex_top : L.tex_side;            // :211-215
-                    const float u = fminf(fmaxf(h.uv[0], 0.0f), 1.0f), v = fminf(fmaxf(h.uv[1], 0.0f), 1.0f);   // :237-238
-                    const uint32_t tx = uint32_t(16.0f * u), ty = uint32_t(16.0f * v);      // :239
-                    const uint8_t* texel = tex + 3u * (ty * 16u + tx);
-                    tex_r = __ldg(texel); tex_g = __ldg(texel + 1); tex_b = __ldg(texel + 2);
-                    gpx = h.pos[0]; gpy = h.pos[1]; gpz = h.pos[2];
-                    rox = h.pos[0] + nx * SCALE * 0.001f; roy = h.pos[1] + ny * SCALE * 0.001f; roz = h.pos[2] + nz * SCALE * 0.001f;   // :139
-                    tlx = L.light[0] - rox; tly = L.light[1] - roy; tlz = L.light[2] - roz;   // :152
-                    normalize3(tlx, tly, tlz);
-                    rdx = tlx; rdy = tly; rdz = tlz; rcoef = 0.0f;
-                    next = kShadow;
-                    break;
-                }
-                case kShadow: {                                              // :155-157
-                    if (!r.hit) light = fmaxf(0.0f, dot3(tlx, tly, tlz, nx, ny, nz));
-                    if (!L.use_gi) break;
-                    const float c1 = lattice(rnd0.z, -1000.0f, 1000.0f), c2 = lattice(rnd0.w, -1000.0f, 1000.0f);   // :180-181
-                    float ax, ay, az;
-                    if (nx != 0.0f) { ax = 0.0f; ay = c1; az = c2; }         // :182-190
-                    else if (ny != 0.0f) { ax = c1; ay = 0.0f; az = c2; }
-                    else if (nz != 0.0f) { ax = c1; ay = c2; az = 0.0f; }
-                    else break;
-                    rox = gpx + nx * n_norm; roy = gpy + ny * n_norm; roz = gpz + nz * n_norm;      // :174
-                    rdx = (nx + ax) * n_norm; rdy = (ny + ay) * n_norm; rdz = (nz + az) * n_norm;   // :192
-                    normalize3(rdx, rdy, rdz);
-                    dot_gi0 = dot3(rdx, rdy, rdz, nx, ny, nz);               // :193
-                    rcoef = 0.5f;
-                    next = kGi0;
-                    break;
-                }
-                case kGi0:
-                case kGi1: {                                                 // :194-198
-                    if (!r.hit) break;
-                    if (stage == kGi0) gi0_hit = true; else gi1_hit = true;
-                    gnx = h.normal[0]; gny = h.normal[1]; gnz = h.normal[2];
-                    gpx = h.pos[0]; gpy = h.pos[1]; gpz = h.pos[2];
-                    rox = gpx + gnx * n_norm; roy = gpy + gny * n_norm; roz = gpz + gnz * n_norm;   // :196
-                    tlx = L.light[0] - rox; tly = L.light[1] - roy; tlz = L.light[2] - roz;         // :197
-                    normalize3(tlx, tly, tlz);
-                    rdx = tlx; rdy = tly; rdz = tlz; rcoef = 0.5f;
-                    next = stage + 1;
-                    break;
-                }
-                case kGi0Shadow: {                                           // :199-200
-                    if (!r.hit) irr0 = fmaxf(0.0f, dot3(gnx, gny, gnz, tlx, tly, tlz));
-                    if (L.gi_bounces < 2) break;
-                    const uint4 rnd1 = philox4x32_10(pixel, uint32_t(L.sample_offset + s), 1u, 0u, L.seed_lo, L.seed_hi);
-                    const float c1 = lattice(rnd1.x, -1000.0f, 1000.0f), c2 = lattice(rnd1.y, -1000.0f, 1000.0f);
-                    float ax, ay, az;
-                    if (gnx != 0.0f) { ax = 0.0f; ay = c1; az = c2; }
-                    else if (gny != 0.0f) { ax = c1; ay = 0.0f; az = c2; }
-                    else if (gnz != 0.0f) { ax = c1; ay = c2; az = 0.0f; }
-                    else break;
-                    rox = gpx + gnx * n_norm; roy = gpy + gny * n_norm; roz = gpz + gnz * n_norm;
-                    rdx = (gnx + ax) * n_norm; rdy = (gny + ay) * n_norm; rdz = (gnz + az) * n_norm;
-                    normalize3(rdx, rdy, rdz);
-                    dot_gi1 = dot3(rdx, rdy, rdz, gnx, gny, gnz);
-                    rcoef = 0.5f;
-                    next = kGi1;
-                    break;
-                }
-                case kGi1Shadow: {
-                    if (!r.hit) irr1 = fmaxf(0.0f, dot3(gnx, gny, gnz, tlx, tly, tlz));
-                    break;
-                }
-                default: break;
-            }
+            const int next = chain_advance(L, c, stage, r, h, pixel, uint32_t(L.sample_offset + s), SCALE, n_norm, nr);
             if (next != kDone) {
                 stage = next;
                 new_ray = true;
             } else {
-                // the sample is complete: colour (raycaster.hpp:161-163) and accumulation (:87-90)
-                if (have_hit) {
-                    float gi = 0.0f;
-                    if (L.use_gi && gi0_hit) {
-                        float irr = irr0;
-                        if (L.gi_bounces >= 2) irr = irr + (gi1_hit ? fminf(0.5f, irr1 * dot_gi1) : 0.0f);
-                        gi = fmaxf(0.0f, 1000000.0f * fminf(0.5f, irr * dot_gi0) / 1.0f);           // :201,:206
-                    }
-                    const float f = fminf(1.0f, fmaxf(0.0f, light + gi));                           // :163
-                    sum_r += mul_u8p(tex_r, f); sum_g += mul_u8p(tex_g, f); sum_b += mul_u8p(tex_b, f);
-                }
+                chain_colour(L, c, sum_r, sum_g, sum_b);                     // the sample is complete
                 ++s;
                 if (s < L.spp) {
                     want_primary = true;
@@ -340,31 +240,15 @@ __global__ void __launch_bounds__(128, 4) render_persistent_kernel(Nodes nodes, 
             chunk_next += __popc(took);
             want &= ~__ballot_sync(kFull, take && valid);                    // off-frame ordinals ask again
         }
-        // ---- C: Camera::getRay (camera_controller.hpp:34-49) for lanes starting a sample ----
+        // ---- C: Camera::getRay for lanes starting a sample ----
         if (want_primary) {
-            rnd0 = philox4x32_10(pixel, uint32_t(L.sample_offset + s), 0u, 0u, L.seed_lo, L.seed_hi);
-            const float u0 = lattice(rnd0.x, -0.5f, 0.5f), u1 = lattice(rnd0.y, -0.5f, 0.5f);
-            float fx = lens_x, fy = lens_y, fz = L.cam.fov;
-            normalize3(fx, fy, fz);
-            fx *= L.cam.focal_length; fy *= L.cam.focal_length; fz *= L.cam.focal_length;
-            const float rx = L.cam.aperture * u0, ry = L.cam.aperture * u1, rz = L.cam.aperture * 0.0f;
-            float qx = fx - rx, qy = fy - ry, qz = fz - rz;
-            normalize3(qx, qy, qz);
-            float wx, wy, wz;
-            view_to_world_p(L.cam.rot_mat, qx, qy, qz, rdx, rdy, rdz);
-            view_to_world_p(L.cam.rot_mat, rx, ry, rz, wx, wy, wz);
-            rox = (L.cam.position[0] + wx) * SCALE + 1.0f;                   // main.cpp:149
-            roy = (L.cam.position[1] + wy) * SCALE + 1.0f;
-            roz = (L.cam.position[2] + wz) * SCALE + 1.0f;
-            rcoef = 0.0f;
+            chain_begin(L, c, pixel, uint32_t(L.sample_offset + s), lens_x, lens_y, SCALE, nr);
             stage = kPrimary;
-            light = 0.f; irr0 = 0.f; irr1 = 0.f;
-            have_hit = false; gi0_hit = false; gi1_hit = false;
             new_ray = true;
         }
         // ---- D: prologue of castRay for every regenerated ray ----
         if (new_ray) {
-            t.init(rox, roy, roz, rdx, rdy, rdz, rcoef, 0.0f);
+            t.init(nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f);
             alive = true;
             has_ray = true;
         }
