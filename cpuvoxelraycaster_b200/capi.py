@@ -57,6 +57,7 @@ _SIGNATURES = {
     "vrt_host_camera_rotation": (C.c_int, [_vp, _vp, _vp]),
     "vrt_lsvo_create": (C.c_int, [_vp, _vp, _u64, _u32, _i32, C.POINTER(_vp)]),
     "vrt_lsvo_create_terrain": (C.c_int, [_vp, _u32, _i32, C.POINTER(_vp)]),
+    "vrt_scene_set_layout": (C.c_int, [_vp, _i32, _i32]),
     "vrt_scene_download_nodes": (C.c_int, [_vp, _vp, _u64, C.POINTER(_u64)]),
     "vrt_grid_create": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, C.POINTER(_vp)]),
     "vrt_svo_create": (C.c_int, [_vp, _vp, _u32, C.POINTER(_vp)]),

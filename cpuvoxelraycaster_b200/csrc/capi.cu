@@ -73,6 +73,9 @@ struct vrt_scene {
     uint64_t n_nodes = 0;
     uint64_t device_bytes = 0;
     unsigned long long* d_counters = nullptr;   // [0] Σ complexity of the last cast; [2..13] render rays/complexity per class
+    uint2* d_compact = nullptr;                 // optional compact breadth-first copy (vrt_scene_set_layout)
+    uint64_t n_compact = 0;
+    bool use_compact = false;
     uint8_t* d_tex = nullptr;                   // top (768 B) then side (768 B)
     bool has_tex = false;
     DeviceBuffer frame_accum, frame_rgba;       // vrt_render staging
@@ -262,6 +265,43 @@ int vrt_lsvo_create_terrain(vrt_context* ctx, uint32_t depth, int32_t guard, vrt
     return VRT_OK;
 }
 
+int vrt_scene_set_layout(vrt_scene* sc, int32_t layout, int32_t l2_persist) {
+    if (!sc) return fail(VRT_ERR_INVALID, "vrt_scene_set_layout: scene is NULL");
+    if (sc->kind != VRT_SCENE_LSVO) return fail(VRT_ERR_INVALID, "vrt_scene_set_layout: not an LSVO scene");
+    if (layout != 0 && layout != 1) return fail(VRT_ERR_INVALID, "vrt_scene_set_layout: layout must be 0 (reference) or 1 (compact)");
+    vrt_context* ctx = sc->ctx;
+    if (int s = use_device(ctx)) return s;
+    if (layout == 1 && !sc->d_compact) {
+        cudaError_t e = vrt::device_compact_lsvo(sc->d_nodes, sc->n_nodes, int(sc->depth), &sc->d_compact, &sc->n_compact, ctx->stream);
+        ctx->launches += 5 * (sc->depth + 1);
+        if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? fail(VRT_ERR_OOM, "vrt_scene_set_layout: device allocation failed")
+                                                                    : cuda_fail(e, "vrt_scene_set_layout");
+        sc->device_bytes += sc->n_compact * sizeof(uint2);
+    }
+    sc->use_compact = layout == 1;
+    // L2 access-policy window over the front of the node array (compact layout = top octree levels first)
+    cudaStreamAttrValue attr;
+    std::memset(&attr, 0, sizeof(attr));
+    if (l2_persist && sc->use_compact) {
+        int max_window = 0, max_persist = 0;
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+        size_t bytes = sc->n_compact * sizeof(uint2);
+        if (bytes > size_t(max_window)) bytes = size_t(max_window);
+        if (bytes > size_t(max_persist)) bytes = size_t(max_persist);
+        if (bytes) {
+            VRT_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes));
+            attr.accessPolicyWindow.base_ptr = sc->d_compact;
+            attr.accessPolicyWindow.num_bytes = bytes;
+            attr.accessPolicyWindow.hitRatio = 1.0f;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        }
+    }
+    VRT_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    return VRT_OK;
+}
+
 int vrt_scene_download_nodes(vrt_scene* sc, vrt_lnode* out, uint64_t cap, uint64_t* count) {
     if (!sc || !count) return fail(VRT_ERR_INVALID, "vrt_scene_download_nodes: NULL argument");
     if (sc->kind != VRT_SCENE_LSVO) return fail(VRT_ERR_INVALID, "vrt_scene_download_nodes: not an LSVO scene");
@@ -280,6 +320,7 @@ int vrt_scene_destroy(vrt_scene* sc) {
     cudaStreamSynchronize(sc->ctx->stream);
     if (sc->d_nodes) cudaFree(sc->d_nodes);
     if (sc->d_counters) cudaFree(sc->d_counters);
+    if (sc->d_compact) cudaFree(sc->d_compact);
     if (sc->d_tex) cudaFree(sc->d_tex);
     if (sc->d_grid_bits) cudaFree(sc->d_grid_bits);
     sc->frame_accum.release();
@@ -309,10 +350,10 @@ int vrt_cast_rays_device(vrt_scene* sc, const float* d_origin, const float* d_di
     switch (sc->kind) {
         case VRT_SCENE_LSVO:
             if (ctx->cast_variant == 0)
-                VRT_CUDA(vrt::launch_lsvo_cast_ref(sc->d_nodes, int(sc->depth), sc->guard, d_origin, d_dir, coef, bias, n, d_out,
+                VRT_CUDA(vrt::launch_lsvo_cast_ref(sc->use_compact ? sc->d_compact : sc->d_nodes, sc->use_compact, int(sc->depth), sc->guard, d_origin, d_dir, coef, bias, n, d_out,
                                                    sc->d_counters, ctx->stream));
             else
-                VRT_CUDA(vrt::launch_lsvo_cast_persistent(sc->d_nodes, int(sc->depth), sc->guard, d_origin, d_dir, coef, bias, n,
+                VRT_CUDA(vrt::launch_lsvo_cast_persistent(sc->use_compact ? sc->d_compact : sc->d_nodes, sc->use_compact, int(sc->depth), sc->guard, d_origin, d_dir, coef, bias, n,
                                                           d_out, sc->d_counters, ctx->refill_cast, ctx->stream));
             ctx->launches += 1;
             return VRT_OK;
@@ -416,7 +457,7 @@ int vrt_render_accumulate_device(vrt_scene* sc, const vrt_camera* cam, const vrt
         VRT_CUDA(vrt::launch_grid_render(sc->grid, sc->use_mip, make_launch(sc, cam, p), d_accum, sc->d_counters + kRenderCounters,
                                          ctx->stream));
     else if (ctx->render_variant == 0)
-        VRT_CUDA(vrt::launch_render_accumulate_ref(sc->d_nodes, make_launch(sc, cam, p), d_accum, sc->d_counters + kRenderCounters,
+        VRT_CUDA(vrt::launch_render_accumulate_ref(sc->use_compact ? sc->d_compact : sc->d_nodes, sc->use_compact, make_launch(sc, cam, p), d_accum, sc->d_counters + kRenderCounters,
                                                    ctx->stream));
     else
         VRT_CUDA(vrt::launch_render_persistent(sc->d_nodes, make_launch(sc, cam, p), d_accum, sc->d_counters + kRenderCounters,

@@ -7,7 +7,7 @@
 namespace vrt {
 
 // K1: LSVO<D>::castRay over a ray buffer, reference node layout (lsvo_kernels.cu)
-cudaError_t launch_lsvo_cast_ref(const uint2* nodes, int depth, int guard, const float* d_origin, const float* d_dir,
+cudaError_t launch_lsvo_cast_ref(const uint2* nodes, bool compact, int depth, int guard, const float* d_origin, const float* d_dir,
                                  float coef, float bias, uint64_t n, vrt_hit* d_out, unsigned long long* d_complexity,
                                  cudaStream_t stream);
 
@@ -49,7 +49,7 @@ struct RenderLaunch {
 };
 
 // K0+K4: ray generation, traversal, shading and accumulation for rows [row_begin,row_end) (render_kernels.cu)
-cudaError_t launch_render_accumulate_ref(const uint2* nodes, const RenderLaunch& L, uint32_t* d_accum,
+cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const RenderLaunch& L, uint32_t* d_accum,
                                          unsigned long long* d_counters, cudaStream_t stream);
 cudaError_t launch_resolve(const uint32_t* d_accum, uint8_t* d_rgba, int width, int row_begin, int row_end, int use_samples,
                            int tile_step, int tile_index, cudaStream_t stream);
@@ -60,7 +60,7 @@ namespace vrt {
 // K1p / K4p: persistent-thread variants with per-lane ray regeneration (persistent_kernels.cu).
 // `refill` = number of parked lanes that makes a warp leave the traversal loop (1..32).
 // d_counters: cast: [0] Σ complexity, [1] work counter; render: [0..11] stats, [12] work counter — zeroed by the caller.
-cudaError_t launch_lsvo_cast_persistent(const uint2* nodes, int depth, int guard, const float* d_origin, const float* d_dir,
+cudaError_t launch_lsvo_cast_persistent(const uint2* nodes, bool compact, int depth, int guard, const float* d_origin, const float* d_dir,
                                         float coef, float bias, uint64_t n, vrt_hit* d_out, unsigned long long* d_counters,
                                         int refill, cudaStream_t stream);
 cudaError_t launch_render_persistent(const uint2* nodes, const RenderLaunch& L, uint32_t* d_accum, unsigned long long* d_counters,
@@ -71,4 +71,6 @@ cudaError_t launch_grid_render(const GridLevels& g, bool use_mip, const RenderLa
 // Scene construction on the device (scene_device.cu): T(depth) in the reference's LNode layout, nothing crosses PCIe.
 // *d_slots is cudaMalloc'ed (the caller frees it); d_heights_out may be null.
 cudaError_t device_build_terrain_lsvo(int depth, uint2** d_slots, uint64_t* n_slots, int32_t* d_heights_out, cudaStream_t stream);
+// Reference layout → compact breadth-first array of live nodes, on the device (scene_device.cu); caller frees *d_out.
+cudaError_t device_compact_lsvo(const uint2* d_ref, uint64_t n_ref, int depth, uint2** d_out, uint64_t* n_out, cudaStream_t stream);
 }  // namespace vrt

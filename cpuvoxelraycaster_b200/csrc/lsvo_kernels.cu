@@ -49,16 +49,19 @@ __global__ void __launch_bounds__(128) lsvo_cast_kernel(Nodes nodes, int depth, 
     if ((threadIdx.x & 31) == 0 && iters) atomicAdd(total_complexity, (unsigned long long)iters);
 }
 
-cudaError_t launch_lsvo_cast_ref(const uint2* nodes, int depth, int guard, const float* d_origin, const float* d_dir,
+cudaError_t launch_lsvo_cast_ref(const uint2* nodes, bool compact, int depth, int guard, const float* d_origin, const float* d_dir,
                                  float coef, float bias, uint64_t n, vrt_hit* d_out, unsigned long long* d_complexity,
                                  cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     const int block = 128;
     const size_t smem = size_t(depth + 1) * block * 8;
     const uint64_t grid = (n + block - 1) / block;
-    RefNodes nv{nodes};
-    lsvo_cast_kernel<RefNodes><<<unsigned(grid), block, smem, stream>>>(nv, depth, guard, d_origin, d_dir, coef, bias, n, d_out,
-                                                                       d_complexity);
+    if (compact)
+        lsvo_cast_kernel<CompactNodes><<<unsigned(grid), block, smem, stream>>>(CompactNodes{nodes}, depth, guard, d_origin, d_dir, coef,
+                                                                               bias, n, d_out, d_complexity);
+    else
+        lsvo_cast_kernel<RefNodes><<<unsigned(grid), block, smem, stream>>>(RefNodes{nodes}, depth, guard, d_origin, d_dir, coef, bias, n,
+                                                                           d_out, d_complexity);
     return cudaGetLastError();
 }
 

@@ -273,19 +273,25 @@ static int resident_blocks(K kernel, int block, size_t smem) {
     return per_sm * sms;            // a whole number of CTAs per SM: 148 x occupancy on B200
 }
 
-cudaError_t launch_lsvo_cast_persistent(const uint2* nodes, int depth, int guard, const float* d_origin, const float* d_dir,
-                                        float coef, float bias, uint64_t n, vrt_hit* d_out, unsigned long long* d_counters,
-                                        int refill, cudaStream_t stream) {
-    if (n == 0) return cudaSuccess;
+template <typename Nodes>
+static cudaError_t cast_persistent(Nodes nv, int depth, int guard, const float* d_origin, const float* d_dir, float coef, float bias,
+                                   uint64_t n, vrt_hit* d_out, unsigned long long* d_counters, int refill, cudaStream_t stream) {
     const int block = 128;
     const size_t smem = size_t(depth + 1) * block * 8;
-    auto kernel = lsvo_cast_persistent_kernel<RefNodes>;
+    auto kernel = lsvo_cast_persistent_kernel<Nodes>;
     uint64_t grid = uint64_t(resident_blocks(kernel, block, smem));
     const uint64_t need = (n + block - 1) / block;
     if (need < grid) grid = need;
-    RefNodes nv{nodes};
     kernel<<<unsigned(grid), block, smem, stream>>>(nv, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_counters, refill);
     return cudaGetLastError();
+}
+
+cudaError_t launch_lsvo_cast_persistent(const uint2* nodes, bool compact, int depth, int guard, const float* d_origin, const float* d_dir,
+                                        float coef, float bias, uint64_t n, vrt_hit* d_out, unsigned long long* d_counters,
+                                        int refill, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    return compact ? cast_persistent(CompactNodes{nodes}, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_counters, refill, stream)
+                   : cast_persistent(RefNodes{nodes}, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_counters, refill, stream);
 }
 
 cudaError_t launch_render_persistent(const uint2* nodes, const RenderLaunch& L, uint32_t* d_accum, unsigned long long* d_counters,

@@ -120,7 +120,7 @@ __global__ void resolve_kernel(const uint32_t* __restrict__ accum, uint8_t* __re
     }
 }
 
-cudaError_t launch_render_accumulate_ref(const uint2* nodes, const RenderLaunch& L, uint32_t* d_accum,
+cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const RenderLaunch& L, uint32_t* d_accum,
                                          unsigned long long* d_counters, cudaStream_t stream) {
     const int rows = L.row_end - L.row_begin;
     if (rows <= 0 || L.width <= 0 || L.spp <= 0) return cudaSuccess;
@@ -128,7 +128,6 @@ cudaError_t launch_render_accumulate_ref(const uint2* nodes, const RenderLaunch&
     const int tiles_x = (L.width + 31) / 32, tiles_y = ((rows + 3) / 4 + L.tile_step - 1 - L.tile_index) / L.tile_step;
     if (tiles_y <= 0) return cudaSuccess;
     const size_t smem = size_t(L.depth + 1) * block * 8;
-    RefNodes nv{nodes};
     // aim for >= ~96 waves of CTAs (4 CTAs x 148 SMs resident): measured 76.1 ms (4 chunks) vs 77.4 ms (1 chunk) on one GPU,
     // and the last wave stays a small fraction of the launch when a GPU owns 1/8 of the frame
     RenderLaunch Lc = L;
@@ -138,7 +137,10 @@ cudaError_t launch_render_accumulate_ref(const uint2* nodes, const RenderLaunch&
     if (chunks < 1) chunks = 1;
     if (L.spp_chunks > 0) chunks = L.spp_chunks < L.spp ? L.spp_chunks : L.spp;      // explicit override
     Lc.spp_chunks = int(chunks);
-    render_accumulate_kernel<RefNodes><<<unsigned(tiles * chunks), block, smem, stream>>>(nv, Lc, d_accum, d_counters);
+    if (compact)
+        render_accumulate_kernel<CompactNodes><<<unsigned(tiles * chunks), block, smem, stream>>>(CompactNodes{nodes}, Lc, d_accum, d_counters);
+    else
+        render_accumulate_kernel<RefNodes><<<unsigned(tiles * chunks), block, smem, stream>>>(RefNodes{nodes}, Lc, d_accum, d_counters);
     return cudaGetLastError();
 }
 

@@ -301,4 +301,76 @@ cudaError_t device_build_terrain_lsvo(int depth, uint2** d_slots, uint64_t* n_sl
     return cudaSuccess;
 }
 
+// ---- compaction: reference layout → breadth-first array of live nodes -------------------------------------------
+namespace {
+
+__global__ void compact_count_kernel(const uint2* __restrict__ ref, const uint32_t* __restrict__ list, uint32_t m,
+                                     uint32_t* __restrict__ cnt) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t raw = ref[list[i]].x;
+    cnt[i] = __popc((raw >> 8) & ~(raw >> 16) & 0xffu);
+}
+
+__global__ void compact_emit_kernel(const uint2* __restrict__ ref, const uint32_t* __restrict__ list, uint32_t m,
+                                    const uint32_t* __restrict__ off, uint32_t cur_base, uint32_t next_base,
+                                    uint2* __restrict__ out, uint32_t* __restrict__ next_list) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t id = list[i];
+    const uint2 w = ref[id];
+    out[cur_base + i] = make_uint2(w.x, next_base + off[i]);
+    uint32_t interior = (w.x >> 8) & ~(w.x >> 16) & 0xffu, k = off[i];
+    while (interior) {
+        const uint32_t s = __ffs(interior) - 1;
+        interior &= interior - 1;
+        next_list[k++] = id + w.y + s;                     // child slot in the reference layout: parent + child_offset + s
+    }
+}
+
+}  // namespace
+
+// Builds the compact array from a reference-layout array on the device.  *d_out is cudaMalloc'ed (caller frees).
+cudaError_t device_compact_lsvo(const uint2* d_ref, uint64_t n_ref, int depth, uint2** d_out, uint64_t* n_out, cudaStream_t stream) {
+    (void)depth;
+    const uint64_t cap = (n_ref - 1) / 8 + 1;              // live nodes = root + one per 8-slot block at most
+    Scratch sc;
+    uint2* out = nullptr;
+    VRT_TRY(cudaMalloc(&out, cap * sizeof(uint2)));
+    uint32_t *list_a = nullptr, *list_b = nullptr, *cnt = nullptr, *off = nullptr, *sums = nullptr, *d_total = nullptr;
+    cudaError_t e = sc.alloc(&list_a, cap);
+    if (e == cudaSuccess) e = sc.alloc(&list_b, cap);
+    if (e == cudaSuccess) e = sc.alloc(&cnt, cap);
+    if (e == cudaSuccess) e = sc.alloc(&off, cap);
+    if (e == cudaSuccess) e = sc.alloc(&sums, cap / kScanBlock + 2);
+    if (e == cudaSuccess) e = sc.alloc(&d_total, 1);
+    if (e == cudaSuccess) e = cudaMemsetAsync(list_a, 0, sizeof(uint32_t), stream);     // level 0: the root, slot 0
+    if (e != cudaSuccess) { cudaFree(out); return e; }
+    uint32_t m = 1, base = 0;
+    uint64_t total_nodes = 0;
+    while (m > 0) {
+        const uint32_t nb = (m + kScanBlock - 1) / kScanBlock;
+        compact_count_kernel<<<(m + 255) / 256, 256, 0, stream>>>(d_ref, list_a, m, cnt);
+        scan_block_sums<<<nb, kScanBlock, 0, stream>>>(cnt, int(m), sums);
+        scan_sums_serial<<<1, 1, 0, stream>>>(sums, int(nb), d_total);
+        scan_apply<<<nb, kScanBlock, 0, stream>>>(cnt, int(m), sums, off);
+        uint32_t next_m = 0;
+        e = cudaMemcpyAsync(&next_m, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e == cudaSuccess && uint64_t(base) + m + next_m > cap) e = cudaErrorInvalidValue;   // malformed input
+        if (e != cudaSuccess) { cudaFree(out); return e; }
+        compact_emit_kernel<<<(m + 255) / 256, 256, 0, stream>>>(d_ref, list_a, m, off, base, base + m, out, list_b);
+        total_nodes += m;
+        base += m;
+        m = next_m;
+        uint32_t* t = list_a; list_a = list_b; list_b = t;
+    }
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { cudaFree(out); return e; }
+    *d_out = out;
+    *n_out = total_nodes;
+    return cudaSuccess;
+}
+
 }  // namespace vrt

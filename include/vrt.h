@@ -122,6 +122,11 @@ int vrt_lsvo_create(vrt_context* ctx, const vrt_lnode* nodes, uint64_t n_nodes, 
  * main.cpp:61-76 and compileSVO lsvo_utils.cpp:4-49 in one pass; byte-identical to vrt_host_build_terrain_lsvo and to
  * the reference's own array) — nothing crosses PCIe. */
 int vrt_lsvo_create_terrain(vrt_context* ctx, uint32_t depth, int32_t guard, vrt_scene** out);
+/* Device-side node layout of an LSVO scene (no reference counterpart; results are identical for both):
+ *   0 = the reference's LNode array (default), 1 = compact breadth-first array of live nodes (8x smaller, built on the
+ *   device on first use).  l2_persist != 0 additionally pins the front of the compact array (the top octree levels)
+ *   in L2 through an access-policy window on the context's stream. */
+int vrt_scene_set_layout(vrt_scene* scene, int32_t layout, int32_t l2_persist);
 /* LSVO::data (lsvo.hpp:287): copy the scene's LNode array back to the host.  out == NULL → *count only. */
 int vrt_scene_download_nodes(vrt_scene* scene, vrt_lnode* out, uint64_t cap, uint64_t* count);
 /* Grid3D<X,Y,Z> (grid_3d.hpp:10-27): cell_types[(x*Y+y)*Z+z] = Cell::Type (0 = Empty).

@@ -134,3 +134,45 @@ def test_device_scene_large_depths(vrt, ctx):
         got = s.cast_rays(o, np.float32([[0.2, 0.5, 0.8]]))
         assert hit_flag(got)[0] and got["complexity"][0] > depth
         s.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_compact_layout_gives_identical_results(vrt, port, terrain9_nodes, textures, variant):
+    """The compact breadth-first node array (live nodes only) changes memory, not results: casts and frames are
+    byte-identical to the reference layout, for random voxel scenes too."""
+    c = vrt.Context(0)
+    c.set_option("cast_variant", variant)
+    s = vrt.LSVO(c, terrain9_nodes, 9)
+    rng = np.random.default_rng(21)
+    n = 200000
+    o = rng.uniform(1, 2, (n, 3)).astype(np.float32)
+    o[:, 1] = rng.uniform(1.0, 1.45, n)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    ref_layout = s.cast_rays(o, d, 0.25, 0.0)
+    s.set_layout(1, l2_persist=True)
+    assert s.info()["device_bytes"] < 1.2 * terrain9_nodes.nbytes       # reference copy + ~1/8
+    compact = s.cast_rays(o, d, 0.25, 0.0)
+    assert np.array_equal(ref_layout.view(np.uint8), compact.view(np.uint8))
+    want = port.lsvo_cast(terrain9_nodes, 9, o[:50000], d[:50000], 0.25, 0.0, threads=8)
+    assert_hits_equal(compact[:50000], want, hit_flag(compact[:50000]), "compact")
+    # a frame through the compact layout
+    s.set_textures(*textures)
+    cam = vrt.Camera(position=(256, 200, 256), view_angle=(0.3, -0.35), aperture=0.5, focal_length=60.0)
+    rc = vrt.RayCaster(s, (160, 90))
+    rc.setLightPosition(np.float32([-200, -1000, -300]) * np.float32(1 / 512.0) + np.float32(1))
+    rc.use_samples, rc.use_gi, rc.gi_bounces = True, True, 2
+    a = rc.render(cam, spp=2).copy()
+    s.set_layout(0)
+    rc.resetSamples()
+    b = rc.render(cam, spp=2)
+    assert np.array_equal(a, b) and a[..., :3].max() > 0
+    # random voxel scene, shallow depth, empty and full octrees
+    g = golden("lsvo_random6.npz")
+    r6 = vrt.LSVO(c, g["nodes"], 6)
+    r6.set_layout(1)
+    hits = r6.cast_rays(g["origin"], g["dir"])
+    assert_hits_equal(hits, g["hits_coef0"], hit_flag(hits), "compact random6")
+    e = vrt.LSVO.from_voxels(c, 4, np.zeros((0, 3), np.uint32))
+    e.set_layout(1)
+    assert not hit_flag(e.cast_rays([[1.5, 1.5, 1.1]], [[0, 0, 1]]))[0]
+    c.close()
