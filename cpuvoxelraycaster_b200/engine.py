@@ -179,6 +179,12 @@ class LSVO(Volumetric):
         self.handle = h
         self.depth = int(depth)
         self.n_nodes = len(nodes)
+        self._layout_from_env()
+
+    def _layout_from_env(self):
+        v = os.environ.get("VRT_LAYOUT")                       # measurement override: "1" compact, "1p" compact + L2 window
+        if v:
+            self.set_layout(int(v[0]), v.endswith("p"))
 
     @classmethod
     def from_terrain(cls, ctx, depth, guard=0, on_device=True):
@@ -192,6 +198,7 @@ class LSVO(Volumetric):
         self.handle = h
         self.depth = int(depth)
         self.n_nodes = len(self)
+        self._layout_from_env()
         return self
 
     def set_layout(self, layout, l2_persist=False):
