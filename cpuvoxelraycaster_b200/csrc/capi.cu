@@ -59,6 +59,7 @@ struct vrt_context {
     // frames keep one lane per pixel (coherent primary/shadow rays lose more from de-phasing than GI rays gain).
     int cast_variant = 1, render_variant = 0;
     int spp_chunks = 0;                        // K4: 0 = automatic
+    int samples_per_warp = 0;                  // K4: lanes sharing a pixel (power of two), 0 = automatic
     int refill_cast = 0, refill_render = 16;   // parked lanes that trigger a refill (1..32); cast: 0 = warp-adaptive
     DeviceBuffer scratch_in, scratch_out;   // host-variant staging
 };
@@ -163,6 +164,7 @@ int vrt_context_set_option(vrt_context* ctx, const char* key, int value) {
     if (k == "cast_variant" && (value == 0 || value == 1)) ctx->cast_variant = value;
     else if (k == "render_variant" && (value == 0 || value == 1)) ctx->render_variant = value;
     else if (k == "spp_chunks" && value >= 0 && value <= 4096) ctx->spp_chunks = value;
+    else if (k == "samples_per_warp" && value >= 0 && value <= 32 && (value & (value - 1)) == 0) ctx->samples_per_warp = value;
     else if (k == "refill_cast" && value >= 0 && value <= 32) ctx->refill_cast = value;
     else if (k == "refill_render" && value >= 1 && value <= 32) ctx->refill_render = value;
     else return fail(VRT_ERR_INVALID, "vrt_context_set_option: unknown key or value out of range: " + k);
@@ -426,6 +428,7 @@ vrt::RenderLaunch make_launch(const vrt_scene* sc, const vrt_camera* cam, const 
     for (int i = 0; i < 3; ++i) L.light[i] = p->light_position[i];
     L.cam = *cam;
     L.spp_chunks = sc->ctx->spp_chunks;
+    L.samples_per_warp = sc->ctx->samples_per_warp;
     L.roughness = p->roughness;
     L.max_bounds = p->max_bounds;
     L.tile_step = p->tile_step > 1 ? p->tile_step : 1;

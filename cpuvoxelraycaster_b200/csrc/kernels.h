@@ -39,6 +39,7 @@ struct RenderLaunch {
     int use_gi, gi_bounces;
     int tile_step, tile_index;   // 4-row tiles t with t % tile_step == tile_index are rendered
     int spp_chunks;              // K4: runs the samples are cut into (0 = chosen by the launcher)
+    int samples_per_warp;        // K4: lanes sharing a pixel, power of two 1..32 (0 = chosen by the launcher)
     uint32_t seed_lo, seed_hi;
     float light[3];
     vrt_camera cam;

@@ -32,50 +32,69 @@ __global__ void __launch_bounds__(128, 4) render_accumulate_kernel(Nodes nodes, 
     const int chunk = int(blockIdx.x) / (tiles_x * tiles_y), tile = int(blockIdx.x) - chunk * tiles_x * tiles_y;
     const int bx = tile % tiles_x, by = tile / tiles_x;
     const int s_begin = (chunk * L.spp) / L.spp_chunks, s_end = ((chunk + 1) * L.spp) / L.spp_chunks;
-    const int x = bx * 32 + warp * 8 + (lane & 7);
-    // 4-row tiles are dealt round-robin to tile_step owners (multi-GPU row partition, balanced sky/terrain)
-    const int y = L.row_begin + (by * L.tile_step + L.tile_index) * 4 + (lane >> 3);
+    // Lane → (pixel, sample) mapping inside the warp's 8x4 pixel tile.  Q = L.samples_per_warp lanes share a pixel and
+    // take consecutive samples; the tile's 32 pixels are walked in Q groups of P = 32/Q pixels.  Q = 1 is the plain
+    // one-lane-per-pixel mapping.  With many samples per pixel, lanes of one pixel cast nearly identical primary and
+    // shadow rays (they differ by the lens jitter only), which keeps the warp converged far better than 32 neighbouring
+    // pixels do.  Sums are integers, so the mapping cannot change the frame.
+    const int Q = L.samples_per_warp, P = 32 / Q;
+    const int sub = lane & (Q - 1);                        // which of the pixel's Q concurrent samples
+    const int runs = (s_end - s_begin) / Q;                // launcher guarantees divisibility
 
     uint32_t n_rays[6] = {0, 0, 0, 0, 0, 0};
     uint32_t n_iter[6] = {0, 0, 0, 0, 0, 0};
+    const float SCALE = 1.0f / float(1 << L.depth);                           // raycaster.hpp:123-124 / main.cpp:82
+    const float n_norm = SCALE * 0.0078125f * 2.0f;                           // raycaster.hpp:171-172
+    const float aspect = float(L.width) / float(L.height);                    // main.cpp:133
 
-    if (x < L.width && y < L.row_end) {
-        const float SCALE = 1.0f / float(1 << L.depth);                       // raycaster.hpp:123-124 / main.cpp:82
-        const float n_norm = SCALE * 0.0078125f * 2.0f;                       // raycaster.hpp:171-172
-        const float aspect = float(L.width) / float(L.height);                // main.cpp:133
-        const float lens_x = float(x) / float(L.height) - aspect * 0.5f;      // main.cpp:145
-        const float lens_y = float(y) / float(L.height) - 0.5f;               // main.cpp:146
+    for (int g = 0; g < Q; ++g) {
+        const int j = g * P + lane / Q;                    // pixel index inside the 8x4 tile
+        const int x = bx * 32 + warp * 8 + (j & 7);
+        // 4-row tiles are dealt round-robin to tile_step owners (multi-GPU row partition, balanced sky/terrain)
+        const int y = L.row_begin + (by * L.tile_step + L.tile_index) * 4 + (j >> 3);
+        const bool active = x < L.width && y < L.row_end;
         const uint32_t pixel = uint32_t(y) * uint32_t(L.width) + uint32_t(x);
         uint32_t sum_r = 0, sum_g = 0, sum_b = 0;
-
-        for (int s = s_begin; s < s_end; ++s) {
-            const uint32_t sample = uint32_t(L.sample_offset + s);
-            ChainState c;
-            NextRay nr;
-            chain_begin(L, c, pixel, sample, lens_x, lens_y, SCALE, nr);
-            int stage = kPrimary;
-            while (stage != kDone) {
-                LsvoResult r;
-                lsvo_cast_ray(nodes, stack, depth_offset, guard, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
+        if (active) {
+            const float lens_x = float(x) / float(L.height) - aspect * 0.5f;  // main.cpp:145
+            const float lens_y = float(y) / float(L.height) - 0.5f;           // main.cpp:146
+            for (int k = 0; k < runs; ++k) {
+                const uint32_t sample = uint32_t(L.sample_offset + s_begin + k * Q + sub);
+                ChainState c;
+                NextRay nr;
+                chain_begin(L, c, pixel, sample, lens_x, lens_y, SCALE, nr);
+                int stage = kPrimary;
+                while (stage != kDone) {
+                    LsvoResult r;
+                    lsvo_cast_ray(nodes, stack, depth_offset, guard, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
 #pragma unroll
-                for (int k = 0; k < 6; ++k) {                                  // predicated: keeps the counters in registers
-                    n_rays[k] += (stage == k) ? 1u : 0u;
-                    n_iter[k] += (stage == k) ? r.complexity : 0u;
+                    for (int k2 = 0; k2 < 6; ++k2) {                           // predicated: keeps the counters in registers
+                        n_rays[k2] += (stage == k2) ? 1u : 0u;
+                        n_iter[k2] += (stage == k2) ? r.complexity : 0u;
+                    }
+                    LsvoHit h;
+                    if (r.hit) lsvo_finish(r, nr.ox, nr.oy, nr.oz, L.depth, h);
+                    stage = chain_advance(L, c, stage, r, h, pixel, sample, SCALE, n_norm, nr);
                 }
-                LsvoHit h;
-                if (r.hit) lsvo_finish(r, nr.ox, nr.oy, nr.oz, L.depth, h);
-                stage = chain_advance(L, c, stage, r, h, pixel, sample, SCALE, n_norm, nr);
+                chain_colour(L, c, sum_r, sum_g, sum_b);
             }
-            chain_colour(L, c, sum_r, sum_g, sum_b);
         }
-        uint4* a = reinterpret_cast<uint4*>(accum) + pixel;                   // Sample, raycaster.hpp:18-24,87-90
-        if (L.spp_chunks == 1) {
-            uint4 v = *a;
-            v.x += sum_r; v.y += sum_g; v.z += sum_b; v.w += uint32_t(L.spp);
-            *a = v;
-        } else {
-            uint32_t* w = reinterpret_cast<uint32_t*>(a);
-            atomicAdd(w, sum_r); atomicAdd(w + 1, sum_g); atomicAdd(w + 2, sum_b); atomicAdd(w + 3, uint32_t(s_end - s_begin));
+        // the Q lanes of a pixel add up their sums; lane sub == 0 commits them
+        for (int o = Q >> 1; o > 0; o >>= 1) {
+            sum_r += __shfl_xor_sync(0xffffffffu, sum_r, o);
+            sum_g += __shfl_xor_sync(0xffffffffu, sum_g, o);
+            sum_b += __shfl_xor_sync(0xffffffffu, sum_b, o);
+        }
+        if (active && sub == 0) {
+            uint4* a = reinterpret_cast<uint4*>(accum) + pixel;               // Sample, raycaster.hpp:18-24,87-90
+            if (L.spp_chunks == 1) {
+                uint4 v = *a;
+                v.x += sum_r; v.y += sum_g; v.z += sum_b; v.w += uint32_t(L.spp);
+                *a = v;
+            } else {
+                uint32_t* w = reinterpret_cast<uint32_t*>(a);
+                atomicAdd(w, sum_r); atomicAdd(w + 1, sum_g); atomicAdd(w + 2, sum_b); atomicAdd(w + 3, uint32_t(s_end - s_begin));
+            }
         }
     }
 
@@ -137,6 +156,14 @@ cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const
     if (chunks < 1) chunks = 1;
     if (L.spp_chunks > 0) chunks = L.spp_chunks < L.spp ? L.spp_chunks : L.spp;      // explicit override
     Lc.spp_chunks = int(chunks);
+    // lanes per pixel: the largest power of two (<= 32) that divides every chunk's sample count
+    int q = 32;
+    for (long c = 0; c < chunks; ++c) {
+        const long ns = ((c + 1) * L.spp) / chunks - (c * L.spp) / chunks;
+        while (q > 1 && ns % q) q >>= 1;
+    }
+    if (L.samples_per_warp > 0 && L.samples_per_warp < q) q = L.samples_per_warp;       // explicit override (power of two)
+    Lc.samples_per_warp = q;
     if (compact)
         render_accumulate_kernel<CompactNodes><<<unsigned(tiles * chunks), block, smem, stream>>>(CompactNodes{nodes}, Lc, d_accum, d_counters);
     else

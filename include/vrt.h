@@ -92,7 +92,8 @@ int vrt_context_set_stream(vrt_context* ctx, void* stream);
  *                    regeneration, 0 = one thread per ray / pixel
  *   "refill_cast", "refill_render"  parked lanes (1..32) that make a persistent warp regenerate rays;
  *                    refill_cast 0 = warp-adaptive (default)
- *   "spp_chunks"     frame kernel: number of runs a pixel's samples are cut into (0 = automatic) */
+ *   "spp_chunks"     frame kernel: number of runs a pixel's samples are cut into (0 = automatic)
+ *   "samples_per_warp"  frame kernel: lanes of a warp sharing one pixel, power of two <= 32 (0 = automatic) */
 int vrt_context_set_option(vrt_context* ctx, const char* key, int value);
 /* number of kernel launches this context has enqueued so far (bench.py's gpu_launches) */
 uint64_t vrt_context_launch_count(const vrt_context* ctx);

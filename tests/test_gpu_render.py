@@ -146,3 +146,23 @@ def test_sample_chunking_is_exact(vrt, port, terrain9_nodes, textures, chunks):
     assert np.array_equal(rc.colors, accum) and np.array_equal(img, rgba)
     assert rc.last_stats["rays"] == list(stats.rays)
     c.close()
+
+
+@pytest.mark.parametrize("q,chunks,spp", [(1, 1, 8), (2, 1, 8), (8, 1, 8), (4, 2, 8), (32, 1, 32), (16, 2, 32), (0, 0, 6)])
+def test_lane_mapping_is_exact(vrt, port, terrain9_nodes, textures, q, chunks, spp):
+    """K4 may give several lanes of a warp the same pixel (consecutive samples) — integer sums, same frame."""
+    c = vrt.Context(0)
+    c.set_option("samples_per_warp", q)
+    c.set_option("spp_chunks", chunks)
+    s = vrt.LSVO(c, terrain9_nodes, 9)
+    s.set_textures(*textures)
+    W, H = 70, 42
+    cam = vrt.Camera(position=(256, 200, 256), view_angle=(0.3, -0.35), aperture=0.5, focal_length=60.0)
+    rc = vrt.RayCaster(s, (W, H))
+    rc.setLightPosition(default_light())
+    rc.use_samples, rc.use_gi, rc.gi_bounces = True, True, 2
+    img = rc.render(cam, spp=spp)
+    accum, rgba, stats = port.render(terrain9_nodes, port_params(W, H, 9, cam, default_light(), 1, 2, True, spp), *textures)
+    assert np.array_equal(rc.colors, accum) and np.array_equal(img, rgba)
+    assert rc.last_stats["rays"] == list(stats.rays) and rc.last_stats["complexity"] == list(stats.complexity)
+    c.close()
