@@ -147,13 +147,14 @@ cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const
     const int tiles_x = (L.width + 31) / 32, tiles_y = ((rows + 3) / 4 + L.tile_step - 1 - L.tile_index) / L.tile_step;
     if (tiles_y <= 0) return cudaSuccess;
     const size_t smem = size_t(L.depth + 1) * block * 8;
-    // aim for >= ~96 waves of CTAs (4 CTAs x 148 SMs resident): measured 76.1 ms (4 chunks) vs 77.4 ms (1 chunk) on one GPU,
-    // and the last wave stays a small fraction of the launch when a GPU owns 1/8 of the frame
+    // Sample runs: a power of two, enough for >= 28 waves of CTAs (4 CTAs x 148 SMs resident) so the last wave is a
+    // small part of the launch even when a GPU owns 1/8 of the frame, but runs of >= 8 samples so that 8+ lanes can
+    // share a pixel.  tools/probe_slice.py: whole frame 74.4 ms at (2 runs, 32 lanes/pixel) vs 77.7 ms at (4, 1);
+    // 1/8 slice 9.60 ms at (8, 8) vs 9.92 ms at (29, 1).
     RenderLaunch Lc = L;
     const long tiles = long(tiles_x) * tiles_y;
-    long chunks = (96L * 4 * 148 + tiles - 1) / tiles;
-    if (chunks > L.spp) chunks = L.spp;
-    if (chunks < 1) chunks = 1;
+    long chunks = 1;
+    while (chunks * tiles < 28L * 4 * 148 && chunks * 2 * 8 <= L.spp) chunks *= 2;
     if (L.spp_chunks > 0) chunks = L.spp_chunks < L.spp ? L.spp_chunks : L.spp;      // explicit override
     Lc.spp_chunks = int(chunks);
     // lanes per pixel: the largest power of two (<= 32) that divides every chunk's sample count
