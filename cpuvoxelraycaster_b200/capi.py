@@ -25,7 +25,13 @@ class RenderParams(C.Structure):
                 ("spp", C.c_int32), ("sample_offset", C.c_int32), ("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32),
                 ("light_position", C.c_float * 3), ("use_gi", C.c_int32), ("gi_bounces", C.c_int32),
                 ("use_samples", C.c_int32), ("accum_in", C.c_int32), ("tile_step", C.c_int32), ("tile_index", C.c_int32),
-                ("roughness", C.c_float), ("max_bounds", C.c_int32)]
+                ("roughness", C.c_float), ("max_bounds", C.c_int32),
+                ("checker", C.c_int32), ("checker_area_height", C.c_int32)]
+
+
+class PresentParams(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("median", C.c_int32),
+                ("old_value_conservation", C.c_float)]
 
 
 class RenderStats(C.Structure):
@@ -73,6 +79,8 @@ _SIGNATURES = {
     "vrt_render": (C.c_int, [_vp, C.POINTER(Camera), C.POINTER(RenderParams), _vp, _vp, C.POINTER(RenderStats)]),
     "vrt_scene_last_render_stats": (C.c_int, [_vp, C.POINTER(RenderStats)]),
     "vrt_autofocus": (C.c_int, [_vp, C.POINTER(Camera), C.POINTER(_f)]),
+    "vrt_present_device": (C.c_int, [_vp, _vp, _vp, C.POINTER(PresentParams)]),
+    "vrt_present": (C.c_int, [_vp, _vp, _vp, C.POINTER(PresentParams)]),
 }
 
 

@@ -415,6 +415,9 @@ int check_render_args(const vrt_scene* sc, const vrt_camera* cam, const vrt_rend
     if (cam && (p->spp <= 0 || p->gi_bounces < 0 || p->gi_bounces > 2)) return fail(VRT_ERR_INVALID, std::string(who) + ": spp must be > 0 and gi_bounces in 0..2");
     if (p->tile_step > 1 && (p->tile_index < 0 || p->tile_index >= p->tile_step)) return fail(VRT_ERR_INVALID, std::string(who) + ": tile_index must be in [0, tile_step)");
     if (cam && !sc->has_tex) return fail(VRT_ERR_INVALID, std::string(who) + ": call vrt_scene_set_textures first (raycaster.hpp:53-54)");
+    if (p->checker < 0 || p->checker > 2 || p->checker_area_height < 0) return fail(VRT_ERR_INVALID, std::string(who) + ": checker must be 0, 1 or 2 and checker_area_height >= 0");
+    if (cam && p->checker && sc->kind == VRT_SCENE_LSVO && sc->ctx->render_variant != 0)
+        return fail(VRT_ERR_UNSUPPORTED, std::string(who) + ": the checkerboard needs render_variant 0");
     return VRT_OK;
 }
 
@@ -431,6 +434,7 @@ vrt::RenderLaunch make_launch(const vrt_scene* sc, const vrt_camera* cam, const 
     L.samples_per_warp = sc->ctx->samples_per_warp;
     L.roughness = p->roughness;
     L.max_bounds = p->max_bounds;
+    L.checker = p->checker; L.checker_area_height = p->checker_area_height;
     L.tile_step = p->tile_step > 1 ? p->tile_step : 1;
     L.tile_index = p->tile_step > 1 ? p->tile_index : 0;
     L.tex_top = sc->d_tex; L.tex_side = sc->d_tex + 768;
@@ -516,6 +520,43 @@ int vrt_render(vrt_scene* sc, const vrt_camera* cam, const vrt_render_params* p,
     if (accum) VRT_CUDA(cudaMemcpyAsync(accum + row0 * 4, d_accum + row0 * 4, nrow * 16, cudaMemcpyDeviceToHost, ctx->stream));
     VRT_CUDA(cudaStreamSynchronize(ctx->stream));
     if (stats) return vrt_scene_last_render_stats(sc, stats);
+    return VRT_OK;
+}
+
+namespace {
+int check_present_args(const vrt_context* ctx, const void* frame, const void* display, const vrt_present_params* p, const char* who) {
+    if (!ctx || !frame || !display || !p) return fail(VRT_ERR_INVALID, std::string(who) + ": NULL argument");
+    if (p->width <= 0 || p->height <= 0 || p->width > 65536 || p->height > 65536) return fail(VRT_ERR_INVALID, std::string(who) + ": bad frame size");
+    if (p->median != 0 && p->median != 3 && p->median != 5) return fail(VRT_ERR_INVALID, std::string(who) + ": median must be 0, 3 or 5");
+    if (!(p->old_value_conservation >= 0.0f && p->old_value_conservation <= 1.0f))
+        return fail(VRT_ERR_INVALID, std::string(who) + ": old_value_conservation must be in [0, 1]");
+    return VRT_OK;
+}
+}  // namespace
+
+int vrt_present_device(vrt_context* ctx, const uint8_t* d_frame, uint8_t* d_display, const vrt_present_params* p) {
+    if (int s = check_present_args(ctx, d_frame, d_display, p, "vrt_present_device")) return s;
+    if (int s = use_device(ctx)) return s;
+    // sf::Color(255 * old_value_conservation, ...) and c2 = 255 * (1.0f - old_value_conservation): float → Uint8 (main.cpp:160-165)
+    const uint32_t c1 = uint8_t(255 * p->old_value_conservation), c2 = uint8_t(255 * (1.0f - p->old_value_conservation));
+    VRT_CUDA(vrt::launch_present(d_frame, d_display, p->width, p->height, p->median, c1, c2, ctx->stream));
+    ctx->launches += 1;
+    return VRT_OK;
+}
+
+int vrt_present(vrt_context* ctx, const uint8_t* frame, uint8_t* display, const vrt_present_params* p) {
+    if (int s = check_present_args(ctx, frame, display, p, "vrt_present")) return s;
+    if (int s = use_device(ctx)) return s;
+    const size_t bytes = size_t(p->width) * p->height * 4;
+    if (ctx->scratch_in.reserve(bytes) != cudaSuccess || ctx->scratch_out.reserve(bytes) != cudaSuccess)
+        return fail(VRT_ERR_OOM, "vrt_present: device allocation failed");
+    uint8_t* d_frame = static_cast<uint8_t*>(ctx->scratch_in.ptr);
+    uint8_t* d_display = static_cast<uint8_t*>(ctx->scratch_out.ptr);
+    VRT_CUDA(cudaMemcpyAsync(d_frame, frame, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    VRT_CUDA(cudaMemcpyAsync(d_display, display, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (int s = vrt_present_device(ctx, d_frame, d_display, p)) return s;
+    VRT_CUDA(cudaMemcpyAsync(display, d_display, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    VRT_CUDA(cudaStreamSynchronize(ctx->stream));
     return VRT_OK;
 }
 

@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(128) grid_render_kernel(GridLevels g, RenderLa
     const int x = bx * 32 + warp * 8 + (lane & 7);
     const int y = L.row_begin + (by * L.tile_step + L.tile_index) * 4 + (lane >> 3);
     uint32_t n_rays[3] = {0, 0, 0}, n_steps[3] = {0, 0, 0};      // primary, shadow, reflection
-    if (x < L.width && y < L.row_end) {
+    if (x < L.width && y < L.row_end && (!L.checker || (x & 1) == checker_x_parity(L.checker, L.checker_area_height, y))) {
         const float aspect = float(L.width) / float(L.height);
         const float lens_x = float(x) / float(L.height) - aspect * 0.5f, lens_y = float(y) / float(L.height) - 0.5f;
         const uint32_t pixel = uint32_t(y) * uint32_t(L.width) + uint32_t(x);

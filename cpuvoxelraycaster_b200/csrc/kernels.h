@@ -47,13 +47,25 @@ struct RenderLaunch {
     const uint8_t* tex_side;
     float roughness;           // grid frames: blur of mirror reflections
     int max_bounds;            // grid frames: reflection depth (RayCaster::max_bounds, raycaster.hpp:277)
+    int checker;               // 0 = every pixel, 1 / 2 = checkerboard with offset 0 / 1 (main.cpp:137,143)
+    int checker_area_height;   // thread-area height the checkerboard phase restarts at (0 = never)
 };
+
+// main.cpp:143: inside a thread area, rows start at area_start + (x + offset) % 2 and step by 2.
+// Returns the parity x must have for pixel (x, y) to be rendered this frame.
+__host__ __device__ inline int checker_x_parity(int checker, int area_height, int y) {
+    const int rel = area_height > 0 ? y % area_height : y;
+    return (rel + (checker - 1)) & 1;
+}
 
 // K0+K4: ray generation, traversal, shading and accumulation for rows [row_begin,row_end) (render_kernels.cu)
 cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const RenderLaunch& L, uint32_t* d_accum,
                                          unsigned long long* d_counters, cudaStream_t stream);
 cudaError_t launch_resolve(const uint32_t* d_accum, uint8_t* d_rgba, int width, int row_begin, int row_end, int use_samples,
                            int tile_step, int tile_index, cudaStream_t stream);
+// median filter + persistence blend of main.cpp:159-177 (present_kernels.cu)
+cudaError_t launch_present(const uint8_t* d_frame, uint8_t* d_display, int width, int height, int median, uint32_t c1, uint32_t c2,
+                           cudaStream_t stream);
 
 }  // namespace vrt
 

@@ -14,8 +14,11 @@
 namespace vrt {
 
 // 4 CTAs per SM (128 registers): more resident warps at fewer registers measured slower (profiles/r01_summary.md)
+#ifndef VRT_K4_MIN_CTAS
+#define VRT_K4_MIN_CTAS 4
+#endif
 template <typename Nodes>
-__global__ void __launch_bounds__(128, 4) render_accumulate_kernel(Nodes nodes, RenderLaunch L, uint32_t* __restrict__ accum,
+__global__ void __launch_bounds__(128, VRT_K4_MIN_CTAS) render_accumulate_kernel(Nodes nodes, RenderLaunch L, uint32_t* __restrict__ accum,
                                                                 unsigned long long* __restrict__ counters) {
     extern __shared__ uint2 smem[];
     Stack64<128> stack{smem + threadIdx.x};
@@ -25,7 +28,10 @@ __global__ void __launch_bounds__(128, 4) render_accumulate_kernel(Nodes nodes, 
 
     // 8x4 pixel tile per warp, 4 tiles side by side per block: coherent primary rays share nodes
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tiles_x = (L.width + 31) / 32;
+    // checkerboard frames (main.cpp:137,143) render every other pixel of a row: the tile's columns are then the
+    // indices of the rendered pixels, so that no lane idles
+    const int columns = L.checker ? (L.width + 1) / 2 : L.width;
+    const int tiles_x = (columns + 31) / 32;
     // blockIdx.x = chunk * tiles + tile: the pixel's samples are cut into L.spp_chunks runs handled by different CTAs
     // (more, shorter CTAs: keeps the tail short when a GPU owns only a slice of the frame; sums stay exact — integers)
     const int tiles_y = int(gridDim.x) / (tiles_x * L.spp_chunks);
@@ -41,17 +47,20 @@ __global__ void __launch_bounds__(128, 4) render_accumulate_kernel(Nodes nodes, 
     const int sub = lane & (Q - 1);                        // which of the pixel's Q concurrent samples
     const int runs = (s_end - s_begin) / Q;                // launcher guarantees divisibility
 
-    uint32_t n_rays[6] = {0, 0, 0, 0, 0, 0};
-    uint32_t n_iter[6] = {0, 0, 0, 0, 0, 0};
+    // ray statistics per class: private shared-memory counters (12 registers less across the traversal loop)
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + (L.depth + 1) * 128) + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) cnt[k * 128] = 0u;
     const float SCALE = 1.0f / float(1 << L.depth);                           // raycaster.hpp:123-124 / main.cpp:82
     const float n_norm = SCALE * 0.0078125f * 2.0f;                           // raycaster.hpp:171-172
     const float aspect = float(L.width) / float(L.height);                    // main.cpp:133
 
     for (int g = 0; g < Q; ++g) {
         const int j = g * P + lane / Q;                    // pixel index inside the 8x4 tile
-        const int x = bx * 32 + warp * 8 + (j & 7);
         // 4-row tiles are dealt round-robin to tile_step owners (multi-GPU row partition, balanced sky/terrain)
         const int y = L.row_begin + (by * L.tile_step + L.tile_index) * 4 + (j >> 3);
+        int x = bx * 32 + warp * 8 + (j & 7);
+        if (L.checker) x = 2 * x + checker_x_parity(L.checker, L.checker_area_height, y);
         const bool active = x < L.width && y < L.row_end;
         const uint32_t pixel = uint32_t(y) * uint32_t(L.width) + uint32_t(x);
         uint32_t sum_r = 0, sum_g = 0, sum_b = 0;
@@ -67,11 +76,8 @@ __global__ void __launch_bounds__(128, 4) render_accumulate_kernel(Nodes nodes, 
                 while (stage != kDone) {
                     LsvoResult r;
                     lsvo_cast_ray(nodes, stack, depth_offset, guard, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
-#pragma unroll
-                    for (int k2 = 0; k2 < 6; ++k2) {                           // predicated: keeps the counters in registers
-                        n_rays[k2] += (stage == k2) ? 1u : 0u;
-                        n_iter[k2] += (stage == k2) ? r.complexity : 0u;
-                    }
+                    cnt[stage * 128] += 1u;
+                    cnt[(6 + stage) * 128] += r.complexity;
                     LsvoHit h;
                     if (r.hit) lsvo_finish(r, nr.ox, nr.oy, nr.oz, L.depth, h);
                     stage = chain_advance(L, c, stage, r, h, pixel, sample, SCALE, n_norm, nr);
@@ -101,7 +107,7 @@ __global__ void __launch_bounds__(128, 4) render_accumulate_kernel(Nodes nodes, 
     // statistics: rays and Σ complexity per ray class (warp reduce, one atomic per warp and class)
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-        uint32_t a = n_rays[k], b = n_iter[k];
+        uint32_t a = cnt[k * 128], b = cnt[(6 + k) * 128];
         for (int o = 16; o > 0; o >>= 1) {
             a += __shfl_xor_sync(0xffffffffu, a, o);
             b += __shfl_xor_sync(0xffffffffu, b, o);
@@ -129,6 +135,7 @@ __global__ void resolve_kernel(const uint32_t* __restrict__ accum, uint8_t* __re
         const uint32_t n = a.w ? a.w : 1u;
         *out = make_uchar4(uint8_t(a.x / n), uint8_t(a.y / n), uint8_t(a.z / n), 255);
     } else {
+        if (a.w == 0u) return;                                                // not rendered this frame (checkerboard)
         const uchar4 old = *out;
         // the accumulator holds exactly one sample in this mode
         const uint8_t nr = mul_u8(uint8_t(a.x), 1.0f - 0.4f), ng = mul_u8(uint8_t(a.y), 1.0f - 0.4f), nb = mul_u8(uint8_t(a.z), 1.0f - 0.4f);
@@ -144,9 +151,10 @@ cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const
     const int rows = L.row_end - L.row_begin;
     if (rows <= 0 || L.width <= 0 || L.spp <= 0) return cudaSuccess;
     const int block = 128;
-    const int tiles_x = (L.width + 31) / 32, tiles_y = ((rows + 3) / 4 + L.tile_step - 1 - L.tile_index) / L.tile_step;
+    const int columns = L.checker ? (L.width + 1) / 2 : L.width;
+    const int tiles_x = (columns + 31) / 32, tiles_y = ((rows + 3) / 4 + L.tile_step - 1 - L.tile_index) / L.tile_step;
     if (tiles_y <= 0) return cudaSuccess;
-    const size_t smem = size_t(L.depth + 1) * block * 8;
+    const size_t smem = size_t(L.depth + 1) * block * 8 + 12 * block * sizeof(uint32_t);   // stacks + statistics
     // Sample runs: a power of two, enough for >= 28 waves of CTAs (4 CTAs x 148 SMs resident) so the last wave is a
     // small part of the launch even when a GPU owns 1/8 of the frame, but runs of >= 8 samples so that 8+ lanes can
     // share a pixel.  tools/probe_slice.py: whole frame 74.4 ms at (2 runs, 32 lanes/pixel) vs 77.7 ms at (4, 1);

@@ -335,6 +335,9 @@ class RayCaster:
         self.gi_bounces = 1
         self.roughness = 0.0            # grid volumes: blur of Cell::Mirror reflections (extension)
         self.max_bounds = 4             # raycaster.hpp:277
+        self.checker_board_offset = None   # None = every pixel; 0 / 1 = the checkerboard of main.cpp:137,143
+        self.checker_area_height = 0       # RENDER_HEIGHT / area_count (main.cpp:132); 0 = one area
+        self.display = None                # denoised_tex of main.cpp:159-177, made by present()
         self.seed = (0x5EED, 0)
         self.sample_count = 0
         self.last_stats = None
@@ -358,11 +361,14 @@ class RayCaster:
         p.light_position[:] = [float(x) for x in self.light_position]
         p.use_gi, p.gi_bounces, p.use_samples = int(self.use_gi), int(self.gi_bounces), int(self.use_samples)
         p.roughness, p.max_bounds = float(self.roughness), int(self.max_bounds)
+        p.checker = 0 if self.checker_board_offset is None else 1 + (int(self.checker_board_offset) & 1)
+        p.checker_area_height = int(self.checker_area_height)
         return p
 
     def render(self, camera, spp=1, row_begin=0, row_end=0):
-        """One frame (all pixels, no checkerboard): `spp` renderRay passes per pixel, then samples_to_image when
-        use_samples, else the 0.4/0.6 temporal blend into render_image (raycaster.hpp:77-91)."""
+        """One frame: `spp` renderRay passes per pixel (every pixel, or the checkerboard half selected by
+        checker_board_offset), then samples_to_image when use_samples, else the 0.4/0.6 temporal blend into
+        render_image (raycaster.hpp:77-91)."""
         p = self.params(spp, row_begin, row_end)
         stats = capi.RenderStats()
         if self.use_samples:
@@ -375,6 +381,18 @@ class RayCaster:
             self.sample_count += int(spp)
         self.last_stats = dict(rays=list(stats.rays), complexity=list(stats.complexity))
         return self.render_image
+
+    def present(self, median=0, old_value_conservation=None):
+        """The presentation step of the main loop (src/main.cpp:159-177): optional 3x3 / 5x5 median
+        (res/median_3.frag, res/median.frag) and the persistence blend into `display`."""
+        if old_value_conservation is None:
+            old_value_conservation = 0.0 if self.use_samples else 0.1          # main.cpp:160
+        W, H = self.render_size
+        if self.display is None:
+            self.display = np.zeros((H, W, 4), np.uint8)
+        p = capi.PresentParams(W, H, int(median), float(old_value_conservation))
+        check(lib().vrt_present(self.svo.ctx.handle, ptr(self.render_image), ptr(self.display), C.byref(p)))
+        return self.display
 
     def samples_to_image(self):
         """raycaster.hpp:94-103 — already applied on the device by render() when use_samples."""

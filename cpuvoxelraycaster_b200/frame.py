@@ -66,6 +66,8 @@ class FrameRenderer:
         self.host_frame = torch.empty(self.H * self.row_bytes, dtype=torch.uint8).pin_memory()
         self.use_gi, self.gi_bounces, self.use_samples = False, 1, True
         self.roughness, self.max_bounds = 0.0, 4
+        self.checker_board_offset, self.checker_area_height = None, 0     # main.cpp:137,143 / :132
+        self.display = None                                               # denoised_tex of main.cpp:159-177
         self.seed = (0x5EED, 0)
         self.light = np.zeros(3, np.float32)
 
@@ -78,6 +80,8 @@ class FrameRenderer:
         p.use_gi, p.gi_bounces, p.use_samples = int(self.use_gi), int(self.gi_bounces), int(self.use_samples)
         p.tile_step, p.tile_index = self.world, self.rank
         p.roughness, p.max_bounds = float(self.roughness), int(self.max_bounds)
+        p.checker = 0 if self.checker_board_offset is None else 1 + (int(self.checker_board_offset) & 1)
+        p.checker_area_height = int(self.checker_area_height)
         return p
 
     # -- device-resident frame: enqueue only (the caller owns stream/synchronisation) --
@@ -102,6 +106,16 @@ class FrameRenderer:
             self.resolve(p)
             frame = self.gather()
         return frame.view(self.H_pad, self.W, 4)[: self.H]
+
+    def present_device(self, frame, median=0, old_value_conservation=0.1):
+        """main.cpp:159-177 on the device: optional median, then the persistence blend of `frame` (a device uint8
+        [H, W, 4] view such as render_device returns) into the display surface, which is returned."""
+        if self.display is None:
+            self.display = torch.zeros(self.H * self.W * 4, dtype=torch.uint8, device=self.device)
+        p = capi.PresentParams(self.W, self.H, int(median), float(old_value_conservation))
+        with torch.cuda.stream(self.stream):
+            check(lib().vrt_present_device(self.scene.ctx.handle, ptr(frame), ptr(self.display), C.byref(p)))
+        return self.display.view(self.H, self.W, 4)
 
     def render(self, camera, spp, sample_offset=0):
         """The user-facing call: a finished frame in host memory (pinned), as numpy [H, W, 4] uint8."""

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VRT_ABI_VERSION 1
+#define VRT_ABI_VERSION 2
 
 typedef enum vrt_status {
     VRT_OK = 0,
@@ -180,6 +180,11 @@ typedef struct vrt_render_params {
     int32_t tile_index;          /*      are rendered/resolved — the balanced multi-GPU row partition */
     float roughness;             /* grid scenes: blur of Cell::Mirror reflections (0 = perfect mirror) */
     int32_t max_bounds;          /* grid scenes: reflection depth, RayCaster::max_bounds = 4 (raycaster.hpp:277) */
+    int32_t checker;             /* 0 = every pixel; 1 / 2 = the checkerboard of main.cpp:137,143 with
+                                  * checker_board_offset 0 / 1: pixel (x,y) is rendered iff
+                                  * (y - area_start(y)) % 2 == (x + offset) % 2; other pixels keep their value */
+    int32_t checker_area_height; /* height of the reference's thread areas (RENDER_HEIGHT / area_count, main.cpp:132;
+                                  * 135 in the demo): area_start(y) = y - y % area_height.  0 = one area (start 0) */
 } vrt_render_params;
 
 typedef struct vrt_render_stats {
@@ -206,6 +211,23 @@ int vrt_render_resolve_device(vrt_scene* scene, const vrt_render_params* p, cons
 int vrt_render(vrt_scene* scene, const vrt_camera* cam, const vrt_render_params* p, uint8_t* rgba, uint32_t* accum,
                vrt_render_stats* stats);
 int vrt_scene_last_render_stats(vrt_scene* scene, vrt_render_stats* stats);
+
+/* Presentation step of the main loop (main.cpp:159-177), fused into one kernel:
+ *   frame'   = median filter of `frame` (median = 0: none; 3 / 5: per-channel 3x3 / 5x5 median, clamp to edge — what
+ *              res/median_3.frag / res/median.frag compute; the reference ships them but never binds them)
+ *   display  = min(255, mul8(display, c1) + mul8(frame', c2))       "Add some persistence to reduce the noise"
+ * with c1 = uint8(255 * old_value_conservation), c2 = uint8(255 * (1 - old_value_conservation)) (main.cpp:160-165; the
+ * demo uses 0.1 without samples, 0 with) and mul8(a, c) = (a * c + 127) / 255, the round-to-nearest product of two
+ * 8-bit unorm values that sf::BlendMultiply / sf::BlendAdd leave in an RGBA8 render texture.  Alpha is set to 255.
+ * d_frame and d_display are [height*width*4] uint8 device buffers and must not overlap. */
+typedef struct vrt_present_params {
+    int32_t width, height;
+    int32_t median;                  /* 0, 3 or 5 */
+    float old_value_conservation;    /* main.cpp:160 */
+} vrt_present_params;
+int vrt_present_device(vrt_context* ctx, const uint8_t* d_frame, uint8_t* d_display, const vrt_present_params* p);
+/* The same with host buffers (display is in/out). */
+int vrt_present(vrt_context* ctx, const uint8_t* frame, uint8_t* display, const vrt_present_params* p);
 /* Camera::getClosestPoint + the focal-length rule of main.cpp:115-121. */
 int vrt_autofocus(vrt_scene* scene, const vrt_camera* cam, float* focal_length);
 

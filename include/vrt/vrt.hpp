@@ -378,10 +378,21 @@ struct RayCasterT {
         p.light_position[0] = light_position.x; p.light_position[1] = light_position.y; p.light_position[2] = light_position.z;
         p.use_gi = use_gi; p.gi_bounces = gi_bounces; p.use_samples = use_samples;
         p.accum_in = use_samples ? 1 : 0;
+        p.checker = checker_board_offset < 0 ? 0 : 1 + (checker_board_offset & 1);
+        p.checker_area_height = checker_area_height;
         if (!use_samples) std::fill(colors.begin(), colors.end(), 0u);
         const vrt_camera c = camera.as_struct();
         vrt::check(vrt_render(svo.scene(), &c, &p, render_image.data(), colors.data(), &last_stats));
         if (use_samples) sample_count += uint32_t(p.spp);
+    }
+    // The presentation step of the main loop (main.cpp:159-177): optional 3x3 / 5x5 median (res/median_3.frag,
+    // res/median.frag) and the persistence blend of render_image into `display` (denoised_tex).
+    void present(int median = 0, float old_value_conservation = -1.0f) {
+        if (old_value_conservation < 0.0f) old_value_conservation = use_samples ? 0.0f : 0.1f;   // main.cpp:160
+        if (display.empty()) display.assign(render_image.size(), 0);
+        vrt_present_params p;
+        p.width = render_size.x; p.height = render_size.y; p.median = median; p.old_value_conservation = old_value_conservation;
+        vrt::check(vrt_present(vrt::default_context(), render_image.data(), display.data(), &p));
     }
     void samples_to_image() {}                          // raycaster.hpp:94-103: done on the device by render()
     void resetSamples() {                               // raycaster.hpp:105-116
@@ -396,6 +407,9 @@ struct RayCasterT {
 
     std::vector<uint32_t> colors;                       // Sample accumulators r,g,b,count per pixel (raycaster.hpp:259)
     std::vector<uint8_t> render_image;                  // RGBA8, row major (sf::Image render_image, raycaster.hpp:261)
+    std::vector<uint8_t> display;                       // RGBA8: denoised_tex of main.cpp:168-172, made by present()
+    int checker_board_offset = -1;                      // -1 = every pixel; 0 / 1 = the checkerboard of main.cpp:137,143
+    int checker_area_height = 0;                        // RENDER_HEIGHT / area_count (main.cpp:132); 0 = one area
     const LSVO<SVO_DEPTH_>& svo;
     const vrt::Vector2i render_size;
     glm::vec3 light_position;

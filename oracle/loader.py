@@ -31,7 +31,8 @@ class PortRenderParams(C.Structure):
                 ("use_gi", C.c_int32), ("gi_bounces", C.c_int32), ("use_samples", C.c_int32), ("spp", C.c_int32),
                 ("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32), ("sample_offset", C.c_int32),
                 ("row_begin", C.c_int32), ("row_end", C.c_int32), ("threads", C.c_int32),
-                ("tile_step", C.c_int32), ("tile_index", C.c_int32), ("roughness", C.c_float), ("max_bounds", C.c_int32)]
+                ("tile_step", C.c_int32), ("tile_index", C.c_int32), ("roughness", C.c_float), ("max_bounds", C.c_int32),
+                ("checker", C.c_int32), ("checker_area_height", C.c_int32)]
 
 
 class PortRenderStats(C.Structure):
@@ -43,7 +44,8 @@ class RefRenderParams(C.Structure):
                 ("view_angle", C.c_float * 2), ("fov", C.c_float), ("aperture", C.c_float),
                 ("focal_length", C.c_float), ("light_position", C.c_float * 3),
                 ("use_gi", C.c_int32), ("use_samples", C.c_int32), ("spp", C.c_int32), ("threads", C.c_int32),
-                ("row_begin", C.c_int32), ("row_end", C.c_int32), ("tile_step", C.c_int32), ("tile_index", C.c_int32)]
+                ("row_begin", C.c_int32), ("row_end", C.c_int32), ("tile_step", C.c_int32), ("tile_index", C.c_int32),
+                ("checker", C.c_int32), ("checker_area_height", C.c_int32), ("frames", C.c_int32)]
 
 
 class RefRayCounts(C.Structure):
@@ -162,6 +164,14 @@ class Port:
         tt, ts = np.ascontiguousarray(tex_top, np.uint8), np.ascontiguousarray(tex_side, np.uint8)
         self.lib.vo_grid_render(_p(cells), X, Y, Z, C.byref(params), _p(tt), _p(ts), _p(accum), _p(rgba), C.byref(stats))
         return accum, rgba, stats
+
+    def present(self, frame, display, median=0, old_value_conservation=0.1):
+        """main.cpp:159-177: returns the new display image (uint8 [H,W,4])."""
+        frame = np.ascontiguousarray(frame, np.uint8)
+        out = np.ascontiguousarray(display, np.uint8).copy()
+        H, W = frame.shape[:2]
+        self.lib.vo_present(_p(frame), _p(out), W, H, int(median), C.c_float(old_value_conservation))
+        return out
 
     def camera_ray(self, params, x, y, sample=0):
         o = np.zeros(3, np.float32)

@@ -671,6 +671,10 @@ static void render_range(void* c_, uint64_t b, uint64_t e) {
     for (uint64_t i = b; i < e; ++i) {
         const int32_t y = p->row_begin + (int32_t)(i / W), x = (int32_t)(i % W);
         if (p->tile_step > 1 && (((y - p->row_begin) >> 2) % p->tile_step) != p->tile_index) continue;
+        if (p->checker) {                                                                           /* main.cpp:143 */
+            const int32_t rel = p->checker_area_height > 0 ? y % p->checker_area_height : y;
+            if ((rel & 1) != ((x + p->checker - 1) & 1)) continue;
+        }
         const size_t px = (size_t)y * W + (size_t)x;
         for (int32_t s = 0; s < p->spp; ++s) {
             uint8_t rgb[3];
@@ -817,3 +821,33 @@ void vo_grid_render(const uint8_t* cells, int X, int Y, int Z, const vo_render_p
     pthread_mutex_destroy(&c.lock);
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* Presentation: median + persistence blend, main.cpp:159-177 (specified in port.h)             */
+static int cmp_u8_(const void* a, const void* b) { return (int)*(const uint8_t*)a - (int)*(const uint8_t*)b; }
+
+void vo_present(const uint8_t* frame, uint8_t* display, int32_t width, int32_t height, int32_t median,
+                float old_value_conservation) {
+    const uint32_t c1 = (uint8_t)(255 * old_value_conservation);                 /* main.cpp:162 */
+    const uint32_t c2 = (uint8_t)(255 * (1.0f - old_value_conservation));        /* main.cpp:164-165 */
+    const int r = median == 3 ? 1 : median == 5 ? 2 : 0;
+    for (int32_t y = 0; y < height; ++y)
+        for (int32_t x = 0; x < width; ++x) {
+            uint8_t* d = display + 4 * ((size_t)y * width + x);
+            for (int k = 0; k < 3; ++k) {
+                uint8_t w[25];
+                int n = 0;
+                for (int dy = -r; dy <= r; ++dy)
+                    for (int dx = -r; dx <= r; ++dx) {
+                        int sx = x + dx, sy = y + dy;
+                        sx = sx < 0 ? 0 : sx >= width ? width - 1 : sx;
+                        sy = sy < 0 ? 0 : sy >= height ? height - 1 : sy;
+                        w[n++] = frame[4 * ((size_t)sy * width + sx) + k];
+                    }
+                qsort(w, (size_t)n, 1, cmp_u8_);
+                const uint32_t f = w[n / 2];
+                const uint32_t v = (d[k] * c1 + 127u) / 255u + (f * c2 + 127u) / 255u;
+                d[k] = (uint8_t)(v > 255u ? 255u : v);
+            }
+            d[3] = 255;
+        }
+}

@@ -80,6 +80,8 @@ typedef struct vo_render_params {
     int32_t tile_step, tile_index; /* > 1: only 4-row tiles t (from row_begin) with t % tile_step == tile_index */
     float roughness;               /* vo_grid_render: blur of mirror reflections (0 = perfect mirror) */
     int32_t max_bounds;            /* vo_grid_render: reflection depth, RayCaster::max_bounds = 4 (raycaster.hpp:277) */
+    int32_t checker;               /* 0 = all pixels; 1 / 2 = checker_board_offset 0 / 1 of main.cpp:137,143 */
+    int32_t checker_area_height;   /* RENDER_HEIGHT / area_count (main.cpp:132); 0 = a single area */
 } vo_render_params;
 
 typedef struct vo_render_stats {
@@ -108,6 +110,15 @@ void vo_render(const vo_lnode* nodes, const vo_render_params* p, const uint8_t* 
  * cells[(x*Y+y)*Z+z] = Cell::Type.  stats->rays: [0] primary, [1] shadow, [2] reflection rays. */
 void vo_grid_render(const uint8_t* cells, int X, int Y, int Z, const vo_render_params* p, const uint8_t* tex_top,
                     const uint8_t* tex_side, uint32_t* accum, uint8_t* rgba, vo_render_stats* stats);
+
+/* Presentation step, main.cpp:159-177 ("parity unpinned": the reference does this with OpenGL blending through SFML,
+ * which is not available here; the arithmetic below is the round-to-nearest 8-bit unorm blending a GPU performs):
+ *   frame' = per-channel median of the (median x median) window around each pixel, edges clamped (res/median_3.frag,
+ *            res/median.frag; median = 0: frame itself);
+ *   display = min(255, (display * c1 + 127) / 255 + (frame' * c2 + 127) / 255), alpha 255,
+ *   c1 = (uint8)(255 * old_value_conservation), c2 = (uint8)(255 * (1 - old_value_conservation))   (main.cpp:160-165). */
+void vo_present(const uint8_t* frame, uint8_t* display, int32_t width, int32_t height, int32_t median,
+                float old_value_conservation);
 
 /* Camera::getRay + main.cpp:145-149 for one pixel/sample with the Philox lattice RNG. */
 void vo_camera_ray(const vo_render_params* p, int32_t x, int32_t y, int32_t sample, float origin[3], float dir[3]);

@@ -74,6 +74,10 @@ struct vrt_ref_render_params {
     int32_t threads;          // 1 = deterministic single thread, >1 = swarm tiles (racy RNG, as the reference)
     int32_t row_begin, row_end;  // rows [begin,end) only (bounded samples for the CPU baseline)
     int32_t tile_step, tile_index;  // > 1: only 4-row tiles t (from row_begin) with t % tile_step == tile_index
+    int32_t checker;          // 0 = every pixel; 1 / 2 = checker_board_offset 0 / 1 in the FIRST frame (main.cpp:137,143)
+    int32_t checker_area_height;  // RENDER_HEIGHT / area_count (main.cpp:132); 0 = a single area starting at row 0
+    int32_t frames;           // > 1: that many consecutive frames on the same RayCaster (the temporal blend of
+                              // raycaster.hpp:79-85 accumulates), the checkerboard offset flipping each frame (main.cpp:137)
 };
 
 // castRay invocations seen by the counting subclass below, split by cone coefficient:
@@ -353,11 +357,19 @@ int vrt_ref_render(void* scene, const vrt_ref_render_params* p, uint8_t* rgba_ra
     const auto t0 = std::chrono::steady_clock::now();
     // Workers take interleaved columns; the reference's 4x4 tiles (main.cpp:140-143) are the special
     // case threads == 16 up to the assignment of pixels to workers, which does not change the work.
-    const int code = run_parallel(threads, [&](uint32_t id, uint32_t total) {
+    const int32_t frames = p->frames > 1 ? p->frames : 1;
+    int code = 0;
+    for (int32_t frame = 0; frame < frames && code >= 0; ++frame) {
+    const int32_t checker_offset = p->checker ? ((p->checker - 1 + frame) & 1) : 0;
+    code = run_parallel(threads, [&](uint32_t id, uint32_t total) {
         for (int32_t pass = 0; pass < p->spp; ++pass)
             for (uint32_t x = id; x < W; x += total)
                 for (uint32_t y = r0; y < r1; ++y) {
                     if (p->tile_step > 1 && int32_t(((y - r0) >> 2) % uint32_t(p->tile_step)) != p->tile_index) continue;
+                    if (p->checker) {   // main.cpp:143: y = area_start + (x + offset) % 2, step 2
+                        const uint32_t rel = p->checker_area_height > 0 ? y % uint32_t(p->checker_area_height) : y;
+                        if ((rel & 1u) != ((x + uint32_t(checker_offset)) & 1u)) continue;
+                    }
                     const float lens_x = float(x) / float(H) - aspect_ratio * 0.5f;
                     const float lens_y = float(y) / float(H) - 0.5f;
                     const CameraRay cr = cam.getRay(glm::vec2(lens_x, lens_y));
@@ -373,6 +385,7 @@ int vrt_ref_render(void* scene, const vrt_ref_render_params* p, uint8_t* rgba_ra
                     raycaster.renderRay(sf::Vector2i(x, y), start, cr.ray, time);
                 }
     });
+    }
     const auto t1 = std::chrono::steady_clock::now();
     if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
     if (counts) {

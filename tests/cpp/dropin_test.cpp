@@ -67,6 +67,18 @@ int main(int argc, char** argv) {
         raycaster.render(camera, 1);                       // progressive: 3 samples in total
         std::printf("frame hash=%016llx samples=%u rays=%llu\n", (unsigned long long)fnv1a(raycaster.render_image.data(), raycaster.render_image.size()),
                     raycaster.sample_count, (unsigned long long)(raycaster.last_stats.rays[0] + raycaster.last_stats.rays[1]));
+        // --- the interactive loop: checkerboard halves, 0.4/0.6 temporal blend, median + persistence (main.cpp:137-172)
+        RayCaster live(lsvo, vrt::Vector2i(256, 144), tex.data(), tex.data() + 768);
+        live.setLightPosition(glm::vec3(-200, -1000, -300) * scale + glm::vec3(1.0f));
+        live.checker_area_height = 36;                     // 144 / 4 areas (main.cpp:132)
+        camera.aperture = 0.0f;
+        for (int frame = 0; frame < 3; ++frame) {
+            live.checker_board_offset = 1 - (frame & 1);   // main.cpp:137 flips before rendering, starting from 0
+            live.render(camera);
+            live.present(3);
+        }
+        std::printf("live hash=%016llx display=%016llx\n", (unsigned long long)fnv1a(live.render_image.data(), live.render_image.size()),
+                    (unsigned long long)fnv1a(live.display.data(), live.display.size()));
         // --- Grid3D / MipmapGrid3D agree
         Grid3D<32, 32, 32>* g = new Grid3D<32, 32, 32>();
         MipmapGrid3D<32, 32, 32, 3>* m = new MipmapGrid3D<32, 32, 32, 3>();

@@ -19,7 +19,7 @@ def test_library_exports_every_symbol(vrt):
     lib = vrt.capi.lib()
     for name in declared_in_header():
         assert getattr(lib, name) is not None
-    assert lib.vrt_abi_version() == 1
+    assert lib.vrt_abi_version() == 2
     assert b"sm_100a" in lib.vrt_build_info()
 
 
@@ -27,7 +27,8 @@ def test_struct_sizes(vrt):
     import ctypes as C
     assert vrt.HIT.itemsize == 64 and vrt.LNODE.itemsize == 8
     assert C.sizeof(vrt.capi.Camera) == 15 * 4
-    assert C.sizeof(vrt.capi.RenderParams) == 19 * 4
+    assert C.sizeof(vrt.capi.RenderParams) == 21 * 4
+    assert C.sizeof(vrt.capi.PresentParams) == 4 * 4
     assert C.sizeof(vrt.capi.RenderStats) == 12 * 8
 
 

@@ -57,5 +57,21 @@ def test_dropin_matches_python_api(vrt, ctx, terrain9_nodes, textures):
     for b in rc.render_image.tobytes():
         h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
     assert out["frame"].startswith("hash=%016x samples=3" % h)
+    # the interactive loop (checkerboard + temporal blend + median/persistence presentation)
+    live = vrt.RayCaster(s, (256, 144))
+    live.setLightPosition(rc.light_position)
+    live.checker_area_height = 36
+    cam0 = vrt.Camera(position=(256, 200, 256), view_angle=(0.3, -0.35), aperture=0.0, focal_length=60.0)
+    for frame in range(3):
+        live.checker_board_offset = 1 - (frame & 1)
+        live.render(cam0)
+        live.present(median=3)
+
+    def fnv(a):
+        h = 1469598103934665603
+        for b in a.tobytes():
+            h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return h
+    assert out["live"] == "hash=%016x display=%016x" % (fnv(live.render_image), fnv(live.display))
     af = vrt.Camera(position=(256, 200, 256), view_angle=(0.3, -0.35)).autofocus(s)
     assert out["autofocus"] == "%.6f" % af

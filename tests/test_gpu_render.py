@@ -100,6 +100,53 @@ def test_temporal_blend_mode(vrt, scene9, port, terrain9_nodes, textures):
         prev = want
 
 
+@pytest.mark.parametrize("W,H,area_height,use_samples", [(160, 90, 0, False), (161, 75, 15, False), (96, 60, 15, True), (70, 44, 11, True)])
+def test_checkerboard_frames(vrt, scene9, port, terrain9_nodes, textures, W, H, area_height, use_samples):
+    """main.cpp:137-143: alternating checkerboard halves; the unrendered pixels keep their value."""
+    cam = vrt.Camera(position=(256, 200, 256), view_angle=(0.3, -0.35), focal_length=80.0, aperture=0.4)
+    rc = vrt.RayCaster(scene9, (W, H))
+    rc.setLightPosition(default_light())
+    rc.use_samples, rc.use_gi = use_samples, True
+    rc.checker_area_height = area_height
+    prev, acc = None, np.zeros((H, W, 4), np.uint32)
+    for frame in range(4):
+        rc.checker_board_offset = 1 - (frame & 1)
+        img = rc.render(cam, spp=2 if use_samples else 1).copy()
+        p = port_params(W, H, 9, cam, default_light(), 1, 1, use_samples, 2 if use_samples else 1, offset=2 * frame if use_samples else 0)
+        p.checker, p.checker_area_height = 1 + (1 - (frame & 1)), area_height
+        a, want, _ = port.render(terrain9_nodes, p, *textures, prev_rgba=prev)
+        if use_samples:
+            acc += a
+            assert np.array_equal(rc.colors, acc), "frame %d" % frame
+            rendered = acc[..., 3] > 0
+            assert np.array_equal(img[rendered][:, :3], (acc[rendered][:, :3] // acc[rendered][:, 3:4]).astype(np.uint8))
+        else:
+            assert np.array_equal(img, want), "frame %d" % frame
+            prev = want
+    n = rc.last_stats["rays"][0]
+    assert abs(n - (2 if use_samples else 1) * W * H / 2) <= (2 if use_samples else 1) * (H + W)
+
+
+@pytest.mark.parametrize("W,H", [(160, 90), (333, 77), (31, 9)])
+def test_present_matches_oracle(vrt, ctx, port, W, H):
+    """vrt_present (median + persistence blend, main.cpp:159-177) byte-exact against the oracle."""
+    import ctypes as C
+    from cpuvoxelraycaster_b200 import capi
+    rng = np.random.default_rng(W)
+    frame = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    for median in (0, 3, 5):
+        for ovc in (0.1, 0.0, 0.7):
+            display = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+            want = port.present(frame, display, median, ovc)
+            got = display.copy()
+            p = capi.PresentParams(W, H, median, ovc)
+            capi.check(capi.lib().vrt_present(ctx.handle, capi.ptr(frame), capi.ptr(got), C.byref(p)))
+            assert np.array_equal(got, want), (median, ovc)
+    bad = capi.PresentParams(W, H, 4, 0.1)
+    with pytest.raises(capi.VrtError):
+        capi.check(capi.lib().vrt_present(ctx.handle, capi.ptr(frame), capi.ptr(got), C.byref(bad)))
+
+
 def test_autofocus(vrt, scene9, port, terrain9_nodes):
     cam = vrt.Camera(position=(256, 200, 256), view_angle=(0.0, -0.6))
     f = cam.autofocus(scene9)

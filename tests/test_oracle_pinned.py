@@ -154,6 +154,60 @@ def test_raycaster_deterministic_frame_and_camera(port, ref, textures):
     ref.scene_destroy(sc)
 
 
+@pytest.mark.parametrize("W,H,area_height", [(128, 72, 18), (96, 60, 15), (64, 36, 0)])
+def test_checkerboard_frames_match_the_reference_loop(port, ref, textures, W, H, area_height):
+    """main.cpp:137-143 on the reference's own RayCaster: alternating checkerboard halves with the 0.4/0.6 temporal
+    blend (raycaster.hpp:79-85), 4 frames; area heights even, odd (the demo's 135 is odd) and a single area."""
+    from oracle import loader
+    ref.register_textures(*textures)
+    light = np.float32([-200, -1000, -300]) * np.float32(1 / 512.0) + np.float32(1)
+    sc = ref.scene_terrain(9)
+    nodes = port.build_terrain(9)
+    view = [0.7, -0.4]
+    pr = _ref_params(loader, W, H, view, 0.0, 0, 0, 1, light)
+    pr.checker, pr.checker_area_height, pr.frames = 2, area_height, 4       # main.cpp:98,137: the first frame has offset 1
+    want = ref.render(sc, pr)["image"]
+    pp = _port_params(loader, ref, W, H, view, 0.0, 0, 0, 1, light)
+    pp.checker_area_height = area_height
+    img = None
+    for frame in range(4):
+        pp.checker = 1 + ((1 + frame) & 1)
+        _, img, _ = port.render(nodes, pp, *textures, prev_rgba=img)
+    assert np.array_equal(img, want)
+    # sample mode: each half accumulates its own pixels
+    pr = _ref_params(loader, W, H, view, 0.0, 0, 1, 1, light)
+    pr.checker, pr.checker_area_height, pr.frames = 1, area_height, 2
+    want = ref.render(sc, pr)
+    pp = _port_params(loader, ref, W, H, view, 0.0, 0, 1, 1, light)
+    pp.checker_area_height = area_height
+    acc = np.zeros((H, W, 4), np.uint32)
+    for frame in range(2):
+        pp.checker = 1 + (frame & 1)
+        a, _, _ = port.render(nodes, pp, *textures)
+        acc += a
+    assert np.array_equal(acc, want["samples"].astype(np.uint32)) and (acc[..., 3] == 1).all()
+    ref.scene_destroy(sc)
+
+
+def test_present_restatement(port):
+    """vo_present against an independent numpy statement of main.cpp:159-177 (median_3.frag / median.frag windows)."""
+    rng = np.random.default_rng(5)
+    H, W = 37, 53
+    frame = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    display = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    for median in (0, 3, 5):
+        for ovc in (0.1, 0.0, 0.5, 1.0):
+            got = port.present(frame, display, median, ovc)
+            r = median // 2
+            pad = np.pad(frame[..., :3], ((r, r), (r, r), (0, 0)), mode="edge")
+            win = np.stack([pad[dy:dy + H, dx:dx + W] for dy in range(2 * r + 1) for dx in range(2 * r + 1)], 0)
+            f = np.sort(win, axis=0)[win.shape[0] // 2].astype(np.uint32)
+            c1, c2 = int(np.float32(255) * np.float32(ovc)), int(np.float32(255) * (np.float32(1.0) - np.float32(ovc)))
+            want = np.minimum(255, (display[..., :3].astype(np.uint32) * c1 + 127) // 255 + (f * c2 + 127) // 255)
+            assert np.array_equal(got[..., :3], want.astype(np.uint8)), (median, ovc)
+            assert (got[..., 3] == 255).all()
+
+
 def psnr(a, b):
     mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
     return 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
