@@ -9,8 +9,8 @@ reference too, src/main.cpp:59-86, and is exposed as `host_*`.)
 """
 from . import capi
 from .capi import HIT, LNODE, VrtError
-from .engine import (Camera, Context, Grid3D, LSVO, MipmapGrid3D, RayCaster, SVO, Volumetric, host_build_lsvo_from_voxels,
+from .engine import (Camera, CameraController, FlyController, ReplayElements, Context, Grid3D, LSVO, MipmapGrid3D, RayCaster, SVO, Volumetric, host_build_lsvo_from_voxels,
                      host_build_terrain_lsvo, host_terrain_heights)
 
 __all__ = ["capi", "HIT", "LNODE", "VrtError", "Context", "Volumetric", "LSVO", "Grid3D", "MipmapGrid3D", "SVO",
-           "RayCaster", "Camera", "host_terrain_heights", "host_build_terrain_lsvo", "host_build_lsvo_from_voxels"]
+           "RayCaster", "Camera", "CameraController", "FlyController", "ReplayElements", "host_terrain_heights", "host_build_terrain_lsvo", "host_build_lsvo_from_voxels"]

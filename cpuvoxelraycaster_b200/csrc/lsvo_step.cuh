@@ -54,7 +54,9 @@ struct Trav {
 
     __device__ __forceinline__ float scale_f() const { return __uint_as_float(uint32_t(scale - kSvoMaxDepth + 127) << 23); }
 
-    __device__ __forceinline__ void init(float ox_, float oy_, float oz_, float dx_, float dy_, float dz_, float coef_, float bias_) {
+    // Returns false for a ray with a non-finite origin or direction: the reference's loop does not terminate on those
+    // (every comparison with NaN fails: no descent, no step, no pop); here such a ray is a miss of complexity 0.
+    __device__ __forceinline__ bool init(float ox_, float oy_, float oz_, float dx_, float dy_, float dz_, float coef_, float bias_) {
         ox = ox_; oy = oy_; oz = oz_; coef = coef_; bias = bias_;
         if (fabsf(dx_) < kEps) dx_ = copysignf(kEps, dx_);                 // lsvo.hpp:44-46
         if (fabsf(dy_) < kEps) dy_ = copysignf(kEps, dy_);
@@ -79,6 +81,7 @@ struct Trav {
         if (1.5f * tcz - toz > t_min) { child ^= 4u; pz = 1.5f; }
         iters = 0u;
         hit = false;
+        return (((ox_ + oy_) + oz_) + ((dx_ + dy_) + dz_)) * 0.0f == 0.0f;   // inf * 0 and NaN * 0 are NaN
     }
 
     // One trip of the loop.  Returns true while the ray is alive (the loop condition :72 still holds and no hit).
@@ -149,8 +152,8 @@ template <typename Nodes, typename Stack>
 __device__ __forceinline__ void lsvo_cast_ray(const Nodes& nodes, Stack& stack, int depth_offset, int guard, float ox, float oy,
                                               float oz, float dx, float dy, float dz, float coef, float bias, LsvoResult& r) {
     Trav t;
-    t.init(ox, oy, oz, dx, dy, dz, coef, bias);
-    while (t.step(nodes, stack, depth_offset, guard)) {}
+    if (t.init(ox, oy, oz, dx, dy, dz, coef, bias))
+        while (t.step(nodes, stack, depth_offset, guard)) {}
     t.result(r);
 }
 

@@ -110,9 +110,8 @@ __global__ void __launch_bounds__(128, 4) lsvo_cast_persistent_kernel(Nodes node
             const bool take = ((want >> lane) & 1u) && (uint64_t(rank) < chunk_end - chunk_next);
             if (take) {
                 ray = chunk_next + rank;
-                t.init(origin[3 * ray], origin[3 * ray + 1], origin[3 * ray + 2], dir[3 * ray], dir[3 * ray + 1], dir[3 * ray + 2],
-                       coef, bias);
-                alive = true;
+                alive = t.init(origin[3 * ray], origin[3 * ray + 1], origin[3 * ray + 2], dir[3 * ray], dir[3 * ray + 1], dir[3 * ray + 2],
+                               coef, bias);
                 has_result = true;
             }
             const unsigned took = __ballot_sync(kFull, take);
@@ -248,8 +247,7 @@ __global__ void __launch_bounds__(128, 4) render_persistent_kernel(Nodes nodes, 
         }
         // ---- D: prologue of castRay for every regenerated ray ----
         if (new_ray) {
-            t.init(nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f);
-            alive = true;
+            alive = t.init(nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f);
             has_ray = true;
         }
         if (!__ballot_sync(kFull, alive)) break;

@@ -319,6 +319,57 @@ class Camera:
         return f.value
 
 
+class CameraController:
+    """include/camera_controller.hpp:64-78."""
+    movement_speed = 1.0
+
+    def updateCameraView(self, d_view_angle, camera):
+        new_angle = camera.view_angle + np.asarray(d_view_angle, np.float32)
+        half_pi = np.float32(3.141592653) * np.float32(0.5)          # PI, camera_controller.hpp:8
+        new_angle[1] = min(max(new_angle[1], -half_pi), half_pi)
+        camera.setViewAngle(new_angle)
+
+    def move(self, move_vector, camera):
+        raise NotImplementedError
+
+
+class FlyController(CameraController):
+    """include/fly_controller.hpp:6-12."""
+
+    def move(self, move_vector, camera):
+        camera.position = camera.position + np.asarray(move_vector, np.float32)
+
+
+class ReplayElements:
+    """include/replay.hpp:8-33: one tick of a recorded camera path, `timestamp x y z view_x view_y` per line."""
+    __slots__ = ("timestamp", "x", "y", "z", "view_x", "view_y")
+
+    def __init__(self, timestamp, x, y, z, view_x, view_y):
+        self.timestamp, self.x, self.y, self.z, self.view_x, self.view_y = (float(np.float32(v)) for v in (timestamp, x, y, z, view_x, view_y))
+
+    @staticmethod
+    def loadFromFile(filename):
+        """Whitespace-separated floats, six per tick; reading stops at the first token that is not a number or at an
+        incomplete tick, like `file >> ...` (replay.hpp:26).  A missing file gives an empty list (:24)."""
+        try:
+            with open(filename) as f:
+                tokens = f.read().split()
+        except OSError:
+            return []
+        values = []
+        for t in tokens:
+            try:
+                values.append(float(t))
+            except ValueError:
+                break
+        return [ReplayElements(*values[i:i + 6]) for i in range(0, len(values) - len(values) % 6, 6)]
+
+    def apply(self, camera):
+        """Puts the camera where the tick was recorded."""
+        camera.position = np.float32([self.x, self.y, self.z])
+        camera.setViewAngle((self.view_x, self.view_y))
+
+
 # ---- renderer -----------------------------------------------------------------------------------------
 class RayCaster:
     """include/raycaster.hpp:43.  render() replaces the swarm lambda of src/main.cpp:139-154."""

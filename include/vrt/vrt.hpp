@@ -325,6 +325,41 @@ struct Camera {
     }
 };
 
+struct CameraController {                                                 // camera_controller.hpp:64-78
+    virtual ~CameraController() {}
+    virtual void updateCameraView(const glm::vec2& d_view_angle, Camera& camera) {
+        glm::vec2 new_angle(camera.view_angle.x + d_view_angle.x, camera.view_angle.y + d_view_angle.y);
+        const float half_pi = 3.141592653f * 0.5f;
+        new_angle.y = new_angle.y < -half_pi ? -half_pi : new_angle.y > half_pi ? half_pi : new_angle.y;
+        camera.setViewAngle(new_angle);
+    }
+    virtual void move(const glm::vec3& move_vector, Camera& camera) = 0;
+    float movement_speed = 1.0f;
+};
+struct FlyController : CameraController {                                 // fly_controller.hpp:6-12
+    void move(const glm::vec3& move_vector, Camera& camera) override {
+        camera.position = glm::vec3(camera.position.x + move_vector.x, camera.position.y + move_vector.y, camera.position.z + move_vector.z);
+    }
+};
+
+// ---- include/replay.hpp: a recorded camera path, `timestamp x y z view_x view_y` per tick --------------------
+struct ReplayElements {
+    float timestamp, x, y, z, view_x, view_y;
+    static std::vector<ReplayElements> loadFromFile(const std::string& filename) {
+        std::vector<ReplayElements> ticks;
+        FILE* f = std::fopen(filename.c_str(), "r");
+        if (!f) return ticks;
+        ReplayElements e;
+        while (std::fscanf(f, "%f %f %f %f %f %f", &e.timestamp, &e.x, &e.y, &e.z, &e.view_x, &e.view_y) == 6) ticks.push_back(e);
+        std::fclose(f);
+        return ticks;
+    }
+    void apply(Camera& camera) const {
+        camera.position = glm::vec3(x, y, z);
+        camera.setViewAngle(glm::vec2(view_x, view_y));
+    }
+};
+
 // ---- include/raycaster.hpp --------------------------------------------------------------------------------
 namespace vrt {
 struct Vector2i { int x = 0, y = 0; Vector2i() {} Vector2i(int a, int b) : x(a), y(b) {} };   // sf::Vector2i stand-in

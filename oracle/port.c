@@ -283,6 +283,9 @@ static void lsvo_cast_one(const vo_lnode* nodes, int depth, int guard, const flo
     float d[3], tc[3], to[3], p[3];
     uint32_t mirror = 7u;
     memset(res, 0, sizeof(*res));
+    /* A ray with a non-finite origin or direction never leaves the reference's loop (comparisons with NaN all fail:
+     * no descent, no step, no pop).  The engine and this restatement define it as a miss of complexity 0. */
+    if ((((o[0] + o[1]) + o[2]) + ((din[0] + din[1]) + din[2])) * 0.0f != 0.0f) return;
     for (int a = 0; a < 3; ++a) {
         d[a] = din[a];
         if (fabsf(d[a]) < EPS) d[a] = copysignf(EPS, d[a]);           /* :44-46 */

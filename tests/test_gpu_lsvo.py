@@ -85,6 +85,30 @@ def test_edge_cases(vrt, ctx, port):
     assert hit_flag(got)[0] and got["distance"][0] == 0.5 and not np.any(got["normal"][0])
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+def test_non_finite_rays_are_misses(vrt, port, terrain9_nodes, variant):
+    """The reference's loop never ends on a NaN / infinite ray; engine and oracle define a miss of complexity 0."""
+    c = vrt.Context(0)
+    c.set_option("cast_variant", variant)
+    s = vrt.LSVO(c, terrain9_nodes, 9)
+    rng = np.random.default_rng(9)
+    n = 4096
+    o = rng.uniform(1.0, 2.0, (n, 3)).astype(np.float32)
+    o[:, 1] = rng.uniform(1.0, 1.3, n)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    bad = rng.random(n) < 0.3
+    which = rng.integers(0, 6, n)
+    value = rng.choice(np.float32([np.nan, np.inf, -np.inf]), n)
+    for i in np.flatnonzero(bad):
+        (o if which[i] < 3 else d)[i, which[i] % 3] = value[i]
+    got = s.cast_rays(o, d)
+    want = port.lsvo_cast(terrain9_nodes, 9, o, d)
+    assert_hits_equal(got, want, hit_flag(got), "non-finite rays")
+    assert not hit_flag(got)[bad].any() and (got["complexity"][bad] == 0).all() and (got["complexity"][~bad] > 0).all()
+    s.close()
+    c.close()
+
+
 @pytest.mark.parametrize("variant,refill", [(0, 8), (1, 0), (1, 1), (1, 8), (1, 20), (1, 32)])
 def test_kernel_variants_agree(vrt, port, terrain9_nodes, variant, refill):
     """One-thread-per-ray and persistent/regenerating kernels give byte-identical hit records for every refill

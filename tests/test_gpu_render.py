@@ -147,6 +147,23 @@ def test_present_matches_oracle(vrt, ctx, port, W, H):
         capi.check(capi.lib().vrt_present(ctx.handle, capi.ptr(frame), capi.ptr(got), C.byref(bad)))
 
 
+def test_camera_inside_solid_terminates(vrt, scene9, port, terrain9_nodes, textures):
+    """Autofocus from inside a hill gives focal_length 0 (main.cpp:116-118); with an open aperture Camera::getRay then
+    normalises a zero vector whenever both lens numbers are 0 — a NaN ray the reference would never finish.  Such
+    samples are black here and in the oracle, and the frame still matches."""
+    W, H = 128, 72
+    cam = vrt.Camera(position=(307.2727, 210.45, 400.7897), view_angle=(2.801253, -0.355602), aperture=0.3)
+    assert cam.autofocus(scene9) == 0.0
+    rc = vrt.RayCaster(scene9, (W, H))
+    rc.setLightPosition(default_light())
+    rc.use_samples, rc.use_gi = True, True
+    rc.render(cam, spp=4)
+    p = port_params(W, H, 9, cam, default_light(), 1, 1, True, 4)
+    acc, _, st = port.render(terrain9_nodes, p, *textures)
+    assert np.array_equal(rc.colors, acc) and rc.last_stats["rays"] == list(st.rays)
+    assert rc.last_stats["complexity"][0] < 40 * W * H * 4
+
+
 def test_autofocus(vrt, scene9, port, terrain9_nodes):
     cam = vrt.Camera(position=(256, 200, 256), view_angle=(0.0, -0.6))
     f = cam.autofocus(scene9)

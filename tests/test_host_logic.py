@@ -51,3 +51,23 @@ def test_camera_basis(vrt):
     cam = vrt.Camera(view_angle=g["view_angle"])
     assert np.array_equal(cam.rot_mat.view(np.uint32), g["rot_mat"].view(np.uint32))
     assert np.array_equal(cam.camera_vec.view(np.uint32), g["camera_vec"].view(np.uint32))
+
+
+def test_replay_file_and_controllers(vrt, tmp_path):
+    """include/replay.hpp:18-33 (six floats per tick, reading stops at the first bad token or incomplete tick) and the
+    camera controllers (camera_controller.hpp:64-78, fly_controller.hpp)."""
+    f = tmp_path / "replay.txt"
+    f.write_text("0.0 256 200 256 0.0 0.0\n0.016 257.5 199 256 0.1 -0.2\n0.033 259 198 256.5 0.2\t-0.4\n0.05 1 2 oops 4 5\n")
+    ticks = vrt.ReplayElements.loadFromFile(str(f))
+    assert len(ticks) == 3
+    assert (ticks[1].timestamp, ticks[1].x, ticks[1].view_y) == (float(np.float32(0.016)), 257.5, float(np.float32(-0.2)))
+    assert vrt.ReplayElements.loadFromFile(str(tmp_path / "missing.txt")) == []
+    cam = vrt.Camera()
+    ticks[2].apply(cam)
+    assert np.array_equal(cam.position, np.float32([259, 198, 256.5])) and np.array_equal(cam.view_angle, np.float32([0.2, -0.4]))
+    ctl = vrt.FlyController()
+    ctl.updateCameraView((0.5, -3.0), cam)                 # pitch clamps at -PI/2 with the reference's PI literal
+    assert cam.view_angle[0] == np.float32(0.2) + np.float32(0.5)
+    assert cam.view_angle[1] == -(np.float32(3.141592653) * np.float32(0.5))
+    ctl.move((1.0, -2.0, 0.5), cam)
+    assert np.array_equal(cam.position, np.float32([260, 196, 257]))
