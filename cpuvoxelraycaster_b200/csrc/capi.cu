@@ -403,6 +403,7 @@ int vrt_scene_last_complexity(vrt_scene* sc, uint64_t* total) {
 // ---- rendering -------------------------------------------------------------------------------------
 namespace {
 constexpr int kRenderCounters = 2;   // offset of the 12 render counters inside d_counters
+constexpr int kFocalSlot = 15;       // d_counters[15] holds the float focal length of vrt_render_params::autofocus
 
 int check_render_args(const vrt_scene* sc, const vrt_camera* cam, const vrt_render_params* p, const char* who) {
     if (!sc || !p) return fail(VRT_ERR_INVALID, std::string(who) + ": NULL argument");
@@ -416,6 +417,7 @@ int check_render_args(const vrt_scene* sc, const vrt_camera* cam, const vrt_rend
     if (p->tile_step > 1 && (p->tile_index < 0 || p->tile_index >= p->tile_step)) return fail(VRT_ERR_INVALID, std::string(who) + ": tile_index must be in [0, tile_step)");
     if (cam && !sc->has_tex) return fail(VRT_ERR_INVALID, std::string(who) + ": call vrt_scene_set_textures first (raycaster.hpp:53-54)");
     if (p->checker < 0 || p->checker > 2 || p->checker_area_height < 0) return fail(VRT_ERR_INVALID, std::string(who) + ": checker must be 0, 1 or 2 and checker_area_height >= 0");
+    if (cam && p->autofocus && sc->kind != VRT_SCENE_LSVO) return fail(VRT_ERR_UNSUPPORTED, std::string(who) + ": autofocus needs an LSVO scene");
     if (cam && p->checker && sc->kind == VRT_SCENE_LSVO && sc->ctx->render_variant != 0)
         return fail(VRT_ERR_UNSUPPORTED, std::string(who) + ": the checkerboard needs render_variant 0");
     return VRT_OK;
@@ -435,6 +437,7 @@ vrt::RenderLaunch make_launch(const vrt_scene* sc, const vrt_camera* cam, const 
     L.roughness = p->roughness;
     L.max_bounds = p->max_bounds;
     L.checker = p->checker; L.checker_area_height = p->checker_area_height;
+    L.focal = p->autofocus ? reinterpret_cast<const float*>(sc->d_counters + kFocalSlot) : nullptr;
     L.tile_step = p->tile_step > 1 ? p->tile_step : 1;
     L.tile_index = p->tile_step > 1 ? p->tile_index : 0;
     L.tex_top = sc->d_tex; L.tex_side = sc->d_tex + 768;
@@ -460,6 +463,11 @@ int vrt_render_accumulate_device(vrt_scene* sc, const vrt_camera* cam, const vrt
     if (int s = use_device(ctx)) return s;
     VRT_CUDA(cudaMemsetAsync(sc->d_counters + kRenderCounters, 0, 13 * sizeof(unsigned long long), ctx->stream));
     if (p->row_end == p->row_begin) return VRT_OK;
+    if (p->autofocus) {
+        VRT_CUDA(vrt::launch_autofocus(sc->use_compact ? sc->d_compact : sc->d_nodes, sc->use_compact, int(sc->depth), sc->guard, *cam,
+                                       reinterpret_cast<float*>(sc->d_counters + kFocalSlot), ctx->stream));
+        ctx->launches += 1;
+    }
     if (sc->kind != VRT_SCENE_LSVO)
         VRT_CUDA(vrt::launch_grid_render(sc->grid, sc->use_mip, make_launch(sc, cam, p), d_accum, sc->d_counters + kRenderCounters,
                                          ctx->stream));

@@ -47,6 +47,7 @@ struct RenderLaunch {
     const uint8_t* tex_side;
     float roughness;           // grid frames: blur of mirror reflections
     int max_bounds;            // grid frames: reflection depth (RayCaster::max_bounds, raycaster.hpp:277)
+    const float* focal;        // device: focal length computed by the autofocus kernel, or null = cam.focal_length
     int checker;               // 0 = every pixel, 1 / 2 = checkerboard with offset 0 / 1 (main.cpp:137,143)
     int checker_area_height;   // thread-area height the checkerboard phase restarts at (0 = never)
 };
@@ -61,6 +62,9 @@ __host__ __device__ inline int checker_x_parity(int checker, int area_height, in
 // K0+K4: ray generation, traversal, shading and accumulation for rows [row_begin,row_end) (render_kernels.cu)
 cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const RenderLaunch& L, uint32_t* d_accum,
                                          unsigned long long* d_counters, cudaStream_t stream);
+// Camera::getClosestPoint + main.cpp:114-121 on the device: *d_focal = hit ? distance * 2^depth : 100
+cudaError_t launch_autofocus(const uint2* nodes, bool compact, int depth, int guard, const vrt_camera& cam, float* d_focal,
+                             cudaStream_t stream);
 cudaError_t launch_resolve(const uint32_t* d_accum, uint8_t* d_rgba, int width, int row_begin, int row_end, int use_samples,
                            int tile_step, int tile_index, cudaStream_t stream);
 // median filter + persistence blend of main.cpp:159-177 (present_kernels.cu)

@@ -54,9 +54,13 @@ struct Trav {
 
     __device__ __forceinline__ float scale_f() const { return __uint_as_float(uint32_t(scale - kSvoMaxDepth + 127) << 23); }
 
-    // Returns false for a ray with a non-finite origin or direction: the reference's loop does not terminate on those
-    // (every comparison with NaN fails: no descent, no step, no pop); here such a ray is a miss of complexity 0.
-    __device__ __forceinline__ bool init(float ox_, float oy_, float oz_, float dx_, float dy_, float dz_, float coef_, float bias_) {
+    // A ray with a non-finite origin or direction never leaves the reference's loop (every comparison with NaN fails: no
+    // descent, no step, no pop); here it is a miss of complexity 0.  To keep the loop itself untouched such a ray is
+    // replaced by one that starts outside the cube pointing away (one trip, no descent) and is marked in bit 3 of
+    // `mirror`, which result() reads.
+    __device__ __forceinline__ void init(float ox_, float oy_, float oz_, float dx_, float dy_, float dz_, float coef_, float bias_) {
+        const bool finite = (((ox_ + oy_) + oz_) + ((dx_ + dy_) + dz_)) * 0.0f == 0.0f;   // inf * 0 and NaN * 0 are NaN
+        if (!finite) { ox_ = 3.0f; oy_ = 3.0f; oz_ = 3.0f; dx_ = 1.0f; dy_ = 1.0f; dz_ = 1.0f; }
         ox = ox_; oy = oy_; oz = oz_; coef = coef_; bias = bias_;
         if (fabsf(dx_) < kEps) dx_ = copysignf(kEps, dx_);                 // lsvo.hpp:44-46
         if (fabsf(dy_) < kEps) dy_ = copysignf(kEps, dy_);
@@ -64,7 +68,7 @@ struct Trav {
         dx = dx_; dy = dy_; dz = dz_;
         tcx = -1.0f / fabsf(dx); tcy = -1.0f / fabsf(dy); tcz = -1.0f / fabsf(dz);   // :47
         tox = ox * tcx; toy = oy * tcy; toz = oz * tcz;                     // :48
-        mirror = 7u;
+        mirror = finite ? 7u : 15u;
         if (dx > 0.0f) { mirror ^= 1u; tox = 3.0f * tcx - tox; }           // :50-52
         if (dy > 0.0f) { mirror ^= 2u; toy = 3.0f * tcy - toy; }
         if (dz > 0.0f) { mirror ^= 4u; toz = 3.0f * tcz - toz; }
@@ -81,7 +85,6 @@ struct Trav {
         if (1.5f * tcz - toz > t_min) { child ^= 4u; pz = 1.5f; }
         iters = 0u;
         hit = false;
-        return (((ox_ + oy_) + oz_) + ((dx_ + dy_) + dz_)) * 0.0f == 0.0f;   // inf * 0 and NaN * 0 are NaN
     }
 
     // One trip of the loop.  Returns true while the ray is alive (the loop condition :72 still holds and no hit).
@@ -141,8 +144,8 @@ struct Trav {
 
     __device__ __forceinline__ void result(LsvoResult& r) const {
         r.px = px; r.py = py; r.pz = pz;
-        r.t_min = t_min; r.scale_f = scale_f(); r.scale = scale; r.face = face; r.mirror = mirror;
-        r.complexity = iters; r.hit = hit;
+        r.t_min = t_min; r.scale_f = scale_f(); r.scale = scale; r.face = face; r.mirror = mirror & 7u;
+        r.complexity = (mirror & 8u) ? 0u : iters; r.hit = hit;
         r.dx = dx; r.dy = dy; r.dz = dz;
     }
 };
@@ -152,8 +155,8 @@ template <typename Nodes, typename Stack>
 __device__ __forceinline__ void lsvo_cast_ray(const Nodes& nodes, Stack& stack, int depth_offset, int guard, float ox, float oy,
                                               float oz, float dx, float dy, float dz, float coef, float bias, LsvoResult& r) {
     Trav t;
-    if (t.init(ox, oy, oz, dx, dy, dz, coef, bias))
-        while (t.step(nodes, stack, depth_offset, guard)) {}
+    t.init(ox, oy, oz, dx, dy, dz, coef, bias);
+    while (t.step(nodes, stack, depth_offset, guard)) {}
     t.result(r);
 }
 

@@ -110,8 +110,9 @@ __global__ void __launch_bounds__(128, 4) lsvo_cast_persistent_kernel(Nodes node
             const bool take = ((want >> lane) & 1u) && (uint64_t(rank) < chunk_end - chunk_next);
             if (take) {
                 ray = chunk_next + rank;
-                alive = t.init(origin[3 * ray], origin[3 * ray + 1], origin[3 * ray + 2], dir[3 * ray], dir[3 * ray + 1], dir[3 * ray + 2],
-                               coef, bias);
+                t.init(origin[3 * ray], origin[3 * ray + 1], origin[3 * ray + 2], dir[3 * ray], dir[3 * ray + 1], dir[3 * ray + 2],
+                       coef, bias);
+                alive = true;
                 has_result = true;
             }
             const unsigned took = __ballot_sync(kFull, take);
@@ -241,13 +242,14 @@ __global__ void __launch_bounds__(128, 4) render_persistent_kernel(Nodes nodes, 
         }
         // ---- C: Camera::getRay for lanes starting a sample ----
         if (want_primary) {
-            chain_begin(L, c, pixel, uint32_t(L.sample_offset + s), lens_x, lens_y, SCALE, nr);
+            chain_begin(L, c, pixel, uint32_t(L.sample_offset + s), lens_x, lens_y, SCALE, L.focal ? __ldg(L.focal) : L.cam.focal_length, nr);
             stage = kPrimary;
             new_ray = true;
         }
         // ---- D: prologue of castRay for every regenerated ray ----
         if (new_ray) {
-            alive = t.init(nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f);
+            t.init(nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f);
+            alive = true;
             has_ray = true;
         }
         if (!__ballot_sync(kFull, alive)) break;

@@ -47,7 +47,7 @@ __device__ __forceinline__ void view_to_world(const float* m, float vx, float vy
 
 // Starts sample `sample` of `pixel`: the primary ray.
 __device__ __forceinline__ void chain_begin(const RenderLaunch& L, ChainState& c, uint32_t pixel, uint32_t sample, float lens_x,
-                                            float lens_y, float SCALE, NextRay& nr) {
+                                            float lens_y, float SCALE, float focal_length, NextRay& nr) {
     const uint4 rnd0 = philox4x32_10(pixel, sample, 0u, 0u, L.seed_lo, L.seed_hi);
     c.rnd_z = rnd0.z; c.rnd_w = rnd0.w;
     c.light = 0.f; c.irr0 = 0.f; c.irr1 = 0.f;
@@ -55,7 +55,7 @@ __device__ __forceinline__ void chain_begin(const RenderLaunch& L, ChainState& c
     const float u0 = lattice(rnd0.x, -0.5f, 0.5f), u1 = lattice(rnd0.y, -0.5f, 0.5f);    // camera_controller.hpp:40
     float fx = lens_x, fy = lens_y, fz = L.cam.fov;                                     // :37-39
     normalize3(fx, fy, fz);
-    fx *= L.cam.focal_length; fy *= L.cam.focal_length; fz *= L.cam.focal_length;
+    fx *= focal_length; fy *= focal_length; fz *= focal_length;
     const float rx = L.cam.aperture * u0, ry = L.cam.aperture * u1, rz = L.cam.aperture * 0.0f;
     float qx = fx - rx, qy = fy - ry, qz = fz - rz;                                     // :42
     normalize3(qx, qy, qz);

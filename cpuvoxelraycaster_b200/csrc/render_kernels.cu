@@ -17,7 +17,10 @@ namespace vrt {
 #ifndef VRT_K4_MIN_CTAS
 #define VRT_K4_MIN_CTAS 4
 #endif
-template <typename Nodes>
+// kLive: the interactive-loop extras (checkerboard pixel mapping, focal length read from the autofocus kernel's output).
+// Compiled out of the plain instantiation so that they cost the many-sample frames nothing (register allocation of the
+// traversal loop is sensitive to every extra live value: 73.9 vs 75.6 ms on cfg 4).
+template <typename Nodes, bool kLive>
 __global__ void __launch_bounds__(128, VRT_K4_MIN_CTAS) render_accumulate_kernel(Nodes nodes, RenderLaunch L, uint32_t* __restrict__ accum,
                                                                 unsigned long long* __restrict__ counters) {
     extern __shared__ uint2 smem[];
@@ -30,7 +33,8 @@ __global__ void __launch_bounds__(128, VRT_K4_MIN_CTAS) render_accumulate_kernel
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // checkerboard frames (main.cpp:137,143) render every other pixel of a row: the tile's columns are then the
     // indices of the rendered pixels, so that no lane idles
-    const int columns = L.checker ? (L.width + 1) / 2 : L.width;
+    const int checker = kLive ? L.checker : 0;
+    const int columns = checker ? (L.width + 1) / 2 : L.width;
     const int tiles_x = (columns + 31) / 32;
     // blockIdx.x = chunk * tiles + tile: the pixel's samples are cut into L.spp_chunks runs handled by different CTAs
     // (more, shorter CTAs: keeps the tail short when a GPU owns only a slice of the frame; sums stay exact — integers)
@@ -54,13 +58,14 @@ __global__ void __launch_bounds__(128, VRT_K4_MIN_CTAS) render_accumulate_kernel
     const float SCALE = 1.0f / float(1 << L.depth);                           // raycaster.hpp:123-124 / main.cpp:82
     const float n_norm = SCALE * 0.0078125f * 2.0f;                           // raycaster.hpp:171-172
     const float aspect = float(L.width) / float(L.height);                    // main.cpp:133
+    const float focal_length = (kLive && L.focal) ? __ldg(L.focal) : L.cam.focal_length;   // main.cpp:114-121 on the device
 
     for (int g = 0; g < Q; ++g) {
         const int j = g * P + lane / Q;                    // pixel index inside the 8x4 tile
         // 4-row tiles are dealt round-robin to tile_step owners (multi-GPU row partition, balanced sky/terrain)
         const int y = L.row_begin + (by * L.tile_step + L.tile_index) * 4 + (j >> 3);
         int x = bx * 32 + warp * 8 + (j & 7);
-        if (L.checker) x = 2 * x + checker_x_parity(L.checker, L.checker_area_height, y);
+        if (checker) x = 2 * x + checker_x_parity(checker, L.checker_area_height, y);
         const bool active = x < L.width && y < L.row_end;
         const uint32_t pixel = uint32_t(y) * uint32_t(L.width) + uint32_t(x);
         uint32_t sum_r = 0, sum_g = 0, sum_b = 0;
@@ -71,7 +76,7 @@ __global__ void __launch_bounds__(128, VRT_K4_MIN_CTAS) render_accumulate_kernel
                 const uint32_t sample = uint32_t(L.sample_offset + s_begin + k * Q + sub);
                 ChainState c;
                 NextRay nr;
-                chain_begin(L, c, pixel, sample, lens_x, lens_y, SCALE, nr);
+                chain_begin(L, c, pixel, sample, lens_x, lens_y, SCALE, focal_length, nr);
                 int stage = kPrimary;
                 while (stage != kDone) {
                     LsvoResult r;
@@ -117,6 +122,21 @@ __global__ void __launch_bounds__(128, VRT_K4_MIN_CTAS) render_accumulate_kernel
             atomicAdd(counters + 6 + k, (unsigned long long)b);
         }
     }
+}
+
+// Camera::getClosestPoint (camera_controller.hpp:56-60) and the focal-length rule of main.cpp:114-121, one thread.
+template <typename Nodes>
+__global__ void __launch_bounds__(128) autofocus_kernel(Nodes nodes, int depth, int guard, vrt_camera cam, float* __restrict__ focal) {
+    extern __shared__ uint2 smem[];
+    if (threadIdx.x != 0) return;
+    Stack64<128> stack{smem};
+    const float scale = 1.0f / float(1 << depth);
+    const float ox = cam.position[0] * scale + 1.0f, oy = cam.position[1] * scale + 1.0f, oz = cam.position[2] * scale + 1.0f;
+    float dx, dy, dz;
+    view_to_world(cam.rot_mat, 0.0f, 0.0f, 1.0f, dx, dy, dz);                 // camera_vec, camera_controller.hpp:31
+    LsvoResult r;
+    lsvo_cast_ray(nodes, stack, kSvoMaxDepth - depth, guard, ox, oy, oz, dx, dy, dz, 0.0f, 0.0f, r);
+    *focal = r.hit ? r.t_min * float(1 << depth) : 100.0f;
 }
 
 // samples_to_image (raycaster.hpp:94-103) or the 0.4/0.6 temporal blend of renderRay (:79-85).
@@ -173,10 +193,20 @@ cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const
     }
     if (L.samples_per_warp > 0 && L.samples_per_warp < q) q = L.samples_per_warp;       // explicit override (power of two)
     Lc.samples_per_warp = q;
-    if (compact)
-        render_accumulate_kernel<CompactNodes><<<unsigned(tiles * chunks), block, smem, stream>>>(CompactNodes{nodes}, Lc, d_accum, d_counters);
-    else
-        render_accumulate_kernel<RefNodes><<<unsigned(tiles * chunks), block, smem, stream>>>(RefNodes{nodes}, Lc, d_accum, d_counters);
+    const unsigned grid = unsigned(tiles * chunks);
+    const bool live = L.checker != 0 || L.focal != nullptr;
+    if (compact && live) render_accumulate_kernel<CompactNodes, true><<<grid, block, smem, stream>>>(CompactNodes{nodes}, Lc, d_accum, d_counters);
+    else if (compact) render_accumulate_kernel<CompactNodes, false><<<grid, block, smem, stream>>>(CompactNodes{nodes}, Lc, d_accum, d_counters);
+    else if (live) render_accumulate_kernel<RefNodes, true><<<grid, block, smem, stream>>>(RefNodes{nodes}, Lc, d_accum, d_counters);
+    else render_accumulate_kernel<RefNodes, false><<<grid, block, smem, stream>>>(RefNodes{nodes}, Lc, d_accum, d_counters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_autofocus(const uint2* nodes, bool compact, int depth, int guard, const vrt_camera& cam, float* d_focal,
+                             cudaStream_t stream) {
+    const size_t smem = size_t(depth + 1) * 128 * 8;
+    if (compact) autofocus_kernel<CompactNodes><<<1, 128, smem, stream>>>(CompactNodes{nodes}, depth, guard, cam, d_focal);
+    else autofocus_kernel<RefNodes><<<1, 128, smem, stream>>>(RefNodes{nodes}, depth, guard, cam, d_focal);
     return cudaGetLastError();
 }
 

@@ -389,6 +389,7 @@ class RayCaster:
         self.checker_board_offset = None   # None = every pixel; 0 / 1 = the checkerboard of main.cpp:137,143
         self.checker_area_height = 0       # RENDER_HEIGHT / area_count (main.cpp:132); 0 = one area
         self.display = None                # denoised_tex of main.cpp:159-177, made by present()
+        self.autofocus = False             # True: focal length from the centre ray on the device (main.cpp:114-121)
         self.seed = (0x5EED, 0)
         self.sample_count = 0
         self.last_stats = None
@@ -414,6 +415,7 @@ class RayCaster:
         p.roughness, p.max_bounds = float(self.roughness), int(self.max_bounds)
         p.checker = 0 if self.checker_board_offset is None else 1 + (int(self.checker_board_offset) & 1)
         p.checker_area_height = int(self.checker_area_height)
+        p.autofocus = int(bool(self.autofocus))
         return p
 
     def render(self, camera, spp=1, row_begin=0, row_end=0):

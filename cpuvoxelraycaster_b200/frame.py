@@ -68,6 +68,7 @@ class FrameRenderer:
         self.roughness, self.max_bounds = 0.0, 4
         self.checker_board_offset, self.checker_area_height = None, 0     # main.cpp:137,143 / :132
         self.display = None                                               # denoised_tex of main.cpp:159-177
+        self.autofocus = False                                            # device-side centre-ray focus, main.cpp:114-121
         self.seed = (0x5EED, 0)
         self.light = np.zeros(3, np.float32)
 
@@ -82,6 +83,7 @@ class FrameRenderer:
         p.roughness, p.max_bounds = float(self.roughness), int(self.max_bounds)
         p.checker = 0 if self.checker_board_offset is None else 1 + (int(self.checker_board_offset) & 1)
         p.checker_area_height = int(self.checker_area_height)
+        p.autofocus = int(bool(self.autofocus))
         return p
 
     # -- device-resident frame: enqueue only (the caller owns stream/synchronisation) --

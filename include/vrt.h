@@ -185,6 +185,10 @@ typedef struct vrt_render_params {
                                   * (y - area_start(y)) % 2 == (x + offset) % 2; other pixels keep their value */
     int32_t checker_area_height; /* height of the reference's thread areas (RENDER_HEIGHT / area_count, main.cpp:132;
                                   * 135 in the demo): area_start(y) = y - y % area_height.  0 = one area (start 0) */
+    int32_t autofocus;           /* 1 = LSVO scenes: focal length from the centre ray, cast on the device in front of the
+                                  * frame (Camera::getClosestPoint camera_controller.hpp:56-60 + main.cpp:114-121:
+                                  * distance * 2^depth, or 100 on a miss); cam->focal_length is ignored.  No host
+                                  * round trip: the interactive loop stays asynchronous */
 } vrt_render_params;
 
 typedef struct vrt_render_stats {

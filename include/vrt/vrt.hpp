@@ -415,6 +415,7 @@ struct RayCasterT {
         p.accum_in = use_samples ? 1 : 0;
         p.checker = checker_board_offset < 0 ? 0 : 1 + (checker_board_offset & 1);
         p.checker_area_height = checker_area_height;
+        p.autofocus = autofocus ? 1 : 0;
         if (!use_samples) std::fill(colors.begin(), colors.end(), 0u);
         const vrt_camera c = camera.as_struct();
         vrt::check(vrt_render(svo.scene(), &c, &p, render_image.data(), colors.data(), &last_stats));
@@ -445,6 +446,7 @@ struct RayCasterT {
     std::vector<uint8_t> display;                       // RGBA8: denoised_tex of main.cpp:168-172, made by present()
     int checker_board_offset = -1;                      // -1 = every pixel; 0 / 1 = the checkerboard of main.cpp:137,143
     int checker_area_height = 0;                        // RENDER_HEIGHT / area_count (main.cpp:132); 0 = one area
+    bool autofocus = false;                             // focal length from the centre ray on the device (main.cpp:114-121)
     const LSVO<SVO_DEPTH_>& svo;
     const vrt::Vector2i render_size;
     glm::vec3 light_position;

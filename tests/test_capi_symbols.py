@@ -27,7 +27,7 @@ def test_struct_sizes(vrt):
     import ctypes as C
     assert vrt.HIT.itemsize == 64 and vrt.LNODE.itemsize == 8
     assert C.sizeof(vrt.capi.Camera) == 15 * 4
-    assert C.sizeof(vrt.capi.RenderParams) == 21 * 4
+    assert C.sizeof(vrt.capi.RenderParams) == 22 * 4
     assert C.sizeof(vrt.capi.PresentParams) == 4 * 4
     assert C.sizeof(vrt.capi.RenderStats) == 12 * 8
 

@@ -164,6 +164,24 @@ def test_camera_inside_solid_terminates(vrt, scene9, port, terrain9_nodes, textu
     assert rc.last_stats["complexity"][0] < 40 * W * H * 4
 
 
+@pytest.mark.parametrize("view", [(0.0, -0.6), (0.3, -0.35), (0.0, 0.9)])
+def test_device_side_autofocus(vrt, scene9, view):
+    """vrt_render_params::autofocus: the frame equals the one rendered with Camera::autofocus's focal length."""
+    W, H = 128, 72
+    cam = vrt.Camera(position=(256, 200, 256), view_angle=view, aperture=0.5, focal_length=3.0)
+    rc = vrt.RayCaster(scene9, (W, H))
+    rc.setLightPosition(default_light())
+    rc.use_samples, rc.autofocus = True, True
+    a = rc.render(cam, spp=3).copy()
+    cam.autofocus(scene9)
+    assert cam.focal_length != 3.0
+    rc2 = vrt.RayCaster(scene9, (W, H))
+    rc2.setLightPosition(default_light())
+    rc2.use_samples = True
+    b = rc2.render(cam, spp=3)
+    assert np.array_equal(a, b) and np.array_equal(rc.colors, rc2.colors)
+
+
 def test_autofocus(vrt, scene9, port, terrain9_nodes):
     cam = vrt.Camera(position=(256, 200, 256), view_angle=(0.0, -0.6))
     f = cam.autofocus(scene9)

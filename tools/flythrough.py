@@ -32,8 +32,9 @@ def write_replay(path, depth, ticks):
             f.write("%.6f %.4f %.4f %.4f %.6f %.6f\n" % (i / 60.0, x, y, z, a + math.pi / 2, -0.45 + 0.15 * math.sin(2 * a)))
 
 
-def fly(scene, W, H, ticks, use_gi, checker, median, save_png=None):
+def fly(scene, W, H, ticks, use_gi, checker, median, save_png=None, host_focus=False):
     fr = FrameRenderer(scene, W, H)
+    fr.autofocus = not host_focus                                          # centre-ray focus on the device
     fr.use_samples, fr.use_gi = False, use_gi
     fr.light = np.float32([-200, -1000, -300]) * np.float32(1.0 / (1 << scene.depth)) + np.float32(1.0)
     fr.checker_area_height = H // 4 if checker else 0                      # main.cpp:91,132: 4x4 thread areas
@@ -46,7 +47,8 @@ def fly(scene, W, H, ticks, use_gi, checker, median, save_png=None):
             ev0.record(fr.stream)
         for k, tick in enumerate(ticks if timed else ticks[:8]):
             tick.apply(cam)
-            cam.autofocus(scene)
+            if host_focus:
+                cam.autofocus(scene)                                       # host round trip per frame
             offset = 1 - offset
             fr.checker_board_offset = offset if checker else None
             frame = fr.render_device(cam, 1)
@@ -61,6 +63,7 @@ def fly(scene, W, H, ticks, use_gi, checker, median, save_png=None):
         from render_gallery import save
         save(save_png, display.cpu().numpy())
     return dict(width=W, height=H, ticks=len(ticks), gi=bool(use_gi), checkerboard=bool(checker), median=median,
+                autofocus="host" if host_focus else "device",
                 ms_per_frame=round(ms, 4), frames_per_s=round(1000.0 / ms, 1), mrays_s=round(rays / len(ticks) / ms / 1e3, 1))
 
 
@@ -79,10 +82,11 @@ def main():
     write_replay(path, a.depth, a.ticks)
     ticks = vrt.ReplayElements.loadFromFile(path)
     assert len(ticks) == a.ticks
-    for (W, H, gi, checker, median) in ((960, 540, True, True, 0), (960, 540, True, False, 0), (1920, 1080, True, True, 0),
-                                        (1920, 1080, True, True, 3), (3840, 2160, True, True, 0)):
+    for (W, H, gi, checker, median, host_focus) in ((960, 540, True, True, 0, True), (960, 540, True, True, 0, False),
+                                                    (960, 540, True, False, 0, False), (1920, 1080, True, True, 0, False),
+                                                    (1920, 1080, True, True, 3, False), (3840, 2160, True, True, 0, False)):
         png = a.png if (a.png and (W, checker, median) == (1920, True, 0)) else None
-        print(json.dumps(dict(depth=a.depth, **fly(scene, W, H, ticks, gi, checker, median, png))), flush=True)
+        print(json.dumps(dict(depth=a.depth, **fly(scene, W, H, ticks, gi, checker, median, png, host_focus))), flush=True)
 
 
 if __name__ == "__main__":
