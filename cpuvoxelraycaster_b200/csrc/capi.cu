@@ -58,6 +58,7 @@ struct vrt_context {
     // Defaults follow the measurements in profiles/r01_summary.md: batched casts regenerate (warp-adaptive),
     // frames keep one lane per pixel (coherent primary/shadow rays lose more from de-phasing than GI rays gain).
     int cast_variant = 1, render_variant = 0;
+    int sort_bins1 = 0, sort_bins2 = 0;         // K5: angle bins of the two GI bounces (0 = automatic)
     int spp_chunks = 0;                        // K4: 0 = automatic
     int samples_per_warp = 0;                  // K4: lanes sharing a pixel (power of two), 0 = automatic
     int refill_cast = 0, refill_render = 16;   // parked lanes that trigger a refill (1..32); cast: 0 = warp-adaptive
@@ -162,7 +163,9 @@ int vrt_context_set_option(vrt_context* ctx, const char* key, int value) {
     if (!ctx || !key) return fail(VRT_ERR_INVALID, "vrt_context_set_option: NULL argument");
     const std::string k(key);
     if (k == "cast_variant" && (value == 0 || value == 1)) ctx->cast_variant = value;
-    else if (k == "render_variant" && (value == 0 || value == 1)) ctx->render_variant = value;
+    else if (k == "render_variant" && value >= 0 && value <= 3) ctx->render_variant = value;
+    else if (k == "sort_bins1" && value >= 0 && value <= 256) ctx->sort_bins1 = value;
+    else if (k == "sort_bins2" && value >= 0 && value <= 256) ctx->sort_bins2 = value;
     else if (k == "spp_chunks" && value >= 0 && value <= 4096) ctx->spp_chunks = value;
     else if (k == "samples_per_warp" && value >= 0 && value <= 32 && (value & (value - 1)) == 0) ctx->samples_per_warp = value;
     else if (k == "refill_cast" && value >= 0 && value <= 32) ctx->refill_cast = value;
@@ -418,8 +421,8 @@ int check_render_args(const vrt_scene* sc, const vrt_camera* cam, const vrt_rend
     if (cam && !sc->has_tex) return fail(VRT_ERR_INVALID, std::string(who) + ": call vrt_scene_set_textures first (raycaster.hpp:53-54)");
     if (p->checker < 0 || p->checker > 2 || p->checker_area_height < 0) return fail(VRT_ERR_INVALID, std::string(who) + ": checker must be 0, 1 or 2 and checker_area_height >= 0");
     if (cam && p->autofocus && sc->kind != VRT_SCENE_LSVO) return fail(VRT_ERR_UNSUPPORTED, std::string(who) + ": autofocus needs an LSVO scene");
-    if (cam && p->checker && sc->kind == VRT_SCENE_LSVO && sc->ctx->render_variant != 0)
-        return fail(VRT_ERR_UNSUPPORTED, std::string(who) + ": the checkerboard needs render_variant 0");
+    if (cam && p->checker && sc->kind == VRT_SCENE_LSVO && (sc->ctx->render_variant == 1 || sc->ctx->render_variant == 3))
+        return fail(VRT_ERR_UNSUPPORTED, std::string(who) + ": the checkerboard needs render_variant 0 or 2");
     return VRT_OK;
 }
 
@@ -434,6 +437,8 @@ vrt::RenderLaunch make_launch(const vrt_scene* sc, const vrt_camera* cam, const 
     L.cam = *cam;
     L.spp_chunks = sc->ctx->spp_chunks;
     L.samples_per_warp = sc->ctx->samples_per_warp;
+    L.mapping = sc->ctx->render_variant == 1 ? 0 : sc->ctx->render_variant;
+    L.sort_bins1 = sc->ctx->sort_bins1; L.sort_bins2 = sc->ctx->sort_bins2;
     L.roughness = p->roughness;
     L.max_bounds = p->max_bounds;
     L.checker = p->checker; L.checker_area_height = p->checker_area_height;
@@ -471,7 +476,7 @@ int vrt_render_accumulate_device(vrt_scene* sc, const vrt_camera* cam, const vrt
     if (sc->kind != VRT_SCENE_LSVO)
         VRT_CUDA(vrt::launch_grid_render(sc->grid, sc->use_mip, make_launch(sc, cam, p), d_accum, sc->d_counters + kRenderCounters,
                                          ctx->stream));
-    else if (ctx->render_variant == 0)
+    else if (ctx->render_variant != 1)
         VRT_CUDA(vrt::launch_render_accumulate_ref(sc->use_compact ? sc->d_compact : sc->d_nodes, sc->use_compact, make_launch(sc, cam, p), d_accum, sc->d_counters + kRenderCounters,
                                                    ctx->stream));
     else

@@ -40,6 +40,8 @@ struct RenderLaunch {
     int tile_step, tile_index;   // 4-row tiles t with t % tile_step == tile_index are rendered
     int spp_chunks;              // K4: runs the samples are cut into (0 = chosen by the launcher)
     int samples_per_warp;        // K4: lanes sharing a pixel, power of two 1..32 (0 = chosen by the launcher)
+    int sort_bins1, sort_bins2;  // K5: angle bins per GI bounce (0 = chosen by the launcher; product <= 256)
+    int mapping;                 // 0 = automatic (K5 for many-sample GI frames, else K4), 2 = K4, 3 = K5
     uint32_t seed_lo, seed_hi;
     float light[3];
     vrt_camera cam;

@@ -124,6 +124,186 @@ __global__ void __launch_bounds__(128, VRT_K4_MIN_CTAS) render_accumulate_kernel
     }
 }
 
+// ---- K5: the same frame with the samples of a CTA's pixel block regrouped by GI direction -----------------------------
+//
+// In K4 the four GI ray classes take 69 % of the many-sample frame at 10.8 of 32 lanes (profiles/r01_summary.md): the GI
+// rays of a warp leave in unrelated directions (raycaster.hpp:178-192 draws them from a 100x100 lattice), so after the
+// common initial descent every loop trip executes all three branch paths and the warp waits for its longest ray.
+// Which lane runs which (pixel, sample) is free — the sums are integers — and the sample's random numbers are a pure
+// function of (pixel, sample) (Philox), so they can be evaluated BEFORE tracing anything: the CTA computes, for every
+// sample of its 32x4-pixel block, the angles of the first- and second-bounce GI noise, counting-sorts the samples by
+// (angle 1 bin, angle 2 bin) in shared memory and hands them out to its warps 32 at a time.  A warp then traces GI rays
+// that are nearly parallel and start within a few voxels of each other — as coherent as primary rays.
+// tools/probe_gi_sorting.py measured the effect on the traversal alone: 192 -> 300 G loop trips/s on first-bounce rays,
+// 219 -> 299 on their shadow rays.  Results cannot change: same samples, same numbers, integer sums.
+
+// pseudo-angle of the tangent-plane noise (c1, c2) = 20 * (i - 50, j - 50): 0 <= a < 4 around the circle ("diamond angle")
+__device__ __forceinline__ float noise_angle(uint32_t w1, uint32_t w2) {
+    const float x = float(int(w1 % 100u) - 50), y = float(int(w2 % 100u) - 50);
+    const float s = fabsf(x) + fabsf(y);
+    if (s == 0.0f) return 0.0f;
+    const float t = y / s;                                                     // -1..1
+    return x >= 0.0f ? (y >= 0.0f ? t : 4.0f + t) : 2.0f - t;
+}
+
+struct SortPlan {
+    int bins1, bins2;      // angle bins of bounce 1 and 2 (bins1 * bins2 <= 256)
+};
+
+template <typename Nodes>
+__global__ void __launch_bounds__(128, VRT_K4_MIN_CTAS) render_sorted_kernel(Nodes nodes, RenderLaunch L, SortPlan plan,
+                                                                            uint32_t* __restrict__ accum,
+                                                                            unsigned long long* __restrict__ counters) {
+    extern __shared__ uint2 smem[];
+    Stack64<128> stack{smem + threadIdx.x};
+    nodes.slots = pin(nodes.slots);
+    const int guard = pin(L.guard);
+    const int depth_offset = pin(kSvoMaxDepth - L.depth);
+    const int lane = threadIdx.x & 31;
+
+    // blockIdx.x = chunk * tiles + tile, a tile = 32x4 pixels, a chunk = one run of the pixels' samples (as in K4)
+    const int tiles_x = (L.width + 31) / 32;
+    const int tiles_y = int(gridDim.x) / (tiles_x * L.spp_chunks);
+    const int chunk = int(blockIdx.x) / (tiles_x * tiles_y), tile = int(blockIdx.x) - chunk * tiles_x * tiles_y;
+    const int bx = tile % tiles_x, by = tile / tiles_x;
+    const int s_begin = (chunk * L.spp) / L.spp_chunks, s_end = ((chunk + 1) * L.spp) / L.spp_chunks;
+    const int n_s = s_end - s_begin;
+    const int n_chains = 128 * n_s;                                            // launcher: <= 8192
+    const int x0 = bx * 32, y0 = L.row_begin + (by * L.tile_step + L.tile_index) * 4;
+    // sample c of the block: pixel c / n_s (walked 8x4 sub-tile by sub-tile), sample c % n_s.  The scatter below runs in
+    // ascending c and is nearly stable, so inside one direction bin consecutive list entries are samples of the same or of
+    // neighbouring pixels: their primary and sun-shadow rays stay coherent too.
+    auto pixel_of = [&](int j, int& x, int& y) { x = x0 + (j >> 5) * 8 + (j & 7); y = y0 + ((j >> 3) & 3); };
+
+    // shared memory: stacks | statistics | sorted sample list | histogram / cursors | pixel sums | work counter
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + (L.depth + 1) * 128) + threadIdx.x;
+    uint32_t* base = reinterpret_cast<uint32_t*>(smem + (L.depth + 1) * 128) + 12 * 128;
+    uint32_t* hist = base;                                                     // 257 words
+    uint32_t* sums = base + 260;                                               // 128 pixels x (r, g, b, count)
+    uint32_t* next_round = base + 260 + 512;
+    uint16_t* ids = reinterpret_cast<uint16_t*>(base + 260 + 512 + 4);        // n_chains entries
+#pragma unroll
+    for (int k = 0; k < 12; ++k) cnt[k * 128] = 0u;
+    for (int i = threadIdx.x; i < 257; i += 128) hist[i] = 0u;
+    for (int i = threadIdx.x; i < 512; i += 128) sums[i] = 0u;
+    if (threadIdx.x == 0) *next_round = 0u;
+    __syncthreads();
+
+    // ---- sort the block's samples by GI direction: histogram, scan, scatter (keys are recomputed, not stored) ----
+    const int n_keys = plan.bins1 * plan.bins2;
+    auto sample_key = [&](int c, bool& active) -> int {
+        const int j = c / n_s, s = s_begin + (c - j * n_s);
+        int x, y;
+        pixel_of(j, x, y);
+        active = x < L.width && y < L.row_end;
+        const uint32_t pixel = uint32_t(y) * uint32_t(L.width) + uint32_t(x), sample = uint32_t(L.sample_offset + s);
+        const uint4 r0 = philox4x32_10(pixel, sample, 0u, 0u, L.seed_lo, L.seed_hi);
+        int key = min(plan.bins1 - 1, int(noise_angle(r0.z, r0.w) * (float(plan.bins1) * 0.25f)));
+        if (plan.bins2 > 1) {
+            const uint4 r1 = philox4x32_10(pixel, sample, 1u, 0u, L.seed_lo, L.seed_hi);
+            key = key * plan.bins2 + min(plan.bins2 - 1, int(noise_angle(r1.x, r1.y) * (float(plan.bins2) * 0.25f)));
+        }
+        return key;
+    };
+    for (int c = threadIdx.x; c < n_chains; c += 128) {
+        bool active;
+        const int key = sample_key(c, active);
+        if (active) atomicAdd(hist + key, 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {                                                    // exclusive scan of <= 256 counters by one warp
+        uint32_t v[8], run = 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int i = lane * 8 + k; v[k] = i < n_keys ? hist[i] : 0u; run += v[k]; }
+        uint32_t incl = run;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        uint32_t excl = incl - run;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int i = lane * 8 + k; if (i < n_keys) hist[i] = excl; excl += v[k]; }
+        if (lane == 31) hist[256] = incl;                                      // number of active samples
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < n_chains; c += 128) {
+        bool active;
+        const int key = sample_key(c, active);
+        if (active) ids[atomicAdd(hist + key, 1u)] = uint16_t(c);
+    }
+    __syncthreads();
+    const uint32_t total = hist[256];
+
+    // ---- trace: warps fetch rounds of 32 consecutive sorted samples ----
+    const float SCALE = 1.0f / float(1 << L.depth);                           // raycaster.hpp:123-124 / main.cpp:82
+    const float n_norm = SCALE * 0.0078125f * 2.0f;                           // raycaster.hpp:171-172
+    const float aspect = float(L.width) / float(L.height);                    // main.cpp:133
+    const float focal_length = L.focal ? __ldg(L.focal) : L.cam.focal_length;
+    for (;;) {
+        uint32_t round = 0u;
+        if (lane == 0) round = atomicAdd(next_round, 1u);
+        round = __shfl_sync(0xffffffffu, round, 0);
+        if (round * 32u >= total) break;
+        const uint32_t slot = round * 32u + uint32_t(lane);
+        if (slot < total) {
+            const int c = ids[slot];
+            const int j = c / n_s, s = s_begin + (c - j * n_s);
+            int x, y;
+            pixel_of(j, x, y);
+            const uint32_t pixel = uint32_t(y) * uint32_t(L.width) + uint32_t(x), sample = uint32_t(L.sample_offset + s);
+            const float lens_x = float(x) / float(L.height) - aspect * 0.5f;  // main.cpp:145
+            const float lens_y = float(y) / float(L.height) - 0.5f;           // main.cpp:146
+            ChainState cs;
+            NextRay nr;
+            chain_begin(L, cs, pixel, sample, lens_x, lens_y, SCALE, focal_length, nr);
+            int stage = kPrimary;
+            while (stage != kDone) {
+                LsvoResult r;
+                lsvo_cast_ray(nodes, stack, depth_offset, guard, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
+                cnt[stage * 128] += 1u;
+                cnt[(6 + stage) * 128] += r.complexity;
+                LsvoHit h;
+                if (r.hit) lsvo_finish(r, nr.ox, nr.oy, nr.oz, L.depth, h);
+                stage = chain_advance(L, cs, stage, r, h, pixel, sample, SCALE, n_norm, nr);
+            }
+            uint32_t cr = 0, cg = 0, cb = 0;
+            chain_colour(L, cs, cr, cg, cb);
+            if (cr) atomicAdd(sums + 4 * j, cr);
+            if (cg) atomicAdd(sums + 4 * j + 1, cg);
+            if (cb) atomicAdd(sums + 4 * j + 2, cb);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- commit the block's pixel sums (every active pixel received s_end - s_begin samples) ----
+    {
+        const int j = threadIdx.x;
+        int x, y;
+        pixel_of(j, x, y);
+        if (x < L.width && y < L.row_end) {
+            uint32_t* w = accum + 4 * (size_t(y) * size_t(L.width) + size_t(x));   // Sample, raycaster.hpp:18-24,87-90
+            if (L.spp_chunks == 1) {
+                uint4 v = *reinterpret_cast<uint4*>(w);
+                v.x += sums[4 * j]; v.y += sums[4 * j + 1]; v.z += sums[4 * j + 2]; v.w += uint32_t(L.spp);
+                *reinterpret_cast<uint4*>(w) = v;
+            } else {
+                atomicAdd(w, sums[4 * j]); atomicAdd(w + 1, sums[4 * j + 1]); atomicAdd(w + 2, sums[4 * j + 2]);
+                atomicAdd(w + 3, uint32_t(s_end - s_begin));
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        uint32_t a = cnt[k * 128], b = cnt[(6 + k) * 128];
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (lane == 0 && a) {
+            atomicAdd(counters + k, (unsigned long long)a);
+            atomicAdd(counters + 6 + k, (unsigned long long)b);
+        }
+    }
+}
+
 // Camera::getClosestPoint (camera_controller.hpp:56-60) and the focal-length rule of main.cpp:114-121, one thread.
 template <typename Nodes>
 __global__ void __launch_bounds__(128) autofocus_kernel(Nodes nodes, int depth, int guard, vrt_camera cam, float* __restrict__ focal) {
@@ -184,6 +364,35 @@ cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const
     long chunks = 1;
     while (chunks * tiles < 28L * 4 * 148 && chunks * 2 * 8 <= L.spp) chunks *= 2;
     if (L.spp_chunks > 0) chunks = L.spp_chunks < L.spp ? L.spp_chunks : L.spp;      // explicit override
+    // K5 (samples regrouped by GI direction) when there is a GI pass and enough samples per run to sort
+    const bool sorted = L.mapping == 3 || (L.mapping == 0 && L.use_gi && !L.checker && L.spp / chunks >= 8);
+    if (sorted && !L.checker) {
+        // K5 sorts better with long runs (more samples per direction bin): 12 waves of CTAs are enough here.
+        // tools/probe_sorted.py, cfg 4: whole frame 67.8 ms at (1 run, 16 bins) vs 70.2 at (4, 16); the 1/8 slice of an
+        // 8-GPU rank 9.07 ms at (4, 8) vs 9.69 at (1, 16).  Sorting by the second bounce's angle as well did not pay.
+        if (L.spp_chunks <= 0) {
+            chunks = 1;
+            while (chunks * tiles < 12L * 4 * 148 && chunks * 2 * 8 <= L.spp) chunks *= 2;
+        }
+        while ((L.spp + chunks - 1) / chunks > 64) chunks *= 2;                     // <= 8192 samples per CTA (16-bit list)
+        Lc.spp_chunks = int(chunks);
+        const int n = 128 * int(L.spp / chunks);                                    // samples in the shortest run
+        SortPlan plan;
+        plan.bins1 = n >= 2048 ? 16 : n >= 512 ? 8 : n >= 128 ? 4 : 1;              // 22.5 degree sectors when they fill >= 4 rounds
+        plan.bins2 = 1;
+        if (L.sort_bins1 > 0) {                                                     // explicit override (measurements)
+            plan.bins1 = L.sort_bins1;
+            plan.bins2 = L.sort_bins2 > 0 ? L.sort_bins2 : 1;
+            if (plan.bins1 * plan.bins2 > 256) plan.bins2 = 256 / plan.bins1;
+        }
+        const int longest = int((L.spp + chunks - 1) / chunks);
+        const size_t smem5 = size_t(L.depth + 1) * block * 8 + 12 * block * sizeof(uint32_t) + (260 + 512 + 4) * sizeof(uint32_t) +
+                             size_t(128) * longest * sizeof(uint16_t);
+        const unsigned grid5 = unsigned(tiles * chunks);
+        if (compact) render_sorted_kernel<CompactNodes><<<grid5, block, smem5, stream>>>(CompactNodes{nodes}, Lc, plan, d_accum, d_counters);
+        else render_sorted_kernel<RefNodes><<<grid5, block, smem5, stream>>>(RefNodes{nodes}, Lc, plan, d_accum, d_counters);
+        return cudaGetLastError();
+    }
     Lc.spp_chunks = int(chunks);
     // lanes per pixel: the largest power of two (<= 32) that divides every chunk's sample count
     int q = 32;

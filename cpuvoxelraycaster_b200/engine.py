@@ -65,7 +65,7 @@ class Context:
         self.device = int(device)
         self._scenes = weakref.WeakSet()      # scenes hold a pointer to the context: they must die first
 
-        for key in ("cast_variant", "render_variant", "refill_cast", "refill_render", "spp_chunks", "samples_per_warp"):      # measurement overrides (tools/, profiles/)
+        for key in ("cast_variant", "render_variant", "refill_cast", "refill_render", "spp_chunks", "samples_per_warp", "sort_bins1", "sort_bins2"):      # measurement overrides (tools/, profiles/)
             v = os.environ.get("VRT_" + key.upper())
             if v is not None:
                 self.set_option(key, int(v))

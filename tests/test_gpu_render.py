@@ -182,6 +182,32 @@ def test_device_side_autofocus(vrt, scene9, view):
     assert np.array_equal(a, b) and np.array_equal(rc.colors, rc2.colors)
 
 
+@pytest.mark.parametrize("W,H,spp,chunks,bounces,variant", [(150, 70, 16, 0, 2, 0), (150, 70, 16, 2, 1, 0), (97, 41, 64, 0, 2, 0),
+                                                            (64, 36, 5, 0, 2, 3), (64, 36, 70, 0, 2, 3), (33, 9, 24, 3, 1, 3),
+                                                            (64, 36, 12, 0, 0, 3)])
+def test_direction_sorted_kernel_is_exact(vrt, port, terrain9_nodes, textures, W, H, spp, chunks, bounces, variant):
+    """K5 regroups the samples of a 32x4 pixel block by GI direction before tracing them: integer sums, same frame,
+    same ray statistics.  Ragged frames, uneven runs, more than 64 samples per pixel (forced extra runs), no GI."""
+    c = vrt.Context(0)
+    c.set_option("render_variant", variant)
+    c.set_option("spp_chunks", chunks)
+    s = vrt.LSVO(c, terrain9_nodes, 9)
+    s.set_textures(*textures)
+    cam = vrt.Camera(position=(256, 200, 256), view_angle=(0.3, -0.35), aperture=0.5, focal_length=60.0)
+    rc = vrt.RayCaster(s, (W, H))
+    rc.setLightPosition(default_light())
+    rc.use_samples, rc.use_gi, rc.gi_bounces = True, bounces > 0, max(1, bounces)
+    img = rc.render(cam, spp=spp).copy()
+    accum, rgba, stats = port.render(terrain9_nodes, port_params(W, H, 9, cam, default_light(), int(bounces > 0), max(1, bounces), True, spp), *textures)
+    assert np.array_equal(rc.colors, accum) and np.array_equal(img, rgba)
+    assert rc.last_stats["rays"] == list(stats.rays) and rc.last_stats["complexity"] == list(stats.complexity)
+    rc.render(cam, spp=8)                               # progressive: 8 more samples on top
+    p2 = port_params(W, H, 9, cam, default_light(), int(bounces > 0), max(1, bounces), True, 8, offset=spp)
+    accum2, _, _ = port.render(terrain9_nodes, p2, *textures)
+    assert np.array_equal(rc.colors, accum + accum2)
+    c.close()
+
+
 def test_autofocus(vrt, scene9, port, terrain9_nodes):
     cam = vrt.Camera(position=(256, 200, 256), view_angle=(0.0, -0.6))
     f = cam.autofocus(scene9)
@@ -191,7 +217,7 @@ def test_autofocus(vrt, scene9, port, terrain9_nodes):
     assert vrt.Camera(position=(256, 200, 256), view_angle=(0.0, 0.0)).autofocus(scene9) == 100.0   # centre ray misses
 
 
-@pytest.mark.parametrize("variant,refill", [(0, 8), (1, 1), (1, 12), (1, 32)])
+@pytest.mark.parametrize("variant,refill", [(0, 8), (1, 1), (1, 12), (1, 32), (2, 8), (3, 8)])
 def test_render_kernel_variants_agree(vrt, port, terrain9_nodes, textures, variant, refill):
     c = vrt.Context(0)
     c.set_option("render_variant", variant)
@@ -234,6 +260,7 @@ def test_sample_chunking_is_exact(vrt, port, terrain9_nodes, textures, chunks):
 def test_lane_mapping_is_exact(vrt, port, terrain9_nodes, textures, q, chunks, spp):
     """K4 may give several lanes of a warp the same pixel (consecutive samples) — integer sums, same frame."""
     c = vrt.Context(0)
+    c.set_option("render_variant", 2)
     c.set_option("samples_per_warp", q)
     c.set_option("spp_chunks", chunks)
     s = vrt.LSVO(c, terrain9_nodes, 9)
