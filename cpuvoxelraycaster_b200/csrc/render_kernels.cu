@@ -146,12 +146,17 @@ __device__ __forceinline__ float noise_angle(uint32_t w1, uint32_t w2) {
     return x >= 0.0f ? (y >= 0.0f ? t : 4.0f + t) : 2.0f - t;
 }
 
+// 5 CTAs per SM: K5 needs 95 registers without spilling (K4 does not fit: 12 B of spills and slower).  Measured on cfg 4:
+// 67.8 ms at 4 CTAs, 63.9 ms at 5, 74.4 ms at 6 (80 registers, spills).
+#ifndef VRT_K5_MIN_CTAS
+#define VRT_K5_MIN_CTAS 5
+#endif
 struct SortPlan {
     int bins1, bins2;      // angle bins of bounce 1 and 2 (bins1 * bins2 <= 256)
 };
 
 template <typename Nodes>
-__global__ void __launch_bounds__(128, VRT_K4_MIN_CTAS) render_sorted_kernel(Nodes nodes, RenderLaunch L, SortPlan plan,
+__global__ void __launch_bounds__(128, VRT_K5_MIN_CTAS) render_sorted_kernel(Nodes nodes, RenderLaunch L, SortPlan plan,
                                                                             uint32_t* __restrict__ accum,
                                                                             unsigned long long* __restrict__ counters) {
     extern __shared__ uint2 smem[];
