@@ -211,6 +211,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL prints its version banner on stdout: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=device)
 
     w = workload(args)
