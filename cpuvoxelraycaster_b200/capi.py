@@ -79,6 +79,9 @@ _SIGNATURES = {
     "vrt_render": (C.c_int, [_vp, C.POINTER(Camera), C.POINTER(RenderParams), _vp, _vp, C.POINTER(RenderStats)]),
     "vrt_scene_last_render_stats": (C.c_int, [_vp, C.POINTER(RenderStats)]),
     "vrt_autofocus": (C.c_int, [_vp, C.POINTER(Camera), C.POINTER(_f)]),
+    "vrt_lsvo_create_heightfield": (C.c_int, [_vp, _u32, _vp, _i32, C.POINTER(_vp)]),
+    "vrt_scene_edit_heights": (C.c_int, [_vp, _u32, _u32, _u32, _u32, _vp]),
+    "vrt_scene_download_heights": (C.c_int, [_vp, _vp]),
     "vrt_present_device": (C.c_int, [_vp, _vp, _vp, C.POINTER(PresentParams)]),
     "vrt_present": (C.c_int, [_vp, _vp, _vp, C.POINTER(PresentParams)]),
 }

@@ -78,6 +78,7 @@ struct vrt_scene {
     uint2* d_compact = nullptr;                 // optional compact breadth-first copy (vrt_scene_set_layout)
     uint64_t n_compact = 0;
     bool use_compact = false;
+    int32_t* d_heights = nullptr;               // heightfield scenes: column heights [S*S], resident for edits
     uint8_t* d_tex = nullptr;                   // top (768 B) then side (768 B)
     bool has_tex = false;
     DeviceBuffer frame_accum, frame_rgba;       // vrt_render staging
@@ -270,6 +271,83 @@ int vrt_lsvo_create_terrain(vrt_context* ctx, uint32_t depth, int32_t guard, vrt
     return VRT_OK;
 }
 
+int vrt_lsvo_create_heightfield(vrt_context* ctx, uint32_t depth, const int32_t* heights, int32_t guard, vrt_scene** out) {
+    if (!ctx || !out) return fail(VRT_ERR_INVALID, "vrt_lsvo_create_heightfield: NULL argument");
+    if (depth < 5 || depth > 12) return fail(VRT_ERR_INVALID, "vrt_lsvo_create_heightfield: depth must be 5..12");
+    if (!heights && depth < 8) return fail(VRT_ERR_INVALID, "vrt_lsvo_create_heightfield: the demo terrain needs depth 8..12");
+    if (int s = use_device(ctx)) return s;
+    vrt_scene* sc = new (std::nothrow) vrt_scene();
+    if (!sc) return fail(VRT_ERR_OOM, "vrt_lsvo_create_heightfield: host allocation failed");
+    sc->ctx = ctx;
+    sc->kind = VRT_SCENE_LSVO;
+    sc->depth = depth;
+    sc->guard = guard > 0 ? guard : (guard < 0 ? 0 : int32_t(depth));
+    const size_t columns = size_t(1) << (2 * depth);
+    cudaError_t e = cudaMalloc(&sc->d_heights, columns * sizeof(int32_t));
+    if (e == cudaSuccess && heights) e = cudaMemcpyAsync(sc->d_heights, heights, columns * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+    // heights == NULL: the demo terrain (FastNoise heights, main.cpp:61-68), kept resident so that it can be edited
+    if (e == cudaSuccess)
+        e = vrt::device_build_terrain_lsvo(int(depth), &sc->d_nodes, &sc->n_nodes, heights ? nullptr : sc->d_heights, ctx->stream,
+                                           heights ? sc->d_heights : nullptr);
+    ctx->launches += 7 + 9 * depth;
+    if (e == cudaSuccess) e = cudaMalloc(&sc->d_counters, 16 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemsetAsync(sc->d_counters, 0, 16 * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        vrt_scene_destroy(sc);
+        return e == cudaErrorMemoryAllocation ? fail(VRT_ERR_OOM, "vrt_lsvo_create_heightfield: device allocation failed")
+                                              : cuda_fail(e, "vrt_lsvo_create_heightfield");
+    }
+    sc->device_bytes = sc->n_nodes * sizeof(uint2) + columns * sizeof(int32_t);
+    *out = sc;
+    return VRT_OK;
+}
+
+int vrt_scene_edit_heights(vrt_scene* sc, uint32_t x0, uint32_t z0, uint32_t nx, uint32_t nz, const int32_t* heights) {
+    if (!sc || !heights) return fail(VRT_ERR_INVALID, "vrt_scene_edit_heights: NULL argument");
+    if (sc->kind != VRT_SCENE_LSVO || !sc->d_heights)
+        return fail(VRT_ERR_UNSUPPORTED, "vrt_scene_edit_heights: the scene was not created by vrt_lsvo_create_heightfield");
+    const uint64_t S = uint64_t(1) << sc->depth;
+    if (nx == 0 || nz == 0 || uint64_t(x0) + nx > S || uint64_t(z0) + nz > S) return fail(VRT_ERR_INVALID, "vrt_scene_edit_heights: rectangle out of range");
+    vrt_context* ctx = sc->ctx;
+    if (int s = use_device(ctx)) return s;
+    VRT_CUDA(cudaMemcpy2DAsync(sc->d_heights + size_t(x0) * S + z0, S * sizeof(int32_t), heights, size_t(nz) * sizeof(int32_t),
+                               size_t(nz) * sizeof(int32_t), nx, cudaMemcpyHostToDevice, ctx->stream));
+    uint2* d_new = nullptr;
+    uint64_t n_new = 0;
+    cudaError_t e = vrt::device_build_terrain_lsvo(int(sc->depth), &d_new, &n_new, nullptr, ctx->stream, sc->d_heights);
+    ctx->launches += 7 + 9 * sc->depth;
+    if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? fail(VRT_ERR_OOM, "vrt_scene_edit_heights: device allocation failed")
+                                                                : cuda_fail(e, "vrt_scene_edit_heights");
+    // the builder synchronised the stream: nothing in flight reads the old arrays any more
+    cudaFree(sc->d_nodes);
+    sc->device_bytes += n_new * sizeof(uint2);
+    sc->device_bytes -= sc->n_nodes * sizeof(uint2);
+    sc->d_nodes = d_new;
+    sc->n_nodes = n_new;
+    if (sc->d_compact) {                                    // the compact copy is rebuilt from the new array
+        cudaFree(sc->d_compact);
+        sc->device_bytes -= sc->n_compact * sizeof(uint2);
+        sc->d_compact = nullptr;
+        sc->n_compact = 0;
+        if (sc->use_compact) {
+            sc->use_compact = false;
+            return vrt_scene_set_layout(sc, 1, 0);
+        }
+    }
+    return VRT_OK;
+}
+
+int vrt_scene_download_heights(vrt_scene* sc, int32_t* heights) {
+    if (!sc || !heights) return fail(VRT_ERR_INVALID, "vrt_scene_download_heights: NULL argument");
+    if (!sc->d_heights) return fail(VRT_ERR_UNSUPPORTED, "vrt_scene_download_heights: not a heightfield scene");
+    if (int s = use_device(sc->ctx)) return s;
+    const size_t columns = size_t(1) << (2 * sc->depth);
+    VRT_CUDA(cudaMemcpyAsync(heights, sc->d_heights, columns * sizeof(int32_t), cudaMemcpyDeviceToHost, sc->ctx->stream));
+    VRT_CUDA(cudaStreamSynchronize(sc->ctx->stream));
+    return VRT_OK;
+}
+
 int vrt_scene_set_layout(vrt_scene* sc, int32_t layout, int32_t l2_persist) {
     if (!sc) return fail(VRT_ERR_INVALID, "vrt_scene_set_layout: scene is NULL");
     if (sc->kind != VRT_SCENE_LSVO) return fail(VRT_ERR_INVALID, "vrt_scene_set_layout: not an LSVO scene");
@@ -326,6 +404,7 @@ int vrt_scene_destroy(vrt_scene* sc) {
     if (sc->d_nodes) cudaFree(sc->d_nodes);
     if (sc->d_counters) cudaFree(sc->d_counters);
     if (sc->d_compact) cudaFree(sc->d_compact);
+    if (sc->d_heights) cudaFree(sc->d_heights);
     if (sc->d_tex) cudaFree(sc->d_tex);
     if (sc->d_grid_bits) cudaFree(sc->d_grid_bits);
     sc->frame_accum.release();

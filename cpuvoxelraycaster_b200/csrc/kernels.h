@@ -89,7 +89,9 @@ cudaError_t launch_grid_render(const GridLevels& g, bool use_mip, const RenderLa
                                unsigned long long* d_counters, cudaStream_t stream);
 // Scene construction on the device (scene_device.cu): T(depth) in the reference's LNode layout, nothing crosses PCIe.
 // *d_slots is cudaMalloc'ed (the caller frees it); d_heights_out may be null.
-cudaError_t device_build_terrain_lsvo(int depth, uint2** d_slots, uint64_t* n_slots, int32_t* d_heights_out, cudaStream_t stream);
+// d_heights_in (device, [S*S] int32, index x*S+z): build from these column heights instead of the FastNoise terrain.
+cudaError_t device_build_terrain_lsvo(int depth, uint2** d_slots, uint64_t* n_slots, int32_t* d_heights_out, cudaStream_t stream,
+                                      const int32_t* d_heights_in = nullptr);
 // Reference layout → compact breadth-first array of live nodes, on the device (scene_device.cu); caller frees *d_out.
 cudaError_t device_compact_lsvo(const uint2* d_ref, uint64_t n_ref, int depth, uint2** d_out, uint64_t* n_out, cudaStream_t stream);
 }  // namespace vrt

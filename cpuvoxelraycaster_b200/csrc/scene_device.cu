@@ -86,6 +86,14 @@ __global__ void heights_kernel(int S, float bounding, int32_t* __restrict__ heig
     top0[size_t(x) * S + z] = S / 2 + hmax - 1;
 }
 
+// the same fill rule for caller-supplied column heights (dynamic scenes)
+__global__ void tops_kernel(int S, const int32_t* __restrict__ heights, int32_t* __restrict__ top0) {
+    const int z = blockIdx.x * blockDim.x + threadIdx.x, x = blockIdx.y;
+    if (z >= S) return;
+    const int32_t hmax = max(16, min(S / 2, heights[size_t(x) * S + z]));   // min(S, h) wherever y + S/2 stays inside the world
+    top0[size_t(x) * S + z] = S / 2 + hmax - 1;
+}
+
 __global__ void pyramid_kernel(int n, const int32_t* __restrict__ lo, int32_t* __restrict__ hi) {
     const int z = blockIdx.x * blockDim.x + threadIdx.x, x = blockIdx.y;
     if (z >= n) return;
@@ -231,27 +239,34 @@ struct Scratch {
 
 }  // namespace
 
-// Builds T(depth) on the device.  *d_slots is cudaMalloc'ed (caller frees); optional d_heights_out [S*S] int32.
-cudaError_t device_build_terrain_lsvo(int depth, uint2** d_slots, uint64_t* n_slots, int32_t* d_heights_out, cudaStream_t stream) {
+// Builds T(depth) on the device — or, with d_heights_in, the same fill rule (main.cpp:70-76) over caller-supplied
+// column heights.  *d_slots is cudaMalloc'ed (caller frees); optional d_heights_out [S*S] int32 receives the heights.
+cudaError_t device_build_terrain_lsvo(int depth, uint2** d_slots, uint64_t* n_slots, int32_t* d_heights_out, cudaStream_t stream,
+                                      const int32_t* d_heights_in) {
     const int S = 1 << depth, bottom = S / 2 + 1;
-    uint8_t perm[512], perm12[512];
-    float bounding;
-    host_simplex_tables(perm, perm12, &bounding);
-    VRT_TRY(cudaMemcpyToSymbolAsync(c_perm, perm, 512, 0, cudaMemcpyHostToDevice, stream));
-    VRT_TRY(cudaMemcpyToSymbolAsync(c_perm12, perm12, 512, 0, cudaMemcpyHostToDevice, stream));
-
     Scratch sc;
     int32_t* d_heights = nullptr;
     std::vector<int32_t*> top(depth + 1, nullptr);
-    VRT_TRY(sc.alloc(&d_heights, size_t(S) * S));
     for (int l = 0; l <= depth; ++l) VRT_TRY(sc.alloc(&top[l], size_t(S >> l) * (S >> l)));
     const dim3 blk(128);
-    heights_kernel<<<dim3((S + 127) / 128, S), blk, 0, stream>>>(S, bounding, d_heights, top[0]);
+    if (d_heights_in) {
+        d_heights = const_cast<int32_t*>(d_heights_in);
+        tops_kernel<<<dim3((S + 127) / 128, S), blk, 0, stream>>>(S, d_heights_in, top[0]);
+    } else {
+        uint8_t perm[512], perm12[512];
+        float bounding;
+        host_simplex_tables(perm, perm12, &bounding);
+        VRT_TRY(cudaMemcpyToSymbolAsync(c_perm, perm, 512, 0, cudaMemcpyHostToDevice, stream));
+        VRT_TRY(cudaMemcpyToSymbolAsync(c_perm12, perm12, 512, 0, cudaMemcpyHostToDevice, stream));
+        VRT_TRY(sc.alloc(&d_heights, size_t(S) * S));
+        heights_kernel<<<dim3((S + 127) / 128, S), blk, 0, stream>>>(S, bounding, d_heights, top[0]);
+    }
     for (int l = 1; l <= depth; ++l) {
         const int n = S >> l;
         pyramid_kernel<<<dim3((n + 127) / 128, n), blk, 0, stream>>>(n, top[l - 1], top[l]);
     }
-    if (d_heights_out) VRT_TRY(cudaMemcpyAsync(d_heights_out, d_heights, size_t(S) * S * 4, cudaMemcpyDeviceToDevice, stream));
+    if (d_heights_out && d_heights_out != d_heights)
+        VRT_TRY(cudaMemcpyAsync(d_heights_out, d_heights, size_t(S) * S * 4, cudaMemcpyDeviceToDevice, stream));
 
     // node counts and storage offsets per level
     std::vector<Level> lv(depth + 1);

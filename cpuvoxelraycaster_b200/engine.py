@@ -201,6 +201,40 @@ class LSVO(Volumetric):
         self._layout_from_env()
         return self
 
+    @classmethod
+    def from_heightfield(cls, ctx, depth, heights=None, guard=0):
+        """A world given by column heights[x, z] with the demo's fill rule (src/main.cpp:70-76), flattened on the GPU and
+        editable afterwards (edit_heights).  heights=None: the demo's FastNoise terrain."""
+        S = 1 << int(depth)
+        self = cls.__new__(cls)
+        Volumetric.__init__(self, ctx)
+        h = C.c_void_p()
+        hp = None
+        if heights is not None:
+            hh = np.ascontiguousarray(heights, np.int32)
+            if hh.shape != (S, S):
+                raise ValueError("heights must be [2^depth, 2^depth]")
+            hp = ptr(hh)
+        check(lib().vrt_lsvo_create_heightfield(ctx.handle, int(depth), hp, int(guard), C.byref(h)))
+        self.handle = h
+        self.depth = int(depth)
+        self.n_nodes = len(self)
+        self._layout_from_env()
+        return self
+
+    def edit_heights(self, x0, z0, heights):
+        """Dynamic scene (the reference's LSVO::setCell is a no-op, lsvo.hpp:26): replaces the heights of the columns
+        [x0, x0+nx) x [z0, z0+nz) and re-flattens the world on the device."""
+        hh = np.ascontiguousarray(heights, np.int32)
+        check(lib().vrt_scene_edit_heights(self.handle, int(x0), int(z0), hh.shape[0], hh.shape[1], ptr(hh)))
+        self.n_nodes = len(self)
+
+    def heights(self):
+        S = 1 << self.depth
+        out = np.zeros((S, S), np.int32)
+        check(lib().vrt_scene_download_heights(self.handle, ptr(out)))
+        return out
+
     def set_layout(self, layout, l2_persist=False):
         """0 = the reference's LNode array, 1 = compact breadth-first live nodes (same results, 8x smaller)."""
         check(lib().vrt_scene_set_layout(self.handle, int(layout), int(bool(l2_persist))))

@@ -125,6 +125,17 @@ int vrt_lsvo_create(vrt_context* ctx, const vrt_lnode* nodes, uint64_t n_nodes, 
  * main.cpp:61-76 and compileSVO lsvo_utils.cpp:4-49 in one pass; byte-identical to vrt_host_build_terrain_lsvo and to
  * the reference's own array) — nothing crosses PCIe. */
 int vrt_lsvo_create_terrain(vrt_context* ctx, uint32_t depth, int32_t guard, vrt_scene** out);
+/* Dynamic scenes (the reference's LSVO::setCell is a no-op, lsvo.hpp:26, so its world cannot change once
+ * flattened).  A heightfield scene keeps its column heights resident on the device and is re-flattened there after an edit.
+ *   heights[x * S + z], S = 2^depth (depth 5..12): column (x, z) is solid for y in [1, max(16, min(S/2, height))) stored
+ *   at y + S/2 — the fill rule of main.cpp:70-76 (256 → S/2) wherever that rule stays inside the world (the reference's
+ *   min(S, height) would write past it for height > S/2); NULL = the demo's FastNoise heights (main.cpp:61-68).
+ * vrt_scene_edit_heights replaces the heights of the rectangle [x0, x0+nx) x [z0, z0+nz) (heights[i * nz + j] is column
+ * (x0+i, z0+j)) and rebuilds the node array on the device: the result is byte-identical to flattening the edited world
+ * from scratch (compileSVO order), so every cast and frame stays bit-exact.  Synchronises the context stream. */
+int vrt_lsvo_create_heightfield(vrt_context* ctx, uint32_t depth, const int32_t* heights, int32_t guard, vrt_scene** out);
+int vrt_scene_edit_heights(vrt_scene* scene, uint32_t x0, uint32_t z0, uint32_t nx, uint32_t nz, const int32_t* heights);
+int vrt_scene_download_heights(vrt_scene* scene, int32_t* heights /* [S*S] */);
 /* Device-side node layout of an LSVO scene (no reference counterpart; results are identical for both):
  *   0 = the reference's LNode array (default), 1 = compact breadth-first array of live nodes (8x smaller, built on the
  *   device on first use).  l2_persist != 0 additionally pins the front of the compact array (the top octree levels)

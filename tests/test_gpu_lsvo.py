@@ -200,3 +200,53 @@ def test_compact_layout_gives_identical_results(vrt, port, terrain9_nodes, textu
     e.set_layout(1)
     assert not hit_flag(e.cast_rays([[1.5, 1.5, 1.1]], [[0, 0, 1]]))[0]
     c.close()
+
+
+def _heightfield_voxels(heights):
+    """The fill rule of main.cpp:70-76 as a voxel list in SVO::setCell coordinates (for the host flattener)."""
+    S = heights.shape[0]
+    out = []
+    for x in range(S):
+        for z in range(S):
+            hmax = max(16, min(S // 2, int(heights[x, z])))
+            ys = np.arange(1, hmax) + S // 2
+            out.append(np.stack([np.full(len(ys), x), ys, np.full(len(ys), z)], 1))
+    return np.concatenate(out).astype(np.uint32)
+
+
+@pytest.mark.parametrize("depth", [5, 6, 8])
+def test_heightfield_scene_and_edits(vrt, ctx, port, depth):
+    """Dynamic scenes: a world given by column heights is flattened on the device byte-identically to the host
+    flattener (compileSVO order), also after rectangles of columns were edited; casts stay bit-exact."""
+    S = 1 << depth
+    rng = np.random.default_rng(depth)
+    heights = rng.integers(-5, S // 2 + 8, (S, S)).astype(np.int32)         # some below the 16-voxel floor, some above S/2
+    s = vrt.LSVO.from_heightfield(ctx, depth, heights)
+    want = vrt.host_build_lsvo_from_voxels(depth, _heightfield_voxels(heights))
+    assert np.array_equal(s.download_nodes().view(np.uint64), want.view(np.uint64))
+    for k in range(3):
+        nx, nz = int(rng.integers(1, S // 2)), int(rng.integers(1, S // 2))
+        x0, z0 = int(rng.integers(0, S - nx + 1)), int(rng.integers(0, S - nz + 1))
+        patch = rng.integers(0, S // 2, (nx, nz)).astype(np.int32)
+        heights[x0:x0 + nx, z0:z0 + nz] = patch
+        if k == 1:
+            s.set_layout(1)                                # edits rebuild the compact copy as well
+        s.edit_heights(x0, z0, patch)
+        assert np.array_equal(s.heights(), heights)
+        want = vrt.host_build_lsvo_from_voxels(depth, _heightfield_voxels(heights))
+        assert np.array_equal(s.download_nodes().view(np.uint64), want.view(np.uint64)), "edit %d" % k
+        o = rng.uniform(1.0, 2.0, (2000, 3)).astype(np.float32)
+        o[:, 1] = rng.uniform(1.0, 1.2, 2000)
+        d = rng.normal(size=(2000, 3)).astype(np.float32)
+        got = s.cast_rays(o, d)
+        assert_hits_equal(got, port.lsvo_cast(want, depth, o, d), hit_flag(got), "after edit %d" % k)
+    with pytest.raises(vrt.VrtError):
+        s.edit_heights(S - 1, 0, np.zeros((2, 1), np.int32))       # rectangle out of range
+    s.close()
+    # the demo terrain as an editable scene equals the terrain scene
+    t = vrt.LSVO.from_heightfield(ctx, 8)
+    assert np.array_equal(t.download_nodes().view(np.uint64), vrt.host_build_terrain_lsvo(8).view(np.uint64))
+    assert np.array_equal(t.heights().reshape(-1), vrt.host_terrain_heights(256).reshape(-1))
+    with pytest.raises(vrt.VrtError):
+        vrt.LSVO.from_terrain(ctx, 8).edit_heights(0, 0, np.zeros((1, 1), np.int32))   # not a heightfield scene
+    t.close()
