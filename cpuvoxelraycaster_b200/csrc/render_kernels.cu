@@ -369,8 +369,9 @@ cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const
     long chunks = 1;
     while (chunks * tiles < 28L * 4 * 148 && chunks * 2 * 8 <= L.spp) chunks *= 2;
     if (L.spp_chunks > 0) chunks = L.spp_chunks < L.spp ? L.spp_chunks : L.spp;      // explicit override
-    // K5 (samples regrouped by GI direction) when there is a GI pass and enough samples per run to sort
-    const bool sorted = L.mapping == 3 || (L.mapping == 0 && L.use_gi && !L.checker && L.spp / chunks >= 8);
+    // K5 for many-sample frames: samples regrouped by GI direction when there is a GI pass; without one the list stays in
+    // pixel order (one bin) and K5 still wins through its 5 CTAs per SM (no-GI cfg-4 frame: 31.3 ms vs K4's 33.6)
+    const bool sorted = L.mapping == 3 || (L.mapping == 0 && !L.checker && L.spp / chunks >= 8);
     if (sorted && !L.checker) {
         // K5 sorts better with long runs (more samples per direction bin): 12 waves of CTAs are enough here.
         // tools/probe_sorted.py, cfg 4: whole frame 67.8 ms at (1 run, 16 bins) vs 70.2 at (4, 16); the 1/8 slice of an
@@ -383,7 +384,7 @@ cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const
         Lc.spp_chunks = int(chunks);
         const int n = 128 * int(L.spp / chunks);                                    // samples in the shortest run
         SortPlan plan;
-        plan.bins1 = n >= 2048 ? 16 : n >= 512 ? 8 : n >= 128 ? 4 : 1;              // 22.5 degree sectors when they fill >= 4 rounds
+        plan.bins1 = !L.use_gi ? 1 : n >= 2048 ? 16 : n >= 512 ? 8 : n >= 128 ? 4 : 1;   // 22.5 degree sectors when they fill >= 4 rounds
         plan.bins2 = 1;
         if (L.sort_bins1 > 0) {                                                     // explicit override (measurements)
             plan.bins1 = L.sort_bins1;
