@@ -296,10 +296,10 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if world == 1 and os.path.exists(tpath):      # the ncu capture is of the 1-GPU launch (whole frame)
         try:
-            traffic = json.load(open(tpath)).get("render_sorted_kernel_dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get("render_rounds_kernel_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "render_sorted_kernel (K5)", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "render_rounds_kernel (K6; timed with its sort_samples_kernel)", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": round(kernel_ms, 4),
                 "kernel_share_of_step": round(kernel_ms_max / ms_per_step, 4),

@@ -82,6 +82,7 @@ struct vrt_scene {
     uint8_t* d_tex = nullptr;                   // top (768 B) then side (768 B)
     bool has_tex = false;
     DeviceBuffer frame_accum, frame_rgba;       // vrt_render staging
+    DeviceBuffer frame_lists;                   // K6: sorted sample lists of the frame in flight
     // Grid3D / MipmapGrid3D / SVO: bit-packed occupancy pyramid
     vrt::GridLevels grid{};
     uint32_t* d_grid_bits = nullptr;
@@ -164,7 +165,7 @@ int vrt_context_set_option(vrt_context* ctx, const char* key, int value) {
     if (!ctx || !key) return fail(VRT_ERR_INVALID, "vrt_context_set_option: NULL argument");
     const std::string k(key);
     if (k == "cast_variant" && (value == 0 || value == 1)) ctx->cast_variant = value;
-    else if (k == "render_variant" && value >= 0 && value <= 3) ctx->render_variant = value;
+    else if (k == "render_variant" && value >= 0 && value <= 4) ctx->render_variant = value;
     else if (k == "sort_bins1" && value >= 0 && value <= 256) ctx->sort_bins1 = value;
     else if (k == "sort_bins2" && value >= 0 && value <= 256) ctx->sort_bins2 = value;
     else if (k == "spp_chunks" && value >= 0 && value <= 4096) ctx->spp_chunks = value;
@@ -409,6 +410,7 @@ int vrt_scene_destroy(vrt_scene* sc) {
     if (sc->d_grid_bits) cudaFree(sc->d_grid_bits);
     sc->frame_accum.release();
     sc->frame_rgba.release();
+    sc->frame_lists.release();
     delete sc;
     return VRT_OK;
 }
@@ -500,7 +502,7 @@ int check_render_args(const vrt_scene* sc, const vrt_camera* cam, const vrt_rend
     if (cam && !sc->has_tex) return fail(VRT_ERR_INVALID, std::string(who) + ": call vrt_scene_set_textures first (raycaster.hpp:53-54)");
     if (p->checker < 0 || p->checker > 2 || p->checker_area_height < 0) return fail(VRT_ERR_INVALID, std::string(who) + ": checker must be 0, 1 or 2 and checker_area_height >= 0");
     if (cam && p->autofocus && sc->kind != VRT_SCENE_LSVO) return fail(VRT_ERR_UNSUPPORTED, std::string(who) + ": autofocus needs an LSVO scene");
-    if (cam && p->checker && sc->kind == VRT_SCENE_LSVO && (sc->ctx->render_variant == 1 || sc->ctx->render_variant == 3))
+    if (cam && p->checker && sc->kind == VRT_SCENE_LSVO && (sc->ctx->render_variant == 1 || sc->ctx->render_variant >= 3))
         return fail(VRT_ERR_UNSUPPORTED, std::string(who) + ": the checkerboard needs render_variant 0 or 2");
     return VRT_OK;
 }
@@ -517,6 +519,7 @@ vrt::RenderLaunch make_launch(const vrt_scene* sc, const vrt_camera* cam, const 
     L.spp_chunks = sc->ctx->spp_chunks;
     L.samples_per_warp = sc->ctx->samples_per_warp;
     L.mapping = sc->ctx->render_variant == 1 ? 0 : sc->ctx->render_variant;
+    L.scratch = nullptr; L.scratch_bytes = 0;
     L.sort_bins1 = sc->ctx->sort_bins1; L.sort_bins2 = sc->ctx->sort_bins2;
     L.roughness = p->roughness;
     L.max_bounds = p->max_bounds;
@@ -555,9 +558,19 @@ int vrt_render_accumulate_device(vrt_scene* sc, const vrt_camera* cam, const vrt
     if (sc->kind != VRT_SCENE_LSVO)
         VRT_CUDA(vrt::launch_grid_render(sc->grid, sc->use_mip, make_launch(sc, cam, p), d_accum, sc->d_counters + kRenderCounters,
                                          ctx->stream));
-    else if (ctx->render_variant != 1)
-        VRT_CUDA(vrt::launch_render_accumulate_ref(sc->use_compact ? sc->d_compact : sc->d_nodes, sc->use_compact, make_launch(sc, cam, p), d_accum, sc->d_counters + kRenderCounters,
+    else if (ctx->render_variant != 1) {
+        vrt::RenderLaunch L = make_launch(sc, cam, p);
+        const size_t need = vrt::render_scratch_bytes(L);
+        if (need) {
+            if (need > sc->frame_lists.bytes) VRT_CUDA(cudaStreamSynchronize(ctx->stream));     // an earlier frame may still read the old buffer
+            if (sc->frame_lists.reserve(need) != cudaSuccess) return fail(VRT_ERR_OOM, "vrt_render_accumulate_device: scratch allocation failed");
+            L.scratch = sc->frame_lists.ptr;
+            L.scratch_bytes = sc->frame_lists.bytes;
+            ctx->launches += 1;                                                                  // the sort kernel
+        }
+        VRT_CUDA(vrt::launch_render_accumulate_ref(sc->use_compact ? sc->d_compact : sc->d_nodes, sc->use_compact, L, d_accum, sc->d_counters + kRenderCounters,
                                                    ctx->stream));
+    }
     else
         VRT_CUDA(vrt::launch_render_persistent(sc->d_nodes, make_launch(sc, cam, p), d_accum, sc->d_counters + kRenderCounters,
                                                ctx->refill_render, ctx->stream));

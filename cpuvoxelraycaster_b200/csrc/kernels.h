@@ -41,6 +41,8 @@ struct RenderLaunch {
     int spp_chunks;              // K4: runs the samples are cut into (0 = chosen by the launcher)
     int samples_per_warp;        // K4: lanes sharing a pixel, power of two 1..32 (0 = chosen by the launcher)
     int sort_bins1, sort_bins2;  // K5: angle bins per GI bounce (0 = chosen by the launcher; product <= 256)
+    void* scratch;               // K6: device scratch for the sorted sample lists (render_scratch_bytes)
+    size_t scratch_bytes;
     int mapping;                 // 0 = automatic (K5 for many-sample GI frames, else K4), 2 = K4, 3 = K5
     uint32_t seed_lo, seed_hi;
     float light[3];
@@ -62,6 +64,8 @@ __host__ __device__ inline int checker_x_parity(int checker, int area_height, in
 }
 
 // K0+K4: ray generation, traversal, shading and accumulation for rows [row_begin,row_end) (render_kernels.cu)
+// device scratch launch_render_accumulate_ref needs for this launch (0 unless the K6 mapping is selected)
+size_t render_scratch_bytes(const RenderLaunch& L);
 cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const RenderLaunch& L, uint32_t* d_accum,
                                          unsigned long long* d_counters, cudaStream_t stream);
 // Camera::getClosestPoint + main.cpp:114-121 on the device: *d_focal = hit ? distance * 2^depth : 100

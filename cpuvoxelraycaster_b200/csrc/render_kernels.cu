@@ -309,6 +309,200 @@ __global__ void __launch_bounds__(128, VRT_K5_MIN_CTAS) render_sorted_kernel(Nod
     }
 }
 
+// ---- K6: K5's sorted lists in global memory + persistent CTAs that help each other finish ------------------------------
+//
+// K5's unit of scheduling is a CTA-sized block of samples (2.9 ms of work on the headline frame): the launch ends with SMs
+// idling while the last blocks finish, and on an 8-GPU slice the blocks must be cut into short runs (less to sort) to keep
+// that tail small.  K6 splits the two jobs: `sort_samples_kernel` writes every block's direction-sorted sample list to
+// global memory (16 KB per block), `render_rounds_kernel` runs one persistent CTA set that takes blocks from a global
+// counter — the CTA's warps pull rounds of 32 list entries from the block's own counter, so a block still has the L1 of one
+// SM to itself — and, once no blocks are left, every warp looks for blocks that still have rounds and helps with them.
+// A round commits its colours with one warp-aggregated atomic per pixel (match_any + redux), so several CTAs can work
+// on one block.  Same samples, same numbers, integer sums: the frame cannot change.
+
+struct BlockGeometry {
+    int tiles_x, tiles_y;      // 32x4-pixel blocks owned by this launch
+    int runs;                  // sample runs per block (1 unless spp > 64)
+    int cap;                   // list capacity per (block, run): 128 * longest run
+};
+
+__device__ __forceinline__ void block_origin(const RenderLaunch& L, const BlockGeometry& G, int work, int& x0, int& y0, int& s_begin, int& n_s) {
+    const int tiles = G.tiles_x * G.tiles_y;
+    const int run = work / tiles, tile = work - run * tiles;
+    const int bx = tile % G.tiles_x, by = tile / G.tiles_x;
+    x0 = bx * 32;
+    y0 = L.row_begin + (by * L.tile_step + L.tile_index) * 4;
+    s_begin = (run * L.spp) / G.runs;
+    n_s = ((run + 1) * L.spp) / G.runs - s_begin;
+}
+__device__ __forceinline__ void block_pixel(int x0, int y0, int j, int& x, int& y) {     // 8x4 sub-tile by sub-tile
+    x = x0 + (j >> 5) * 8 + (j & 7);
+    y = y0 + ((j >> 3) & 3);
+}
+
+__global__ void __launch_bounds__(128) sort_samples_kernel(RenderLaunch L, SortPlan plan, BlockGeometry G, uint16_t* __restrict__ lists,
+                                                           uint32_t* __restrict__ meta) {
+    __shared__ uint32_t hist[260];
+    const int lane = threadIdx.x & 31, work = blockIdx.x;
+    int x0, y0, s_begin, n_s;
+    block_origin(L, G, work, x0, y0, s_begin, n_s);
+    const int n_chains = 128 * n_s, n_keys = plan.bins1 * plan.bins2;
+    uint16_t* ids = lists + size_t(work) * G.cap;
+    for (int i = threadIdx.x; i < 257; i += 128) hist[i] = 0u;
+    __syncthreads();
+    auto sample_key = [&](int c, bool& active) -> int {
+        const int j = c / n_s, s = s_begin + (c - j * n_s);
+        int x, y;
+        block_pixel(x0, y0, j, x, y);
+        active = x < L.width && y < L.row_end;
+        if (n_keys == 1) return 0;
+        const uint32_t pixel = uint32_t(y) * uint32_t(L.width) + uint32_t(x), sample = uint32_t(L.sample_offset + s);
+        const uint4 r0 = philox4x32_10(pixel, sample, 0u, 0u, L.seed_lo, L.seed_hi);
+        int key = min(plan.bins1 - 1, int(noise_angle(r0.z, r0.w) * (float(plan.bins1) * 0.25f)));
+        if (plan.bins2 > 1) {
+            const uint4 r1 = philox4x32_10(pixel, sample, 1u, 0u, L.seed_lo, L.seed_hi);
+            key = key * plan.bins2 + min(plan.bins2 - 1, int(noise_angle(r1.x, r1.y) * (float(plan.bins2) * 0.25f)));
+        }
+        return key;
+    };
+    for (int c = threadIdx.x; c < n_chains; c += 128) {
+        bool active;
+        const int key = sample_key(c, active);
+        if (active) atomicAdd(hist + key, 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t v[8], run = 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int i = lane * 8 + k; v[k] = i < n_keys ? hist[i] : 0u; run += v[k]; }
+        uint32_t incl = run;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        uint32_t excl = incl - run;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int i = lane * 8 + k; if (i < n_keys) hist[i] = excl; excl += v[k]; }
+        if (lane == 31) { meta[2 * work] = incl; meta[2 * work + 1] = 0u; }  // samples in the list, next round to hand out
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < n_chains; c += 128) {
+        bool active;
+        const int key = sample_key(c, active);
+        if (active) ids[atomicAdd(hist + key, 1u)] = uint16_t(c);
+    }
+}
+
+template <typename Nodes>
+__global__ void __launch_bounds__(128, VRT_K5_MIN_CTAS) render_rounds_kernel(Nodes nodes, RenderLaunch L, BlockGeometry G,
+                                                                            const uint16_t* __restrict__ lists, uint32_t* meta,
+                                                                            uint32_t* next_block, uint32_t* __restrict__ accum,
+                                                                            unsigned long long* __restrict__ counters) {
+    extern __shared__ uint2 smem[];
+    __shared__ int s_block;
+    Stack64<128> stack{smem + threadIdx.x};
+    nodes.slots = pin(nodes.slots);
+    const int guard = pin(L.guard);
+    const int depth_offset = pin(kSvoMaxDepth - L.depth);
+    const int lane = threadIdx.x & 31;
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + (L.depth + 1) * 128) + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) cnt[k * 128] = 0u;
+    const float SCALE = 1.0f / float(1 << L.depth);                           // raycaster.hpp:123-124 / main.cpp:82
+    const float n_norm = SCALE * 0.0078125f * 2.0f;                           // raycaster.hpp:171-172
+    const float aspect = float(L.width) / float(L.height);                    // main.cpp:133
+    const float focal_length = L.focal ? __ldg(L.focal) : L.cam.focal_length;
+    const int n_blocks = G.tiles_x * G.tiles_y * G.runs;
+
+    // all rounds this warp can get of block `work`
+    auto trace_block = [&](int work) {
+        int x0, y0, s_begin, n_s;
+        block_origin(L, G, work, x0, y0, s_begin, n_s);
+        const uint32_t total = meta[2 * work];
+        for (;;) {
+            uint32_t round = 0u;
+            if (lane == 0) round = atomicAdd(meta + 2 * work + 1, 1u);
+            round = __shfl_sync(0xffffffffu, round, 0);
+            if (round * 32u >= total) break;
+            const uint32_t slot = round * 32u + uint32_t(lane);
+            uint32_t cr = 0, cg = 0, cb = 0, key = 0xffffffffu;
+            if (slot < total) {
+                const int c = lists[size_t(work) * G.cap + slot];
+                const int j = c / n_s, s = s_begin + (c - j * n_s);
+                int x, y;
+                block_pixel(x0, y0, j, x, y);
+                const uint32_t pixel = uint32_t(y) * uint32_t(L.width) + uint32_t(x);
+                key = uint32_t(j);
+                const uint32_t sample = uint32_t(L.sample_offset + s);
+                const float lens_x = float(x) / float(L.height) - aspect * 0.5f;  // main.cpp:145
+                const float lens_y = float(y) / float(L.height) - 0.5f;           // main.cpp:146
+                ChainState cs;
+                NextRay nr;
+                chain_begin(L, cs, pixel, sample, lens_x, lens_y, SCALE, focal_length, nr);
+                int stage = kPrimary;
+                while (stage != kDone) {
+                    LsvoResult r;
+                    lsvo_cast_ray(nodes, stack, depth_offset, guard, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
+                    cnt[stage * 128] += 1u;
+                    cnt[(6 + stage) * 128] += r.complexity;
+                    LsvoHit h;
+                    if (r.hit) lsvo_finish(r, nr.ox, nr.oy, nr.oz, L.depth, h);
+                    stage = chain_advance(L, cs, stage, r, h, pixel, sample, SCALE, n_norm, nr);
+                }
+                chain_colour(L, cs, cr, cg, cb);
+            }
+            __syncwarp();
+            // one atomic per pixel and channel: the lanes holding samples of the same pixel add up first
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            cr = __reduce_add_sync(peers, cr);
+            cg = __reduce_add_sync(peers, cg);
+            cb = __reduce_add_sync(peers, cb);
+            if (key != 0xffffffffu && lane == __ffs(peers) - 1) {
+                int x, y;
+                block_pixel(x0, y0, int(key), x, y);
+                uint32_t* w = accum + 4 * (size_t(y) * size_t(L.width) + size_t(x));   // Sample, raycaster.hpp:18-24,87-90
+                if (cr) atomicAdd(w, cr);
+                if (cg) atomicAdd(w + 1, cg);
+                if (cb) atomicAdd(w + 2, cb);
+                atomicAdd(w + 3, uint32_t(__popc(peers)));
+            }
+        }
+    };
+
+    // ---- own blocks: the CTA takes a block, its warps share the block's rounds ----
+    for (;;) {
+        if (threadIdx.x == 0) s_block = int(atomicAdd(next_block, 1u));
+        __syncthreads();
+        const int work = s_block;
+        __syncthreads();
+        if (work >= n_blocks) break;
+        trace_block(work);
+    }
+    // ---- help: blocks are started in order, so unfinished ones are among the last started ----
+    for (int base = n_blocks - 1; base >= 0; base -= 32) {
+        const int work = base - lane;
+        bool open = false;
+        if (work >= 0) open = *reinterpret_cast<volatile uint32_t*>(meta + 2 * work + 1) * 32u < meta[2 * work];
+        unsigned m = __ballot_sync(0xffffffffu, open);
+        if (!m && base < n_blocks - 1 - 32 * 256) break;                           // far behind the frontier: everything is done
+        while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            trace_block(base - l);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        uint32_t a = cnt[k * 128], b = cnt[(6 + k) * 128];
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (lane == 0 && a) {
+            atomicAdd(counters + k, (unsigned long long)a);
+            atomicAdd(counters + 6 + k, (unsigned long long)b);
+        }
+    }
+}
+
 // Camera::getClosestPoint (camera_controller.hpp:56-60) and the focal-length rule of main.cpp:114-121, one thread.
 template <typename Nodes>
 __global__ void __launch_bounds__(128) autofocus_kernel(Nodes nodes, int depth, int guard, vrt_camera cam, float* __restrict__ focal) {
@@ -351,6 +545,52 @@ __global__ void resolve_kernel(const uint32_t* __restrict__ accum, uint8_t* __re
     }
 }
 
+namespace {
+// K6's launch plan: blocks, runs, list capacity, bins — shared by the scratch-size query and the launcher
+struct RoundsPlan {
+    BlockGeometry G;
+    SortPlan sort;
+    size_t lists_bytes, meta_bytes;
+};
+RoundsPlan plan_rounds(const RenderLaunch& L) {
+    RoundsPlan P;
+    const int rows = L.row_end - L.row_begin;
+    P.G.tiles_x = (L.width + 31) / 32;
+    P.G.tiles_y = ((rows + 3) / 4 + L.tile_step - 1 - L.tile_index) / L.tile_step;
+    if (P.G.tiles_y < 0) P.G.tiles_y = 0;
+    int runs = 1;
+    while ((L.spp + runs - 1) / runs > 64) runs *= 2;                               // <= 8192 samples per list (16-bit entries)
+    P.G.runs = runs;
+    P.G.cap = 128 * ((L.spp + runs - 1) / runs);
+    const int n = 128 * (L.spp / runs);
+    P.sort.bins1 = !L.use_gi ? 1 : n >= 2048 ? 16 : n >= 512 ? 8 : n >= 128 ? 4 : 1;
+    P.sort.bins2 = 1;
+    if (L.sort_bins1 > 0) {
+        P.sort.bins1 = L.sort_bins1;
+        P.sort.bins2 = L.sort_bins2 > 0 ? L.sort_bins2 : 1;
+        if (P.sort.bins1 * P.sort.bins2 > 256) P.sort.bins2 = 256 / P.sort.bins1;
+    }
+    const size_t blocks = size_t(P.G.tiles_x) * P.G.tiles_y * runs;
+    P.lists_bytes = (blocks * P.G.cap * sizeof(uint16_t) + 255) & ~size_t(255);
+    P.meta_bytes = ((blocks * 2 + 1) * sizeof(uint32_t) + 255) & ~size_t(255);
+    return P;
+}
+}  // namespace
+
+// 2 = K4, 3 = K5, 4 = K6.  Automatic: K6 for many-sample frames (with or without a GI pass: without one the lists stay
+// in pixel order and K6 still wins through 5 CTAs per SM and its even finish), K4 for the interactive loop.
+static int choose_mapping(const RenderLaunch& L) {
+    if (L.checker) return 2;
+    if (L.mapping >= 2) return L.mapping;
+    return L.spp >= 8 ? 4 : 2;
+}
+
+size_t render_scratch_bytes(const RenderLaunch& L) {
+    if (choose_mapping(L) != 4 || L.row_end <= L.row_begin || L.width <= 0 || L.spp <= 0) return 0;
+    const RoundsPlan P = plan_rounds(L);
+    return P.lists_bytes + P.meta_bytes;
+}
+
 cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const RenderLaunch& L, uint32_t* d_accum,
                                          unsigned long long* d_counters, cudaStream_t stream) {
     const int rows = L.row_end - L.row_begin;
@@ -360,6 +600,28 @@ cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const
     const int tiles_x = (columns + 31) / 32, tiles_y = ((rows + 3) / 4 + L.tile_step - 1 - L.tile_index) / L.tile_step;
     if (tiles_y <= 0) return cudaSuccess;
     const size_t smem = size_t(L.depth + 1) * block * 8 + 12 * block * sizeof(uint32_t);   // stacks + statistics
+    const int mapping = choose_mapping(L);
+    if (mapping == 4) {                                                                  // K6
+        const RoundsPlan P = plan_rounds(L);
+        if (!L.scratch || L.scratch_bytes < P.lists_bytes + P.meta_bytes) return cudaErrorInvalidValue;
+        uint16_t* lists = static_cast<uint16_t*>(L.scratch);
+        uint32_t* meta = reinterpret_cast<uint32_t*>(static_cast<char*>(L.scratch) + P.lists_bytes);
+        const unsigned blocks = unsigned(P.G.tiles_x) * P.G.tiles_y * P.G.runs;
+        uint32_t* next_block = meta + 2 * size_t(blocks);
+        cudaError_t e = cudaMemsetAsync(next_block, 0, sizeof(uint32_t), stream);
+        if (e != cudaSuccess) return e;
+        sort_samples_kernel<<<blocks, 128, 0, stream>>>(L, P.sort, P.G, lists, meta);
+        int per_sm = 0, sms = 0, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (compact) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_rounds_kernel<CompactNodes>, block, smem);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_rounds_kernel<RefNodes>, block, smem);
+        unsigned grid6 = unsigned(per_sm > 0 ? per_sm : 1) * unsigned(sms);
+        if (grid6 > blocks) grid6 = blocks;
+        if (compact) render_rounds_kernel<CompactNodes><<<grid6, block, smem, stream>>>(CompactNodes{nodes}, L, P.G, lists, meta, next_block, d_accum, d_counters);
+        else render_rounds_kernel<RefNodes><<<grid6, block, smem, stream>>>(RefNodes{nodes}, L, P.G, lists, meta, next_block, d_accum, d_counters);
+        return cudaGetLastError();
+    }
     // Sample runs: a power of two, enough for >= 28 waves of CTAs (4 CTAs x 148 SMs resident) so the last wave is a
     // small part of the launch even when a GPU owns 1/8 of the frame, but runs of >= 8 samples so that 8+ lanes can
     // share a pixel.  tools/probe_slice.py: whole frame 74.4 ms at (2 runs, 32 lanes/pixel) vs 77.7 ms at (4, 1);
@@ -369,10 +631,7 @@ cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const
     long chunks = 1;
     while (chunks * tiles < 28L * 4 * 148 && chunks * 2 * 8 <= L.spp) chunks *= 2;
     if (L.spp_chunks > 0) chunks = L.spp_chunks < L.spp ? L.spp_chunks : L.spp;      // explicit override
-    // K5 for many-sample frames: samples regrouped by GI direction when there is a GI pass; without one the list stays in
-    // pixel order (one bin) and K5 still wins through its 5 CTAs per SM (no-GI cfg-4 frame: 31.3 ms vs K4's 33.6)
-    const bool sorted = L.mapping == 3 || (L.mapping == 0 && !L.checker && L.spp / chunks >= 8);
-    if (sorted && !L.checker) {
+    if (mapping == 3) {                                                                  // K5 (kept selectable: render_variant 3)
         // K5 sorts better with long runs (more samples per direction bin): 12 waves of CTAs are enough here.
         // tools/probe_sorted.py, cfg 4: whole frame 67.8 ms at (1 run, 16 bins) vs 70.2 at (4, 16); the 1/8 slice of an
         // 8-GPU rank 9.07 ms at (4, 8) vs 9.69 at (1, 16).  Sorting by the second bounce's angle as well did not pay.

@@ -89,9 +89,10 @@ int vrt_context_synchronize(vrt_context* ctx);
 int vrt_context_set_stream(vrt_context* ctx, void* stream);
 /* Tuning knobs (no reference counterpart):
  *   "cast_variant" (default 1): 1 = persistent threads with per-lane ray regeneration, 0 = one thread per ray
- *   "render_variant" (default 0): 0 = automatic (K5 for many-sample GI frames, else K4), 1 = K4p persistent
+ *   "render_variant" (default 0): 0 = automatic (K6 for frames with >= 8 samples, else K4), 1 = K4p persistent
  *                    regenerating warps, 2 = K4 one lane per pixel/sample group, 3 = K5 samples of a pixel block
- *                    regrouped by GI direction
+ *                    regrouped by GI direction inside the CTA, 4 = K6 the same lists in global memory traced by
+ *                    persistent CTAs that help each other finish
  *   "refill_cast", "refill_render"  parked lanes (1..32) that make a persistent warp regenerate rays;
  *                    refill_cast 0 = warp-adaptive (default)
  *   "spp_chunks"     frame kernel: number of runs a pixel's samples are cut into (0 = automatic)

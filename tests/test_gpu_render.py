@@ -184,10 +184,12 @@ def test_device_side_autofocus(vrt, scene9, view):
 
 @pytest.mark.parametrize("W,H,spp,chunks,bounces,variant", [(150, 70, 16, 0, 2, 0), (150, 70, 16, 2, 1, 0), (97, 41, 64, 0, 2, 0),
                                                             (64, 36, 5, 0, 2, 3), (64, 36, 70, 0, 2, 3), (33, 9, 24, 3, 1, 3),
-                                                            (64, 36, 12, 0, 0, 3)])
+                                                            (64, 36, 12, 0, 0, 3), (150, 70, 16, 0, 2, 4), (64, 36, 5, 0, 2, 4),
+                                                            (64, 36, 70, 0, 2, 4), (33, 9, 24, 0, 1, 4), (203, 77, 12, 0, 0, 4)])
 def test_direction_sorted_kernel_is_exact(vrt, port, terrain9_nodes, textures, W, H, spp, chunks, bounces, variant):
     """K5 regroups the samples of a 32x4 pixel block by GI direction before tracing them: integer sums, same frame,
-    same ray statistics.  Ragged frames, uneven runs, more than 64 samples per pixel (forced extra runs), no GI."""
+    same ray statistics.  Ragged frames, uneven runs, more than 64 samples per pixel (forced extra runs), no GI.
+    Variant 4 = K6: the sorted lists in global memory, persistent CTAs that help each other with unfinished blocks."""
     c = vrt.Context(0)
     c.set_option("render_variant", variant)
     c.set_option("spp_chunks", chunks)
