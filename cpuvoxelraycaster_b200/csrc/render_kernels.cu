@@ -343,6 +343,7 @@ __device__ __forceinline__ void block_pixel(int x0, int y0, int j, int& x, int& 
 __global__ void __launch_bounds__(128) sort_samples_kernel(RenderLaunch L, SortPlan plan, BlockGeometry G, uint16_t* __restrict__ lists,
                                                            uint32_t* __restrict__ meta) {
     __shared__ uint32_t hist[260];
+    __shared__ uint8_t keys[8192];                                             // one key per sample of the block (255 = off-frame)
     const int lane = threadIdx.x & 31, work = blockIdx.x;
     int x0, y0, s_begin, n_s;
     block_origin(L, G, work, x0, y0, s_begin, n_s);
@@ -350,28 +351,35 @@ __global__ void __launch_bounds__(128) sort_samples_kernel(RenderLaunch L, SortP
     uint16_t* ids = lists + size_t(work) * G.cap;
     for (int i = threadIdx.x; i < 257; i += 128) hist[i] = 0u;
     __syncthreads();
-    auto sample_key = [&](int c, bool& active) -> int {
-        const int j = c / n_s, s = s_begin + (c - j * n_s);
-        int x, y;
-        block_pixel(x0, y0, j, x, y);
-        active = x < L.width && y < L.row_end;
-        if (n_keys == 1) return 0;
-        const uint32_t pixel = uint32_t(y) * uint32_t(L.width) + uint32_t(x), sample = uint32_t(L.sample_offset + s);
-        const uint4 r0 = philox4x32_10(pixel, sample, 0u, 0u, L.seed_lo, L.seed_hi);
-        int key = min(plan.bins1 - 1, int(noise_angle(r0.z, r0.w) * (float(plan.bins1) * 0.25f)));
-        if (plan.bins2 > 1) {
-            const uint4 r1 = philox4x32_10(pixel, sample, 1u, 0u, L.seed_lo, L.seed_hi);
-            key = key * plan.bins2 + min(plan.bins2 - 1, int(noise_angle(r1.x, r1.y) * (float(plan.bins2) * 0.25f)));
+    // pass 1: keys and histogram.  Lanes of a warp holding the same key add up first (one shared-memory atomic per key
+    // and warp instead of one per sample: with 16 sectors the plain version serialises 8 deep)
+    const int n_padded = (n_chains + 31) & ~31;
+    for (int c = threadIdx.x; c < n_padded; c += 128) {
+        uint32_t key = 255u;
+        if (c < n_chains) {
+            const int j = c / n_s, s = s_begin + (c - j * n_s);
+            int x, y;
+            block_pixel(x0, y0, j, x, y);
+            if (x < L.width && y < L.row_end) {
+                key = 0u;
+                if (n_keys > 1) {
+                    const uint32_t pixel = uint32_t(y) * uint32_t(L.width) + uint32_t(x), sample = uint32_t(L.sample_offset + s);
+                    const uint4 r0 = philox4x32_10(pixel, sample, 0u, 0u, L.seed_lo, L.seed_hi);
+                    key = uint32_t(min(plan.bins1 - 1, int(noise_angle(r0.z, r0.w) * (float(plan.bins1) * 0.25f))));
+                    if (plan.bins2 > 1) {
+                        const uint4 r1 = philox4x32_10(pixel, sample, 1u, 0u, L.seed_lo, L.seed_hi);
+                        key = key * uint32_t(plan.bins2) + uint32_t(min(plan.bins2 - 1, int(noise_angle(r1.x, r1.y) * (float(plan.bins2) * 0.25f))));
+                    }
+                    key = min(key, 254u);
+                }
+            }
+            keys[c] = uint8_t(key);
         }
-        return key;
-    };
-    for (int c = threadIdx.x; c < n_chains; c += 128) {
-        bool active;
-        const int key = sample_key(c, active);
-        if (active) atomicAdd(hist + key, 1u);
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (key != 255u && lane == __ffs(peers) - 1) atomicAdd(hist + key, uint32_t(__popc(peers)));
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
+    if (threadIdx.x < 32) {                                                    // exclusive scan of <= 256 counters by one warp
         uint32_t v[8], run = 0u;
 #pragma unroll
         for (int k = 0; k < 8; ++k) { const int i = lane * 8 + k; v[k] = i < n_keys ? hist[i] : 0u; run += v[k]; }
@@ -383,10 +391,16 @@ __global__ void __launch_bounds__(128) sort_samples_kernel(RenderLaunch L, SortP
         if (lane == 31) { meta[2 * work] = incl; meta[2 * work + 1] = 0u; }  // samples in the list, next round to hand out
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < n_chains; c += 128) {
-        bool active;
-        const int key = sample_key(c, active);
-        if (active) ids[atomicAdd(hist + key, 1u)] = uint16_t(c);
+    // pass 2: scatter, again one atomic per key and warp; inside a warp the samples keep their order (ascending c =
+    // pixel by pixel), so a sector's list stays nearly pixel-ordered
+    for (int c = threadIdx.x; c < n_padded; c += 128) {
+        const uint32_t key = c < n_chains ? keys[c] : 255u;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        uint32_t first = 0u;
+        const int leader = __ffs(peers) - 1;
+        if (key != 255u && lane == leader) first = atomicAdd(hist + key, uint32_t(__popc(peers)));
+        first = __shfl_sync(0xffffffffu, first, leader);
+        if (key != 255u) ids[first + uint32_t(__popc(peers & ((1u << lane) - 1u)))] = uint16_t(c);
     }
 }
 
