@@ -191,7 +191,7 @@ def run_reference(args):
             "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample_desc},
             "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
     return 0
 
 
@@ -211,8 +211,6 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL prints its version banner on stdout: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=device)
 
     w = workload(args)
@@ -345,10 +343,13 @@ def run_ours(args):
                 "mean_complexity": round(sum(cx) / max(1, total_rays), 2),
                 "ms_per_frame": round(ms_per_step, 4), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clocks}
-        print(json.dumps(line), flush=True)
+        _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+_emit = print
 
 
 def main():
@@ -371,6 +372,13 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    # stdout must carry the ONE JSON line: libraries (NCCL's version banner, for one) printf to file descriptor 1, so the
+    # run happens with fd 1 pointing at stderr and the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    _emit = lambda text: os.write(real_stdout, (text + "\n").encode())
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 
 
