@@ -1,13 +1,17 @@
-// Frame rendering — kernels K0 (ray generation) + K4 (shading and secondary rays), fused; and the resolve.
+// Frame rendering: ray generation (K0), traversal, shading and accumulation fused into one kernel per frame; resolve.
 //
 // Replaces the swarm lambda src/main.cpp:139-154, Camera::getRay (camera_controller.hpp:34-54),
 // RayCaster::renderRay/castRay/getGlobalIllumination and the texture lookup (raycaster.hpp:67-240),
-// samples_to_image (raycaster.hpp:94-103).  The per-sample arithmetic is in render_chain.cuh.
-//
-// Structure: each lane owns one pixel (8x4 pixel tile per warp) and walks a run of its samples; a sample is
-// a chain of up to six rays.  The chain is a small state machine around ONE inlined copy of the traversal loop,
-// so lanes at different chain stages still execute the traversal converged.  This one-lane-per-pixel kernel is
-// the default: measured against persistent/regenerating and shared-memory-state variants in profiles/.
+// samples_to_image (raycaster.hpp:94-103).  The per-sample arithmetic is in render_chain.cuh: a sample is a chain of up
+// to six rays, a small state machine around ONE inlined copy of the traversal loop, so lanes at different chain stages
+// still execute the traversal converged.  Three ways of giving samples to lanes, all with bit-identical results
+// (integer sums), measured against each other in profiles/r01_summary.md:
+//   K4  render_accumulate_kernel   a lane walks samples of one pixel (8x4 pixel tile per warp, Q lanes per pixel);
+//                                  the interactive loop (1 sample, checkerboard, device-side autofocus)
+//   K5  render_sorted_kernel       the samples of a 32x4-pixel block are counting-sorted by GI direction in shared
+//                                  memory and traced 32 neighbours at a time
+//   K6  sort_samples_kernel + render_rounds_kernel   the same lists in global memory, traced by persistent CTAs that
+//                                  help each other finish; the default for frames with >= 8 samples per pixel
 #include "lsvo_step.cuh"
 #include "render_chain.cuh"
 
