@@ -10,6 +10,9 @@
   svo_random5.npz     intended-SVO<5> (patched build): same occupancy, rays, HitPoints
   terrain_heights.npz heights of T(8) (256x256) + sha256 of T(9), T(10) heights and of T(9) LNode array
   frame_cfg1_small.npz  RayCaster (reference, depth 9) 160x90 deterministic frame: primary+shadow colours
+  frame_checker_small.npz  the reference's RayCaster driven like main.cpp:137-143 for 4 frames: alternating checkerboard
+                      halves (thread-area height 18 and the odd 15) with the 0.4/0.6 temporal blend, and the
+                      accumulators of two half frames in sample mode   (`make_golden.py checker` makes only this file)
 """
 import hashlib
 import os
@@ -49,7 +52,32 @@ def rays(rng, n, lo=(1, 1, 1), hi=(2, 2, 2)):
     return o, d.astype(np.float32)
 
 
+def make_checker_frames(R):
+    T = R.scene_terrain(9)
+    R.register_textures(*[read_bmp24(os.path.join(REF, "res", n)) for n in ("grass_top_16x16.bmp", "grass_side_16x16.bmp")])
+    light = np.float32([-200, -1000, -300]) * np.float32(1.0 / 512.0) + np.float32(1.0)
+    out = dict(cam_position=np.float32([256, 200, 256]), view_angle=np.float32([0.7, -0.4]), light=light)
+    for tag, W, H, area in (("a", 128, 72, 18), ("b", 96, 60, 15)):
+        p = loader.RefRenderParams()
+        p.width, p.height = W, H
+        p.cam_position[:] = [256.0, 200.0, 256.0]
+        p.view_angle[:] = [0.7, -0.4]
+        p.fov, p.aperture, p.focal_length = 1.0, 0.0, 100.0
+        p.light_position[:] = [float(x) for x in light]
+        p.use_gi, p.use_samples, p.spp, p.threads = 0, 0, 1, 1
+        p.checker, p.checker_area_height, p.frames = 2, area, 4          # main.cpp:98,137: the first frame has offset 1
+        blend = R.render(T, p)["image"]
+        p.use_samples, p.checker, p.frames = 1, 1, 2
+        samples = R.render(T, p)["samples"].astype(np.uint32)
+        out.update({"size_" + tag: np.int32([W, H, area]), "blend4_" + tag: blend, "samples2_" + tag: samples})
+    np.savez_compressed(os.path.join(OUT, "frame_checker_small.npz"), **out)
+    R.scene_destroy(T)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "checker":
+        make_checker_frames(loader.ref())
+        return
     R = loader.ref()
     RP = loader.ref_patched()
     assert R is not None and RP is not None, "build oracle/_ref first (make -C oracle)"
@@ -130,6 +158,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "svo_random5.npz"), occ=occ, origin=o, dir=d, hits=RP.svo_cast(s, o, d, 1 << 20),
                         hits_iter16=RP.svo_cast(s, o, d, 16))
     RP.svo_destroy(s)
+    make_checker_frames(R)
     print("golden fixtures written to", OUT)
 
 

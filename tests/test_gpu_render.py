@@ -100,6 +100,29 @@ def test_temporal_blend_mode(vrt, scene9, port, terrain9_nodes, textures):
         prev = want
 
 
+def test_golden_checkerboard_frames(vrt, scene9):
+    """K4's checkerboard mapping + resolve against frames the reference's own RayCaster produced when driven like
+    main.cpp:137-143 (4 alternating half frames with the 0.4/0.6 blend; two half frames in sample mode)."""
+    g = golden("frame_checker_small.npz")
+    cam = vrt.Camera(position=g["cam_position"], view_angle=g["view_angle"], focal_length=100.0)
+    for tag in ("a", "b"):
+        W, H, area = (int(v) for v in g["size_" + tag])
+        rc = vrt.RayCaster(scene9, (W, H))
+        rc.setLightPosition(g["light"])
+        rc.checker_area_height = area
+        for frame in range(4):
+            rc.checker_board_offset = (1 + frame) & 1
+            img = rc.render(cam)
+        assert np.array_equal(img, g["blend4_" + tag]), tag
+        rs = vrt.RayCaster(scene9, (W, H))
+        rs.setLightPosition(g["light"])
+        rs.checker_area_height, rs.use_samples = area, True
+        for frame in range(2):
+            rs.checker_board_offset = frame & 1
+            rs.render(cam)
+        assert np.array_equal(rs.colors, g["samples2_" + tag]), tag
+
+
 @pytest.mark.parametrize("W,H,area_height,use_samples", [(160, 90, 0, False), (161, 75, 15, False), (96, 60, 15, True), (70, 44, 11, True)])
 def test_checkerboard_frames(vrt, scene9, port, terrain9_nodes, textures, W, H, area_height, use_samples):
     """main.cpp:137-143: alternating checkerboard halves; the unrendered pixels keep their value."""

@@ -99,3 +99,33 @@ def test_frame_primary_shadow(port, textures):
     assert np.array_equal(accum, g["samples"])
     assert np.array_equal(rgba, g["image"])
     assert stats.rays[0] == p.width * p.height and 0 < stats.rays[1] < stats.rays[0]
+
+
+def test_checkerboard_frames(port, vrt, textures):
+    """The interactive loop's checkerboard halves (main.cpp:137-143) with the temporal blend, 4 frames, and two half frames in
+    sample mode: the oracle against frames produced by the reference's own RayCaster (golden)."""
+    from oracle import loader
+    g = golden("frame_checker_small.npz")
+    nodes = port.build_terrain(9)
+    cam = vrt.Camera(position=g["cam_position"], view_angle=g["view_angle"], focal_length=100.0)   # host-side basis only
+    for tag in ("a", "b"):
+        W, H, area = (int(v) for v in g["size_" + tag])
+        p = loader.PortRenderParams()
+        p.width, p.height, p.depth, p.guard = W, H, 9, 9
+        p.cam_position[:] = [float(x) for x in g["cam_position"]]
+        p.rot_mat[:] = [float(x) for x in cam.rot_mat]
+        p.fov, p.aperture, p.focal_length = 1.0, 0.0, 100.0
+        p.light_position[:] = [float(x) for x in g["light"]]
+        p.use_gi, p.gi_bounces, p.use_samples, p.spp = 0, 1, 0, 1
+        p.seed_lo, p.threads, p.checker_area_height = 0x5EED, 4, area
+        img = None
+        for frame in range(4):
+            p.checker = 1 + ((1 + frame) & 1)
+            _, img, _ = port.render(nodes, p, *textures, prev_rgba=img)
+        assert np.array_equal(img, g["blend4_" + tag]), tag
+        p.use_samples = 1
+        acc = np.zeros((H, W, 4), np.uint32)
+        for frame in range(2):
+            p.checker = 1 + (frame & 1)
+            acc += port.render(nodes, p, *textures)[0]
+        assert np.array_equal(acc, g["samples2_" + tag]), tag
