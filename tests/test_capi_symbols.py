@@ -54,6 +54,21 @@ def test_bad_arguments_are_errors(vrt):
         vrt.host_build_lsvo_from_voxels(4, [[16, 0, 0]])       # out of range: UB in the reference, an error here
 
 
+def test_new_entry_points_validate_before_touching_the_device(vrt):
+    """Presentation and dynamic-scene calls: NULL / malformed arguments are VRT_ERR_INVALID on any box."""
+    import ctypes as C
+    lib = vrt.capi.lib()
+    p = vrt.capi.PresentParams(16, 16, 3, 0.1)
+    buf = (C.c_uint8 * (16 * 16 * 4))()
+    assert lib.vrt_present(None, buf, buf, C.byref(p)) == -1
+    assert lib.vrt_present_device(None, buf, buf, C.byref(p)) == -1
+    h = C.c_void_p()
+    assert lib.vrt_lsvo_create_heightfield(None, 9, None, 0, C.byref(h)) == -1
+    assert lib.vrt_scene_edit_heights(None, 0, 0, 1, 1, buf) == -1
+    assert lib.vrt_scene_download_heights(None, buf) == -1
+    assert b"NULL" in lib.vrt_last_error()
+
+
 def test_node_array_validation_is_host_side(vrt):
     """vrt_lsvo_create rejects malformed arrays before touching the device (the traversal trusts child_offset)."""
     import ctypes as C
