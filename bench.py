@@ -297,10 +297,20 @@ def run_ours(args):
             traffic = json.load(open(tpath)).get("render_rounds_kernel_dram_bytes_per_launch")
         except Exception:
             traffic = None
+    l1_bytes = l2_bytes = None
+    if traffic is not None:
+        try:
+            tj = json.load(open(tpath))
+            l1_bytes, l2_bytes = tj.get("render_rounds_kernel_l1_global_load_bytes_per_launch"), tj.get("render_rounds_kernel_l2_bytes_per_launch")
+        except Exception:
+            pass
     roofline = {"bound": "hbm", "kernel": "render_rounds_kernel (K6; timed with its sort_samples_kernel)", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": round(kernel_ms, 4),
                 "kernel_share_of_step": round(kernel_ms_max / ms_per_step, 4),
+                # SURVEY.md 8(d) diagnostics: one 32-byte sector per inspected node, and what ncu saw move through L1 / L2
+                "sector_granular_GBs": round((32 * l_cx + 64 * l_rays + 16 * my_pixels) / (kernel_ms * 1e-3) / 1e9, 1),
+                "l1_global_load_bytes": l1_bytes, "l2_bytes": l2_bytes,
                 "note": "pointer chasing: latency/divergence bound by design, see DESIGN.md; node fetches are mostly L1/L2 hits"}
 
     # ---- end to end through the public API (host in, host out) -------------------------------------------
