@@ -8,6 +8,11 @@
  *     reference behaviour ("parity unpinned" for those, specified in DESIGN.md §2).  gi_bounces == 1 follows the
  *     reference expression; feeding both sides the same random numbers is impossible with the reference's racy
  *     global RNG, so that pin is statistical (PSNR of images, tests/test_oracle_pinned.py);
+ *   - vo_present (main.cpp:159-177): the reference blends through SFML/OpenGL, absent here — "parity unpinned", the
+ *     arithmetic is round-to-nearest 8-bit unorm blending; the checkerboard / temporal blend that feeds it IS pinned
+ *     (the reference's RayCaster driven by the main.cpp loop, tests/test_oracle_pinned.py, tests/golden/frame_checker_small.npz);
+ *   - rays with a non-finite origin or direction: the reference never returns for them; defined here as a miss of
+ *     complexity 0 (lsvo_cast_one);
  *   - glm itself is un-vendored and unpinned in the reference; the shim restates its public
  *     definitions (oracle/shim/glm/glm.hpp).
  */
