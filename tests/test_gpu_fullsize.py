@@ -100,6 +100,34 @@ def test_cfg4_frame_bookkeeping_and_partitions(vrt, ctx, textures):
     s.close()
 
 
+def test_cfg4_headline_frame_is_kernel_independent(vrt, textures):
+    """The headline workload itself (1080p, 64 spp, GI 2 bounces, DOF, 2048^3): K4 (lane per pixel), K5 (samples sorted by
+    GI direction inside a CTA) and K6 (sorted lists + persistent helping CTAs, the default) give the same accumulators,
+    the same image and the same per-class ray and loop-trip counts — 451 M rays, compared exactly."""
+    S, W, H, spp = 2048.0, 1920, 1080, 64
+    light = np.float32([-200, -1000, -300]) * np.float32(1 / S) + np.float32(1)
+    results = []
+    for variant in (0, 2, 3):
+        c = vrt.Context(0)
+        c.set_option("render_variant", variant)
+        s = vrt.LSVO.from_terrain(c, 11)
+        s.set_textures(*textures)
+        cam = vrt.Camera(position=(S / 2, S / 2 - 56, S / 2), view_angle=(0, 0), aperture=0.5)
+        cam.autofocus(s)
+        r = vrt.RayCaster(s, (W, H))
+        r.setLightPosition(light)
+        r.use_samples, r.use_gi, r.gi_bounces = True, True, 2
+        img = r.render(cam, spp).copy()
+        results.append((r.colors.copy(), img, r.last_stats))
+        s.close()
+        c.close()
+    ref = results[0]
+    assert sum(ref[2]["rays"]) > 4.4e8 and int(ref[0][..., 3].min()) == spp == int(ref[0][..., 3].max())
+    for other in results[1:]:
+        assert np.array_equal(ref[0], other[0]) and np.array_equal(ref[1], other[1])
+        assert ref[2]["rays"] == other[2]["rays"] and ref[2]["complexity"] == other[2]["complexity"]
+
+
 def test_cfg5_lsvo4096_random_rays(vrt, port):
     """configs[4]: LSVO 4096^3 (built on the GPU, lsvo.hpp:72 guard lifted), incoherent random rays: the persistent
     regenerating kernel and the one-thread-per-ray kernel agree byte for byte on 4 M rays; a 100 k prefix is bit-exact
