@@ -79,6 +79,9 @@ _SIGNATURES = {
     "vrt_render": (C.c_int, [_vp, C.POINTER(Camera), C.POINTER(RenderParams), _vp, _vp, C.POINTER(RenderStats)]),
     "vrt_scene_last_render_stats": (C.c_int, [_vp, C.POINTER(RenderStats)]),
     "vrt_autofocus": (C.c_int, [_vp, C.POINTER(Camera), C.POINTER(_f)]),
+    "vrt_lsvo_create_from_voxels": (C.c_int, [_vp, _u32, _vp, _u64, _i32, C.POINTER(_vp)]),
+    "vrt_scene_set_cells": (C.c_int, [_vp, _vp, _u64, _i32]),
+    "vrt_scene_voxel_count": (C.c_int, [_vp, C.POINTER(_u64)]),
     "vrt_lsvo_create_heightfield": (C.c_int, [_vp, _u32, _vp, _i32, C.POINTER(_vp)]),
     "vrt_scene_edit_heights": (C.c_int, [_vp, _u32, _u32, _u32, _u32, _vp]),
     "vrt_scene_download_heights": (C.c_int, [_vp, _vp]),

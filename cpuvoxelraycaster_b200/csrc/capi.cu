@@ -79,6 +79,8 @@ struct vrt_scene {
     uint64_t n_compact = 0;
     bool use_compact = false;
     int32_t* d_heights = nullptr;               // heightfield scenes: column heights [S*S], resident for edits
+    uint64_t* d_voxel_keys = nullptr;           // voxel-set scenes: sorted distinct path keys, resident for edits
+    uint32_t n_voxel_keys = 0;
     uint8_t* d_tex = nullptr;                   // top (768 B) then side (768 B)
     bool has_tex = false;
     DeviceBuffer frame_accum, frame_rgba;       // vrt_render staging
@@ -105,7 +107,7 @@ const char* vrt_build_info(void) {
            "lsvo_cast_persistent_kernel (K1p, default), render_accumulate_kernel (K4, interactive frames), render_sorted_kernel (K5), "
            "sort_samples_kernel + render_rounds_kernel (K6, default for >= 8 samples per pixel), render_persistent_kernel (K4p), "
            "autofocus_kernel, resolve_kernel, present_kernel, grid_cast_kernel<mip> (K2/K2m), svo_cast_kernel (K3), "
-           "grid_render_kernel<mip>, terrain / heightfield builder";
+           "grid_render_kernel<mip>, terrain / heightfield / voxel-set builders";
 }
 
 int vrt_context_create(int device, void* stream, vrt_context** out) {
@@ -341,6 +343,113 @@ int vrt_scene_edit_heights(vrt_scene* sc, uint32_t x0, uint32_t z0, uint32_t nx,
     return VRT_OK;
 }
 
+namespace {
+// uploads a host voxel list and turns it into sorted distinct path keys on the device
+int upload_voxel_keys(vrt_context* ctx, uint32_t depth, const uint32_t* xyz, uint64_t n, uint64_t** d_keys, uint32_t* n_keys, const char* who) {
+    if (n && !xyz) return fail(VRT_ERR_INVALID, std::string(who) + ": NULL voxel list");
+    if (n > 0xffffffffull) return fail(VRT_ERR_INVALID, std::string(who) + ": too many voxels");
+    const uint32_t S = 1u << depth;
+    for (uint64_t i = 0; i < 3 * n; ++i)
+        if (xyz[i] >= S) return fail(VRT_ERR_INVALID, std::string(who) + ": voxel out of range (UB in the reference, svo.hpp:72)");
+    uint32_t* d_xyz = nullptr;
+    cudaError_t e = cudaMalloc(&d_xyz, (n ? n : 1) * 3 * sizeof(uint32_t));
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(d_xyz, xyz, n * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = vrt::device_voxel_keys(d_xyz, n, int(depth), d_keys, n_keys, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (d_xyz) cudaFree(d_xyz);
+    ctx->launches += 4;
+    if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? fail(VRT_ERR_OOM, std::string(who) + ": device allocation failed") : cuda_fail(e, who);
+    return VRT_OK;
+}
+
+// re-flattens a voxel-set scene from its resident keys and swaps the node array in
+int rebuild_from_keys(vrt_scene* sc, const char* who) {
+    vrt_context* ctx = sc->ctx;
+    uint2* d_new = nullptr;
+    uint64_t n_new = 0;
+    cudaError_t e = vrt::device_build_lsvo_from_keys(int(sc->depth), sc->d_voxel_keys, sc->n_voxel_keys, &d_new, &n_new, ctx->stream);
+    ctx->launches += 2 + 4 * sc->depth;
+    if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? fail(VRT_ERR_OOM, std::string(who) + ": device allocation failed") : cuda_fail(e, who);
+    if (sc->d_nodes) cudaFree(sc->d_nodes);                 // the builder synchronised the stream
+    sc->device_bytes += n_new * sizeof(uint2);
+    sc->device_bytes -= sc->n_nodes * sizeof(uint2);
+    sc->d_nodes = d_new;
+    sc->n_nodes = n_new;
+    if (sc->d_compact) {
+        cudaFree(sc->d_compact);
+        sc->device_bytes -= sc->n_compact * sizeof(uint2);
+        sc->d_compact = nullptr;
+        sc->n_compact = 0;
+        if (sc->use_compact) {
+            sc->use_compact = false;
+            return vrt_scene_set_layout(sc, 1, 0);
+        }
+    }
+    return VRT_OK;
+}
+}  // namespace
+
+int vrt_lsvo_create_from_voxels(vrt_context* ctx, uint32_t depth, const uint32_t* xyz, uint64_t n, int32_t guard, vrt_scene** out) {
+    if (!ctx || !out) return fail(VRT_ERR_INVALID, "vrt_lsvo_create_from_voxels: NULL argument");
+    if (depth < 1 || depth > 12) return fail(VRT_ERR_INVALID, "vrt_lsvo_create_from_voxels: depth must be 1..12");
+    if (int s = use_device(ctx)) return s;
+    vrt_scene* sc = new (std::nothrow) vrt_scene();
+    if (!sc) return fail(VRT_ERR_OOM, "vrt_lsvo_create_from_voxels: host allocation failed");
+    sc->ctx = ctx;
+    sc->kind = VRT_SCENE_LSVO;
+    sc->depth = depth;
+    sc->guard = guard > 0 ? guard : (guard < 0 ? 0 : int32_t(depth));
+    int s = upload_voxel_keys(ctx, depth, xyz, n, &sc->d_voxel_keys, &sc->n_voxel_keys, "vrt_lsvo_create_from_voxels");
+    if (s == VRT_OK) s = rebuild_from_keys(sc, "vrt_lsvo_create_from_voxels");
+    if (s == VRT_OK) {
+        cudaError_t e = cudaMalloc(&sc->d_counters, 16 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMemsetAsync(sc->d_counters, 0, 16 * sizeof(unsigned long long), ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) s = cuda_fail(e, "vrt_lsvo_create_from_voxels");
+    }
+    if (s != VRT_OK) {
+        vrt_scene_destroy(sc);
+        return s;
+    }
+    sc->device_bytes += uint64_t(sc->n_voxel_keys) * sizeof(uint64_t);
+    *out = sc;
+    return VRT_OK;
+}
+
+int vrt_scene_set_cells(vrt_scene* sc, const uint32_t* xyz, uint64_t n, int32_t solid) {
+    if (!sc) return fail(VRT_ERR_INVALID, "vrt_scene_set_cells: scene is NULL");
+    if (sc->kind != VRT_SCENE_LSVO || !sc->d_voxel_keys)
+        return fail(VRT_ERR_UNSUPPORTED, "vrt_scene_set_cells: the scene was not created by vrt_lsvo_create_from_voxels");
+    if (n == 0) return VRT_OK;
+    vrt_context* ctx = sc->ctx;
+    if (int s = use_device(ctx)) return s;
+    VRT_CUDA(cudaStreamSynchronize(ctx->stream));           // nothing in flight may still read the arrays replaced below
+    uint64_t* d_edit = nullptr;
+    uint32_t n_edit = 0;
+    if (int s = upload_voxel_keys(ctx, sc->depth, xyz, n, &d_edit, &n_edit, "vrt_scene_set_cells")) return s;
+    uint64_t* d_merged = nullptr;
+    uint32_t n_merged = 0;
+    cudaError_t e = vrt::device_edit_voxel_keys(sc->d_voxel_keys, sc->n_voxel_keys, d_edit, n_edit, solid != 0, int(sc->depth), &d_merged,
+                                                &n_merged, ctx->stream);
+    cudaFree(d_edit);
+    ctx->launches += 3;
+    if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? fail(VRT_ERR_OOM, "vrt_scene_set_cells: device allocation failed")
+                                                                : cuda_fail(e, "vrt_scene_set_cells");
+    cudaFree(sc->d_voxel_keys);
+    sc->device_bytes += uint64_t(n_merged) * sizeof(uint64_t);
+    sc->device_bytes -= uint64_t(sc->n_voxel_keys) * sizeof(uint64_t);
+    sc->d_voxel_keys = d_merged;
+    sc->n_voxel_keys = n_merged;
+    return rebuild_from_keys(sc, "vrt_scene_set_cells");
+}
+
+int vrt_scene_voxel_count(const vrt_scene* sc, uint64_t* count) {
+    if (!sc || !count) return fail(VRT_ERR_INVALID, "vrt_scene_voxel_count: NULL argument");
+    if (!sc->d_voxel_keys) return fail(VRT_ERR_UNSUPPORTED, "vrt_scene_voxel_count: not a voxel-set scene");
+    *count = sc->n_voxel_keys;
+    return VRT_OK;
+}
+
 int vrt_scene_download_heights(vrt_scene* sc, int32_t* heights) {
     if (!sc || !heights) return fail(VRT_ERR_INVALID, "vrt_scene_download_heights: NULL argument");
     if (!sc->d_heights) return fail(VRT_ERR_UNSUPPORTED, "vrt_scene_download_heights: not a heightfield scene");
@@ -408,6 +517,7 @@ int vrt_scene_destroy(vrt_scene* sc) {
     if (sc->d_counters) cudaFree(sc->d_counters);
     if (sc->d_compact) cudaFree(sc->d_compact);
     if (sc->d_heights) cudaFree(sc->d_heights);
+    if (sc->d_voxel_keys) cudaFree(sc->d_voxel_keys);
     if (sc->d_tex) cudaFree(sc->d_tex);
     if (sc->d_grid_bits) cudaFree(sc->d_grid_bits);
     sc->frame_accum.release();

@@ -97,5 +97,11 @@ cudaError_t launch_grid_render(const GridLevels& g, bool use_mip, const RenderLa
 cudaError_t device_build_terrain_lsvo(int depth, uint2** d_slots, uint64_t* n_slots, int32_t* d_heights_out, cudaStream_t stream,
                                       const int32_t* d_heights_in = nullptr);
 // Reference layout → compact breadth-first array of live nodes, on the device (scene_device.cu); caller frees *d_out.
+// voxel_build.cu: arbitrary voxel sets on the device (sorted path keys → LNode array) and voxel edits
+cudaError_t device_voxel_keys(const uint32_t* d_xyz, uint64_t n, int depth, uint64_t** d_keys, uint32_t* n_keys, cudaStream_t stream);
+cudaError_t device_edit_voxel_keys(const uint64_t* d_keys, uint32_t n_keys, const uint64_t* d_edit, uint32_t n_edit, int add, int depth,
+                                   uint64_t** d_out, uint32_t* n_out, cudaStream_t stream);
+cudaError_t device_build_lsvo_from_keys(int depth, const uint64_t* d_keys, uint32_t n_keys, uint2** d_slots, uint64_t* n_slots,
+                                        cudaStream_t stream);
 cudaError_t device_compact_lsvo(const uint2* d_ref, uint64_t n_ref, int depth, uint2** d_out, uint64_t* n_out, cudaStream_t stream);
 }  // namespace vrt

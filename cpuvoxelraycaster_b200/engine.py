@@ -253,12 +253,36 @@ class LSVO(Volumetric):
         return nodes
 
     @classmethod
-    def from_voxels(cls, ctx, depth, xyz, guard=0):
-        """SVO::setCell for every voxel (svo.hpp:72) followed by LSVO(const SVO&) (lsvo.hpp:12)."""
-        return cls(ctx, host_build_lsvo_from_voxels(depth, xyz), depth, guard)
+    def from_voxels(cls, ctx, depth, xyz, guard=0, on_device=False):
+        """SVO::setCell for every voxel (svo.hpp:72) followed by LSVO(const SVO&) (lsvo.hpp:12).  on_device=True: the
+        voxel list is flattened on the GPU (byte-identical) and stays editable through set_cells."""
+        if not on_device:
+            return cls(ctx, host_build_lsvo_from_voxels(depth, xyz), depth, guard)
+        v = np.ascontiguousarray(np.asarray(xyz, np.uint32).reshape(-1, 3))
+        self = cls.__new__(cls)
+        Volumetric.__init__(self, ctx)
+        h = C.c_void_p()
+        check(lib().vrt_lsvo_create_from_voxels(ctx.handle, int(depth), ptr(v) if len(v) else None, len(v), int(guard), C.byref(h)))
+        self.handle = h
+        self.depth = int(depth)
+        self.n_nodes = len(self)
+        self._layout_from_env()
+        return self
+
+    def set_cells(self, xyz, solid=True):
+        """Dynamic scene: adds (solid) or removes voxels of a from_voxels(on_device=True) world and re-flattens it on
+        the device — what LSVO::setCell would do if it were not a no-op (lsvo.hpp:26)."""
+        v = np.ascontiguousarray(np.asarray(xyz, np.uint32).reshape(-1, 3))
+        check(lib().vrt_scene_set_cells(self.handle, ptr(v) if len(v) else None, len(v), int(bool(solid))))
+        self.n_nodes = len(self)
+
+    def voxel_count(self):
+        n = C.c_uint64(0)
+        check(lib().vrt_scene_voxel_count(self.handle, C.byref(n)))
+        return int(n.value)
 
     def setCell(self, *a):
-        """No-op, as in the reference (lsvo.hpp:26)."""
+        """No-op, as in the reference (lsvo.hpp:26); see set_cells."""
 
 
 class Grid3D(Volumetric):

@@ -134,6 +134,16 @@ int vrt_lsvo_create_terrain(vrt_context* ctx, uint32_t depth, int32_t guard, vrt
  * vrt_scene_edit_heights replaces the heights of the rectangle [x0, x0+nx) x [z0, z0+nz) (heights[i * nz + j] is column
  * (x0+i, z0+j)) and rebuilds the node array on the device: the result is byte-identical to flattening the edited world
  * from scratch (compileSVO order), so every cast and frame stays bit-exact.  Synchronises the context stream. */
+/* The general form: the world is a set of voxels (SVO::setCell coordinates, svo.hpp:72), flattened on the device —
+ * sorted path keys, DFS numbering by binary searches, no pointer octree (cpuvoxelraycaster_b200/csrc/voxel_build.cu); the
+ * array is byte-identical to LSVO<D>(const SVO<D>&) over the same voxels.  The sorted keys stay resident:
+ * vrt_scene_set_cells adds (solid != 0) or removes (solid == 0) voxels — what LSVO::setCell would do if it were not
+ * a no-op (lsvo.hpp:26) — and re-flattens; duplicates and removals of absent voxels are ignored.  Both synchronise
+ * the context stream. */
+int vrt_lsvo_create_from_voxels(vrt_context* ctx, uint32_t depth, const uint32_t* xyz, uint64_t n_voxels, int32_t guard,
+                                vrt_scene** out);
+int vrt_scene_set_cells(vrt_scene* scene, const uint32_t* xyz, uint64_t n_voxels, int32_t solid);
+int vrt_scene_voxel_count(const vrt_scene* scene, uint64_t* count);
 int vrt_lsvo_create_heightfield(vrt_context* ctx, uint32_t depth, const int32_t* heights, int32_t guard, vrt_scene** out);
 int vrt_scene_edit_heights(vrt_scene* scene, uint32_t x0, uint32_t z0, uint32_t nx, uint32_t nz, const int32_t* heights);
 int vrt_scene_download_heights(vrt_scene* scene, int32_t* heights /* [S*S] */);

@@ -66,6 +66,10 @@ def test_new_entry_points_validate_before_touching_the_device(vrt):
     assert lib.vrt_lsvo_create_heightfield(None, 9, None, 0, C.byref(h)) == -1
     assert lib.vrt_scene_edit_heights(None, 0, 0, 1, 1, buf) == -1
     assert lib.vrt_scene_download_heights(None, buf) == -1
+    assert lib.vrt_lsvo_create_from_voxels(None, 5, None, 0, 0, C.byref(h)) == -1
+    assert lib.vrt_scene_set_cells(None, None, 0, 1) == -1
+    n = C.c_uint64(0)
+    assert lib.vrt_scene_voxel_count(None, C.byref(n)) == -1
     assert b"NULL" in lib.vrt_last_error()
 
 

@@ -250,3 +250,62 @@ def test_heightfield_scene_and_edits(vrt, ctx, port, depth):
     with pytest.raises(vrt.VrtError):
         vrt.LSVO.from_terrain(ctx, 8).edit_heights(0, 0, np.zeros((1, 1), np.int32))   # not a heightfield scene
     t.close()
+
+
+@pytest.mark.parametrize("depth,n", [(1, 3), (2, 40), (3, 200), (5, 3000), (6, 20000), (8, 150000)])
+def test_voxel_set_scene_built_on_device(vrt, ctx, port, depth, n):
+    """Arbitrary voxel sets flattened on the GPU (sorted path keys, DFS numbering by binary searches): byte-identical to
+    the host flattener (= compileSVO order), duplicates included; casts bit-exact."""
+    S = 1 << depth
+    rng = np.random.default_rng(100 + depth)
+    vox = rng.integers(0, S, (n, 3)).astype(np.uint32)
+    vox = np.concatenate([vox, vox[: n // 3]])                              # duplicates, like repeated setCell calls
+    s = vrt.LSVO.from_voxels(ctx, depth, vox, on_device=True)
+    want = vrt.host_build_lsvo_from_voxels(depth, vox)
+    assert np.array_equal(s.download_nodes().view(np.uint64), want.view(np.uint64))
+    assert s.voxel_count() == len(np.unique(vox, axis=0))
+    o = rng.uniform(0.8, 2.2, (4000, 3)).astype(np.float32)
+    d = rng.normal(size=(4000, 3)).astype(np.float32)
+    got = s.cast_rays(o, d)
+    assert_hits_equal(got, port.lsvo_cast(want, depth, o, d), hit_flag(got), "device-built voxel scene")
+    s.close()
+
+
+def test_voxel_set_edge_cases_and_edits(vrt, ctx, port):
+    """Empty and full worlds, and LSVO::setCell given a meaning (a no-op in the reference, lsvo.hpp:26): voxels added and
+    removed on the device; after every edit the array equals a fresh flattening of the edited set."""
+    depth, S = 5, 32
+    e = vrt.LSVO.from_voxels(ctx, depth, np.zeros((0, 3), np.uint32), on_device=True)
+    assert np.array_equal(e.download_nodes().view(np.uint64), vrt.host_build_lsvo_from_voxels(depth, np.zeros((0, 3), np.uint32)).view(np.uint64))
+    full = np.stack(np.meshgrid(*[np.arange(8)] * 3, indexing="ij"), -1).reshape(-1, 3).astype(np.uint32)
+    f = vrt.LSVO.from_voxels(ctx, 3, full, on_device=True)
+    assert np.array_equal(f.download_nodes().view(np.uint64), vrt.host_build_lsvo_from_voxels(3, full).view(np.uint64))
+    f.close()
+    rng = np.random.default_rng(77)
+    world = set()
+    for step in range(6):
+        if step % 2 == 0:
+            vox = rng.integers(0, S, (int(rng.integers(1, 900)), 3)).astype(np.uint32)
+            e.set_cells(vox, True)
+            world |= set(map(tuple, vox.tolist()))
+        else:
+            have = np.array(sorted(world), np.uint32)
+            gone = have[rng.random(len(have)) < 0.4]
+            gone = np.concatenate([gone, rng.integers(0, S, (50, 3)).astype(np.uint32)])   # some were never set
+            e.set_cells(gone, False)
+            world -= set(map(tuple, gone.tolist()))
+        have = np.array(sorted(world), np.uint32).reshape(-1, 3)
+        want = vrt.host_build_lsvo_from_voxels(depth, have)
+        assert e.voxel_count() == len(have)
+        assert np.array_equal(e.download_nodes().view(np.uint64), want.view(np.uint64)), "step %d" % step
+        o = rng.uniform(0.8, 2.2, (2000, 3)).astype(np.float32)
+        d = rng.normal(size=(2000, 3)).astype(np.float32)
+        got = e.cast_rays(o, d)
+        assert_hits_equal(got, port.lsvo_cast(want, depth, o, d), hit_flag(got), "after edit %d" % step)
+    e.set_cells(np.array(sorted(world), np.uint32), False)                  # remove everything: the empty world again
+    assert e.voxel_count() == 0 and len(e.download_nodes()) == 1
+    with pytest.raises(vrt.VrtError):
+        e.set_cells([[S, 0, 0]], True)                                      # out of range: UB in the reference, an error here
+    with pytest.raises(vrt.VrtError):
+        vrt.LSVO.from_terrain(ctx, 8).set_cells([[1, 1, 1]], True)          # not a voxel-set scene
+    e.close()
