@@ -98,6 +98,33 @@ def main():
                 flat.close()
             print(json.dumps(line), flush=True)
             scene.close()
+            if cfg == 3:
+                # the configuration's frame: primary + sun shadow + blurry reflections off a Cell::Mirror lake that floods
+                # the valleys (columns whose top lies below the water level), 3840x2160, device resident
+                from cpuvoxelraycaster_b200.frame import FrameRenderer
+                h = vrt.host_terrain_heights(size)[::-1, ::-1]
+                top = size // 2 - np.maximum(16, np.minimum(size, h))          # first solid y of each column (up = -y)
+                water = size // 2 - 30
+                xs, zs = np.nonzero(top > water)
+                for x, z in zip(xs.tolist(), zs.tolist()):
+                    cells[x, water + 1:top[x, z], z] = 1
+                cells[xs, water, zs] = 2
+                lake = vrt.MipmapGrid3D(ctx, cells, mip)
+                lake.set_textures(tex["top"], tex["side"])
+                fr = FrameRenderer(lake, W, H, 0, 1, None, None, stream)
+                fr.use_gi, fr.roughness, fr.max_bounds = False, 0.06, 4
+                fr.light = np.float32([-200, -1000, -300]) * np.float32(size / 512.0)
+                cam = vrt.Camera(position=(size / 2, size / 2 - 56, size / 2), view_angle=(0.0, 0.0), focal_length=100.0)
+                for spp in (1, 4):
+                    ms = timed(stream, lambda: fr.render_device(cam, spp), a.iters)
+                    st = fr.stats()
+                    rays, steps = sum(st["rays"][:3]), sum(st["complexity"][:3])
+                    print(json.dumps(dict(cfg=3, what="T(%d) mip grid %d^3 with a mirror lake, %dx%d frame: primary + sun shadow + blurry reflections "
+                                          "(roughness 0.06, max_bounds 4), %d spp" % (D, size, W, H, spp), ms_per_frame=round(ms, 4),
+                                          rays=dict(primary=st["rays"][0], shadow=st["rays"][1], reflection=st["rays"][2]),
+                                          mirror_cells=int(len(xs)), mrays_s=round(rays / ms / 1e3, 1), mean_steps=round(steps / max(rays, 1), 1),
+                                          algo_GBs=round((steps + 64 * rays + 16 * W * H) / ms / 1e6, 1))), flush=True)
+                lake.close()
             del cells
 
     if 5 in want:   # LSVO 4096^3, incoherent random rays
