@@ -4,6 +4,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "host_util.h"
@@ -60,9 +61,11 @@ struct vrt_context {
     int cast_variant = 1, render_variant = 0;
     int sort_bins1 = 0, sort_bins2 = 0;         // K5: angle bins of the two GI bounces (0 = automatic)
     int spp_chunks = 0;                        // K4: 0 = automatic
+    int trav_policy = -1;                      // K6: traversal loop variant (kernels.h RenderLaunch::trav_policy)
     int samples_per_warp = 0;                  // K4: lanes sharing a pixel (power of two), 0 = automatic
     int refill_cast = 0, refill_render = 16;   // parked lanes that trigger a refill (1..32); cast: 0 = warp-adaptive
     DeviceBuffer scratch_in, scratch_out;   // host-variant staging
+    cudaAccessPolicyWindow l2_window{};     // installed by vrt_scene_set_layout(.., l2_persist); follows the stream (set_stream)
 };
 
 struct vrt_scene {
@@ -160,6 +163,13 @@ int vrt_context_set_stream(vrt_context* ctx, void* stream) {
         ctx->owns_stream = false;
     }
     ctx->stream = static_cast<cudaStream_t>(stream);
+    if (ctx->l2_window.num_bytes) {                       // the access-policy window is a stream attribute: carry it over
+        if (int s = use_device(ctx)) return s;
+        cudaStreamAttrValue attr;
+        std::memset(&attr, 0, sizeof(attr));
+        attr.accessPolicyWindow = ctx->l2_window;
+        VRT_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    }
     return VRT_OK;
 }
 
@@ -173,6 +183,7 @@ int vrt_context_set_option(vrt_context* ctx, const char* key, int value) {
     else if (k == "sort_bins1" && value >= 0 && value <= 256) ctx->sort_bins1 = value;
     else if (k == "sort_bins2" && value >= 0 && value <= 256) ctx->sort_bins2 = value;
     else if (k == "spp_chunks" && value >= 0 && value <= 4096) ctx->spp_chunks = value;
+    else if (k == "trav_policy" && value >= -1 && value <= 4) ctx->trav_policy = value;
     else if (k == "samples_per_warp" && value >= 0 && value <= 32 && (value & (value - 1)) == 0) ctx->samples_per_warp = value;
     else if (k == "refill_cast" && value >= 0 && value <= 32) ctx->refill_cast = value;
     else if (k == "refill_render" && value >= 1 && value <= 32) ctx->refill_render = value;
@@ -219,14 +230,33 @@ int vrt_lsvo_create(vrt_context* ctx, const vrt_lnode* nodes, uint64_t n_nodes, 
     if (!ctx || !nodes || !n_nodes || !out) return fail(VRT_ERR_INVALID, "vrt_lsvo_create: NULL argument");
     if (depth < 1 || depth > 12) return fail(VRT_ERR_INVALID, "vrt_lsvo_create: depth must be 1..12");
     if (n_nodes > 0xffffffffull) return fail(VRT_ERR_UNSUPPORTED, "vrt_lsvo_create: more than 2^32 slots");
-    // The traversal follows child_offset blindly; a malformed array would fault (or spin) on the device, so the
-    // structure is checked once here: every referenced child block must lie inside the array and in front of
-    // its parent (compileSVO emits children after their parent, lsvo_utils.cpp:7-10), leaves have no block.
-    for (uint64_t i = 0; i < n_nodes; ++i) {
-        const vrt_lnode& nd = nodes[i];
-        if (!nd.child_mask) continue;
-        if ((nd.leaf_mask & ~nd.child_mask) || nd.child_offset == 0 || i + nd.child_offset + 8 > n_nodes)
-            return fail(VRT_ERR_INVALID, "vrt_lsvo_create: malformed node array at slot " + std::to_string(i));
+    // The traversal follows child_offset blindly and indexes its stack by level; a malformed array would fault (or spin)
+    // on the device, so the structure is checked once here by walking it from the root with each node's level:
+    // every referenced child block lies inside the array and behind its parent (compileSVO emits children after their
+    // parent, lsvo_utils.cpp:7-10: indices grow along every path, so the walk terminates), leaves have no block, the
+    // children of a node on level depth-1 are voxels (all leaves), and nothing is interior below that level — a tree
+    // deeper than `depth` would drive the stack index scale - (23 - depth) negative (lsvo.hpp:97-100).
+    {
+        std::vector<std::pair<uint64_t, uint32_t>> todo;
+        todo.emplace_back(0, 0u);
+        while (!todo.empty()) {
+            const uint64_t i = todo.back().first;
+            const uint32_t level = todo.back().second;
+            todo.pop_back();
+            const vrt_lnode& nd = nodes[i];
+            if (!nd.child_mask) {
+                if (nd.leaf_mask) return fail(VRT_ERR_INVALID, "vrt_lsvo_create: malformed node array at slot " + std::to_string(i));
+                continue;
+            }
+            if ((nd.leaf_mask & ~nd.child_mask) || nd.child_offset == 0 || i + nd.child_offset + 8 > n_nodes)
+                return fail(VRT_ERR_INVALID, "vrt_lsvo_create: malformed node array at slot " + std::to_string(i));
+            if (level + 1 >= depth && nd.leaf_mask != nd.child_mask)
+                return fail(VRT_ERR_INVALID, "vrt_lsvo_create: the tree is deeper than the declared depth " + std::to_string(depth) +
+                                                 " (interior child below slot " + std::to_string(i) + ")");
+            const uint32_t interior = nd.child_mask & ~nd.leaf_mask;
+            for (uint32_t c = 0; c < 8; ++c)
+                if (interior & (1u << c)) todo.emplace_back(i + nd.child_offset + c, level + 1);
+        }
     }
     if (int s = use_device(ctx)) return s;
     vrt_scene* sc = new (std::nothrow) vrt_scene();
@@ -316,14 +346,29 @@ int vrt_scene_edit_heights(vrt_scene* sc, uint32_t x0, uint32_t z0, uint32_t nx,
     if (nx == 0 || nz == 0 || uint64_t(x0) + nx > S || uint64_t(z0) + nz > S) return fail(VRT_ERR_INVALID, "vrt_scene_edit_heights: rectangle out of range");
     vrt_context* ctx = sc->ctx;
     if (int s = use_device(ctx)) return s;
-    VRT_CUDA(cudaMemcpy2DAsync(sc->d_heights + size_t(x0) * S + z0, S * sizeof(int32_t), heights, size_t(nz) * sizeof(int32_t),
-                               size_t(nz) * sizeof(int32_t), nx, cudaMemcpyHostToDevice, ctx->stream));
+    // the edit is staged: the old rectangle is kept until the new node array exists, and put back if the rebuild fails,
+    // so that the resident heights always describe the world that is being rendered
+    int32_t* d_old = nullptr;
+    VRT_CUDA(cudaMalloc(&d_old, size_t(nx) * nz * sizeof(int32_t)));
+    cudaError_t e = cudaMemcpy2DAsync(d_old, size_t(nz) * sizeof(int32_t), sc->d_heights + size_t(x0) * S + z0, S * sizeof(int32_t),
+                                      size_t(nz) * sizeof(int32_t), nx, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(sc->d_heights + size_t(x0) * S + z0, S * sizeof(int32_t), heights, size_t(nz) * sizeof(int32_t),
+                              size_t(nz) * sizeof(int32_t), nx, cudaMemcpyHostToDevice, ctx->stream);
     uint2* d_new = nullptr;
     uint64_t n_new = 0;
-    cudaError_t e = vrt::device_build_terrain_lsvo(int(sc->depth), &d_new, &n_new, nullptr, ctx->stream, sc->d_heights);
+    if (e == cudaSuccess) e = vrt::device_build_terrain_lsvo(int(sc->depth), &d_new, &n_new, nullptr, ctx->stream, sc->d_heights);
     ctx->launches += 7 + 9 * sc->depth;
-    if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? fail(VRT_ERR_OOM, "vrt_scene_edit_heights: device allocation failed")
-                                                                : cuda_fail(e, "vrt_scene_edit_heights");
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaMemcpy2DAsync(sc->d_heights + size_t(x0) * S + z0, S * sizeof(int32_t), d_old, size_t(nz) * sizeof(int32_t),
+                          size_t(nz) * sizeof(int32_t), nx, cudaMemcpyDeviceToDevice, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_old);
+        return e == cudaErrorMemoryAllocation ? fail(VRT_ERR_OOM, "vrt_scene_edit_heights: device allocation failed (scene unchanged)")
+                                              : cuda_fail(e, "vrt_scene_edit_heights (scene unchanged)");
+    }
+    cudaFree(d_old);
     // the builder synchronised the stream: nothing in flight reads the old arrays any more
     cudaFree(sc->d_nodes);
     sc->device_bytes += n_new * sizeof(uint2);
@@ -363,11 +408,11 @@ int upload_voxel_keys(vrt_context* ctx, uint32_t depth, const uint32_t* xyz, uin
 }
 
 // re-flattens a voxel-set scene from its resident keys and swaps the node array in
-int rebuild_from_keys(vrt_scene* sc, const char* who) {
+int rebuild_from_keys(vrt_scene* sc, const uint64_t* d_keys, uint32_t n_keys, const char* who) {
     vrt_context* ctx = sc->ctx;
     uint2* d_new = nullptr;
     uint64_t n_new = 0;
-    cudaError_t e = vrt::device_build_lsvo_from_keys(int(sc->depth), sc->d_voxel_keys, sc->n_voxel_keys, &d_new, &n_new, ctx->stream);
+    cudaError_t e = vrt::device_build_lsvo_from_keys(int(sc->depth), d_keys, n_keys, &d_new, &n_new, ctx->stream);
     ctx->launches += 2 + 4 * sc->depth;
     if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? fail(VRT_ERR_OOM, std::string(who) + ": device allocation failed") : cuda_fail(e, who);
     if (sc->d_nodes) cudaFree(sc->d_nodes);                 // the builder synchronised the stream
@@ -400,7 +445,7 @@ int vrt_lsvo_create_from_voxels(vrt_context* ctx, uint32_t depth, const uint32_t
     sc->depth = depth;
     sc->guard = guard > 0 ? guard : (guard < 0 ? 0 : int32_t(depth));
     int s = upload_voxel_keys(ctx, depth, xyz, n, &sc->d_voxel_keys, &sc->n_voxel_keys, "vrt_lsvo_create_from_voxels");
-    if (s == VRT_OK) s = rebuild_from_keys(sc, "vrt_lsvo_create_from_voxels");
+    if (s == VRT_OK) s = rebuild_from_keys(sc, sc->d_voxel_keys, sc->n_voxel_keys, "vrt_lsvo_create_from_voxels");
     if (s == VRT_OK) {
         cudaError_t e = cudaMalloc(&sc->d_counters, 16 * sizeof(unsigned long long));
         if (e == cudaSuccess) e = cudaMemsetAsync(sc->d_counters, 0, 16 * sizeof(unsigned long long), ctx->stream);
@@ -435,12 +480,17 @@ int vrt_scene_set_cells(vrt_scene* sc, const uint32_t* xyz, uint64_t n, int32_t 
     ctx->launches += 3;
     if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? fail(VRT_ERR_OOM, "vrt_scene_set_cells: device allocation failed")
                                                                 : cuda_fail(e, "vrt_scene_set_cells");
+    // staged: the node array is rebuilt from the candidate key set first; the resident keys are replaced only when that worked
+    if (int s = rebuild_from_keys(sc, d_merged, n_merged, "vrt_scene_set_cells")) {
+        cudaFree(d_merged);
+        return s;
+    }
     cudaFree(sc->d_voxel_keys);
     sc->device_bytes += uint64_t(n_merged) * sizeof(uint64_t);
     sc->device_bytes -= uint64_t(sc->n_voxel_keys) * sizeof(uint64_t);
     sc->d_voxel_keys = d_merged;
     sc->n_voxel_keys = n_merged;
-    return rebuild_from_keys(sc, "vrt_scene_set_cells");
+    return VRT_OK;
 }
 
 int vrt_scene_voxel_count(const vrt_scene* sc, uint64_t* count) {
@@ -494,6 +544,7 @@ int vrt_scene_set_layout(vrt_scene* sc, int32_t layout, int32_t l2_persist) {
         }
     }
     VRT_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    ctx->l2_window = attr.accessPolicyWindow;
     return VRT_OK;
 }
 
@@ -540,7 +591,7 @@ int vrt_cast_rays_device(vrt_scene* sc, const float* d_origin, const float* d_di
                          vrt_hit* d_out) {
     if (!sc) return fail(VRT_ERR_INVALID, "vrt_cast_rays_device: scene is NULL");
     if (n && (!d_origin || !d_dir || !d_out)) return fail(VRT_ERR_INVALID, "vrt_cast_rays_device: NULL buffer");
-    if (n > (1ull << 31) * 128ull) return fail(VRT_ERR_UNSUPPORTED, "vrt_cast_rays_device: too many rays for one launch");
+    if (n > ((1ull << 31) - 1ull) * 128ull) return fail(VRT_ERR_UNSUPPORTED, "vrt_cast_rays_device: too many rays for one launch (gridDim.x <= 2^31 - 1)");
     vrt_context* ctx = sc->ctx;
     if (int s = use_device(ctx)) return s;
     VRT_CUDA(cudaMemsetAsync(sc->d_counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
@@ -632,6 +683,7 @@ vrt::RenderLaunch make_launch(const vrt_scene* sc, const vrt_camera* cam, const 
     L.samples_per_warp = sc->ctx->samples_per_warp;
     L.mapping = sc->ctx->render_variant == 1 ? 0 : sc->ctx->render_variant;
     L.scratch = nullptr; L.scratch_bytes = 0;
+    L.trav_policy = sc->ctx->trav_policy;
     L.sort_bins1 = sc->ctx->sort_bins1; L.sort_bins2 = sc->ctx->sort_bins2;
     L.roughness = p->roughness;
     L.max_bounds = p->max_bounds;

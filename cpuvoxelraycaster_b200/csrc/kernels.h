@@ -44,6 +44,7 @@ struct RenderLaunch {
     void* scratch;               // K6: device scratch for the sorted sample lists (render_scratch_bytes)
     size_t scratch_bytes;
     int mapping;                 // 0 = automatic (K5 for many-sample GI frames, else K4), 2 = K4, 3 = K5
+    int trav_policy;             // K6: -1 = plain loop per lane, 0..4 = warp-synchronous loop with path voting (lsvo_step.cuh)
     uint32_t seed_lo, seed_hi;
     float light[3];
     vrt_camera cam;

@@ -59,7 +59,8 @@ struct Trav {
     // replaced by one that starts outside the cube pointing away (one trip, no descent) and is marked in bit 3 of
     // `mirror`, which result() reads.
     __device__ __forceinline__ void init(float ox_, float oy_, float oz_, float dx_, float dy_, float dz_, float coef_, float bias_) {
-        const bool finite = (((ox_ + oy_) + oz_) + ((dx_ + dy_) + dz_)) * 0.0f == 0.0f;   // inf * 0 and NaN * 0 are NaN
+        // inf * 0 and NaN * 0 are NaN; per component, so that large finite components cannot overflow a sum
+        const bool finite = (((ox_ * 0.0f + oy_ * 0.0f) + oz_ * 0.0f) + ((dx_ * 0.0f + dy_ * 0.0f) + dz_ * 0.0f)) == 0.0f;
         if (!finite) { ox_ = 3.0f; oy_ = 3.0f; oz_ = 3.0f; dx_ = 1.0f; dy_ = 1.0f; dz_ = 1.0f; }
         ox = ox_; oy = oy_; oz = oz_; coef = coef_; bias = bias_;
         if (fabsf(dx_) < kEps) dx_ = copysignf(kEps, dx_);                 // lsvo.hpp:44-46
@@ -142,6 +143,76 @@ struct Trav {
         return true;
     }
 
+    // ---- the same trip cut into its three parts, for warp-synchronous callers (lsvo_cast_ray_warp below) ----
+    // head(): node fetch, child test and the two terminating exits (:74-95).  Returns 0 = the ray hit (terminated),
+    // 1 = the trip continues with descend() (:97-110), 2 = with advance() (:113-145).  head() changes no state except on a hit,
+    // so a lane whose continuation is postponed by the warp's vote simply runs head() again in the next trip.
+    struct Head {
+        NodeView nd;
+        float sf, cx, cy, cz, tc_max, tv_max;
+        uint32_t shift;
+    };
+    template <typename Nodes>
+    __device__ __forceinline__ int head(const Nodes& nodes, Head& H) {
+        H.sf = scale_f();
+        H.nd = nodes.fetch(parent);                                          // :74
+        H.cx = px * tcx - tox; H.cy = py * tcy - toy; H.cz = pz * tcz - toz; // :76
+        H.tc_max = fminf(H.cx, fminf(H.cy, H.cz));
+        H.shift = child ^ mirror;                                            // :79
+        const uint32_t child_bit = 0x100u << H.shift;
+        if ((H.nd.raw & child_bit) && t_min <= t_max) {                      // :80-81
+            if (H.tc_max * coef + bias >= H.sf) { ++iters; hit = true; return 0; }   // :82-85
+            H.tv_max = fminf(t_max, H.tc_max);
+            if (t_min <= H.tv_max) {                                         // :89
+                if (H.nd.raw & (child_bit << 8)) { ++iters; hit = true; return 0; }  // :90-95
+                return 1;
+            }
+        }
+        return 2;
+    }
+    template <typename Nodes, typename Stack>
+    __device__ __forceinline__ bool descend(const Nodes& nodes, Stack& stack, int depth_offset, int guard, const Head& H) {
+        ++iters;
+        const float half = H.sf * 0.5f;
+        if (H.tc_max < h) stack.push(scale - depth_offset, parent, t_max);   // :97-100
+        h = H.tc_max;
+        parent = nodes.child(H.nd, H.shift);                                 // :103
+        child = 0u;
+        --scale;
+        if (half * tcx + H.cx > t_min) { child ^= 1u; px += half; }          // :88,107-109
+        if (half * tcy + H.cy > t_min) { child ^= 2u; py += half; }
+        if (half * tcz + H.cz > t_min) { child ^= 4u; pz += half; }
+        t_max = H.tv_max;
+        return scale > guard;                                                // :72
+    }
+    template <typename Stack>
+    __device__ __forceinline__ bool advance(Stack& stack, int depth_offset, int guard, const Head& H) {
+        ++iters;
+        const uint32_t ox_bits = __float_as_uint(px), oy_bits = __float_as_uint(py), oz_bits = __float_as_uint(pz);
+        uint32_t step_mask = 0u;                                             // :115-118
+        if (H.cx <= H.tc_max) { step_mask ^= 1u; px -= H.sf; }
+        if (H.cy <= H.tc_max) { step_mask ^= 2u; py -= H.sf; }
+        if (H.cz <= H.tc_max) { step_mask ^= 4u; pz -= H.sf; }
+        t_min = H.tc_max;
+        child ^= step_mask;
+        face = step_mask;
+        if (child & step_mask) {                                             // :124-145, see step()
+            const uint32_t ix = __float_as_uint(px), iy = __float_as_uint(py), iz = __float_as_uint(pz);
+            const uint32_t diff = (ix ^ ox_bits) | (iy ^ oy_bits) | (iz ^ oz_bits);
+            scale = 31 - __clz(int(diff));
+            if (scale >= kSvoMaxDepth) return false;
+            stack.pop(scale - depth_offset, parent, t_max);
+            const uint32_t keep = 0xffffffffu << scale;
+            px = __uint_as_float(ix & keep);
+            py = __uint_as_float(iy & keep);
+            pz = __uint_as_float(iz & keep);
+            child = ((ix >> scale) & 1u) | (((iy >> scale) & 1u) << 1) | (((iz >> scale) & 1u) << 2);
+            h = 0.0f;
+            return scale > guard;
+        }
+        return true;
+    }
+
     __device__ __forceinline__ void result(LsvoResult& r) const {
         r.px = px; r.py = py; r.pz = pz;
         r.t_min = t_min; r.scale_f = scale_f(); r.scale = scale; r.face = face; r.mirror = mirror & 7u;
@@ -157,6 +228,43 @@ __device__ __forceinline__ void lsvo_cast_ray(const Nodes& nodes, Stack& stack, 
     Trav t;
     t.init(ox, oy, oz, dx, dy, dz, coef, bias);
     while (t.step(nodes, stack, depth_offset, guard)) {}
+    t.result(r);
+}
+
+// Warp-synchronous castRay: all 32 lanes of the warp call this together (lanes without a ray pass alive = false).
+// Every trip the warp evaluates head() and then VOTES which continuation it executes: in the plain loop above a trip
+// in which some lanes descend and others advance issues both paths (and the pop) at a fraction of the lanes each
+// (profiles/r01: 41 + 16 + 30 instructions at 17.7 / 14.2 / 9.6 of 32 lanes).  Here lanes whose path is not executed this
+// trip wait (no state change) and run it in a later trip together with the lanes that have caught up.
+// The per-ray sequence of operations is unchanged, so results and iteration counts are bit-identical.
+//   kPolicy 0: both paths every trip (the plain loop, warp-uniform form)      1: descend has priority (while-while)
+//           2: the path with more lanes                                        3/4: both when the minority has >= 8 / 12 lanes
+template <int kPolicy, typename Nodes, typename Stack>
+__device__ __forceinline__ void lsvo_cast_ray_warp(const Nodes& nodes, Stack& stack, int depth_offset, int guard, bool alive, float ox,
+                                                   float oy, float oz, float dx, float dy, float dz, float coef, float bias,
+                                                   LsvoResult& r) {
+    Trav t;
+    t.init(ox, oy, oz, dx, dy, dz, coef, bias);
+    while (__any_sync(0xffffffffu, alive)) {
+        typename Trav::Head H;
+        int want = 0;
+        if (alive) {
+            want = t.head(nodes, H);
+            alive = want != 0;
+        }
+        bool do_d = true, do_a = true;
+        if (kPolicy == 1) {
+            do_d = __any_sync(0xffffffffu, want == 1);
+            do_a = !do_d;
+        } else if (kPolicy >= 2) {
+            const int nd = __popc(__ballot_sync(0xffffffffu, want == 1)), na = __popc(__ballot_sync(0xffffffffu, want == 2));
+            const int theta = kPolicy == 2 ? 33 : kPolicy == 3 ? 8 : 12;
+            do_d = nd >= theta || nd >= na;
+            do_a = na >= theta || na > nd;
+        }
+        if (do_d && want == 1) alive = t.descend(nodes, stack, depth_offset, guard, H);
+        if (do_a && want == 2) alive = t.advance(stack, depth_offset, guard, H);
+    }
     t.result(r);
 }
 

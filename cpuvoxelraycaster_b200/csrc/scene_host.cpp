@@ -175,7 +175,9 @@ uint64_t host_build_terrain_lsvo(uint32_t depth, const int32_t* heights, vrt_lno
     occ.top.resize(depth + 1);
     occ.top[0].resize(size_t(S) * S);
     for (size_t i = 0; i < size_t(S) * S; ++i) {
-        const int32_t hmax = std::max(16, std::min(S, heights[i]));   // main.cpp:71-72
+        // main.cpp:71-72; columns cannot leave the world: tops are clamped to S/2 like tops_kernel (scene_device.cu) does,
+        // so the count-only call, the fill call and the device builder agree for any caller-supplied heights
+        const int32_t hmax = std::max(16, std::min(S / 2, heights[i]));
         occ.top[0][i] = S / 2 + hmax - 1;                             // y in [1,hmax) stored at y + S/2
     }
     for (uint32_t l = 1; l <= depth; ++l) {

@@ -42,7 +42,7 @@ def host_build_terrain_lsvo(depth, heights=None):
     check(lib().vrt_host_build_terrain_lsvo(depth, ptr(heights), None, 0, C.byref(n)))
     nodes = np.zeros(n.value, LNODE)
     check(lib().vrt_host_build_terrain_lsvo(depth, ptr(heights), ptr(nodes), n.value, C.byref(n)))
-    return nodes
+    return nodes[:n.value]
 
 
 def host_build_lsvo_from_voxels(depth, xyz):
@@ -51,7 +51,7 @@ def host_build_lsvo_from_voxels(depth, xyz):
     check(lib().vrt_host_build_lsvo_from_voxels(depth, ptr(xyz), len(xyz), None, 0, C.byref(n)))
     nodes = np.zeros(n.value, LNODE)
     check(lib().vrt_host_build_lsvo_from_voxels(depth, ptr(xyz), len(xyz), ptr(nodes), n.value, C.byref(n)))
-    return nodes
+    return nodes[:n.value]
 
 
 # ---- execution resource -------------------------------------------------------------------------------

@@ -58,7 +58,8 @@ class FrameRenderer:
         self.device = device if device is not None else torch.device("cuda", scene.ctx.device)
         # libvrt's launches and torch's copies/collectives must share one stream
         self.stream = stream if stream is not None else torch.cuda.Stream(self.device)
-        scene.ctx.set_stream(self.stream.cuda_stream)
+        scene.ctx.set_stream(self.stream.cuda_stream)      # libvrt re-applies an installed L2 access-policy window to it
+        scene.ctx.torch_stream = self.stream               # keeps the cudaStream_t alive as long as the context uses it
         self.exchange = TileExchange(self.W, self.H, self.rank, self.world, self.device, group)
         self.H_pad, self.row_bytes = self.exchange.H_pad, self.exchange.row_bytes
         self.accum = torch.zeros(self.H_pad * self.W * 4, dtype=torch.int32, device=self.device)   # r,g,b,count sums

@@ -290,7 +290,8 @@ static void lsvo_cast_one(const vo_lnode* nodes, int depth, int guard, const flo
     memset(res, 0, sizeof(*res));
     /* A ray with a non-finite origin or direction never leaves the reference's loop (comparisons with NaN all fail:
      * no descent, no step, no pop).  The engine and this restatement define it as a miss of complexity 0. */
-    if ((((o[0] + o[1]) + o[2]) + ((din[0] + din[1]) + din[2])) * 0.0f != 0.0f) return;
+    /* x * 0 is NaN exactly for infinite / NaN x: tested per component, so that finite rays whose components would overflow a sum stay finite */
+    if ((((o[0] * 0.0f + o[1] * 0.0f) + o[2] * 0.0f) + ((din[0] * 0.0f + din[1] * 0.0f) + din[2] * 0.0f)) != 0.0f) return;
     for (int a = 0; a < 3; ++a) {
         d[a] = din[a];
         if (fabsf(d[a]) < EPS) d[a] = copysignf(EPS, d[a]);           /* :44-46 */

@@ -13,6 +13,10 @@
   frame_checker_small.npz  the reference's RayCaster driven like main.cpp:137-143 for 4 frames: alternating checkerboard
                       halves (thread-area height 18 and the odd 15) with the 0.4/0.6 temporal blend, and the
                       accumulators of two half frames in sample mode   (`make_golden.py checker` makes only this file)
+  cfg1_full.json      BASELINE configs[0] at its full size: the reference's RayCaster + Camera at 1280x720, 1 sample, primary +
+                      sun shadow, camera (256,200,256) view (0,0): sha256 of the image and of the integer accumulators, the
+                      number of primary hits and sha256 of the packed hit/complexity arrays of the 921 600 camera rays
+                      (`make_golden.py cfg1` makes only this file)
 """
 import hashlib
 import os
@@ -74,9 +78,41 @@ def make_checker_frames(R):
     R.scene_destroy(T)
 
 
+def make_cfg1_full(R):
+    import json
+    T = R.scene_terrain(9)
+    R.register_textures(*[read_bmp24(os.path.join(REF, "res", n)) for n in ("grass_top_16x16.bmp", "grass_side_16x16.bmp")])
+    light = np.float32([-200, -1000, -300]) * np.float32(1.0 / 512.0) + np.float32(1.0)
+    p = loader.RefRenderParams()
+    p.width, p.height = 1280, 720
+    p.cam_position[:] = [256.0, 200.0, 256.0]
+    p.view_angle[:] = [0.0, 0.0]
+    p.fov, p.aperture, p.focal_length = 1.0, 0.0, 100.0
+    p.light_position[:] = [float(x) for x in light]
+    p.use_gi, p.use_samples, p.spp, p.threads = 0, 1, 1, 8
+    res = R.render(T, p)
+    o, d = R.camera_rays(p)
+    hits = R.lsvo_cast(T, o, d, 0.0, 0.0, threads=8)
+    out = dict(width=1280, height=720, cam_position=[256.0, 200.0, 256.0], view_angle=[0.0, 0.0], focal_length=100.0,
+               light=[float(x) for x in light],
+               sha256_image=hashlib.sha256(res["image"].tobytes()).hexdigest(),
+               sha256_samples_u32=hashlib.sha256(res["samples"].astype(np.uint32).tobytes()).hexdigest(),
+               primary_hits=int((hits["hit"] != 0).sum()),
+               sha256_hit_flags=hashlib.sha256((hits["hit"] != 0).astype(np.uint8).tobytes()).hexdigest(),
+               sha256_complexity=hashlib.sha256(hits["complexity"].astype(np.uint32).tobytes()).hexdigest(),
+               sha256_distance_of_hits=hashlib.sha256(hits["distance"][hits["hit"] != 0].astype(np.float32).tobytes()).hexdigest(),
+               sum_complexity=int(hits["complexity"].astype(np.int64).sum()))
+    json.dump(out, open(os.path.join(OUT, "cfg1_full.json"), "w"), indent=1)
+    R.scene_destroy(T)
+    print(out)
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "checker":
         make_checker_frames(loader.ref())
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "cfg1":
+        make_cfg1_full(loader.ref())
         return
     R = loader.ref()
     RP = loader.ref_patched()
@@ -159,6 +195,7 @@ def main():
                         hits_iter16=RP.svo_cast(s, o, d, 16))
     RP.svo_destroy(s)
     make_checker_frames(R)
+    make_cfg1_full(R)
     print("golden fixtures written to", OUT)
 
 

@@ -241,3 +241,89 @@ def test_lattice_rng_matches_getrand_distribution(port, ref):
     assert np.allclose(np.unique((g + 0.5) * 100 - levels), 0, atol=1e-4)     # 100-point lattice
     counts = np.bincount(levels, minlength=100)
     assert counts.min() > 1600 and counts.max() < 2400
+
+
+# ---- the benchmark depth: oracle/port.c against the reference's RayCaster rebuilt at depth 11 (oracle/_ref/libvrt_ref_d11.so) ----
+def _c11_params(loader, R, W, H, view, aperture, use_gi, spp, light, focal, threads=8):
+    S = 2048.0
+    pr = loader.RefRenderParams()
+    pr.width, pr.height = W, H
+    pr.cam_position[:] = [S / 2, S / 2 - 56.0, S / 2]
+    pr.view_angle[:] = view
+    pr.fov, pr.aperture, pr.focal_length = 1.0, aperture, focal
+    pr.light_position[:] = [float(x) for x in light]
+    pr.use_gi, pr.use_samples, pr.spp, pr.threads = use_gi, 1, spp, threads
+    pp = loader.PortRenderParams()
+    pp.width, pp.height, pp.depth, pp.guard = W, H, 11, 11
+    pp.cam_position[:] = [S / 2, S / 2 - 56.0, S / 2]
+    rot, _ = R.camera_basis(np.float32(view))
+    pp.rot_mat[:] = [float(x) for x in rot]
+    pp.fov, pp.aperture, pp.focal_length = 1.0, aperture, focal
+    pp.light_position[:] = [float(x) for x in light]
+    pp.use_gi, pp.gi_bounces, pp.use_samples, pp.spp = use_gi, 1, 1, spp
+    pp.seed_lo, pp.threads = 0x5EED, threads
+    return pr, pp
+
+
+def test_depth11_raycaster_matches_the_reference_build(port, textures):
+    """The depth-dependent constants of the shading path (SCALE = 1/2^D, n_norm, the 512s of camera_controller.hpp:36,58
+    and raycaster.hpp:171) at the BENCHMARK depth: deterministic frames u8- and accumulator-exact, the autofocus rule
+    exact, and the 1-bounce GI + DOF frame within the reference's own run-to-run PSNR."""
+    from oracle import loader
+    R = loader.ref_depth(11)
+    if R is None:
+        pytest.skip("oracle/_ref/libvrt_ref_d11.so not built")
+    assert R.depth == 11
+    R.register_textures(*textures)
+    light = np.float32([-200, -1000, -300]) * np.float32(1 / 2048.0) + np.float32(1)
+    nodes = port.build_terrain(11)
+    sc = R.scene_from_nodes(11, nodes)
+    for (W, H, view) in ((160, 90, [0.0, 0.0]), (128, 72, [0.7, -0.4])):
+        pr, pp = _c11_params(loader, R, W, H, view, 0.0, 0, 1, light, 100.0)
+        want = R.render(sc, pr)
+        accum, rgba, _ = port.render(nodes, pp, *textures)
+        assert np.array_equal(accum, want["samples"].astype(np.uint32)) and np.array_equal(rgba, want["image"])
+        assert 0.2 < (accum[..., :3].sum(-1) > 0).mean() < 0.99         # lit terrain, and sky or shadow
+    # main.cpp:115-121 at depth 11
+    pr, pp = _c11_params(loader, R, 160, 90, [0.0, 0.0], 0.5, 0, 1, light, 100.0)
+    f = R.autofocus(sc, pr)
+    _, cv = R.camera_basis(np.float32([0.0, 0.0]))
+    h = port.lsvo_cast(nodes, 11, [np.float32([1024, 968, 1024]) * np.float32(1 / 2048.0) + np.float32(1)], [cv])[0]
+    assert h["hit"] and np.float32(f) == np.float32(h["distance"]) * np.float32(2048.0)
+    # stochastic: GI (one bounce, the reference's) + DOF, 64 spp
+    W, H, view, spp = 96, 54, [0.0, 0.0], 64
+    pr, pp = _c11_params(loader, R, W, H, view, 0.5, 1, spp, light, f)
+    r1 = R.render(sc, pr)["image"][..., :3]
+    R.getrand(12345)
+    r2 = R.render(sc, pr)["image"][..., :3]
+    _, p1, _ = port.render(nodes, pp, *textures)
+    rr, pq = psnr(r1, r2), psnr(p1[..., :3], r1)
+    assert pq >= rr - 1.5, "port vs reference %.2f dB, reference vs reference %.2f dB" % (pq, rr)
+    assert abs(float(p1[..., :3].mean()) - float(r1.mean())) < 1.0
+    R.scene_destroy(sc)
+
+
+def test_cfg1_full_frame_known_answers(port, textures):
+    """BASELINE configs[0] at its full size against the values frozen from the reference's own RayCaster / Camera /
+    LSVO<9>::castRay (tests/golden/cfg1_full.json, made by make_golden.py): 468 025 primary hits, frame and hit hashes."""
+    import hashlib
+    import json
+    import os
+    from conftest import GOLDEN
+    from oracle import loader
+    g = json.load(open(os.path.join(GOLDEN, "cfg1_full.json")))
+    assert g["primary_hits"] == 468025
+    import cpuvoxelraycaster_b200 as vrt
+    cam = vrt.Camera(position=g["cam_position"], view_angle=g["view_angle"], focal_length=g["focal_length"])   # host code only
+    nodes = port.build_terrain(9)
+    pp = loader.PortRenderParams()
+    pp.width, pp.height, pp.depth, pp.guard = g["width"], g["height"], 9, 9
+    pp.cam_position[:] = g["cam_position"]
+    pp.rot_mat[:] = [float(x) for x in cam.rot_mat]
+    pp.fov, pp.aperture, pp.focal_length = 1.0, 0.0, g["focal_length"]
+    pp.light_position[:] = g["light"]
+    pp.use_gi, pp.gi_bounces, pp.use_samples, pp.spp, pp.seed_lo, pp.threads = 0, 1, 1, 1, 0x5EED, 8
+    accum, rgba, st = port.render(nodes, pp, *textures)
+    assert hashlib.sha256(rgba.tobytes()).hexdigest() == g["sha256_image"]
+    assert hashlib.sha256(accum.tobytes()).hexdigest() == g["sha256_samples_u32"]
+    assert st.rays[0] == g["width"] * g["height"] and st.rays[1] == g["primary_hits"] and st.complexity[0] == g["sum_complexity"]
