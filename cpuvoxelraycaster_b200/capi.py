@@ -87,7 +87,18 @@ _SIGNATURES = {
     "vrt_scene_download_heights": (C.c_int, [_vp, _vp]),
     "vrt_present_device": (C.c_int, [_vp, _vp, _vp, C.POINTER(PresentParams)]),
     "vrt_present": (C.c_int, [_vp, _vp, _vp, C.POINTER(PresentParams)]),
+    "vrt_comm_create_local": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "vrt_comm_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "vrt_comm_export": (C.c_int, [_vp, _vp]),
+    "vrt_comm_connect": (C.c_int, [_vp, _vp]),
+    "vrt_comm_destroy": (C.c_int, [_vp]),
+    "vrt_comm_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(_u64)]),
+    "vrt_render_distributed": (C.c_int, [_vp, _vp, C.POINTER(Camera), C.POINTER(RenderParams), C.c_int, C.c_int, _vp]),
+    "vrt_comm_frame_wait": (C.c_int, [_vp]),
+    "vrt_comm_frame_device": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
 }
+COMM_HANDLE_BYTES = 256
+SPLIT_TILES, SPLIT_SAMPLES = 0, 1
 
 
 def declared_symbols():

@@ -7,13 +7,13 @@
 #include <utility>
 #include <vector>
 
+#include "capi_internal.h"
 #include "host_util.h"
-#include "kernels.h"
 
 namespace {
-
 thread_local std::string g_last_error;
-
+}  // namespace
+namespace vrt {
 int fail(int code, const std::string& msg) {
     g_last_error = msg;
     return code;
@@ -21,85 +21,11 @@ int fail(int code, const std::string& msg) {
 int cuda_fail(cudaError_t e, const char* what) {
     return fail(VRT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
-#define VRT_CUDA(call)                                      \
-    do {                                                    \
-        cudaError_t e_ = (call);                            \
-        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
-    } while (0)
+}  // namespace vrt
+using vrt::cuda_fail;
+using vrt::fail;
+using vrt::use_device;
 
-// grow-only device scratch buffer
-struct DeviceBuffer {
-    void* ptr = nullptr;
-    size_t bytes = 0;
-    cudaError_t reserve(size_t want) {
-        if (want <= bytes) return cudaSuccess;
-        if (ptr) cudaFree(ptr);
-        ptr = nullptr;
-        bytes = 0;
-        cudaError_t e = cudaMalloc(&ptr, want);
-        if (e == cudaSuccess) bytes = want;
-        return e;
-    }
-    void release() {
-        if (ptr) cudaFree(ptr);
-        ptr = nullptr;
-        bytes = 0;
-    }
-};
-
-}  // namespace
-
-struct vrt_context {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool owns_stream = false;
-    uint64_t launches = 0;
-    int sm_count = 0;
-    // 1 = persistent threads with per-lane ray regeneration; 0 = one thread per ray / pixel.
-    // Defaults follow the measurements in profiles/r01_summary.md: batched casts regenerate (warp-adaptive),
-    // frames keep one lane per pixel (coherent primary/shadow rays lose more from de-phasing than GI rays gain).
-    int cast_variant = 1, render_variant = 0;
-    int sort_bins1 = 0, sort_bins2 = 0;         // K5: angle bins of the two GI bounces (0 = automatic)
-    int spp_chunks = 0;                        // K4: 0 = automatic
-    int trav_policy = -1;                      // K6: traversal loop variant (kernels.h RenderLaunch::trav_policy)
-    int samples_per_warp = 0;                  // K4: lanes sharing a pixel (power of two), 0 = automatic
-    int refill_cast = 0, refill_render = 16;   // parked lanes that trigger a refill (1..32); cast: 0 = warp-adaptive
-    DeviceBuffer scratch_in, scratch_out;   // host-variant staging
-    cudaAccessPolicyWindow l2_window{};     // installed by vrt_scene_set_layout(.., l2_persist); follows the stream (set_stream)
-};
-
-struct vrt_scene {
-    vrt_context* ctx = nullptr;
-    int kind = 0;
-    uint32_t depth = 0;
-    int32_t guard = 0;
-    // LSVO
-    uint2* d_nodes = nullptr;
-    uint64_t n_nodes = 0;
-    uint64_t device_bytes = 0;
-    unsigned long long* d_counters = nullptr;   // [0] Σ complexity of the last cast; [2..13] render rays/complexity per class
-    uint2* d_compact = nullptr;                 // optional compact breadth-first copy (vrt_scene_set_layout)
-    uint64_t n_compact = 0;
-    bool use_compact = false;
-    int32_t* d_heights = nullptr;               // heightfield scenes: column heights [S*S], resident for edits
-    uint64_t* d_voxel_keys = nullptr;           // voxel-set scenes: sorted distinct path keys, resident for edits
-    uint32_t n_voxel_keys = 0;
-    uint8_t* d_tex = nullptr;                   // top (768 B) then side (768 B)
-    bool has_tex = false;
-    DeviceBuffer frame_accum, frame_rgba;       // vrt_render staging
-    DeviceBuffer frame_lists;                   // K6: sorted sample lists of the frame in flight
-    // Grid3D / MipmapGrid3D / SVO: bit-packed occupancy pyramid
-    vrt::GridLevels grid{};
-    uint32_t* d_grid_bits = nullptr;
-    bool use_mip = false;
-};
-
-namespace {
-int use_device(const vrt_context* ctx) {
-    cudaError_t e = cudaSetDevice(ctx->device);
-    return e == cudaSuccess ? VRT_OK : cuda_fail(e, "cudaSetDevice");
-}
-}  // namespace
 
 extern "C" {
 
@@ -178,12 +104,12 @@ uint64_t vrt_context_launch_count(const vrt_context* ctx) { return ctx ? ctx->la
 int vrt_context_set_option(vrt_context* ctx, const char* key, int value) {
     if (!ctx || !key) return fail(VRT_ERR_INVALID, "vrt_context_set_option: NULL argument");
     const std::string k(key);
-    if (k == "cast_variant" && (value == 0 || value == 1)) ctx->cast_variant = value;
+    if (k == "cast_variant" && value >= 0 && value <= 2) ctx->cast_variant = value;
     else if (k == "render_variant" && value >= 0 && value <= 4) ctx->render_variant = value;
     else if (k == "sort_bins1" && value >= 0 && value <= 256) ctx->sort_bins1 = value;
     else if (k == "sort_bins2" && value >= 0 && value <= 256) ctx->sort_bins2 = value;
     else if (k == "spp_chunks" && value >= 0 && value <= 4096) ctx->spp_chunks = value;
-    else if (k == "trav_policy" && value >= -1 && value <= 4) ctx->trav_policy = value;
+    else if (k == "trav_policy" && value >= 0 && value <= 2) ctx->trav_policy = value;
     else if (k == "samples_per_warp" && value >= 0 && value <= 32 && (value & (value - 1)) == 0) ctx->samples_per_warp = value;
     else if (k == "refill_cast" && value >= 0 && value <= 32) ctx->refill_cast = value;
     else if (k == "refill_render" && value >= 1 && value <= 32) ctx->refill_render = value;
@@ -598,7 +524,9 @@ int vrt_cast_rays_device(vrt_scene* sc, const float* d_origin, const float* d_di
     if (n == 0) return VRT_OK;
     switch (sc->kind) {
         case VRT_SCENE_LSVO:
-            if (ctx->cast_variant == 0)
+            if (ctx->cast_variant == 2 && !sc->use_compact)
+                VRT_CUDA(vrt::launch_lsvo_cast2(sc->d_nodes, int(sc->depth), sc->guard, d_origin, d_dir, coef, bias, n, d_out, sc->d_counters, ctx->stream));
+            else if (ctx->cast_variant == 0 || ctx->cast_variant == 2)
                 VRT_CUDA(vrt::launch_lsvo_cast_ref(sc->use_compact ? sc->d_compact : sc->d_nodes, sc->use_compact, int(sc->depth), sc->guard, d_origin, d_dir, coef, bias, n, d_out,
                                                    sc->d_counters, ctx->stream));
             else

@@ -10,6 +10,9 @@ namespace vrt {
 cudaError_t launch_lsvo_cast_ref(const uint2* nodes, bool compact, int depth, int guard, const float* d_origin, const float* d_dir,
                                  float coef, float bias, uint64_t n, vrt_hit* d_out, unsigned long long* d_complexity,
                                  cudaStream_t stream);
+// K1b: the same on Trav2 (lsvo_step.cuh), reference layout
+cudaError_t launch_lsvo_cast2(const uint2* nodes, int depth, int guard, const float* d_origin, const float* d_dir, float coef, float bias,
+                              uint64_t n, vrt_hit* d_out, unsigned long long* d_complexity, cudaStream_t stream);
 
 // Bit-packed occupancy pyramid of a dense grid: level l holds cubes of edge 2^l, z-contiguous like
 // Grid3D::m_cells[x][y][z] (grid_3d.hpp:26); bit i of the level = word i>>5, bit i&31.
@@ -44,7 +47,7 @@ struct RenderLaunch {
     void* scratch;               // K6: device scratch for the sorted sample lists (render_scratch_bytes)
     size_t scratch_bytes;
     int mapping;                 // 0 = automatic (K5 for many-sample GI frames, else K4), 2 = K4, 3 = K5
-    int trav_policy;             // K6: -1 = plain loop per lane, 0..4 = warp-synchronous loop with path voting (lsvo_step.cuh)
+    int trav_policy;             // K6 traversal loop: 0 = Trav, 1 = Trav2, 2 = Trav2 without the cone test on coef-0 rays (default)
     uint32_t seed_lo, seed_hi;
     float light[3];
     vrt_camera cam;

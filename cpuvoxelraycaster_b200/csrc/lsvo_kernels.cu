@@ -49,6 +49,45 @@ __global__ void __launch_bounds__(128) lsvo_cast_kernel(Nodes nodes, int depth, 
     if ((threadIdx.x & 31) == 0 && iters) atomicAdd(total_complexity, (unsigned long long)iters);
 }
 
+// K1b: the same kernel on Trav2 (bookkeeping off the ALU pipe, cone test compiled out for coef = bias = 0)
+template <typename Nodes, bool kCone>
+__global__ void __launch_bounds__(128) lsvo_cast2_kernel(Nodes nodes, int depth, int guard, const float* __restrict__ origin,
+                                                         const float* __restrict__ dir, float coef, float bias, uint64_t n,
+                                                         vrt_hit* __restrict__ out, unsigned long long* __restrict__ total_complexity) {
+    extern __shared__ uint2 smem[];
+    nodes.slots = pin(nodes.slots);
+    guard = pin(guard);
+    Stack64s<128> stack = Stack64s<128>::make(smem + threadIdx.x, pin(kSvoMaxDepth - depth));
+    const float guard_sf = pin(guard_scale_f(guard));
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    uint32_t iters = 0u;
+    if (i < n) {
+        const float ox = origin[3 * i], oy = origin[3 * i + 1], oz = origin[3 * i + 2];
+        const float dx = dir[3 * i], dy = dir[3 * i + 1], dz = dir[3 * i + 2];
+        LsvoResult r;
+        lsvo_cast_ray2<kCone>(nodes, stack, guard, guard_sf, ox, oy, oz, dx, dy, dz, coef, bias, r);
+        LsvoHit h;
+        if (r.hit) lsvo_finish(r, ox, oy, oz, depth, h);
+        store_hit(out + i, r, h, depth);
+        iters = r.complexity;
+    }
+    for (int o = 16; o > 0; o >>= 1) iters += __shfl_xor_sync(0xffffffffu, iters, o);
+    if ((threadIdx.x & 31) == 0 && iters) atomicAdd(total_complexity, (unsigned long long)iters);
+}
+
+cudaError_t launch_lsvo_cast2(const uint2* nodes, int depth, int guard, const float* d_origin, const float* d_dir, float coef, float bias,
+                              uint64_t n, vrt_hit* d_out, unsigned long long* d_complexity, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const int block = 128;
+    const size_t smem = size_t(depth + 1) * block * 8;
+    const uint64_t grid = (n + block - 1) / block;
+    if (coef == 0.0f && bias == 0.0f)
+        lsvo_cast2_kernel<RefNodes, false><<<unsigned(grid), block, smem, stream>>>(RefNodes{nodes}, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_complexity);
+    else
+        lsvo_cast2_kernel<RefNodes, true><<<unsigned(grid), block, smem, stream>>>(RefNodes{nodes}, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_complexity);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_lsvo_cast_ref(const uint2* nodes, bool compact, int depth, int guard, const float* d_origin, const float* d_dir,
                                  float coef, float bias, uint64_t n, vrt_hit* d_out, unsigned long long* d_complexity,
                                  cudaStream_t stream) {

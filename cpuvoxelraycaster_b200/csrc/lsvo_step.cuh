@@ -143,76 +143,6 @@ struct Trav {
         return true;
     }
 
-    // ---- the same trip cut into its three parts, for warp-synchronous callers (lsvo_cast_ray_warp below) ----
-    // head(): node fetch, child test and the two terminating exits (:74-95).  Returns 0 = the ray hit (terminated),
-    // 1 = the trip continues with descend() (:97-110), 2 = with advance() (:113-145).  head() changes no state except on a hit,
-    // so a lane whose continuation is postponed by the warp's vote simply runs head() again in the next trip.
-    struct Head {
-        NodeView nd;
-        float sf, cx, cy, cz, tc_max, tv_max;
-        uint32_t shift;
-    };
-    template <typename Nodes>
-    __device__ __forceinline__ int head(const Nodes& nodes, Head& H) {
-        H.sf = scale_f();
-        H.nd = nodes.fetch(parent);                                          // :74
-        H.cx = px * tcx - tox; H.cy = py * tcy - toy; H.cz = pz * tcz - toz; // :76
-        H.tc_max = fminf(H.cx, fminf(H.cy, H.cz));
-        H.shift = child ^ mirror;                                            // :79
-        const uint32_t child_bit = 0x100u << H.shift;
-        if ((H.nd.raw & child_bit) && t_min <= t_max) {                      // :80-81
-            if (H.tc_max * coef + bias >= H.sf) { ++iters; hit = true; return 0; }   // :82-85
-            H.tv_max = fminf(t_max, H.tc_max);
-            if (t_min <= H.tv_max) {                                         // :89
-                if (H.nd.raw & (child_bit << 8)) { ++iters; hit = true; return 0; }  // :90-95
-                return 1;
-            }
-        }
-        return 2;
-    }
-    template <typename Nodes, typename Stack>
-    __device__ __forceinline__ bool descend(const Nodes& nodes, Stack& stack, int depth_offset, int guard, const Head& H) {
-        ++iters;
-        const float half = H.sf * 0.5f;
-        if (H.tc_max < h) stack.push(scale - depth_offset, parent, t_max);   // :97-100
-        h = H.tc_max;
-        parent = nodes.child(H.nd, H.shift);                                 // :103
-        child = 0u;
-        --scale;
-        if (half * tcx + H.cx > t_min) { child ^= 1u; px += half; }          // :88,107-109
-        if (half * tcy + H.cy > t_min) { child ^= 2u; py += half; }
-        if (half * tcz + H.cz > t_min) { child ^= 4u; pz += half; }
-        t_max = H.tv_max;
-        return scale > guard;                                                // :72
-    }
-    template <typename Stack>
-    __device__ __forceinline__ bool advance(Stack& stack, int depth_offset, int guard, const Head& H) {
-        ++iters;
-        const uint32_t ox_bits = __float_as_uint(px), oy_bits = __float_as_uint(py), oz_bits = __float_as_uint(pz);
-        uint32_t step_mask = 0u;                                             // :115-118
-        if (H.cx <= H.tc_max) { step_mask ^= 1u; px -= H.sf; }
-        if (H.cy <= H.tc_max) { step_mask ^= 2u; py -= H.sf; }
-        if (H.cz <= H.tc_max) { step_mask ^= 4u; pz -= H.sf; }
-        t_min = H.tc_max;
-        child ^= step_mask;
-        face = step_mask;
-        if (child & step_mask) {                                             // :124-145, see step()
-            const uint32_t ix = __float_as_uint(px), iy = __float_as_uint(py), iz = __float_as_uint(pz);
-            const uint32_t diff = (ix ^ ox_bits) | (iy ^ oy_bits) | (iz ^ oz_bits);
-            scale = 31 - __clz(int(diff));
-            if (scale >= kSvoMaxDepth) return false;
-            stack.pop(scale - depth_offset, parent, t_max);
-            const uint32_t keep = 0xffffffffu << scale;
-            px = __uint_as_float(ix & keep);
-            py = __uint_as_float(iy & keep);
-            pz = __uint_as_float(iz & keep);
-            child = ((ix >> scale) & 1u) | (((iy >> scale) & 1u) << 1) | (((iz >> scale) & 1u) << 2);
-            h = 0.0f;
-            return scale > guard;
-        }
-        return true;
-    }
-
     __device__ __forceinline__ void result(LsvoResult& r) const {
         r.px = px; r.py = py; r.pz = pz;
         r.t_min = t_min; r.scale_f = scale_f(); r.scale = scale; r.face = face; r.mirror = mirror & 7u;
@@ -231,41 +161,157 @@ __device__ __forceinline__ void lsvo_cast_ray(const Nodes& nodes, Stack& stack, 
     t.result(r);
 }
 
-// Warp-synchronous castRay: all 32 lanes of the warp call this together (lanes without a ray pass alive = false).
-// Every trip the warp evaluates head() and then VOTES which continuation it executes: in the plain loop above a trip
-// in which some lanes descend and others advance issues both paths (and the pop) at a fraction of the lanes each
-// (profiles/r01: 41 + 16 + 30 instructions at 17.7 / 14.2 / 9.6 of 32 lanes).  Here lanes whose path is not executed this
-// trip wait (no state change) and run it in a later trip together with the lanes that have caught up.
-// The per-ray sequence of operations is unchanged, so results and iteration counts are bit-identical.
-//   kPolicy 0: both paths every trip (the plain loop, warp-uniform form)      1: descend has priority (while-while)
-//           2: the path with more lanes                                        3/4: both when the minority has >= 8 / 12 lanes
-template <int kPolicy, typename Nodes, typename Stack>
-__device__ __forceinline__ void lsvo_cast_ray_warp(const Nodes& nodes, Stack& stack, int depth_offset, int guard, bool alive, float ox,
-                                                   float oy, float oz, float dx, float dy, float dz, float coef, float bias,
-                                                   LsvoResult& r) {
-    Trav t;
-    t.init(ox, oy, oz, dx, dy, dz, coef, bias);
-    while (__any_sync(0xffffffffu, alive)) {
-        typename Trav::Head H;
-        int want = 0;
-        if (alive) {
-            want = t.head(nodes, H);
-            alive = want != 0;
-        }
-        bool do_d = true, do_a = true;
-        if (kPolicy == 1) {
-            do_d = __any_sync(0xffffffffu, want == 1);
-            do_a = !do_d;
-        } else if (kPolicy >= 2) {
-            const int nd = __popc(__ballot_sync(0xffffffffu, want == 1)), na = __popc(__ballot_sync(0xffffffffu, want == 2));
-            const int theta = kPolicy == 2 ? 33 : kPolicy == 3 ? 8 : 12;
-            do_d = nd >= theta || nd >= na;
-            do_a = na >= theta || na > nd;
-        }
-        if (do_d && want == 1) alive = t.descend(nodes, stack, depth_offset, guard, H);
-        if (do_a && want == 2) alive = t.advance(stack, depth_offset, guard, H);
+// ---- Trav2: the same loop with its bookkeeping moved off the ALU pipe --------------------------------------------------
+// ncu (profiles/r01, r02): the frame kernels issue at 75 % with the half-rate ALU pipe (integer, compare, min/max, select,
+// logic) 75 % busy and the full-rate FMA pipe 22 % busy — half of all instructions of the loop are ALU-pipe instructions.
+// Trav2 computes exactly the reference's fp32 operations (results bit-identical) but
+//   * keeps the cell size sf = 2^(scale-23) as a float that is HALVED on a descent (an FMUL that the loop needs anyway for
+//     `half`) instead of rebuilding it from an integer scale every trip (LEA) and decrementing that integer (IADD3); the
+//     integer scale only exists inside POP, where FLO produces it;
+//   * counts loop trips with an FADD (exact below 2^24 trips) instead of an IADD3;
+//   * drops the cone test `tc_max * coef + bias >= sf` (lsvo.hpp:82-85) at compile time for rays cast with coef = bias = 0
+//     (primary and sun-shadow rays: the test can never be true there — 0 >= sf is false for every sf > 0, and a NaN product,
+//     inf * 0, compares false as well);
+//   * addresses the stack from the bits of sf (push) / with one IMAD from the scale (pop).
+template <int kThreads>
+struct Stack64s {
+    uint2* base_scale;   // entry of scale s at base_scale[s * kThreads]          (s = octree scale, 23 - depth .. 22)
+    __device__ __forceinline__ static Stack64s make(uint2* thread_base, int depth_offset) {
+        Stack64s st;
+        st.base_scale = thread_base - depth_offset * kThreads;
+        return st;
     }
+    // sf = 2^(scale - 23): bits = (scale + 104) << 23, so (bits >> 23) - 104 = scale and bits >> 16 = (scale + 104) * 128
+    __device__ __forceinline__ void push_sf(float sf, uint32_t p, float t) {
+        static_assert(kThreads == 128, "the shift below assumes 128 threads per block");
+        // byte offset (scale + 104) * 128 * 8 = bits >> 13 (the low 23 bits of a power of two are zero: no masking needed)
+        char* a = reinterpret_cast<char*>(base_scale - 104 * kThreads) + (__float_as_uint(sf) >> 13);
+        *reinterpret_cast<uint2*>(a) = make_uint2(p, __float_as_uint(t));
+    }
+    __device__ __forceinline__ void pop(int scale, uint32_t& p, float& t) const {
+        const uint2 e = base_scale[scale * kThreads];
+        p = e.x;
+        t = __uint_as_float(e.y);
+    }
+};
+
+template <bool kCone>
+struct Trav2 {
+    float dx, dy, dz, coef, bias;
+    float tcx, tcy, tcz, tox, toy, toz;
+    float px, py, pz;
+    float t_min, t_max, h;
+    float sf, iters_f;
+    uint32_t parent, child, mirror, face;
+    bool hit;
+
+    __device__ __forceinline__ void init(float ox_, float oy_, float oz_, float dx_, float dy_, float dz_, float coef_, float bias_) {
+        const bool finite = (((ox_ * 0.0f + oy_ * 0.0f) + oz_ * 0.0f) + ((dx_ * 0.0f + dy_ * 0.0f) + dz_ * 0.0f)) == 0.0f;
+        if (!finite) { ox_ = 3.0f; oy_ = 3.0f; oz_ = 3.0f; dx_ = 1.0f; dy_ = 1.0f; dz_ = 1.0f; }
+        coef = coef_; bias = bias_;
+        if (fabsf(dx_) < kEps) dx_ = copysignf(kEps, dx_);                 // lsvo.hpp:44-46
+        if (fabsf(dy_) < kEps) dy_ = copysignf(kEps, dy_);
+        if (fabsf(dz_) < kEps) dz_ = copysignf(kEps, dz_);
+        dx = dx_; dy = dy_; dz = dz_;
+        tcx = -1.0f / fabsf(dx); tcy = -1.0f / fabsf(dy); tcz = -1.0f / fabsf(dz);   // :47
+        tox = ox_ * tcx; toy = oy_ * tcy; toz = oz_ * tcz;                  // :48
+        mirror = finite ? 7u : 15u;
+        if (dx > 0.0f) { mirror ^= 1u; tox = 3.0f * tcx - tox; }           // :50-52
+        if (dy > 0.0f) { mirror ^= 2u; toy = 3.0f * tcy - toy; }
+        if (dz > 0.0f) { mirror ^= 4u; toz = 3.0f * tcz - toz; }
+        t_min = fmaxf(2.0f * tcx - tox, fmaxf(2.0f * tcy - toy, 2.0f * tcz - toz));   // :54
+        t_max = fminf(tcx - tox, fminf(tcy - toy, tcz - toz));                         // :55
+        h = t_max;
+        t_min = fmaxf(0.0f, t_min);
+        t_max = fminf(1.0f, t_max);
+        parent = 0u; child = 0u; face = 0u;
+        sf = 0.5f;                                                         // scale = 22
+        px = 1.0f; py = 1.0f; pz = 1.0f;
+        if (1.5f * tcx - tox > t_min) { child ^= 1u; px = 1.5f; }          // :66-68
+        if (1.5f * tcy - toy > t_min) { child ^= 2u; py = 1.5f; }
+        if (1.5f * tcz - toz > t_min) { child ^= 4u; pz = 1.5f; }
+        iters_f = 0.0f;
+        hit = false;
+    }
+
+    // one trip of the loop (:72-146); guard_sf = 2^(guard - 23)
+    template <typename Nodes, typename Stack>
+    __device__ __forceinline__ bool step(const Nodes& nodes, Stack& stack, int guard, float guard_sf) {
+        iters_f += 1.0f;
+        const NodeView nd = nodes.fetch(parent);                             // :74
+        const float cx = px * tcx - tox, cy = py * tcy - toy, cz = pz * tcz - toz;   // :76
+        const float tc_max = fminf(cx, fminf(cy, cz));
+        const uint32_t shift = child ^ mirror;                               // :79
+        const uint32_t child_bit = 0x100u << shift;
+        if ((nd.raw & child_bit) && t_min <= t_max) {                        // :80-81
+            if (kCone) {
+                if (tc_max * coef + bias >= sf) { hit = true; return false; }    // :82-85
+            }
+            const float tv_max = fminf(t_max, tc_max);
+            const float half = sf * 0.5f;
+            if (t_min <= tv_max) {                                           // :89
+                if (nd.raw & (child_bit << 8)) { hit = true; return false; }  // :90-95
+                if (tc_max < h) stack.push_sf(sf, parent, t_max);            // :97-100
+                h = tc_max;
+                parent = nodes.child(nd, shift);                             // :103
+                child = 0u;
+                sf = half;                                                   // --scale
+                if (half * tcx + cx > t_min) { child ^= 1u; px += half; }    // :88,107-109
+                if (half * tcy + cy > t_min) { child ^= 2u; py += half; }
+                if (half * tcz + cz > t_min) { child ^= 4u; pz += half; }
+                t_max = tv_max;
+                return sf > guard_sf;                                        // :72
+            }
+        }
+        // ADVANCE (:113-122).  The step is applied separately on the two continuations, so that POP can XOR the stepped
+        // position with the position still held in px/py/pz (no copies of the old position carried around the loop)
+        const bool sx = cx <= tc_max, sy = cy <= tc_max, sz = cz <= tc_max;   // :115-118
+        uint32_t step_mask = sx ? 1u : 0u;
+        if (sy) step_mask ^= 2u;
+        if (sz) step_mask ^= 4u;
+        t_min = tc_max;
+        child ^= step_mask;
+        face = step_mask;
+        if (child & step_mask) {                                             // :124-145, see Trav::step
+            const float nx = sx ? px - sf : px, ny = sy ? py - sf : py, nz = sz ? pz - sf : pz;
+            const uint32_t ix = __float_as_uint(nx), iy = __float_as_uint(ny), iz = __float_as_uint(nz);
+            const uint32_t diff = (ix ^ __float_as_uint(px)) | (iy ^ __float_as_uint(py)) | (iz ^ __float_as_uint(pz));
+            int scale;                                                       // index of the highest differing bit (:132): FLO
+            asm("bfind.u32 %0, %1;" : "=r"(scale) : "r"(diff));
+            if (scale >= kSvoMaxDepth) return false;                         // left the root cube: miss (the position is not read)
+            stack.pop(scale, parent, t_max);                                 // :134-136
+            sf = __uint_as_float(uint32_t(scale + 104) << 23);               // :133
+            const uint32_t keep = 0xffffffffu << scale;
+            px = __uint_as_float(ix & keep);                                 // :137-142
+            py = __uint_as_float(iy & keep);
+            pz = __uint_as_float(iz & keep);
+            child = ((ix >> scale) & 1u) | (((iy >> scale) & 1u) << 1) | (((iz >> scale) & 1u) << 2);   // :143
+            h = 0.0f;
+            return scale > guard;
+        }
+        px = sx ? px - sf : px;
+        py = sy ? py - sf : py;
+        pz = sz ? pz - sf : pz;
+        return true;
+    }
+
+    __device__ __forceinline__ void result(LsvoResult& r) const {
+        r.px = px; r.py = py; r.pz = pz;
+        r.t_min = t_min; r.scale_f = sf; r.scale = int(__float_as_uint(sf) >> 23) - 104; r.face = face; r.mirror = mirror & 7u;
+        r.complexity = (mirror & 8u) ? 0u : uint32_t(iters_f); r.hit = hit;
+        r.dx = dx; r.dy = dy; r.dz = dz;
+    }
+};
+
+template <bool kCone, typename Nodes, typename Stack>
+__device__ __forceinline__ void lsvo_cast_ray2(const Nodes& nodes, Stack& stack, int guard, float guard_sf, float ox, float oy, float oz,
+                                               float dx, float dy, float dz, float coef, float bias, LsvoResult& r) {
+    Trav2<kCone> t;
+    t.init(ox, oy, oz, dx, dy, dz, coef, bias);
+    while (t.step(nodes, stack, guard, guard_sf)) {}
     t.result(r);
 }
+__device__ __forceinline__ float guard_scale_f(int guard) { return __uint_as_float(uint32_t(guard + 104) << 23); }
+__device__ __forceinline__ float pin(float v) { return v + float(blockIdx.y); }
 
 }  // namespace vrt

@@ -408,9 +408,9 @@ __global__ void __launch_bounds__(128) sort_samples_kernel(RenderLaunch L, SortP
     }
 }
 
-// kPolicy < 0: every lane runs its rays through the plain loop (lsvo_cast_ray); kPolicy >= 0: the warp runs the chain in
-// lock step and casts through lsvo_cast_ray_warp<kPolicy> (path voting, lsvo_step.cuh).  Same samples, same operations per ray.
-template <typename Nodes, int kPolicy>
+// kTrav: 0 = the first traversal loop (Trav), 1 = Trav2, 2 = Trav2 with the cone test compiled out of the primary / sun-shadow
+// casts (they are cast with coef = 0).  Same operations per ray, identical results.
+template <typename Nodes, int kTrav>
 __global__ void __launch_bounds__(128, VRT_K5_MIN_CTAS) render_rounds_kernel(Nodes nodes, RenderLaunch L, BlockGeometry G,
                                                                             const uint16_t* __restrict__ lists, uint32_t* meta,
                                                                             uint32_t* next_block, uint32_t* __restrict__ accum,
@@ -421,6 +421,9 @@ __global__ void __launch_bounds__(128, VRT_K5_MIN_CTAS) render_rounds_kernel(Nod
     nodes.slots = pin(nodes.slots);
     const int guard = pin(L.guard);
     const int depth_offset = pin(kSvoMaxDepth - L.depth);
+    Stack64s<128> stack2 = Stack64s<128>::make(smem + threadIdx.x, depth_offset);
+    const float guard_sf = pin(guard_scale_f(L.guard));
+    (void)stack; (void)stack2; (void)guard_sf;
     const int lane = threadIdx.x & 31;
     uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + (L.depth + 1) * 128) + threadIdx.x;
 #pragma unroll
@@ -443,66 +446,37 @@ __global__ void __launch_bounds__(128, VRT_K5_MIN_CTAS) render_rounds_kernel(Nod
             if (round * 32u >= total) break;
             const uint32_t slot = round * 32u + uint32_t(lane);
             uint32_t cr = 0, cg = 0, cb = 0, key = 0xffffffffu;
-            if constexpr (kPolicy < 0) {
-                if (slot < total) {
-                    const int c = lists[size_t(work) * G.cap + slot];
-                    const int j = c / n_s, s = s_begin + (c - j * n_s);
-                    int x, y;
-                    block_pixel(x0, y0, j, x, y);
-                    const uint32_t pixel = uint32_t(y) * uint32_t(L.width) + uint32_t(x);
-                    key = uint32_t(j);
-                    const uint32_t sample = uint32_t(L.sample_offset + s);
-                    const float lens_x = float(x) / float(L.height) - aspect * 0.5f;  // main.cpp:145
-                    const float lens_y = float(y) / float(L.height) - 0.5f;           // main.cpp:146
-                    ChainState cs;
-                    NextRay nr;
-                    chain_begin(L, cs, pixel, sample, lens_x, lens_y, SCALE, focal_length, nr);
-                    int stage = kPrimary;
-                    while (stage != kDone) {
-                        LsvoResult r;
-                        lsvo_cast_ray(nodes, stack, depth_offset, guard, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
-                        cnt[stage * 128] += 1u;
-                        cnt[(6 + stage) * 128] += r.complexity;
-                        LsvoHit h;
-                        if (r.hit) lsvo_finish(r, nr.ox, nr.oy, nr.oz, L.depth, h);
-                        stage = chain_advance(L, cs, stage, r, h, pixel, sample, SCALE, n_norm, nr);
-                    }
-                    chain_colour(L, cs, cr, cg, cb);
-                }
-            } else {
-                // lock-step chain: iteration k of the loop casts the stage-k rays of all lanes that still have one
+            if (slot < total) {
+                const int c = lists[size_t(work) * G.cap + slot];
+                const int j = c / n_s, s = s_begin + (c - j * n_s);
+                int x, y;
+                block_pixel(x0, y0, j, x, y);
+                const uint32_t pixel = uint32_t(y) * uint32_t(L.width) + uint32_t(x);
+                key = uint32_t(j);
+                const uint32_t sample = uint32_t(L.sample_offset + s);
+                const float lens_x = float(x) / float(L.height) - aspect * 0.5f;  // main.cpp:145
+                const float lens_y = float(y) / float(L.height) - 0.5f;           // main.cpp:146
                 ChainState cs;
                 NextRay nr;
-                uint32_t pixel = 0u, sample = 0u;
-                int stage = kDone;
-                nr.ox = nr.oy = nr.oz = 3.0f; nr.dx = nr.dy = nr.dz = 1.0f; nr.coef = 0.0f;
-                cs.have_hit = false;
-                if (slot < total) {
-                    const int c = lists[size_t(work) * G.cap + slot];
-                    const int j = c / n_s, s = s_begin + (c - j * n_s);
-                    int x, y;
-                    block_pixel(x0, y0, j, x, y);
-                    pixel = uint32_t(y) * uint32_t(L.width) + uint32_t(x);
-                    key = uint32_t(j);
-                    sample = uint32_t(L.sample_offset + s);
-                    const float lens_x = float(x) / float(L.height) - aspect * 0.5f;  // main.cpp:145
-                    const float lens_y = float(y) / float(L.height) - 0.5f;           // main.cpp:146
-                    chain_begin(L, cs, pixel, sample, lens_x, lens_y, SCALE, focal_length, nr);
-                    stage = kPrimary;
-                }
-                while (__any_sync(0xffffffffu, stage != kDone)) {
-                    const bool live = stage != kDone;
+                chain_begin(L, cs, pixel, sample, lens_x, lens_y, SCALE, focal_length, nr);
+                int stage = kPrimary;
+                while (stage != kDone) {
                     LsvoResult r;
-                    lsvo_cast_ray_warp<kPolicy>(nodes, stack, depth_offset, guard, live, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
-                    if (live) {
-                        cnt[stage * 128] += 1u;
-                        cnt[(6 + stage) * 128] += r.complexity;
-                        LsvoHit h;
-                        if (r.hit) lsvo_finish(r, nr.ox, nr.oy, nr.oz, L.depth, h);
-                        stage = chain_advance(L, cs, stage, r, h, pixel, sample, SCALE, n_norm, nr);
+                    if constexpr (kTrav == 0) {
+                        lsvo_cast_ray(nodes, stack, depth_offset, guard, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
+                    } else if constexpr (kTrav == 1) {
+                        lsvo_cast_ray2<true>(nodes, stack2, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
+                    } else {
+                        if (stage < kGi0) lsvo_cast_ray2<false>(nodes, stack2, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, 0.0f, 0.0f, r);
+                        else lsvo_cast_ray2<true>(nodes, stack2, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
                     }
+                    cnt[stage * 128] += 1u;
+                    cnt[(6 + stage) * 128] += r.complexity;
+                    LsvoHit h;
+                    if (r.hit) lsvo_finish(r, nr.ox, nr.oy, nr.oz, L.depth, h);
+                    stage = chain_advance(L, cs, stage, r, h, pixel, sample, SCALE, n_norm, nr);
                 }
-                if (slot < total) chain_colour(L, cs, cr, cg, cb);
+                chain_colour(L, cs, cr, cg, cb);
             }
             __syncwarp();
             // one atomic per pixel and channel: the lanes holding samples of the same pixel add up first
@@ -676,14 +650,11 @@ cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const
             if (grid6 > blocks) grid6 = blocks;
             kernel<<<grid6, block, smem, stream>>>(view, L, P.G, lists, meta, next_block, d_accum, d_counters);
         };
-        if (compact) launch6(render_rounds_kernel<CompactNodes, -1>, CompactNodes{nodes});
+        if (compact) launch6(render_rounds_kernel<CompactNodes, 0>, CompactNodes{nodes});
         else switch (L.trav_policy) {
             case 0: launch6(render_rounds_kernel<RefNodes, 0>, RefNodes{nodes}); break;
             case 1: launch6(render_rounds_kernel<RefNodes, 1>, RefNodes{nodes}); break;
-            case 2: launch6(render_rounds_kernel<RefNodes, 2>, RefNodes{nodes}); break;
-            case 3: launch6(render_rounds_kernel<RefNodes, 3>, RefNodes{nodes}); break;
-            case 4: launch6(render_rounds_kernel<RefNodes, 4>, RefNodes{nodes}); break;
-            default: launch6(render_rounds_kernel<RefNodes, -1>, RefNodes{nodes}); break;
+            default: launch6(render_rounds_kernel<RefNodes, 2>, RefNodes{nodes}); break;
         }
         return cudaGetLastError();
     }

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VRT_ABI_VERSION 2
+#define VRT_ABI_VERSION 3
 
 typedef enum vrt_status {
     VRT_OK = 0,
@@ -258,6 +258,41 @@ int vrt_present_device(vrt_context* ctx, const uint8_t* d_frame, uint8_t* d_disp
 int vrt_present(vrt_context* ctx, const uint8_t* frame, uint8_t* display, const vrt_present_params* p);
 /* Camera::getClosestPoint + the focal-length rule of main.cpp:115-121. */
 int vrt_autofocus(vrt_scene* scene, const vrt_camera* cam, float* focal_length);
+
+/* ---- multi-GPU frames ----------------------------------------------------------------------------
+ * Replaces the reference's only parallel decomposition of a frame — 16 swarm threads, one 4x4 screen area each
+ * (src/main.cpp:139-143, swrm::Swarm src/main.cpp:90-92) — across the GPUs of one box.  The scene is replicated (one
+ * vrt_scene per GPU); a frame is split over the members of a communicator either by 4-row tiles dealt round-robin
+ * (VRT_SPLIT_TILES) or by samples (VRT_SPLIT_SAMPLES: every GPU renders all pixels for spp / world of the samples and the
+ * integer accumulators are added up over NVLink — exact, so both splits give the byte-identical frame, identical to
+ * the single-GPU frame).  No collective library is involved: the resolve kernel stores the finished RGBA pixels straight
+ * into the delivery GPU's frame buffer through peer-mapped memory (cpuvoxelraycaster_b200/csrc/comm.cu).
+ *
+ * One member (vrt_comm) per GPU.  Two ways to form a communicator:
+ *   (a) one process driving several GPUs (what the reference's main() would be): vrt_comm_create_local on an array of
+ *       contexts, one per device (peer access is enabled between them);
+ *   (b) one process per GPU: vrt_comm_create → vrt_comm_export (an opaque VRT_COMM_HANDLE_BYTES blob) → the caller
+ *       all-gathers the blobs in rank order over whatever it has (MPI, torch.distributed, a file) → vrt_comm_connect
+ *       (CUDA IPC).
+ * Frames are delivered to rank 0 (or to every rank with deliver_all) into double-buffered device memory and, if
+ * host_rgba is given on a receiving rank, copied to it on a second stream while the next frame renders.
+ * vrt_render_distributed only enqueues; vrt_comm_frame_wait blocks until the last frame (and its host copy) is complete
+ * and reports a peer that failed to show up.  Every member must call vrt_render_distributed for every frame with the
+ * same camera, parameters and split; row_begin/row_end/tile_step/tile_index/sample_offset/accum_in of *p are ignored. */
+typedef struct vrt_comm vrt_comm;
+#define VRT_COMM_HANDLE_BYTES 256
+typedef enum vrt_split { VRT_SPLIT_TILES = 0, VRT_SPLIT_SAMPLES = 1 } vrt_split;
+int vrt_comm_create_local(vrt_context* const* ctxs, int world, int width, int height, vrt_comm** out /* [world] */);
+int vrt_comm_create(vrt_context* ctx, int rank, int world, int width, int height, vrt_comm** out);
+int vrt_comm_export(vrt_comm* comm, void* blob /* VRT_COMM_HANDLE_BYTES */);
+int vrt_comm_connect(vrt_comm* comm, const void* blobs /* world * VRT_COMM_HANDLE_BYTES, rank order */);
+int vrt_comm_destroy(vrt_comm* comm);
+int vrt_comm_info(const vrt_comm* comm, int* rank, int* world, uint64_t* frames);
+int vrt_render_distributed(vrt_comm* comm, vrt_scene* scene, const vrt_camera* cam, const vrt_render_params* p, int split,
+                           int deliver_all, uint8_t* host_rgba /* receiving ranks; may be NULL */);
+int vrt_comm_frame_wait(vrt_comm* comm);
+/* device address of the assembled frame (frames_ago = 0: the most recent, 1: the one before) on a receiving rank */
+int vrt_comm_frame_device(vrt_comm* comm, int frames_ago, uint8_t** d_rgba);
 
 #ifdef __cplusplus
 }

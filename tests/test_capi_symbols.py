@@ -19,7 +19,7 @@ def test_library_exports_every_symbol(vrt):
     lib = vrt.capi.lib()
     for name in declared_in_header():
         assert getattr(lib, name) is not None
-    assert lib.vrt_abi_version() == 2
+    assert lib.vrt_abi_version() == 3
     assert b"sm_100a" in lib.vrt_build_info()
 
 
