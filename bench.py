@@ -11,12 +11,18 @@ use_samples + use_gi with 2 GI bounces + depth of field (aperture 0.5), camera C
 A "ray" is one distinct castRay (primary, sun shadow, GI, GI shadow, bounce-2 GI, its shadow).
 
 value  = rays of the whole frame / device time with the scene and frame buffers resident in HBM
-e2e    = the same through the user-facing FrameRenderer.render(): camera/params in from the host and the
-         finished RGBA frame copied back to pinned host memory inside the timed region
+e2e    = the same through the user-facing FrameRenderer (libvrt's vrt_render_distributed underneath): camera/params in
+         from the host and every finished RGBA frame copied back to pinned host memory inside the timed region
+         (double buffered: frame i is copied on a second stream while frame i+1 renders)
 The reference arm times the reference's own CPU implementation (oracle/_ref, compiled from the
 reference's sources) on a bounded sample of the same frame on the host cores.
+
+Multi-GPU (N > 1): the frame's 4-row tiles are dealt round-robin to the ranks and every rank's resolve kernel stores its
+pixels straight into rank 0's frame buffer over NVLink (libvrt communicator, csrc/comm.cu); during warm-up rank 0 also
+renders the frame alone and the two frames are compared by hash ("frame_identity" in the JSON line).
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -50,17 +56,14 @@ def load_textures():
     return t["top"], t["side"]
 
 
-def config_json(w, n_gpus, extra=None):
-    c = {"workload": "cfg4: LSVO %d^3 FastNoise terrain T(%d), %dx%d, %d spp, use_samples+use_gi (%d bounces) + DOF aperture %.2f, "
-                     "camera C(%d), 4-row tiles round-robin over %d GPU(s), NCCL all-gather of RGBA tiles"
-                     % (w["size"], w["depth"], w["width"], w["height"], w["spp"], w["gi_bounces"], w["aperture"], w["depth"], n_gpus),
-         "depth": w["depth"], "width": w["width"], "height": w["height"], "spp": w["spp"], "gi_bounces": w["gi_bounces"],
-         "aperture": w["aperture"], "rng": "Philox4x32-10 on getRand's 100-level lattice, key 0x5EED",
-         "ray_definition": "distinct castRay calls (the reference's 4 identical shadow samples count once)",
-         "l2": "inputs larger than L2: %.2f GB node array + 33 MB accumulator vs 126 MB L2" % (w.get("node_gb", 0.0))}
-    if extra:
-        c.update(extra)
-    return c
+def config_json(w, n_gpus):
+    """The same dict for both arms (the driver compares them): everything arm-specific goes into "extra"."""
+    return {"workload": "cfg4: LSVO %d^3 FastNoise terrain T(%d), %dx%d, %d spp, use_samples+use_gi (%d bounces) + DOF aperture %.2f, "
+                        "camera C(%d)" % (w["size"], w["depth"], w["width"], w["height"], w["spp"], w["gi_bounces"], w["aperture"], w["depth"]),
+            "depth": w["depth"], "width": w["width"], "height": w["height"], "spp": w["spp"], "gi_bounces": w["gi_bounces"],
+            "aperture": w["aperture"], "n_gpus": n_gpus, "rng": "Philox4x32-10 on getRand's 100-level lattice, key 0x5EED",
+            "ray_definition": "distinct castRay calls (the reference's 4 identical shadow samples count once)",
+            "l2": "inputs larger than L2: 1.35 GB node array + 33 MB accumulator vs 126 MB L2"}
 
 
 # ---- clocks sampler (B200_PROFILING.md recipe) --------------------------------------------------------
@@ -141,8 +144,10 @@ def cpu_port_sample(w, cores, tile_step, spp, repeat=1, single=None):
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU code (oracle/_ref, RayCaster + Camera + LSVO::castRay compiled
-    from the reference's sources at the workload's depth, swarm-threaded) on a bounded sample per step."""
+    """--impl reference: the reference's own CPU code (oracle/_ref, RayCaster + Camera + LSVO::castRay compiled from the
+    reference's sources at the workload's depth, swarm-threaded).  A step renders WHOLE 4-row tiles of the full frame with all
+    of the workload's samples per pixel — every `ref_tile_step`-th tile, spread over the frame like one GPU's share in the
+    multi-GPU split — so that a step is the same kind of work as the GPU arm's, bounded to a few seconds."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -153,9 +158,8 @@ def run_reference(args):
     P = loader.port()
     top, side = load_textures()
     nodes = P.build_terrain(w["depth"])
-    w["node_gb"] = nodes.nbytes / 1e9
-    tile_step, spp = args.ref_tile_step, args.ref_spp
-    sample_desc = "every %d-th 4-row tile x %d of %d spp = 1/%d of the frame per step" % (
+    tile_step, spp = args.ref_tile_step, (args.ref_spp or w["spp"])
+    sample_desc = "every %d-th 4-row tile of the frame x %d of %d spp = 1/%d of the frame per step" % (
         tile_step, spp, w["spp"], tile_step * w["spp"] // spp)
     if R is not None:
         kind = "reference"
@@ -177,7 +181,8 @@ def run_reference(args):
             pixels = sum(1 for y in range(w["height"]) if (y >> 2) % tile_step == 0) * w["width"] * spp
             shadow = (r["cone0_calls"] - pixels) // 4
             return pixels + shadow + r["cone_gi_calls"], r["seconds"]
-        note = "reference RayCaster has one GI bounce (raycaster.hpp:169-207); the 2-bounce workload is an extension"
+        note = ("the reference's RayCaster has ONE GI bounce (raycaster.hpp:169-207; RayContext::gi_bounce = 2 is never read): this arm "
+                "renders the reference's own estimator; the GPU arm's like-for-like figure is its extra.one_bounce")
     else:
         kind = "port"
         w["focal_length"] = 100.0
@@ -185,21 +190,22 @@ def run_reference(args):
         def step():
             return cpu_port_sample(w, cores, tile_step, spp)
         note = "oracle/_ref absent: timed the C restatement"
-    for _ in range(args.warmup):
+    for _ in range(args.warmup if args.ref_warmup < 0 else args.ref_warmup):
         step()
     rays, secs = 0, 0.0
     for _ in range(args.steps):
-        r, s = step()
+        r, s_ = step()
         rays += r
-        secs += s
+        secs += s_
     value = rays / secs / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * secs / args.steps, 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_json(w, args.gpus, {"note": note}),
+            "config": config_json(w, args.gpus),
             "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample_desc},
             "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "extra": {"note": note, "gi_bounces_rendered": 1 if kind == "reference" else w["gi_bounces"],
+                                         "rays_per_step": rays // max(1, args.steps)}}
     _emit(json.dumps(line))
     return 0
 
@@ -230,13 +236,14 @@ def run_ours(args):
     ctx.synchronize()
     build_s = time.perf_counter() - t0
     n_slots = len(scene)
-    w["node_gb"] = n_slots * 8 / 1e9
     scene.set_textures(*load_textures())
     cam = vrt.Camera(position=w["cam_position"], view_angle=w["view_angle"], aperture=w["aperture"])
     cam.autofocus(scene)                                     # main.cpp:115-121
     w["focal_length"] = cam.focal_length
 
-    fr = FrameRenderer(scene, w["width"], w["height"], rank, world, None, device, stream)
+    # the product path for every N: libvrt's communicator (vrt_render_distributed) — at N = 1 it degenerates to
+    # clear + frame kernels + resolve into the double-buffered frame + host copy on the second stream
+    fr = FrameRenderer(scene, w["width"], w["height"], rank, world, None, device, stream, exchange="peer", split=args.split)
     fr.use_gi, fr.gi_bounces, fr.use_samples, fr.seed = True, w["gi_bounces"], True, w["seed"]
     fr.light = light_normalised(w)
 
@@ -245,33 +252,41 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    # ---- device-resident timing -------------------------------------------------------------------------
+    # ---- warm-up, and the frame-identity check: the frame assembled from all ranks == the frame rank 0 renders alone ----
     for _ in range(args.warmup):
         fr.render_device(cam, w["spp"])
+    host = fr.render(cam, w["spp"])                          # collective; rank 0 gets the frame
+    identity = None
+    if rank == 0:
+        alone = FrameRenderer(scene, w["width"], w["height"], 0, 1, None, device, stream, exchange="nccl")
+        alone.use_gi, alone.gi_bounces, alone.use_samples, alone.seed, alone.light = True, w["gi_bounces"], True, w["seed"], fr.light
+        single = alone.render(cam, w["spp"])
+        h_multi, h_single = hashlib.sha256(host.tobytes()).hexdigest(), hashlib.sha256(single.tobytes()).hexdigest()
+        identity = {"sha256": h_multi[:32], "identical_to_single_gpu_frame": h_multi == h_single, "lit_pixels": int((host[..., :3].sum(-1) > 0).sum())}
+        del alone
+        scene.ctx.set_stream(stream.cuda_stream)
     sync_all()
+
+    # ---- device-resident timing -------------------------------------------------------------------------
     launches0 = ctx.launch_count
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    cam_struct, p = cam.as_struct(), fr.params(w["spp"])
     ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with torch.cuda.stream(stream):
-        ev_start.record(stream)
-        for i in range(args.steps):
-            fr.accum.zero_()
-            k_ev[i][0].record(stream)
-            fr.accumulate(cam_struct, p)                     # the dominant kernel, timed on its own stream
-            k_ev[i][1].record(stream)
-            fr.resolve(p)
-            fr.gather()
-        ev_end.record(stream)
+    ctx.set_option("time_frame_kernels", 1)                  # libvrt brackets its frame kernels with CUDA events on its stream
     sync_all()
+    ev_start.record(stream)
+    for i in range(args.steps):
+        fr.render_device(cam, w["spp"])
+    ev_end.record(stream)
+    sync_all()
+    kernel_times = ctx.take_kernel_timings()                 # ms of the dominant kernel (sort + trace) per frame, this rank
+    ctx.set_option("time_frame_kernels", 0)
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launch_count - launches0
     ms_total = ev_start.elapsed_time(ev_end)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
-    st = fr.stats()                                          # this rank's tiles, last frame
+    kernel_ms = float(np.mean(kernel_times)) if kernel_times else float("nan")
+    st = fr.stats()                                          # this rank's share, last frame
     t = torch.tensor([ms_total, kernel_ms], dtype=torch.float64, device=device)
     cnt = torch.tensor(st["rays"] + st["complexity"] + [launches], dtype=torch.int64, device=device)
     if world > 1:
@@ -291,7 +306,10 @@ def run_ours(args):
     # roofline of the dominant kernel on this rank: algorithmic bytes = sum over its rays of (8 B node per
     # iteration + 64 B ray/hit record) + 16 B accumulator write per pixel
     l_rays, l_cx = int(local_cnt[:6].sum()), int(local_cnt[6:12].sum())
-    my_pixels = sum(1 for y in range(w["height"]) if (y >> 2) % world == rank) * w["width"]
+    if args.split == "samples":
+        my_pixels = w["height"] * w["width"]
+    else:
+        my_pixels = sum(1 for y in range(w["height"]) if (y >> 2) % world == rank) * w["width"]
     algo_bytes = 8 * l_cx + 64 * l_rays + 16 * my_pixels
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -299,42 +317,37 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
-    traffic = None
+    ncu = {}
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if world == 1 and os.path.exists(tpath):      # the ncu capture is of the 1-GPU launch (whole frame)
+    if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("render_rounds_kernel_dram_bytes_per_launch")
+            ncu = json.load(open(tpath)).get("render_rounds_kernel", {})
         except Exception:
-            traffic = None
-    l1_bytes = l2_bytes = None
-    if traffic is not None:
-        try:
-            tj = json.load(open(tpath))
-            l1_bytes, l2_bytes = tj.get("render_rounds_kernel_l1_global_load_bytes_per_launch"), tj.get("render_rounds_kernel_l2_bytes_per_launch")
-        except Exception:
-            pass
-    roofline = {"bound": "hbm", "kernel": "render_rounds_kernel (K6; timed with its sort_samples_kernel)", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+            ncu = {}
+    roofline = {"bound": "hbm", "kernel": "render_rounds_kernel (K6; timed together with its sort_samples_kernel by CUDA events inside libvrt, on its stream)",
+                "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": ncu.get("dram_bytes_per_launch") if world == 1 else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": round(kernel_ms, 4),
                 "kernel_share_of_step": round(kernel_ms_max / ms_per_step, 4),
-                # SURVEY.md 8(d) diagnostics: one 32-byte sector per inspected node, and what ncu saw move through L1 / L2
+                # the binding resource of this kernel is instruction issue at low SIMT width, not HBM: the ncu
+                # counters of the same launch, measured once per round (source named in the file)
+                "issue_active_pct": ncu.get("issue_active_pct"), "lanes_per_instruction": ncu.get("lanes_per_instruction"),
+                "alu_pipe_pct": ncu.get("alu_pipe_pct"), "warp_instructions": ncu.get("warp_instructions"),
+                "l1_global_load_bytes": ncu.get("l1_global_load_bytes_per_launch"), "l2_bytes": ncu.get("l2_bytes_per_launch"),
+                "ncu_source": ncu.get("source"),
                 "sector_granular_GBs": round((32 * l_cx + 64 * l_rays + 16 * my_pixels) / (kernel_ms * 1e-3) / 1e9, 1),
-                "l1_global_load_bytes": l1_bytes, "l2_bytes": l2_bytes,
                 "note": "pointer chasing: latency/divergence bound by design, see DESIGN.md; node fetches are mostly L1/L2 hits"}
 
-    # ---- end to end through the public API (host in, host out) -------------------------------------------
+    # ---- end to end through the public API: camera + parameters in, every frame out to pinned host memory ----------
     for _ in range(2):
         fr.render(cam, w["spp"])
     sync_all()
-    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e_start.record(stream)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        frame = fr.render(cam, w["spp"])
-    e_end.record(stream)
+        fr.render_pipelined(cam, w["spp"])                   # frame i's host copy overlaps frame i+1's rendering
+    frame = fr.flush()                                       # all K frames are in host memory when this returns
     sync_all()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max(e_start.elapsed_time(e_end), wall_ms) / args.steps
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     te = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -342,8 +355,35 @@ def run_ours(args):
     import ctypes as C
     h2d = C.sizeof(vrt.capi.Camera) + C.sizeof(vrt.capi.RenderParams)
     e2e = {"value": round(total_rays / (e2e_ms * 1e-3) / 1e6, 2), "unit": UNIT, "ms_per_step": round(e2e_ms, 3),
-           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(frame.nbytes),
-           "note": "a renderer's per-frame input is the camera + render parameters; the scene is resident like model weights"}
+           "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": w["width"] * w["height"] * 4,
+           "note": "a renderer's per-frame input is the camera + render parameters (per rank); the scene is resident like model weights; "
+                   "the finished frame is delivered to rank 0's pinned host memory every step (wall clock incl. the final flush)"}
+    if rank == 0 and frame is not None and identity is not None:
+        identity["e2e_last_frame_sha256_matches"] = hashlib.sha256(frame.tobytes()).hexdigest()[:32] == identity["sha256"]
+
+    # ---- like-for-like with the reference arm: the reference's own ONE-bounce estimator on the whole frame --------------
+    extra = {"focal_length": w["focal_length"], "lsvo_slots": n_slots, "scene_build_s_device": round(build_s, 3),
+             "split": args.split, "exchange": "libvrt communicator: resolve kernel stores pixels into rank 0's frame over NVLink (peer-mapped, CUDA IPC)"}
+    if not args.no_extra:
+        fr.gi_bounces = 1
+        fr.render_device(cam, w["spp"])
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            fr.render_device(cam, w["spp"])
+        e1.record(stream)
+        sync_all()
+        st1 = fr.stats()
+        t1 = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=device)
+        c1 = torch.tensor(st1["rays"], dtype=torch.int64, device=device)
+        if world > 1:
+            dist.all_reduce(t1, op=dist.ReduceOp.MAX)
+            dist.all_reduce(c1, op=dist.ReduceOp.SUM)
+        extra["one_bounce"] = {"what": "the same frame with the reference's own one-bounce GI (raycaster.hpp:169-207) — the workload the reference arm renders",
+                               "ms_per_step": round(float(t1[0]), 4), "rays_per_frame": int(c1.sum()),
+                               "value": round(int(c1.sum()) / (float(t1[0]) * 1e-3) / 1e6, 2), "unit": UNIT}
+        fr.gi_bounces = w["gi_bounces"]
 
     if rank == 0:
         cpu = None
@@ -354,15 +394,22 @@ def run_ours(args):
                    "sample": "every %d-th 4-row tile x %d of %d spp = 1/%d of the frame, best of 3 runs: %.1f s wall" % (
                        args.cpu_tile_step, args.cpu_spp, w["spp"], args.cpu_tile_step * w["spp"] // args.cpu_spp, c_dt),
                    "single_thread_value": round(c_single / 1e6, 3)}
+        if world == 1 and not args.no_extra:
+            # the other BASELINE.json configurations, device resident (parity for each is in tests/): driver-observed numbers
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import measure_configs
+                extra["configs"] = measure_configs.measure(ctx, stream, [1, 2, 3, 5], 3, args.cfg5_rays)
+            except Exception as e:                           # never lose the headline line over a side measurement
+                extra["configs"] = {"error": repr(e)}
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": config_json(w, world, {"focal_length": w["focal_length"], "lsvo_slots": n_slots,
-                                                 "scene_build_s_device": round(build_s, 3)}),
+                "config": config_json(w, world),
                 "rays_per_frame": dict(zip(["primary", "shadow", "gi", "gi_shadow", "gi2", "gi2_shadow"], rays)),
                 "mean_complexity": round(sum(cx) / max(1, total_rays), 2),
                 "ms_per_frame": round(ms_per_step, 4), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": int(launches), "clocks": clocks}
+                "gpu_launches": int(launches), "clocks": clocks, "frame_identity": identity, "extra": extra}
         _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -387,8 +434,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-tile-step", type=int, default=2)      # cpu_baseline sample: 1/2 of the tiles x 1/2 of the
     ap.add_argument("--cpu-spp", type=int, default=32)           # samples = 1/4 frame, ~30-40 core-seconds
-    ap.add_argument("--ref-tile-step", type=int, default=8)
-    ap.add_argument("--ref-spp", type=int, default=8)
+    ap.add_argument("--ref-tile-step", type=int, default=16)     # reference arm: 1/16 of the frame's tiles, all samples (~1.3 s per step)
+    ap.add_argument("--ref-spp", type=int, default=0)            # 0 = the workload's spp
+    ap.add_argument("--ref-warmup", type=int, default=1)         # CPU code needs no 3 warm-up passes; -1 = --warmup
+    ap.add_argument("--split", default="tiles", choices=["tiles", "samples"])   # multi-GPU partition of the frame
+    ap.add_argument("--no-extra", action="store_true")           # skip extra.one_bounce / extra.configs
+    ap.add_argument("--cfg5-rays", type=int, default=100_000_000)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

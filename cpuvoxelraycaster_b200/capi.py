@@ -57,6 +57,7 @@ _SIGNATURES = {
     "vrt_context_set_stream": (C.c_int, [_vp, _vp]),
     "vrt_context_launch_count": (_u64, [_vp]),
     "vrt_context_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
+    "vrt_context_take_timings": (C.c_int, [_vp, _vp, _i32, C.POINTER(_i32)]),
     "vrt_host_terrain_heights": (C.c_int, [_i32, _vp]),
     "vrt_host_build_terrain_lsvo": (C.c_int, [_u32, _vp, _vp, _u64, C.POINTER(_u64)]),
     "vrt_host_build_lsvo_from_voxels": (C.c_int, [_u32, _vp, _u64, _vp, _u64, C.POINTER(_u64)]),
@@ -115,6 +116,8 @@ def lib():
                               "or `make -C cpuvoxelraycaster_b200`. There is no CPU fallback." % LIB_PATH)
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
+            if os.environ.get("VRT_ALLOW_OLD_LIBRARY") and not hasattr(L, name):
+                continue                   # A/B tools only (tools/probe_policies.py against an earlier build)
             fn = getattr(L, name)          # AttributeError here = header/library mismatch: fail loudly
             fn.restype = res
             fn.argtypes = args

@@ -69,6 +69,7 @@ int vrt_context_destroy(vrt_context* ctx) {
     cudaStreamSynchronize(ctx->stream);
     ctx->scratch_in.release();
     ctx->scratch_out.release();
+    for (auto& ev : ctx->frame_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return VRT_OK;
@@ -101,6 +102,23 @@ int vrt_context_set_stream(vrt_context* ctx, void* stream) {
 
 uint64_t vrt_context_launch_count(const vrt_context* ctx) { return ctx ? ctx->launches : 0; }
 
+int vrt_context_take_timings(vrt_context* ctx, float* ms, int32_t cap, int32_t* count) {
+    if (!ctx || !count) return fail(VRT_ERR_INVALID, "vrt_context_take_timings: NULL argument");
+    if (int s = use_device(ctx)) return s;
+    VRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int32_t n = int32_t(ctx->frame_events.size());
+    *count = n;
+    for (int32_t i = 0; i < n; ++i) {
+        float t = 0.0f;
+        cudaError_t e = cudaEventElapsedTime(&t, ctx->frame_events[i].first, ctx->frame_events[i].second);
+        if (ms && i < cap) ms[i] = e == cudaSuccess ? t : -1.0f;
+        cudaEventDestroy(ctx->frame_events[i].first);
+        cudaEventDestroy(ctx->frame_events[i].second);
+    }
+    ctx->frame_events.clear();
+    return VRT_OK;
+}
+
 int vrt_context_set_option(vrt_context* ctx, const char* key, int value) {
     if (!ctx || !key) return fail(VRT_ERR_INVALID, "vrt_context_set_option: NULL argument");
     const std::string k(key);
@@ -111,6 +129,7 @@ int vrt_context_set_option(vrt_context* ctx, const char* key, int value) {
     else if (k == "spp_chunks" && value >= 0 && value <= 4096) ctx->spp_chunks = value;
     else if (k == "trav_policy" && value >= 0 && value <= 2) ctx->trav_policy = value;
     else if (k == "samples_per_warp" && value >= 0 && value <= 32 && (value & (value - 1)) == 0) ctx->samples_per_warp = value;
+    else if (k == "time_frame_kernels" && (value == 0 || value == 1)) ctx->time_frame_kernels = value != 0;
     else if (k == "refill_cast" && value >= 0 && value <= 32) ctx->refill_cast = value;
     else if (k == "refill_render" && value >= 1 && value <= 32) ctx->refill_render = value;
     else return fail(VRT_ERR_INVALID, "vrt_context_set_option: unknown key or value out of range: " + k);
@@ -642,6 +661,17 @@ int vrt_render_accumulate_device(vrt_scene* sc, const vrt_camera* cam, const vrt
     if (int s = use_device(ctx)) return s;
     VRT_CUDA(cudaMemsetAsync(sc->d_counters + kRenderCounters, 0, 13 * sizeof(unsigned long long), ctx->stream));
     if (p->row_end == p->row_begin) return VRT_OK;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    if (ctx->time_frame_kernels) {                           // device time of this call's frame kernels, on the launching stream
+        VRT_CUDA(cudaEventCreate(&ev_begin));
+        VRT_CUDA(cudaEventCreate(&ev_end));
+        VRT_CUDA(cudaEventRecord(ev_begin, ctx->stream));
+        ctx->frame_events.emplace_back(ev_begin, ev_end);
+    }
+    struct RecordEnd {                                       // records ev_end on every exit path of the function
+        cudaEvent_t ev; cudaStream_t st;
+        ~RecordEnd() { if (ev) cudaEventRecord(ev, st); }
+    } record_end{ev_end, ctx->stream};
     if (p->autofocus) {
         VRT_CUDA(vrt::launch_autofocus(sc->use_compact ? sc->d_compact : sc->d_nodes, sc->use_compact, int(sc->depth), sc->guard, *cam,
                                        reinterpret_cast<float*>(sc->d_counters + kFocalSlot), ctx->stream));

@@ -1,6 +1,8 @@
 // Private to libvrt: the opaque handle types of include/vrt.h and the error helpers, shared by capi.cu and comm.cu.
 #pragma once
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "kernels.h"
 
@@ -50,6 +52,8 @@ struct vrt_context {
     int samples_per_warp = 0;                  // K4: lanes sharing a pixel (power of two), 0 = automatic
     int refill_cast = 0, refill_render = 16;   // parked lanes that trigger a refill (1..32); cast: 0 = warp-adaptive
     DeviceBuffer scratch_in, scratch_out;   // host-variant staging
+    bool time_frame_kernels = false;        // "time_frame_kernels": bracket the frame kernels of every accumulate call with events
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> frame_events;   // recorded, not yet taken (vrt_context_take_timings)
     cudaAccessPolicyWindow l2_window{};     // installed by vrt_scene_set_layout(.., l2_persist); follows the stream (set_stream)
 };
 

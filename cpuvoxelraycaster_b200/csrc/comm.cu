@@ -67,6 +67,9 @@ struct vrt_comm {
     bool opened[kMaxWorld] = {};            // peer[r] came from cudaIpcOpenMemHandle
     bool connected = false;
     uint64_t frame_no = 0;                  // frames started
+    uint64_t sample_frames = 0;             // frames rendered with the sample split so far (orders acc_done / reduced)
+    uint64_t expect_arrived = 0;            // tile pushes this rank's window must have received once all frames so far are in
+    long long last_in_buf[kMaxWorld][2];    // frame ordinal last delivered into buffer b of rank t's window (-1: none); identical on all ranks
     cudaStream_t copy_stream = nullptr;     // root: device-to-host copies overlap the next frame
     cudaEvent_t frame_ready = nullptr, copy_done[2] = {nullptr, nullptr};
     bool copy_pending[2] = {false, false};
@@ -187,6 +190,7 @@ int comm_alloc(vrt_context* ctx, int rank, int world, int width, int height, vrt
         vrt_comm_destroy(c);
         return e == cudaErrorMemoryAllocation ? fail(VRT_ERR_OOM, std::string(who) + ": device allocation failed") : cuda_fail(e, who);
     }
+    for (int t = 0; t < kMaxWorld; ++t) c->last_in_buf[t][0] = c->last_in_buf[t][1] = -1;
     c->peer[rank] = c->window;
     c->connected = world == 1;
     *out = c;
@@ -312,8 +316,8 @@ int vrt_render_distributed(vrt_comm* c, vrt_scene* sc, const vrt_camera* cam, co
     Flags* rf = c->flags(root);
 
     // sample split: the peers read this accumulator during their reduce of the previous frame — wait for all of them
-    if (split == VRT_SPLIT_SAMPLES && W > 1 && f > 0) {
-        wait_kernel<<<1, 1, 0, st>>>(&rf->reduced, f * uint64_t(W), &c->flags(c->rank)->error);
+    if (split == VRT_SPLIT_SAMPLES && W > 1 && c->sample_frames > 0) {
+        wait_kernel<<<1, 1, 0, st>>>(&rf->reduced, c->sample_frames * uint64_t(W), &c->flags(c->rank)->error);
         ctx->launches += 1;
     }
     VRT_CUDA(cudaMemsetAsync(accum, 0, size_t(c->h_pad) * c->width * 16, st));
@@ -326,18 +330,21 @@ int vrt_render_distributed(vrt_comm* c, vrt_scene* sc, const vrt_camera* cam, co
     }
     if (int s = vrt_render_accumulate_device(sc, cam, &p, accum)) return s;
 
-    // the buffer this frame is pushed into was last used by frame f - 2: its host copy must be over
-    if (W > 1 && f >= 2) {
-        for (int t = 0; t < W; ++t) {
-            if (!deliver_all && t != root) continue;
-            if (t == c->rank && !deliver_all) continue;      // the root orders its own copy by events below
-            wait_kernel<<<1, 1, 0, st>>>(&c->flags(t)->consumed, f - 1, &c->flags(c->rank)->error);
-            ctx->launches += 1;
+    // the buffer this frame is pushed into may still hold an earlier frame of the target that its consumer has not taken yet
+    for (int t = 0; t < W; ++t) {
+        if (!deliver_all && t != root) continue;
+        const long long last = c->last_in_buf[t][buf];
+        c->last_in_buf[t][buf] = (long long)f;
+        if (last < 0) continue;
+        if (t == c->rank) {                                  // own window: ordered by the copy's event
+            if (c->copy_pending[buf]) {
+                VRT_CUDA(cudaStreamWaitEvent(st, c->copy_done[buf], 0));
+                c->copy_pending[buf] = false;
+            }
+            continue;
         }
-    }
-    if (c->rank == root && c->copy_pending[buf]) {
-        VRT_CUDA(cudaStreamWaitEvent(st, c->copy_done[buf], 0));
-        c->copy_pending[buf] = false;
+        wait_kernel<<<1, 1, 0, st>>>(&c->flags(t)->consumed, (unsigned long long)(last + 1), &c->flags(c->rank)->error);
+        ctx->launches += 1;
     }
 
     Targets dst;
@@ -352,7 +359,7 @@ int vrt_render_distributed(vrt_comm* c, vrt_scene* sc, const vrt_camera* cam, co
     const unsigned grid = unsigned((n + 255) / 256);
     if (split == VRT_SPLIT_SAMPLES && W > 1) {
         signal_kernel<<<1, 1, 0, st>>>(&rf->acc_done, 1ull);
-        wait_kernel<<<1, 1, 0, st>>>(&rf->acc_done, (f + 1) * uint64_t(W), &c->flags(c->rank)->error);
+        wait_kernel<<<1, 1, 0, st>>>(&rf->acc_done, (c->sample_frames + 1) * uint64_t(W), &c->flags(c->rank)->error);
         for (int r = 0; r < W; ++r)
             if (r != c->rank) src.accum[src.n++] = c->accum(r);
         resolve_push_kernel<true><<<grid, 256, 0, st>>>(src, dst, c->local_rgba, c->width, c->height, p_in->use_samples, W, c->rank);
@@ -372,8 +379,9 @@ int vrt_render_distributed(vrt_comm* c, vrt_scene* sc, const vrt_camera* cam, co
     // consumer side: wait for everybody's tiles, then hand the frame over
     if (deliver_all || c->rank == root) {
         Flags* mine = c->flags(c->rank);
+        c->expect_arrived += uint64_t(W);
         if (W > 1) {
-            wait_kernel<<<1, 1, 0, st>>>(&mine->arrived, (f + 1) * uint64_t(W), &mine->error);
+            wait_kernel<<<1, 1, 0, st>>>(&mine->arrived, c->expect_arrived, &mine->error);
             ctx->launches += 1;
         }
         if (host_rgba) {
@@ -390,6 +398,7 @@ int vrt_render_distributed(vrt_comm* c, vrt_scene* sc, const vrt_camera* cam, co
     }
     VRT_CUDA(cudaGetLastError());
     c->frame_no = f + 1;
+    if (split == VRT_SPLIT_SAMPLES) c->sample_frames += 1;
     return VRT_OK;
 }
 

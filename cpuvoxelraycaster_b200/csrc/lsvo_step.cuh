@@ -35,7 +35,10 @@ struct Stack64 {
 // constant bank (an LDC in front of every node fetch); adding blockIdx.y — always 0, every launch is 1-D, but
 // not provably so — makes the value a computed one that has to stay in a register.
 __device__ __forceinline__ const uint2* pin(const uint2* p) {
-    return reinterpret_cast<const uint2*>(reinterpret_cast<uintptr_t>(p) + blockIdx.y);
+    // threadIdx.z (always 0: every launch is 1-D) rather than a block index: the sum is then a per-thread value in a vector
+    // register pair and the node address is ONE IMAD.WIDE with the immediate 8 (with the pointer in a uniform register ptxas
+    // has to materialise the 8 in a register first, every trip)
+    return reinterpret_cast<const uint2*>(reinterpret_cast<uintptr_t>(p) + blockIdx.y + threadIdx.z);
 }
 __device__ __forceinline__ int pin(int v) { return v + int(blockIdx.y); }
 
@@ -273,9 +276,12 @@ struct Trav2 {
         child ^= step_mask;
         face = step_mask;
         if (child & step_mask) {                                             // :124-145, see Trav::step
-            const float nx = sx ? px - sf : px, ny = sy ? py - sf : py, nz = sz ? pz - sf : pz;
-            const uint32_t ix = __float_as_uint(nx), iy = __float_as_uint(ny), iz = __float_as_uint(nz);
-            const uint32_t diff = (ix ^ __float_as_uint(px)) | (iy ^ __float_as_uint(py)) | (iz ^ __float_as_uint(pz));
+            // stepped axes only: step, and collect the bits the step changed (predicated FADD + LOP3 per axis, no selects)
+            uint32_t diff = 0u;
+            if (sx) { const float n = px - sf; diff |= __float_as_uint(n) ^ __float_as_uint(px); px = n; }
+            if (sy) { const float n = py - sf; diff |= __float_as_uint(n) ^ __float_as_uint(py); py = n; }
+            if (sz) { const float n = pz - sf; diff |= __float_as_uint(n) ^ __float_as_uint(pz); pz = n; }
+            const uint32_t ix = __float_as_uint(px), iy = __float_as_uint(py), iz = __float_as_uint(pz);
             int scale;                                                       // index of the highest differing bit (:132): FLO
             asm("bfind.u32 %0, %1;" : "=r"(scale) : "r"(diff));
             if (scale >= kSvoMaxDepth) return false;                         // left the root cube: miss (the position is not read)

@@ -46,17 +46,17 @@ __device__ __forceinline__ void store_hit_record(vrt_hit* out, const LsvoResult&
 // (ncu: 4.7 of 32 lanes active on random rays without regeneration), probing coherent mode again now and then.
 constexpr int kRayChunk = 64;
 
-template <typename Nodes>
+template <typename Nodes, bool kCone>
 __global__ void __launch_bounds__(128, 4) lsvo_cast_persistent_kernel(Nodes nodes, int depth, int guard,
                                                                       const float* __restrict__ origin,
                                                                       const float* __restrict__ dir, float coef, float bias,
                                                                       uint64_t n, vrt_hit* __restrict__ out,
                                                                       unsigned long long* __restrict__ counters, int refill) {
     extern __shared__ uint2 smem[];
-    Stack64<128> stack{smem + threadIdx.x};
     nodes.slots = pin(nodes.slots);
     guard = pin(guard);
-    const int depth_offset = pin(kSvoMaxDepth - depth);
+    Stack64s<128> stack = Stack64s<128>::make(smem + threadIdx.x, pin(kSvoMaxDepth - depth));
+    const float guard_sf = pin(guard_scale_f(guard));
     const int lane = threadIdx.x & 31;
     const unsigned lt = lanemask_lt();
     const bool adaptive = refill <= 0;
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(128, 4) lsvo_cast_persistent_kernel(Nodes node
     int refills_since_probe = 0;
     bool sync_batch = false;                               // all 32 lanes were started in the same refill phase
 
-    Trav t;
+    Trav2<kCone> t;
     bool alive = false, has_result = false, exhausted = false;
     uint64_t ray = 0, chunk_next = 0, chunk_end = 0;       // chunk_* are warp-uniform
     unsigned long long iter_sum = 0;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(128, 4) lsvo_cast_persistent_kernel(Nodes node
         if (adaptive) {
             const unsigned rmask = __ballot_sync(kFull, retiring);
             if (threshold == 32 && sync_batch && rmask == kFull) {
-                uint32_t sum = t.iters, mx = t.iters;
+                uint32_t sum = uint32_t(t.iters_f), mx = sum;
                 for (int o = 16; o > 0; o >>= 1) {
                     sum += __shfl_xor_sync(kFull, sum, o);
                     mx = max(mx, __shfl_xor_sync(kFull, mx, o));
@@ -90,9 +90,9 @@ __global__ void __launch_bounds__(128, 4) lsvo_cast_persistent_kernel(Nodes node
             LsvoResult r;
             t.result(r);
             LsvoHit h;
-            if (r.hit) lsvo_finish(r, t.ox, t.oy, t.oz, depth, h);
+            if (r.hit) lsvo_finish(r, origin[3 * ray], origin[3 * ray + 1], origin[3 * ray + 2], depth, h);   // re-read, not carried in registers
             store_hit_record(out + ray, r, h, depth);
-            iter_sum += t.iters;
+            iter_sum += r.complexity;
             has_result = false;
         }
         unsigned want = __ballot_sync(kFull, !alive);
@@ -124,12 +124,12 @@ __global__ void __launch_bounds__(128, 4) lsvo_cast_persistent_kernel(Nodes node
         // ---- traversal phase: step until `threshold` lanes are parked (or, at the tail, until all are) ----
         if (exhausted || threshold == 32) {
             // lock-step batch (or tail): every lane runs its ray to the end, no per-trip vote needed
-            while (alive) alive = t.step(nodes, stack, depth_offset, guard);
+            while (alive) alive = t.step(nodes, stack, guard, guard_sf);
             __syncwarp();
         } else {
             const int min_alive = 32 - threshold + 1;
             do {
-                if (alive) alive = t.step(nodes, stack, depth_offset, guard);
+                if (alive) alive = t.step(nodes, stack, guard, guard_sf);
             } while (__popc(__ballot_sync(kFull, alive)) >= min_alive);
         }
     }
@@ -278,11 +278,15 @@ static cudaError_t cast_persistent(Nodes nv, int depth, int guard, const float* 
                                    uint64_t n, vrt_hit* d_out, unsigned long long* d_counters, int refill, cudaStream_t stream) {
     const int block = 128;
     const size_t smem = size_t(depth + 1) * block * 8;
-    auto kernel = lsvo_cast_persistent_kernel<Nodes>;
-    uint64_t grid = uint64_t(resident_blocks(kernel, block, smem));
-    const uint64_t need = (n + block - 1) / block;
-    if (need < grid) grid = need;
-    kernel<<<unsigned(grid), block, smem, stream>>>(nv, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_counters, refill);
+    auto launch = [&](auto kernel) {
+        uint64_t grid = uint64_t(resident_blocks(kernel, block, smem));
+        const uint64_t need = (n + block - 1) / block;
+        if (need < grid) grid = need;
+        kernel<<<unsigned(grid), block, smem, stream>>>(nv, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_counters, refill);
+    };
+    // the cone test is compiled out when it cannot fire (coef = bias = 0: lsvo_step.cuh, Trav2)
+    if (coef == 0.0f && bias == 0.0f) launch(lsvo_cast_persistent_kernel<Nodes, false>);
+    else launch(lsvo_cast_persistent_kernel<Nodes, true>);
     return cudaGetLastError();
 }
 

@@ -28,10 +28,10 @@ template <typename Nodes, bool kLive>
 __global__ void __launch_bounds__(128, VRT_K4_MIN_CTAS) render_accumulate_kernel(Nodes nodes, RenderLaunch L, uint32_t* __restrict__ accum,
                                                                 unsigned long long* __restrict__ counters) {
     extern __shared__ uint2 smem[];
-    Stack64<128> stack{smem + threadIdx.x};
     nodes.slots = pin(nodes.slots);
     const int guard = pin(L.guard);
-    const int depth_offset = pin(kSvoMaxDepth - L.depth);
+    Stack64s<128> stack = Stack64s<128>::make(smem + threadIdx.x, pin(kSvoMaxDepth - L.depth));
+    const float guard_sf = pin(guard_scale_f(L.guard));
 
     // 8x4 pixel tile per warp, 4 tiles side by side per block: coherent primary rays share nodes
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(128, VRT_K4_MIN_CTAS) render_accumulate_kernel
                 int stage = kPrimary;
                 while (stage != kDone) {
                     LsvoResult r;
-                    lsvo_cast_ray(nodes, stack, depth_offset, guard, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
+                    if (stage < kGi0) lsvo_cast_ray2<false>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, 0.0f, 0.0f, r);
+                    else lsvo_cast_ray2<true>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
                     cnt[stage * 128] += 1u;
                     cnt[(6 + stage) * 128] += r.complexity;
                     LsvoHit h;
@@ -538,13 +539,13 @@ template <typename Nodes>
 __global__ void __launch_bounds__(128) autofocus_kernel(Nodes nodes, int depth, int guard, vrt_camera cam, float* __restrict__ focal) {
     extern __shared__ uint2 smem[];
     if (threadIdx.x != 0) return;
-    Stack64<128> stack{smem};
+    Stack64s<128> stack = Stack64s<128>::make(smem, kSvoMaxDepth - depth);
     const float scale = 1.0f / float(1 << depth);
     const float ox = cam.position[0] * scale + 1.0f, oy = cam.position[1] * scale + 1.0f, oz = cam.position[2] * scale + 1.0f;
     float dx, dy, dz;
     view_to_world(cam.rot_mat, 0.0f, 0.0f, 1.0f, dx, dy, dz);                 // camera_vec, camera_controller.hpp:31
     LsvoResult r;
-    lsvo_cast_ray(nodes, stack, kSvoMaxDepth - depth, guard, ox, oy, oz, dx, dy, dz, 0.0f, 0.0f, r);
+    lsvo_cast_ray2<false>(nodes, stack, guard, guard_scale_f(guard), ox, oy, oz, dx, dy, dz, 0.0f, 0.0f, r);
     *focal = r.hit ? r.t_min * float(1 << depth) : 100.0f;
 }
 

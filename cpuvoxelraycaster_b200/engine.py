@@ -73,6 +73,13 @@ class Context:
     def set_option(self, key, value):
         check(lib().vrt_context_set_option(self.handle, key.encode(), int(value)))
 
+    def take_kernel_timings(self):
+        """Device times (ms) of the frame-kernel calls bracketed since the last take (option "time_frame_kernels" = 1)."""
+        n = C.c_int32(0)
+        buf = (C.c_float * 4096)()
+        check(lib().vrt_context_take_timings(self.handle, buf, 4096, C.byref(n)))
+        return [float(buf[i]) for i in range(min(n.value, 4096))]
+
     def synchronize(self):
         check(lib().vrt_context_synchronize(self.handle))
 

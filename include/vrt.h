@@ -88,7 +88,8 @@ int vrt_context_destroy(vrt_context* ctx);
 int vrt_context_synchronize(vrt_context* ctx);
 int vrt_context_set_stream(vrt_context* ctx, void* stream);
 /* Tuning knobs (no reference counterpart):
- *   "cast_variant" (default 1): 1 = persistent threads with per-lane ray regeneration, 0 = one thread per ray
+ *   "cast_variant" (default 1): 1 = persistent threads with per-lane ray regeneration (K1p), 0 = one thread per ray (K1),
+ *                    2 = one thread per ray on the Trav2 loop (K1b)
  *   "render_variant" (default 0): 0 = automatic (K6 for frames with >= 8 samples, else K4), 1 = K4p persistent
  *                    regenerating warps, 2 = K4 one lane per pixel/sample group, 3 = K5 samples of a pixel block
  *                    regrouped by GI direction inside the CTA, 4 = K6 the same lists in global memory traced by
@@ -96,10 +97,17 @@ int vrt_context_set_stream(vrt_context* ctx, void* stream);
  *   "refill_cast", "refill_render"  parked lanes (1..32) that make a persistent warp regenerate rays;
  *                    refill_cast 0 = warp-adaptive (default)
  *   "spp_chunks"     frame kernel: number of runs a pixel's samples are cut into (0 = automatic)
- *   "samples_per_warp"  frame kernel: lanes of a warp sharing one pixel, power of two <= 32 (0 = automatic) */
+ *   "samples_per_warp"  frame kernel: lanes of a warp sharing one pixel, power of two <= 32 (0 = automatic)
+ *   "trav_policy" (default 2): traversal loop of the K6 frame kernel — 0 = Trav (round-1 loop), 1 = Trav2 (bookkeeping moved
+ *                    off the ALU pipe), 2 = Trav2 with the cone test compiled out of the coef-0 casts; results identical
+ *   "time_frame_kernels"  see vrt_context_take_timings */
 int vrt_context_set_option(vrt_context* ctx, const char* key, int value);
 /* number of kernel launches this context has enqueued so far (bench.py's gpu_launches) */
 uint64_t vrt_context_launch_count(const vrt_context* ctx);
+/* With the option "time_frame_kernels" = 1 every vrt_render_accumulate_device call (also inside vrt_render and
+ * vrt_render_distributed) is bracketed by CUDA events on the context's stream.  This synchronises the stream and returns
+ * the device time of each bracketed call since the last take, oldest first (ms[i], i < min(*count, cap)). */
+int vrt_context_take_timings(vrt_context* ctx, float* ms, int32_t cap, int32_t* count);
 
 /* ---- host-side scene construction (pure host code, no GPU needed) ---------------------------- */
 /* FastNoise SimplexFractal heights of the demo terrain, src/main.cpp:61-68; out[x*size+z]. */

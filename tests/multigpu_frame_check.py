@@ -1,5 +1,6 @@
-"""Run under torchrun (one rank per GPU): every rank renders its round-robin tiles, the frame is all-gathered over
-NCCL, and rank 0 compares it byte for byte with the same frame rendered alone on one GPU.
+"""Run under torchrun (one rank per GPU): every rank renders its share of a frame — 4-row tiles dealt round-robin, or
+spp / world of the samples — the frame is assembled on rank 0 by libvrt's communicator (peer stores over NVLink) or
+all-gathered over NCCL, and rank 0 compares it byte for byte with the same frame rendered alone on one GPU.
    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/multigpu_frame_check.py"""
 import os
 import sys
@@ -24,23 +25,34 @@ def main():
     scene = vrt.LSVO(ctx, vrt.host_build_terrain_lsvo(9), 9)
     t = np.load(os.path.join(ROOT, "tests", "golden", "textures.npz"))
     scene.set_textures(t["top"], t["side"])
-    W, H, spp = 330, 187, 3                                  # ragged on purpose
+    W, H = 330, 187                                          # ragged on purpose
+    spp = 2 * world                                          # the sample split needs spp % world == 0
     cam = vrt.Camera(position=(256, 200, 256), view_angle=(0.3, -0.35), aperture=0.5, focal_length=60.0)
     light = np.float32([-200, -1000, -300]) * np.float32(1 / 512.0) + np.float32(1)
 
-    def frame(r, w):
-        fr = FrameRenderer(scene, W, H, r, w, None, device, stream)
+    def frames(r, w, exchange, split, n_frames=3):
+        """n_frames consecutive frames (different sample offsets: exercises the double buffering); returns rank 0's copies."""
+        fr = FrameRenderer(scene, W, H, r, w, None, device, stream, exchange=exchange, split=split)
         fr.use_gi, fr.gi_bounces, fr.light = True, 2, light
-        return fr.render(cam, spp).copy(), fr.stats()
+        out, rays = [], []
+        for k in range(n_frames):
+            f = fr.render(cam, spp, sample_offset=k * spp)
+            out.append(None if f is None else f.copy())
+            rays.append(fr.stats()["rays"])
+        if fr.peer is not None:
+            fr.peer.close()
+        return out, rays
 
-    multi, st = frame(rank, world)
-    rays = torch.tensor(st["rays"], dtype=torch.int64, device=device)
-    dist.all_reduce(rays)
     ok = True
-    if rank == 0:
-        single, st1 = frame(0, 1)
-        ok = np.array_equal(multi, single) and rays.tolist() == st1["rays"] and int(multi[..., :3].max()) > 0
-        print("multigpu frame check world=%d: %s (rays %s)" % (world, "OK" if ok else "MISMATCH", rays.tolist()), flush=True)
+    single, rays1 = frames(0, 1, "nccl", "tiles") if rank == 0 else (None, None)
+    for exchange, split in (("peer", "tiles"), ("peer", "samples"), ("nccl", "tiles")):
+        multi, rays = frames(rank, world, exchange, split)
+        tot = torch.tensor(rays, dtype=torch.int64, device=device)
+        dist.all_reduce(tot)
+        if rank == 0:
+            same = all(np.array_equal(a, b) for a, b in zip(multi, single)) and tot.tolist() == rays1 and int(multi[0][..., :3].max()) > 0
+            print("multigpu frame check world=%d exchange=%s split=%s: %s" % (world, exchange, split, "OK" if same else "MISMATCH"), flush=True)
+            ok = ok and same
     flag = torch.tensor([1 if ok else 0], device=device)
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

@@ -48,16 +48,19 @@ def terrain_grid(size, mirrored):
     return np.ascontiguousarray(g[::-1, ::-1, ::-1]) if mirrored else g
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="1,2,3,5")
-    ap.add_argument("--iters", type=int, default=5)
-    ap.add_argument("--cfg5-rays", type=int, default=100_000_000)
-    a = ap.parse_args()
-    stream = torch.cuda.Stream()
-    ctx = vrt.Context(0, stream.cuda_stream)
+def measure(ctx, stream, want, iters=5, cfg5_rays=100_000_000, emit=None):
+    """Runs the configurations in `want` on `ctx` / `stream`; returns the result dicts (and passes each to `emit`)."""
+    class _A:
+        pass
+    a = _A()
+    a.iters, a.cfg5_rays = iters, cfg5_rays
     tex = np.load(os.path.join(ROOT, "tests", "golden", "textures.npz"))
-    want = [int(c) for c in a.configs.split(",")]
+    results = []
+
+    def out(d):
+        results.append(d)
+        if emit:
+            emit(d)
 
     if 1 in want:   # default terrain in LSVO<9>, primary + sun shadow, 1280x720, 1 spp
         scene = vrt.LSVO(ctx, vrt.host_build_terrain_lsvo(9), 9)
@@ -68,9 +71,9 @@ def main():
         ms = timed(stream, lambda: fr.render_device(cam, 1), a.iters)
         st = fr.stats()
         rays = sum(st["rays"])
-        print(json.dumps(dict(cfg=1, what="T(9) LSVO, 1280x720, 1 spp, primary + sun shadow (K4 + resolve)", ms_per_frame=round(ms, 4),
+        out(dict(cfg=1, what="T(9) LSVO, 1280x720, 1 spp, primary + sun shadow (K4 + resolve)", ms_per_frame=round(ms, 4),
                               rays=st["rays"][:2], mrays_s=round(rays / ms / 1e3, 1),
-                              algo_GBs=round((8 * sum(st["complexity"]) + 64 * rays + 16 * 1280 * 720) / ms / 1e6, 1))), flush=True)
+                              algo_GBs=round((8 * sum(st["complexity"]) + 64 * rays + 16 * 1280 * 720) / ms / 1e6, 1)))
         scene.close()
 
     if 2 in want or 3 in want:
@@ -96,7 +99,7 @@ def main():
                 ms_flat = timed(stream, lambda: flat.cast_rays_device(do, dd, n, out2), a.iters)
                 line.update(ms_flat_grid=round(ms_flat, 4), identical_to_flat=bool(torch.equal(out, out2)))
                 flat.close()
-            print(json.dumps(line), flush=True)
+            out(line)
             scene.close()
             if cfg == 3:
                 # the configuration's frame: primary + sun shadow + blurry reflections off a Cell::Mirror lake that floods
@@ -119,11 +122,11 @@ def main():
                     ms = timed(stream, lambda: fr.render_device(cam, spp), a.iters)
                     st = fr.stats()
                     rays, steps = sum(st["rays"][:3]), sum(st["complexity"][:3])
-                    print(json.dumps(dict(cfg=3, what="T(%d) mip grid %d^3 with a mirror lake, %dx%d frame: primary + sun shadow + blurry reflections "
+                    out(dict(cfg=3, what="T(%d) mip grid %d^3 with a mirror lake, %dx%d frame: primary + sun shadow + blurry reflections "
                                           "(roughness 0.06, max_bounds 4), %d spp" % (D, size, W, H, spp), ms_per_frame=round(ms, 4),
                                           rays=dict(primary=st["rays"][0], shadow=st["rays"][1], reflection=st["rays"][2]),
                                           mirror_cells=int(len(xs)), mrays_s=round(rays / ms / 1e3, 1), mean_steps=round(steps / max(rays, 1), 1),
-                                          algo_GBs=round((steps + 64 * rays + 16 * W * H) / ms / 1e6, 1))), flush=True)
+                                          algo_GBs=round((steps + 64 * rays + 16 * W * H) / ms / 1e6, 1)))
                 lake.close()
             del cells
 
@@ -149,11 +152,24 @@ def main():
             res[variant] = ms
         cx = scene.last_complexity()
         hits = int((out.view(n, 16)[:, 10] & 1).sum())
-        print(json.dumps(dict(cfg=5, what="T(12) LSVO 4096^3, %d random rays" % n, device_build_s=round(tb, 3), slots=n_slots,
+        out(dict(cfg=5, what="T(12) LSVO 4096^3, %d random rays" % n, device_build_s=round(tb, 3), slots=n_slots,
                               ms_persistent_adaptive=round(res[1], 3), ms_one_thread_per_ray=round(res[0], 3),
                               mrays_s=round(n / res[1] / 1e3, 1), hit_fraction=round(hits / n, 4), mean_complexity=round(cx / n, 2),
-                              algo_GBs=round((8 * cx + 64 * n) / res[1] / 1e6, 1))), flush=True)
+                              algo_GBs=round((8 * cx + 64 * n) / res[1] / 1e6, 1)))
         scene.close()
+        ctx.set_option("cast_variant", 1)
+    return results
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="1,2,3,5")
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--cfg5-rays", type=int, default=100_000_000)
+    a = ap.parse_args()
+    stream = torch.cuda.Stream()
+    ctx = vrt.Context(0, stream.cuda_stream)
+    measure(ctx, stream, [int(c) for c in a.configs.split(",")], a.iters, a.cfg5_rays, emit=lambda d: print(json.dumps(d), flush=True))
     ctx.close()
 
 
