@@ -129,7 +129,9 @@ class FrameRenderer:
         self.light = np.zeros(3, np.float32)
         # multi-GPU exchange: "peer" = libvrt communicator (NVLink peer stores), "nccl" = torch.distributed all-gather
         if exchange == "auto":
-            exchange = "peer" if (self.world > 1 and self.device.type == "cuda") else "nccl"
+            import torch.distributed as dist
+            live = dist.is_available() and dist.is_initialized()     # probes simulate "rank r of N" in one process: no peers there
+            exchange = "peer" if (self.world > 1 and self.device.type == "cuda" and live) else "nccl"
         self.exchange_kind = exchange
         self.split = capi.SPLIT_SAMPLES if split == "samples" else capi.SPLIT_TILES
         self.peer = PeerFrame(scene.ctx, self.W, self.H, self.rank, self.world, group) if exchange == "peer" else None

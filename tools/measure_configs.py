@@ -104,7 +104,6 @@ def measure(ctx, stream, want, iters=5, cfg5_rays=100_000_000, emit=None):
             if cfg == 3:
                 # the configuration's frame: primary + sun shadow + blurry reflections off a Cell::Mirror lake that floods
                 # the valleys (columns whose top lies below the water level), 3840x2160, device resident
-                from cpuvoxelraycaster_b200.frame import FrameRenderer
                 h = vrt.host_terrain_heights(size)[::-1, ::-1]
                 top = size // 2 - np.maximum(16, np.minimum(size, h))          # first solid y of each column (up = -y)
                 water = size // 2 - 30

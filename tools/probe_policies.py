@@ -54,7 +54,7 @@ def main():
     cs = cam.as_struct()
     policies = [0, 1, 2] if set_opt(ctx, "trav_policy", 0) else [None]
     for world in (1, 8):
-        fr = FrameRenderer(scene, 1920, 1080, 0, world, None, None, stream)
+        fr = FrameRenderer(scene, 1920, 1080, 0, world, None, None, stream, exchange="nccl")
         fr.light = np.float32([-200, -1000, -300]) * np.float32(1.0 / S) + np.float32(1.0)
         for (gi, bounces) in ((False, 1), (True, 1), (True, 2)):
             if world == 8 and not (gi and bounces == 2):
