@@ -12,7 +12,9 @@ VRT_OK = 0
 LNODE = np.dtype([("color", "u1"), ("child_mask", "u1"), ("leaf_mask", "u1"), ("pad", "u1"), ("child_offset", "u4")])
 HIT = np.dtype([("position", "f4", 3), ("distance", "f4"), ("normal", "f4", 3), ("complexity", "u4"),
                 ("voxel_coord", "f4", 2), ("flags", "u4"), ("scale", "i4"), ("voxel", "i4", 3), ("face", "u4")])
-assert HIT.itemsize == 64 and LNODE.itemsize == 8
+SHADE_JOB = np.dtype([("start", "f4", 3), ("pixel", "u4"), ("direction", "f4", 3), ("sample", "u4")])
+SHADE_RESULT = np.dtype([("r", "u1"), ("g", "u1"), ("b", "u1"), ("hit", "u1"), ("distance", "f4"), ("complexity", "u4"), ("reserved", "u4")])
+assert HIT.itemsize == 64 and LNODE.itemsize == 8 and SHADE_JOB.itemsize == 32 and SHADE_RESULT.itemsize == 16
 
 
 class Camera(C.Structure):
@@ -59,6 +61,7 @@ _SIGNATURES = {
     "vrt_context_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "vrt_context_take_timings": (C.c_int, [_vp, _vp, _i32, C.POINTER(_i32)]),
     "vrt_host_terrain_heights": (C.c_int, [_i32, _vp]),
+    "vrt_host_noise2d": (_f, [_f, _f]),
     "vrt_host_build_terrain_lsvo": (C.c_int, [_u32, _vp, _vp, _u64, C.POINTER(_u64)]),
     "vrt_host_build_lsvo_from_voxels": (C.c_int, [_u32, _vp, _u64, _vp, _u64, C.POINTER(_u64)]),
     "vrt_host_camera_rotation": (C.c_int, [_vp, _vp, _vp]),
@@ -79,6 +82,7 @@ _SIGNATURES = {
     "vrt_render_resolve_device": (C.c_int, [_vp, C.POINTER(RenderParams), _vp, _vp]),
     "vrt_render": (C.c_int, [_vp, C.POINTER(Camera), C.POINTER(RenderParams), _vp, _vp, C.POINTER(RenderStats)]),
     "vrt_scene_last_render_stats": (C.c_int, [_vp, C.POINTER(RenderStats)]),
+    "vrt_shade_rays": (C.c_int, [_vp, C.POINTER(RenderParams), _u64, _vp, _vp]),
     "vrt_autofocus": (C.c_int, [_vp, C.POINTER(Camera), C.POINTER(_f)]),
     "vrt_lsvo_create_from_voxels": (C.c_int, [_vp, _u32, _vp, _u64, _i32, C.POINTER(_vp)]),
     "vrt_scene_set_cells": (C.c_int, [_vp, _vp, _u64, _i32]),

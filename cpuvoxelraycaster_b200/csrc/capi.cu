@@ -130,6 +130,7 @@ int vrt_context_set_option(vrt_context* ctx, const char* key, int value) {
     else if (k == "trav_policy" && value >= 0 && value <= 2) ctx->trav_policy = value;
     else if (k == "samples_per_warp" && value >= 0 && value <= 32 && (value & (value - 1)) == 0) ctx->samples_per_warp = value;
     else if (k == "time_frame_kernels" && (value == 0 || value == 1)) ctx->time_frame_kernels = value != 0;
+    else if (k == "grid_variant" && (value == 0 || value == 1)) ctx->grid_variant = value;
     else if (k == "refill_cast" && value >= 0 && value <= 32) ctx->refill_cast = value;
     else if (k == "refill_render" && value >= 1 && value <= 32) ctx->refill_render = value;
     else return fail(VRT_ERR_INVALID, "vrt_context_set_option: unknown key or value out of range: " + k);
@@ -142,6 +143,8 @@ int vrt_host_terrain_heights(int32_t size, int32_t* out) {
     vrt::host_terrain_heights(size, out);
     return VRT_OK;
 }
+
+float vrt_host_noise2d(float x, float y) { return vrt::host_noise2d(x, y); }
 
 int vrt_host_build_terrain_lsvo(uint32_t depth, const int32_t* heights, vrt_lnode* out, uint64_t cap, uint64_t* count) {
     // the fill writes y + S/2 with y up to max(16, height): needs S/2 + 80 < S like the reference scene
@@ -556,7 +559,7 @@ int vrt_cast_rays_device(vrt_scene* sc, const float* d_origin, const float* d_di
         case VRT_SCENE_GRID:
         case VRT_SCENE_MIPGRID:
             VRT_CUDA(cudaMemsetAsync(sc->d_counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
-            VRT_CUDA(vrt::launch_grid_cast(sc->grid, sc->use_mip, d_origin, d_dir, n, d_out, sc->d_counters, ctx->stream));
+            VRT_CUDA(vrt::launch_grid_cast(sc->grid, sc->use_mip, ctx->grid_variant, d_origin, d_dir, n, d_out, sc->d_counters, ctx->stream));
             ctx->launches += 1;
             return VRT_OK;
         default:
@@ -631,6 +634,7 @@ vrt::RenderLaunch make_launch(const vrt_scene* sc, const vrt_camera* cam, const 
     L.mapping = sc->ctx->render_variant == 1 ? 0 : sc->ctx->render_variant;
     L.scratch = nullptr; L.scratch_bytes = 0;
     L.trav_policy = sc->ctx->trav_policy;
+    L.grid_variant = sc->ctx->grid_variant;
     L.sort_bins1 = sc->ctx->sort_bins1; L.sort_bins2 = sc->ctx->sort_bins2;
     L.roughness = p->roughness;
     L.max_bounds = p->max_bounds;
@@ -709,6 +713,33 @@ int vrt_render_resolve_device(vrt_scene* sc, const vrt_render_params* p, const u
     VRT_CUDA(vrt::launch_resolve(d_accum, d_rgba, p->width, p->row_begin, p->row_end, p->use_samples,
                                  p->tile_step > 1 ? p->tile_step : 1, p->tile_step > 1 ? p->tile_index : 0, ctx->stream));
     ctx->launches += 1;
+    return VRT_OK;
+}
+
+int vrt_shade_rays(vrt_scene* sc, const vrt_render_params* p, uint64_t n, const vrt_shade_job* jobs, vrt_shade_result* out) {
+    if (!sc || !p) return fail(VRT_ERR_INVALID, "vrt_shade_rays: NULL argument");
+    if (sc->kind != VRT_SCENE_LSVO) return fail(VRT_ERR_UNSUPPORTED, "vrt_shade_rays: needs an LSVO scene");
+    if (!sc->has_tex) return fail(VRT_ERR_INVALID, "vrt_shade_rays: call vrt_scene_set_textures first (raycaster.hpp:53-54)");
+    if (p->gi_bounces < 0 || p->gi_bounces > 2) return fail(VRT_ERR_INVALID, "vrt_shade_rays: gi_bounces must be 0..2");
+    if (n == 0) return VRT_OK;
+    if (!jobs || !out) return fail(VRT_ERR_INVALID, "vrt_shade_rays: NULL buffer");
+    if (n > (1ull << 31)) return fail(VRT_ERR_UNSUPPORTED, "vrt_shade_rays: too many rays for one call");
+    vrt_context* ctx = sc->ctx;
+    if (int s = use_device(ctx)) return s;
+    if (ctx->scratch_in.reserve(size_t(n) * sizeof(vrt_shade_job)) != cudaSuccess || ctx->scratch_out.reserve(size_t(n) * sizeof(vrt_shade_result)) != cudaSuccess)
+        return fail(VRT_ERR_OOM, "vrt_shade_rays: device staging allocation failed");
+    vrt_shade_job* d_jobs = static_cast<vrt_shade_job*>(ctx->scratch_in.ptr);
+    vrt_shade_result* d_out = static_cast<vrt_shade_result*>(ctx->scratch_out.ptr);
+    VRT_CUDA(cudaMemcpyAsync(d_jobs, jobs, size_t(n) * sizeof(vrt_shade_job), cudaMemcpyHostToDevice, ctx->stream));
+    vrt_camera cam;
+    std::memset(&cam, 0, sizeof(cam));
+    vrt_render_params q = *p;
+    if (q.width <= 0) q.width = 1;
+    if (q.height <= 0) q.height = 1;
+    VRT_CUDA(vrt::launch_shade_rays(sc->use_compact ? sc->d_compact : sc->d_nodes, sc->use_compact, make_launch(sc, &cam, &q), n, d_jobs, d_out, ctx->stream));
+    ctx->launches += 1;
+    VRT_CUDA(cudaMemcpyAsync(out, d_out, size_t(n) * sizeof(vrt_shade_result), cudaMemcpyDeviceToHost, ctx->stream));
+    VRT_CUDA(cudaStreamSynchronize(ctx->stream));
     return VRT_OK;
 }
 
@@ -854,6 +885,30 @@ int create_grid_scene(vrt_context* ctx, const uint8_t* cells, int X, int Y, int 
         for (size_t i = 0; i < ncell; ++i)
             if (cells[i] == 2) words[mirror_off + (i >> 5)] |= 1u << (i & 31);
     }
+    // level 0 with a solid one-cell border (kernels.h GridLevels::pad_bits): rows are copied with their z bits shifted by one
+    size_t pad_off = 0;
+    const uint64_t PX = uint64_t(X) + 2, PY = uint64_t(Y) + 2, PZ = uint64_t(Z) + 2;
+    const bool padded = kind != VRT_SCENE_SVO && PX * PY * PZ < (1ull << 32);
+    if (padded) {
+        pad_off = words.size();
+        const uint64_t nbits = PX * PY * PZ;
+        words.resize(words.size() + size_t((nbits + 31) / 32), 0u);
+        uint32_t* w = words.data() + pad_off;
+        auto set_bit = [&](uint64_t i) { w[i >> 5] |= 1u << (i & 31); };
+        for (uint64_t x = 0; x < PX; ++x)
+            for (uint64_t y = 0; y < PY; ++y) {
+                const uint64_t row = (x * PY + y) * PZ;
+                if (x == 0 || x == PX - 1 || y == 0 || y == PY - 1) {
+                    for (uint64_t z = 0; z < PZ; ++z) set_bit(row + z);
+                    continue;
+                }
+                set_bit(row);
+                set_bit(row + PZ - 1);
+                const uint8_t* src = cells + ((x - 1) * uint64_t(Y) + (y - 1)) * uint64_t(Z);
+                for (uint64_t z = 0; z < uint64_t(Z); ++z)
+                    if (src[z]) set_bit(row + 1 + z);
+            }
+    }
     cudaError_t e = cudaMalloc(&sc->d_grid_bits, words.size() * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&sc->d_counters, 16 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemcpyAsync(sc->d_grid_bits, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
@@ -862,6 +917,9 @@ int create_grid_scene(vrt_context* ctx, const uint8_t* cells, int X, int Y, int 
     if (e != cudaSuccess) { vrt_scene_destroy(sc); return cuda_fail(e, "grid scene upload"); }
     for (int l = 0; l < levels; ++l) sc->grid.level[l].bits = sc->d_grid_bits + offsets[l];
     sc->grid.mirror = any_mirror ? sc->d_grid_bits + mirror_off : nullptr;
+    sc->grid.pad_bits = padded ? sc->d_grid_bits + pad_off : nullptr;
+    sc->grid.pad_y = uint32_t(PY);
+    sc->grid.pad_z = uint32_t(PZ);
     sc->device_bytes = words.size() * sizeof(uint32_t);
     *out = sc;
     return VRT_OK;

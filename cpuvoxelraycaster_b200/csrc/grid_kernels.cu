@@ -265,9 +265,109 @@ __device__ __forceinline__ void grid_dda(const GridLevels& g, float ox, float oy
     r.hit = hit; r.side = side; r.cx = cx; r.cy = cy; r.cz = cz; r.t = t; r.steps = iter;
 }
 
+// Grid3D::castRay (grid_3d.hpp:35-132) on the bordered bit grid (GridLevels::pad_bits) — the default DDA.
+// ncu on the first kernels (profiles/r02_ncu_summaries.txt, grid_cast_kernel): issue slots 86 % busy, ALU pipe 74-83 %,
+// math-pipe-throttle the top stall — the loop is bound by integer / compare instructions, ~75 of them per cell step:
+// twelve bounds compares, 64-bit index multiplies, a copy of t per step.  Here a step is ~19 instructions:
+//   * the cell is ONE 32-bit linear bit index, stepped by a per-axis stride (two's complement for negative steps);
+//   * no bounds test at all: a ray that leaves the grid lands on a border cell, which is set — the loop ends on it like
+//     on a solid cell, and the decoded coordinate tells the two apart afterwards (once per ray);
+//   * `t_max += t_d` of the stepped axis (:78,86,94) is applied AFTER the occupancy test of the trip, so when the loop stops
+//     the un-incremented t_max of the stepped axis IS the hit distance (:77,85,93) — nothing is copied per step;
+//   * trips are counted with an FADD (FMA pipe; exact below 2^24);
+//   * the 2048-iteration cap (:70) is compiled in only for grids a ray can cross in 2048 steps or more (kCap).
+// The float recurrence and the comparisons are the reference's, so records are byte-identical to the generic loop above.
+template <bool kCap>
+__device__ __forceinline__ void grid_dda_fast(const GridLevels& g, float ox, float oy, float oz, float dx, float dy, float dz, DdaHit& r) {
+    const int X = g.X, Y = g.Y, Z = g.Z;
+    const float tdx = fabsf(1.0f / dx), tdy = fabsf(1.0f / dy), tdz = fabsf(1.0f / dz);       // grid_3d.hpp:42-44
+    const int sx = dx < 0 ? -1 : 1, sy = dy < 0 ? -1 : 1, sz = dz < 0 ? -1 : 1;               // :48-50
+    int cx = int(ox), cy = int(oy), cz = int(oz);                                              // :58-60
+    float tmx = (float(cx + (sx > 0 ? 1 : 0)) - ox) / dx;                                      // :62-64
+    float tmy = (float(cy + (sy > 0 ? 1 : 0)) - oy) / dy;
+    float tmz = (float(cz + (sz > 0 ? 1 : 0)) - oz) / dz;
+    r.hit = false; r.side = 0; r.cx = cx; r.cy = cy; r.cz = cz; r.t = 0.0f; r.steps = 0u;
+    if (!(cx >= 0 && cy >= 0 && cz >= 0 && cx < X && cy < Y && cz < Z)) return;               // :68-69: the loop is not entered
+    const uint32_t PY = g.pad_y, PZ = g.pad_z;
+    uint32_t idx = (uint32_t(cx + 1) * PY + uint32_t(cy + 1)) * PZ + uint32_t(cz + 1);
+    // strides and the grid pointer pinned in registers (ptxas otherwise re-derives them from the constant bank every trip)
+    const uint32_t dix = uint32_t(sx) * PY * PZ + blockIdx.y, diy = uint32_t(sy) * PZ + blockIdx.y, diz = uint32_t(sz) + blockIdx.y;
+    const uint32_t* __restrict__ bits = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(g.pad_bits) + blockIdx.y + threadIdx.z);
+    float it = 0.0f;
+    bool p0 = false, p1 = false, stopped = false;
+    for (;;) {
+        if (kCap) { if (!(it < 2048.0f)) break; }                                              // :70
+        it += 1.0f;
+        const bool xy = tmx < tmy;                                                             // :73-99
+        p0 = xy && (tmx < tmz);
+        p1 = !xy && (tmy < tmz);
+        if (p0) idx += dix; else if (p1) idx += diy; else idx += diz;
+        if ((__ldg(bits + (idx >> 5)) >> (idx & 31u)) & 1u) { stopped = true; break; }         // :103-104, or the border
+        // t_max += t_d AFTER the exit test: when the loop stops, the un-incremented t_max of the stepped axis is the hit distance
+        if (p0) tmx += tdx; else if (p1) tmy += tdy; else tmz += tdz;                          // :78,86,94
+    }
+    r.steps = uint32_t(it);
+    if (!stopped) return;
+    const uint32_t pz = idx % PZ, q = idx / PZ, py = q % PY, px = q / PY;
+    cx = int(px) - 1; cy = int(py) - 1; cz = int(pz) - 1;
+    if (cx < 0 || cy < 0 || cz < 0 || cx >= X || cy >= Y || cz >= Z) return;                   // left the grid: miss
+    r.hit = true;
+    r.side = p0 ? 0 : (p1 ? 1 : 2);
+    r.t = p0 ? tmx : (p1 ? tmy : tmz);                                                         // :77,85,93
+    r.cx = cx; r.cy = cy; r.cz = cz;
+}
+
+// kMode: 0 = generic loop on the flat grid, 1 = generic loop with the fetch-skipping pyramid, 2 = bordered grid, 3 = bordered + cap
+template <int kMode>
+__device__ __forceinline__ void grid_dda_any(const GridLevels& g, float ox, float oy, float oz, float dx, float dy, float dz, DdaHit& r) {
+    if (kMode == 0) grid_dda<false>(g, ox, oy, oz, dx, dy, dz, r);
+    else if (kMode == 1) grid_dda<true>(g, ox, oy, oz, dx, dy, dz, r);
+    else if (kMode == 2) grid_dda_fast<false>(g, ox, oy, oz, dx, dy, dz, r);
+    else grid_dda_fast<true>(g, ox, oy, oz, dx, dy, dz, r);
+}
+
+// K2f: Grid3D::castRay over a ray buffer on the bordered grid; same 64-byte records as grid_cast_kernel
+template <bool kCap>
+__global__ void __launch_bounds__(256) grid_cast_fast_kernel(GridLevels g, const float* __restrict__ origin, const float* __restrict__ dir,
+                                                             uint64_t n, vrt_hit* __restrict__ out,
+                                                             unsigned long long* __restrict__ counters) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    uint32_t iter = 0u;
+    if (i < n) {
+        const float ox = origin[3 * i], oy = origin[3 * i + 1], oz = origin[3 * i + 2];
+        const float dx = dir[3 * i], dy = dir[3 * i + 1], dz = dir[3 * i + 2];
+        DdaHit h;
+        grid_dda_fast<kCap>(g, ox, oy, oz, dx, dy, dz, h);
+        iter = h.steps;
+        float4* q = reinterpret_cast<float4*>(out + i);
+        if (h.hit) {
+            const float t = h.t;
+            const float hx = ox + t * dx, hy = oy + t * dy, hz = oz + t * dz;                  // grid_3d.hpp:105-107
+            float nx = 0.0f, ny = 0.0f, nz = 0.0f, u, v;
+            if (h.side == 0) { nx = float(dx < 0 ? 1 : -1); u = 1.0f - fracf(hz); v = fracf(hy); }   // :112-121
+            else if (h.side == 1) { ny = float(dy < 0 ? 1 : -1); u = fracf(hx); v = fracf(hz); }
+            else { nz = float(dz < 0 ? 1 : -1); u = fracf(hx); v = fracf(hy); }
+            q[0] = make_float4(hx, hy, hz, t);
+            q[1] = make_float4(nx, ny, nz, __uint_as_float(iter));                             // complexity = iter, :124
+            q[2] = make_float4(u, v, __uint_as_float(VRT_HIT_FLAG_HIT), 0.0f);
+            q[3] = make_float4(__int_as_float(h.cx), __int_as_float(h.cy), __int_as_float(h.cz), __uint_as_float(1u << h.side));
+        } else {
+            q[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            q[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            q[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            q[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) iter += __shfl_xor_sync(0xffffffffu, iter, o);
+    if ((threadIdx.x & 31) == 0 && iter) {
+        atomicAdd(counters, (unsigned long long)iter);
+        atomicAdd(counters + 1, (unsigned long long)iter);       // one occupancy fetch per step
+    }
+}
+
 __device__ __forceinline__ uint8_t mul_u8g(uint8_t c, float f) { return uint8_t(fminf(255.0f, float(c) * f)); }   // utils.cpp:43-48
 
-template <bool kMip>
+template <int kMode>
 __global__ void __launch_bounds__(128) grid_render_kernel(GridLevels g, RenderLaunch L, uint32_t* __restrict__ accum,
                                                           unsigned long long* __restrict__ counters) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -303,7 +403,7 @@ __global__ void __launch_bounds__(128) grid_render_kernel(GridLevels g, RenderLa
             int bounds = 0;
             for (;;) {
                 DdaHit h;
-                grid_dda<kMip>(g, ox, oy, oz, dx, dy, dz, h);
+                grid_dda_any<kMode>(g, ox, oy, oz, dx, dy, dz, h);
                 const int cls = bounds == 0 ? 0 : 2;
                 n_rays[0] += cls == 0; n_rays[2] += cls == 2;
                 n_steps[0] += cls == 0 ? h.steps : 0u; n_steps[2] += cls == 2 ? h.steps : 0u;
@@ -341,7 +441,7 @@ __global__ void __launch_bounds__(128) grid_render_kernel(GridLevels g, RenderLa
                 float tlx = L.light[0] - sox, tly = L.light[1] - soy, tlz = L.light[2] - soz;
                 normalize3(tlx, tly, tlz);
                 DdaHit sh;
-                grid_dda<kMip>(g, sox, soy, soz, tlx, tly, tlz, sh);
+                grid_dda_any<kMode>(g, sox, soy, soz, tlx, tly, tlz, sh);
                 n_rays[1] += 1u; n_steps[1] += sh.steps;
                 float light = 0.0f;
                 if (!sh.hit) light = fmaxf(0.0f, dot3(tlx, tly, tlz, nx, ny, nz));
@@ -372,15 +472,24 @@ cudaError_t launch_grid_render(const GridLevels& g, bool use_mip, const RenderLa
     const int tiles_x = (L.width + 31) / 32, tiles_y = ((rows + 3) / 4 + L.tile_step - 1 - L.tile_index) / L.tile_step;
     if (tiles_y <= 0) return cudaSuccess;
     const unsigned grid = unsigned(tiles_x) * unsigned(tiles_y);
-    if (use_mip && g.n_levels > 1) grid_render_kernel<true><<<grid, 128, 0, stream>>>(g, L, d_accum, d_counters);
-    else grid_render_kernel<false><<<grid, 128, 0, stream>>>(g, L, d_accum, d_counters);
+    const bool cap = g.X + g.Y + g.Z >= 2048;
+    if (g.pad_bits && L.grid_variant == 0) {
+        if (cap) grid_render_kernel<3><<<grid, 128, 0, stream>>>(g, L, d_accum, d_counters);
+        else grid_render_kernel<2><<<grid, 128, 0, stream>>>(g, L, d_accum, d_counters);
+    } else if (use_mip && g.n_levels > 1) grid_render_kernel<1><<<grid, 128, 0, stream>>>(g, L, d_accum, d_counters);
+    else grid_render_kernel<0><<<grid, 128, 0, stream>>>(g, L, d_accum, d_counters);
     return cudaGetLastError();
 }
 
-cudaError_t launch_grid_cast(const GridLevels& g, bool use_mip, const float* d_origin, const float* d_dir, uint64_t n,
+cudaError_t launch_grid_cast(const GridLevels& g, bool use_mip, int variant, const float* d_origin, const float* d_dir, uint64_t n,
                              vrt_hit* d_out, unsigned long long* d_counters, cudaStream_t stream) {
     if (!n) return cudaSuccess;
     const unsigned grid = unsigned((n + 255) / 256);
+    if (g.pad_bits && variant == 0) {                     // the bordered grid: Grid3D and MipmapGrid3D alike (identical records)
+        if (g.X + g.Y + g.Z >= 2048) grid_cast_fast_kernel<true><<<grid, 256, 0, stream>>>(g, d_origin, d_dir, n, d_out, d_counters);
+        else grid_cast_fast_kernel<false><<<grid, 256, 0, stream>>>(g, d_origin, d_dir, n, d_out, d_counters);
+        return cudaGetLastError();
+    }
     if (use_mip && g.n_levels > 1) grid_cast_kernel<true><<<grid, 256, 0, stream>>>(g, d_origin, d_dir, n, d_out, d_counters);
     else grid_cast_kernel<false><<<grid, 256, 0, stream>>>(g, d_origin, d_dir, n, d_out, d_counters);
     return cudaGetLastError();

@@ -25,10 +25,16 @@ struct GridLevels {
     int n_levels;
     int X, Y, Z;
     const uint32_t* mirror;   // level-0 bit plane: Cell::type == Mirror (cell.hpp:8); may be null
+    // Level 0 once more with a one-cell border: (X+2) x (Y+2) x (Z+2) bits, cell (x,y,z) at ((x+1) * pad_y + (y+1)) * pad_z + (z+1),
+    // every border cell set.  A ray that leaves the grid lands on a border cell, so the DDA needs no bounds test per step
+    // (grid_kernels.cu, grid_dda_fast).  Null when the padded grid has 2^32 bits or more (the generic loop is used then).
+    const uint32_t* pad_bits;
+    uint32_t pad_y, pad_z;
 };
 
 // K2 / K2m: Grid3D::castRay, flat or with the fetch-skipping pyramid (grid_kernels.cu)
-cudaError_t launch_grid_cast(const GridLevels& g, bool use_mip, const float* d_origin, const float* d_dir, uint64_t n,
+// variant: 0 = the bordered-grid DDA when the scene has one (default), 1 = the generic loop (flat, or with the fetch-skipping pyramid)
+cudaError_t launch_grid_cast(const GridLevels& g, bool use_mip, int variant, const float* d_origin, const float* d_dir, uint64_t n,
                              vrt_hit* d_out, unsigned long long* d_counters, cudaStream_t stream);
 // K3: SVO<N>::castRay with the hit fill restored (grid_kernels.cu)
 cudaError_t launch_svo_cast(const GridLevels& g, int depth, const float* d_origin, const float* d_dir, uint32_t max_iter,
@@ -47,6 +53,7 @@ struct RenderLaunch {
     void* scratch;               // K6: device scratch for the sorted sample lists (render_scratch_bytes)
     size_t scratch_bytes;
     int mapping;                 // 0 = automatic (K5 for many-sample GI frames, else K4), 2 = K4, 3 = K5
+    int grid_variant;            // grid frames: 0 = bordered-grid DDA (default), 1 = generic loop
     int trav_policy;             // K6 traversal loop: 0 = Trav, 1 = Trav2, 2 = Trav2 without the cone test on coef-0 rays (default)
     uint32_t seed_lo, seed_hi;
     float light[3];
@@ -72,6 +79,9 @@ __host__ __device__ inline int checker_x_parity(int checker, int area_height, in
 size_t render_scratch_bytes(const RenderLaunch& L);
 cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const RenderLaunch& L, uint32_t* d_accum,
                                          unsigned long long* d_counters, cudaStream_t stream);
+// RayCaster::castRay for explicit rays (vrt_shade_rays)
+cudaError_t launch_shade_rays(const uint2* nodes, bool compact, const RenderLaunch& L, uint64_t n, const vrt_shade_job* d_jobs,
+                              vrt_shade_result* d_out, cudaStream_t stream);
 // Camera::getClosestPoint + main.cpp:114-121 on the device: *d_focal = hit ? distance * 2^depth : 100
 cudaError_t launch_autofocus(const uint2* nodes, bool compact, int depth, int guard, const vrt_camera& cam, float* d_focal,
                              cudaStream_t stream);

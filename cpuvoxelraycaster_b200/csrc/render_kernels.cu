@@ -534,6 +534,64 @@ __global__ void __launch_bounds__(128, VRT_K5_MIN_CTAS) render_rounds_kernel(Nod
     }
 }
 
+// RayCaster::castRay (raycaster.hpp:118-167) for explicit rays: the caller supplies start and direction — what the
+// reference's renderRay receives from Camera::getRay (main.cpp:147-149) — and gets the sample's colour back.  One thread per
+// ray, the same sample chain as the frame kernels (sun shadow, GI with the Philox numbers of (pixel, sample)), so a ray
+// that equals the frame kernels' primary ray of (pixel, sample) gives exactly that sample's colour.
+template <typename Nodes>
+__global__ void __launch_bounds__(128) shade_rays_kernel(Nodes nodes, RenderLaunch L, uint64_t n, const vrt_shade_job* __restrict__ jobs,
+                                                         vrt_shade_result* __restrict__ out) {
+    extern __shared__ uint2 smem[];
+    nodes.slots = pin(nodes.slots);
+    const int guard = pin(L.guard);
+    Stack64s<128> stack = Stack64s<128>::make(smem + threadIdx.x, pin(kSvoMaxDepth - L.depth));
+    const float guard_sf = pin(guard_scale_f(L.guard));
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const vrt_shade_job job = jobs[i];
+    const float SCALE = 1.0f / float(1 << L.depth);
+    const float n_norm = SCALE * 0.0078125f * 2.0f;
+    ChainState c;
+    const uint4 rnd0 = philox4x32_10(job.pixel, job.sample, 0u, 0u, L.seed_lo, L.seed_hi);
+    c.rnd_z = rnd0.z; c.rnd_w = rnd0.w;
+    c.light = 0.f; c.irr0 = 0.f; c.irr1 = 0.f;
+    c.have_hit = false; c.gi0_hit = false; c.gi1_hit = false;
+    NextRay nr;
+    nr.ox = job.start[0]; nr.oy = job.start[1]; nr.oz = job.start[2];
+    nr.dx = job.direction[0]; nr.dy = job.direction[1]; nr.dz = job.direction[2];
+    nr.coef = 0.0f;
+    int stage = kPrimary;
+    float distance = 0.0f;
+    uint32_t complexity = 0u;
+    while (stage != kDone) {
+        LsvoResult r;
+        if (stage < kGi0) lsvo_cast_ray2<false>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, 0.0f, 0.0f, r);
+        else lsvo_cast_ray2<true>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
+        if (stage == kPrimary) { complexity = r.complexity; if (r.hit) distance = r.t_min; }   // RayContext, raycaster.hpp:132-133,137
+        LsvoHit h;
+        if (r.hit) lsvo_finish(r, nr.ox, nr.oy, nr.oz, L.depth, h);
+        stage = chain_advance(L, c, stage, r, h, job.pixel, job.sample, SCALE, n_norm, nr);
+    }
+    uint32_t cr = 0, cg = 0, cb = 0;
+    chain_colour(L, c, cr, cg, cb);
+    vrt_shade_result res;
+    res.r = uint8_t(cr); res.g = uint8_t(cg); res.b = uint8_t(cb); res.hit = c.have_hit ? 1 : 0;
+    res.distance = distance;
+    res.complexity = complexity;
+    res.reserved = 0u;
+    out[i] = res;
+}
+
+cudaError_t launch_shade_rays(const uint2* nodes, bool compact, const RenderLaunch& L, uint64_t n, const vrt_shade_job* d_jobs,
+                              vrt_shade_result* d_out, cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    const size_t smem = size_t(L.depth + 1) * 128 * 8;
+    const unsigned grid = unsigned((n + 127) / 128);
+    if (compact) shade_rays_kernel<CompactNodes><<<grid, 128, smem, stream>>>(CompactNodes{nodes}, L, n, d_jobs, d_out);
+    else shade_rays_kernel<RefNodes><<<grid, 128, smem, stream>>>(RefNodes{nodes}, L, n, d_jobs, d_out);
+    return cudaGetLastError();
+}
+
 // Camera::getClosestPoint (camera_controller.hpp:56-60) and the focal-length rule of main.cpp:114-121, one thread.
 template <typename Nodes>
 __global__ void __launch_bounds__(128) autofocus_kernel(Nodes nodes, int depth, int guard, vrt_camera cam, float* __restrict__ focal) {

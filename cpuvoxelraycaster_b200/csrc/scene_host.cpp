@@ -96,6 +96,11 @@ private:
 // permutation tables + fractal bounding for the device-side noise (scene_device.cu)
 void host_simplex_tables(uint8_t perm[512], uint8_t perm12[512], float* bounding) { SimplexFbm2D().tables(perm, perm12, bounding); }
 
+float host_noise2d(float x, float y) {
+    static const SimplexFbm2D noise;
+    return noise.fbm(x, y);
+}
+
 void host_terrain_heights(int32_t size, int32_t* out) {
     const SimplexFbm2D noise;
     for (int32_t x = 0; x < size; ++x)

@@ -457,6 +457,7 @@ class RayCaster:
         self.autofocus = False             # True: focal length from the centre ray on the device (main.cpp:114-121)
         self.seed = (0x5EED, 0)
         self.sample_count = 0
+        self.frame_index = 0               # frames rendered in blend mode: selects the random stream of the frame
         self.last_stats = None
         if tex_top is not None:
             svo.set_textures(tex_top, tex_side)
@@ -473,7 +474,9 @@ class RayCaster:
         p.width, p.height = self.render_size
         p.row_begin, p.row_end = int(row_begin), int(row_end) if row_end else self.render_size[1]
         p.spp = int(spp)
-        p.sample_offset = self.sample_count if sample_offset is None else int(sample_offset)
+        if sample_offset is None:
+            sample_offset = self.sample_count if self.use_samples else self.frame_index
+        p.sample_offset = int(sample_offset)
         p.seed_lo, p.seed_hi = self.seed
         p.light_position[:] = [float(x) for x in self.light_position]
         p.use_gi, p.gi_bounces, p.use_samples = int(self.use_gi), int(self.gi_bounces), int(self.use_samples)
@@ -497,6 +500,8 @@ class RayCaster:
                                ptr(self.colors), C.byref(stats)))
         if self.use_samples:
             self.sample_count += int(spp)
+        else:
+            self.frame_index += 1
         self.last_stats = dict(rays=list(stats.rays), complexity=list(stats.complexity))
         return self.render_image
 

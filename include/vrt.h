@@ -112,6 +112,9 @@ int vrt_context_take_timings(vrt_context* ctx, float* ms, int32_t cap, int32_t* 
 /* ---- host-side scene construction (pure host code, no GPU needed) ---------------------------- */
 /* FastNoise SimplexFractal heights of the demo terrain, src/main.cpp:61-68; out[x*size+z]. */
 int vrt_host_terrain_heights(int32_t size, int32_t* out);
+/* FastNoise::GetNoise(x, y) of a default-constructed FastNoise set to SimplexFractal (main.cpp:61-62,68;
+ * lib/fastnoise/FastNoise.cpp:1191-1333: seed 1337, frequency 0.01, 3 octaves FBM, lacunarity 2, gain 0.5), bit-exact. */
+float vrt_host_noise2d(float x, float y);
 /* SVO::setCell fill (main.cpp:70-76, 256 → size/2) + compileSVO (lsvo_utils.hpp:45-55,
  * lsvo_utils.cpp:4-49) in one pass, without the 80-byte pointer nodes.  Two-call protocol:
  * out == NULL → *count only. */
@@ -247,6 +250,26 @@ int vrt_render_resolve_device(vrt_scene* scene, const vrt_render_params* p, cons
 int vrt_render(vrt_scene* scene, const vrt_camera* cam, const vrt_render_params* p, uint8_t* rgba, uint32_t* accum,
                vrt_render_stats* stats);
 int vrt_scene_last_render_stats(vrt_scene* scene, vrt_render_stats* stats);
+
+/* RayCaster::castRay (raycaster.hpp:118-167) for explicit rays — the call the reference's per-pixel loop makes through
+ * renderRay (raycaster.hpp:67-92) with the ray Camera::getRay produced (main.cpp:147-149): start and direction in the
+ * normalised [1,2]^3 frame.  Returns each ray's ColorResult: the shaded 8-bit colour (texture, sun shadow, GI when
+ * p->use_gi, with the Philox numbers of (pixel, sample)), hit flag, HitPoint::distance and complexity of the primary ray.
+ * Only the shading fields of *p are read (light_position, use_gi, gi_bounces, seed); LSVO scenes.  This is the
+ * compatibility path for hosts that keep the reference's loop structure — frames should use vrt_render. */
+typedef struct vrt_shade_job {
+    float start[3];
+    uint32_t pixel;          /* RNG stream: y * width + x */
+    float direction[3];
+    uint32_t sample;         /* RNG stream: index of this sample of the pixel */
+} vrt_shade_job;
+typedef struct vrt_shade_result {
+    uint8_t r, g, b, hit;    /* ColorResult::color; hit = the primary ray found a cell */
+    float distance;          /* ColorResult::distance */
+    uint32_t complexity;     /* RayContext::complexity */
+    uint32_t reserved;
+} vrt_shade_result;
+int vrt_shade_rays(vrt_scene* scene, const vrt_render_params* p, uint64_t n, const vrt_shade_job* jobs, vrt_shade_result* out);
 
 /* Presentation step of the main loop (main.cpp:159-177), fused into one kernel:
  *   frame'   = median filter of `frame` (median = 0: none; 3 / 5: per-channel 3x3 / 5x5 median, clamp to edge — what

@@ -40,18 +40,26 @@
 #endif
 #ifndef VRT_HAVE_GLM
 namespace glm {
-struct vec2 { float x = 0, y = 0; vec2() {} vec2(float a, float b) : x(a), y(b) {} };
+struct vec2 { float x = 0, y = 0; vec2() {} explicit vec2(float s) : x(s), y(s) {} vec2(float a, float b) : x(a), y(b) {} };
 struct vec3 {
     float x = 0, y = 0, z = 0;
     vec3() {}
     explicit vec3(float s) : x(s), y(s), z(s) {}
     vec3(float a, float b, float c) : x(a), y(b), z(c) {}
+    vec3(const vec2& v, float c) : x(v.x), y(v.y), z(c) {}
 };
+inline vec2 operator*(float s, const vec2& a) { return vec2(s * a.x, s * a.y); }
+inline vec2 operator+(const vec2& a, const vec2& b) { return vec2(a.x + b.x, a.y + b.y); }
+inline float dot(const vec3& a, const vec3& b);
+inline vec3 normalize(const vec3& v);
 inline vec3 operator+(const vec3& a, const vec3& b) { return vec3(a.x + b.x, a.y + b.y, a.z + b.z); }
 inline vec3 operator-(const vec3& a, const vec3& b) { return vec3(a.x - b.x, a.y - b.y, a.z - b.z); }
 inline vec3 operator*(const vec3& a, float s) { return vec3(a.x * s, a.y * s, a.z * s); }
 inline vec3 operator*(float s, const vec3& a) { return vec3(s * a.x, s * a.y, s * a.z); }
 struct mat3 { vec3 c[3]; vec3& operator[](int i) { return c[i]; } const vec3& operator[](int i) const { return c[i]; } };
+inline float dot(const vec3& a, const vec3& b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }                  // glm: (x + y) + z
+inline vec3 normalize(const vec3& v) { const float inv = 1.0f / std::sqrt(dot(v, v)); return vec3(v.x * inv, v.y * inv, v.z * inv); }
+inline vec3 operator*(const vec3& v, const mat3& m) { return vec3(dot(m[0], v), dot(m[1], v), dot(m[2], v)); }   // row vector x matrix
 }  // namespace glm
 #endif
 
@@ -64,6 +72,32 @@ struct Error : std::runtime_error {
 inline void check(int status) {
     if (status != VRT_OK) throw Error(status, vrt_last_error());
 }
+
+// Philox4x32-10 (Salmon et al. 2011) on the host: the counter-based generator the device uses, for the host-side calls
+// that draw random numbers in the reference (Camera::getRay, getGlobalIllumination through getRand, utils.cpp:77-81).
+inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = uint64_t(0xD2511F53u) * c[0], p1 = uint64_t(0xCD9E8D57u) * c[2];
+        const uint32_t n0 = uint32_t(p1 >> 32) ^ c[1] ^ k0, n2 = uint32_t(p0 >> 32) ^ c[3] ^ k1;
+        c[0] = n0; c[1] = uint32_t(p1); c[2] = n2; c[3] = uint32_t(p0);
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+struct HostRng {                       // one stream per thread; deterministic per thread, never shared (the reference's is racy)
+    uint64_t counter = 0;
+    uint32_t block[4] = {0, 0, 0, 0};
+    int left = 0;
+    uint32_t next() {
+        if (!left) {
+            block[0] = uint32_t(counter); block[1] = uint32_t(counter >> 32); block[2] = 0x68E31DA4u; block[3] = 0;
+            philox4x32_10(block, 0x5EEDu, 0u);
+            ++counter;
+            left = 4;
+        }
+        return block[--left];
+    }
+};
+inline HostRng& host_rng() { static thread_local HostRng r; return r; }
 
 // One device + stream shared by every drop-in object of the process (replaces swrm::Swarm, main.cpp:90-92).
 inline vrt_context* default_context(int device = 0) {
@@ -85,6 +119,12 @@ struct SceneHandle {
 };
 
 }  // namespace vrt
+
+// ---- include/utils.hpp:19 / src/utils.cpp:77-81: min + (max - min) * (float(rnd % 100) / 100) -----------------------
+inline float getRand(float min = -0.5f, float max = 0.5f) {
+    const float rand_val = float(vrt::host_rng().next() % 100u) / 100.0f;
+    return min + (max - min) * rand_val;
+}
 
 // ---- include/cell.hpp -----------------------------------------------------------------------------------
 struct Cell {
@@ -215,6 +255,26 @@ struct LSVO : public Volumetric {
     }
     vrt_scene* scene() const override { return m_scene.s; }
 
+    // lsvo.hpp:174-285: the node whose leaf child the ray hits (castRay without the cone), or nullptr on a miss.
+    // The ray is cast on the device; the node is then found by walking `data` along the hit voxel's path.
+    vrt_lnode* getAtRayHit(const glm::vec3& position, glm::vec3 d) {
+        const float o[3] = {position.x, position.y, position.z}, dir[3] = {d.x, d.y, d.z};
+        vrt_hit h;
+        vrt::check(vrt_cast_rays(m_scene.s, o, dir, 0.0f, 0.0f, 1, &h));
+        if (!(h.flags & VRT_HIT_FLAG_HIT)) return nullptr;
+        const uint32_t S1 = (1u << MAX_DEPTH) - 1u;
+        uint64_t node = 0;
+        for (int level = int(MAX_DEPTH) - 1; level >= 0; --level) {          // child slot = bits of the mirrored coordinate (lsvo.hpp:79)
+            const uint32_t slot = (((S1 - uint32_t(h.voxel[0])) >> level) & 1u) | ((((S1 - uint32_t(h.voxel[1])) >> level) & 1u) << 1) |
+                                  ((((S1 - uint32_t(h.voxel[2])) >> level) & 1u) << 2);
+            const vrt_lnode& n = data[node];
+            if (!((n.child_mask >> slot) & 1u)) return nullptr;
+            if ((n.leaf_mask >> slot) & 1u) return &data[node];
+            node += n.child_offset + slot;
+        }
+        return nullptr;
+    }
+
     std::vector<vrt_lnode> data;                        // LNode[] in the reference layout (lsvo.hpp:287)
     const vrt_lnode* raw_data = nullptr;                // lsvo.hpp:288
     Cell* cell = nullptr;                               // the one shared Solid/Grass cell (lsvo.hpp:21-23,289)
@@ -293,6 +353,11 @@ template <int32_t X, int32_t Y, int32_t Z> using Grid3D = Grid3DBase<X, Y, Z, 0>
 template <int32_t X, int32_t Y, int32_t Z, uint32_t MipmapDepth> using MipmapGrid3D = Grid3DBase<X, Y, Z, int32_t(MipmapDepth)>;
 
 // ---- include/camera_controller.hpp ------------------------------------------------------------------
+struct CameraRay {                                                         // camera_controller.hpp:10-14
+    glm::vec3 ray;
+    glm::vec3 world_rand_offset;
+};
+
 struct Camera {
     glm::vec3 position;
     glm::vec2 view_angle;
@@ -309,6 +374,31 @@ struct Camera {
         vrt::check(vrt_host_camera_rotation(a, m, v));
         for (int c = 0; c < 3; ++c) rot_mat[c] = glm::vec3(m[3 * c], m[3 * c + 1], m[3 * c + 2]);
         camera_vec = glm::vec3(v[0], v[1], v[2]);
+    }
+    // camera_controller.hpp:34-49.  The two lens numbers come from getRand() like in the reference (host-side stream; the
+    // batched RayCaster::render draws them per (pixel, sample) on the device instead).
+    CameraRay getRay(const glm::vec2& lens_position) {
+        const glm::vec3 screen_position = glm::vec3(lens_position.x, lens_position.y, fov);
+        const glm::vec3 focal_point = glm::normalize(screen_position) * focal_length;
+        const float r0 = getRand(), r1 = getRand();
+        const glm::vec3 rand_vec = glm::vec3(aperture * r0, aperture * r1, aperture * 0.0f);
+        const glm::vec3 ray = glm::normalize(focal_point - rand_vec);
+        CameraRay result;
+        result.ray = viewToWorld(ray);
+        result.world_rand_offset = viewToWorld(rand_vec);
+        return result;
+    }
+    glm::vec3 viewToWorld(const glm::vec3& v) const {                     // camera_controller.hpp:51-54: v * rot_mat
+        return glm::vec3((rot_mat[0].x * v.x + rot_mat[0].y * v.y) + rot_mat[0].z * v.z,
+                         (rot_mat[1].x * v.x + rot_mat[1].y * v.y) + rot_mat[1].z * v.z,
+                         (rot_mat[2].x * v.x + rot_mat[2].y * v.y) + rot_mat[2].z * v.z);
+    }
+    // camera_controller.hpp:56-60; the literal 1/512 is 1/2^depth of the volume
+    HitPoint getClosestPoint(const Volumetric& volume) const {
+        uint32_t depth = 9;
+        vrt::check(vrt_scene_info(volume.scene(), nullptr, &depth, nullptr));
+        const float scale = 1.0f / float(1u << depth);
+        return volume.castRay(glm::vec3(position.x * scale + 1.0f, position.y * scale + 1.0f, position.z * scale + 1.0f), camera_vec, 0.0f, 0.0f);
     }
     vrt_camera as_struct() const {
         vrt_camera c;
@@ -385,8 +475,30 @@ inline bool load_bmp16(const std::string& path, uint8_t out[768]) {
 }
 }  // namespace vrt
 
+struct RayContext {                                       // raycaster.hpp:9-15
+    float distance = 0.0f;
+    uint32_t complexity = 0U;
+    uint32_t bounds = 0U;
+    int32_t gi_bounce = 2U;
+};
+struct ColorResult {                                      // raycaster.hpp:35-39
+    vrt::Color color;
+    float distance = 0.0f;
+};
+
+namespace vrt {
+// every RayCaster with renderRay() calls waiting to be executed; swrm::WorkGroup::waitExecutionDone() flushes them
+struct PendingFlush {
+    virtual void flush() = 0;
+    virtual ~PendingFlush() {}
+};
+inline std::vector<PendingFlush*>& pending_registry() { static std::vector<PendingFlush*> r; return r; }
+inline void flush_all() { for (PendingFlush* p : pending_registry()) p->flush(); }
+inline uint8_t mult_u8(uint8_t c, float f) { const float v = float(c) * f; return uint8_t(v < 255.0f ? v : 255.0f); }   // utils.cpp:43-48
+}  // namespace vrt
+
 template <uint8_t SVO_DEPTH_>
-struct RayCasterT {
+struct RayCasterT : vrt::PendingFlush {
     // raycaster.hpp:48 — loads res/grass_side_16x16.bmp and res/grass_top_16x16.bmp relative to the CWD like the
     // reference; pass explicit textures (16x16 RGB, top-down) to skip the files.
     RayCasterT(const LSVO<SVO_DEPTH_>& svo_, const vrt::Vector2i& render_size_, const uint8_t* top_rgb = nullptr,
@@ -399,7 +511,104 @@ struct RayCasterT {
         vrt::check(vrt_scene_set_textures(svo.scene(), top, side));
         render_image.assign(size_t(render_size.x) * render_size.y * 4, 0);
         colors.assign(size_t(render_size.x) * render_size.y * 4, 0u);
+        vrt::pending_registry().push_back(this);
     }
+    ~RayCasterT() override {
+        std::vector<vrt::PendingFlush*>& r = vrt::pending_registry();
+        for (size_t i = 0; i < r.size(); ++i)
+            if (r[i] == this) { r.erase(r.begin() + i); break; }
+    }
+    RayCasterT(const RayCasterT&) = delete;
+    RayCasterT& operator=(const RayCasterT&) = delete;
+
+    // ---- the reference's per-ray entry points (compatibility path; frames should call render()) --------------------------
+    // raycaster.hpp:67-92.  The ray is queued; the queue is shaded in ONE launch (vrt_shade_rays) at the synchronisation point
+    // the reference's loop already has — swrm::WorkGroup::waitExecutionDone() (main.cpp:156) — or by flush() / samples_to_image().
+    // Pixels keep the order of the calls, so the temporal blend and the accumulators end up as in the reference.
+    void renderRay(const vrt::Vector2i pixel, const glm::vec3& start, const glm::vec3& direction, float /*time*/) {
+        vrt_shade_job j;
+        j.start[0] = start.x; j.start[1] = start.y; j.start[2] = start.z;
+        j.direction[0] = direction.x; j.direction[1] = direction.y; j.direction[2] = direction.z;
+        j.pixel = uint32_t(pixel.y) * uint32_t(render_size.x) + uint32_t(pixel.x);
+        j.sample = use_samples ? colors[4 * size_t(j.pixel) + 3] + pending_count(j.pixel) : frame_index;
+        m_jobs.push_back(j);
+    }
+    void flush() override {
+        if (m_jobs.empty()) return;
+        std::vector<vrt_shade_result> res(m_jobs.size());
+        const vrt_render_params p = shade_params();
+        vrt::check(vrt_shade_rays(svo.scene(), &p, m_jobs.size(), m_jobs.data(), res.data()));
+        for (size_t i = 0; i < m_jobs.size(); ++i) {
+            const size_t px = m_jobs[i].pixel;
+            if (!use_samples) {                                            // raycaster.hpp:79-85: 0.4 old + 0.6 new
+                uint8_t* q = &render_image[4 * px];
+                const uint8_t rgb[3] = {res[i].r, res[i].g, res[i].b};
+                for (int c = 0; c < 3; ++c) {
+                    const int v = int(vrt::mult_u8(q[c], 0.4f)) + int(vrt::mult_u8(rgb[c], 1.0f - 0.4f));   // add(), utils.cpp:35-40
+                    q[c] = uint8_t(v < 255 ? v : 255);
+                }
+                q[3] = 255;
+            } else {                                                       // raycaster.hpp:87-90
+                colors[4 * px] += res[i].r; colors[4 * px + 1] += res[i].g; colors[4 * px + 2] += res[i].b; colors[4 * px + 3] += 1u;
+            }
+        }
+        if (!use_samples) ++frame_index;
+        m_jobs.clear();
+        m_pending.clear();
+    }
+    // raycaster.hpp:118-167: one ray, shaded on the device right away (one tiny launch: not for inner loops)
+    ColorResult castRay(const glm::vec3& start, const glm::vec3& direction, float /*time*/, RayContext& context) {
+        ColorResult result;
+        if (context.bounds > max_bounds) return result;                    // raycaster.hpp:127-129
+        vrt_shade_job j;
+        j.start[0] = start.x; j.start[1] = start.y; j.start[2] = start.z;
+        j.direction[0] = direction.x; j.direction[1] = direction.y; j.direction[2] = direction.z;
+        j.pixel = 0xffffffffu; j.sample = m_cast_counter++;
+        vrt_shade_result r;
+        const vrt_render_params p = shade_params();
+        vrt::check(vrt_shade_rays(svo.scene(), &p, 1, &j, &r));
+        context.complexity += r.complexity;                                // :132-133
+        context.distance = r.distance;
+        result.color.r = r.r; result.color.g = r.g; result.color.b = r.b;
+        result.distance = r.distance;
+        return result;
+    }
+    // raycaster.hpp:169-207 with the host-side getRand stream: two single-ray casts through LSVO::castRay
+    float getGlobalIllumination(const HitPoint& point) {
+        uint32_t depth = SVO_DEPTH_;
+        const float SCALE = 1.0f / float(1u << depth);
+        const float n_normalizer = SCALE * 0.0078125f * 2.0f;
+        const glm::vec3& normal = point.normal;
+        const glm::vec3 gi_start(point.position.x + normal.x * n_normalizer, point.position.y + normal.y * n_normalizer, point.position.z + normal.z * n_normalizer);
+        const float range = 1000.0f;
+        glm::vec3 noise_normal(0.0f, 0.0f, 0.0f);
+        const float coord_1 = getRand(-range, range), coord_2 = getRand(-range, range);
+        if (normal.x != 0.0f) noise_normal = glm::vec3(0.0f, coord_1, coord_2);
+        else if (normal.y != 0.0f) noise_normal = glm::vec3(coord_1, 0.0f, coord_2);
+        else if (normal.z != 0.0f) noise_normal = glm::vec3(coord_1, coord_2, 0.0f);
+        else return 0.0f;                                                  // uninitialised noise_normal in the reference
+        const glm::vec3 gi_ray = glm::normalize(glm::vec3((normal.x + noise_normal.x) * n_normalizer, (normal.y + noise_normal.y) * n_normalizer,
+                                                          (normal.z + noise_normal.z) * n_normalizer));
+        const float dot_gi = glm::dot(gi_ray, normal);
+        float acc = 0.0f;
+        const HitPoint gi_point = svo.castRay(gi_start, gi_ray, 0.5f, 0.0f);
+        if (gi_point.cell) {
+            const glm::vec3 gi_light_start(gi_point.position.x + gi_point.normal.x * n_normalizer, gi_point.position.y + gi_point.normal.y * n_normalizer,
+                                           gi_point.position.z + gi_point.normal.z * n_normalizer);
+            const glm::vec3 to_light = glm::normalize(glm::vec3(light_position.x - gi_light_start.x, light_position.y - gi_light_start.y,
+                                                                light_position.z - gi_light_start.z));
+            const HitPoint gi_light_point = svo.castRay(gi_light_start, to_light, 0.5f, 0.0f);
+            if (!gi_light_point.cell) {
+                const float d = glm::dot(gi_point.normal, to_light);
+                acc += sun_intensity * std::min(0.5f, std::max(0.0f, d) * dot_gi);
+            }
+        }
+        return std::max(0.0f, acc / 1.0f);
+    }
+    const float eps = 0.001f;                           // raycaster.hpp:45-46
+    const float sun_intensity = 1000000.0f;
+    const uint32_t max_bounds = 4;                      // raycaster.hpp:277
+
     void setLightPosition(const glm::vec3& position) { light_position = position; }          // raycaster.hpp:62
 
     // Replaces the swarm lambda main.cpp:139-154 (+ samples_to_image when use_samples): every pixel, `spp` passes.
@@ -408,7 +617,8 @@ struct RayCasterT {
         std::memset(&p, 0, sizeof(p));
         p.width = render_size.x; p.height = render_size.y; p.row_begin = 0; p.row_end = render_size.y;
         p.spp = use_samples ? spp : 1;
-        p.sample_offset = int32_t(sample_count);
+        flush();
+        p.sample_offset = int32_t(use_samples ? sample_count : frame_index);   // blend mode: a new random stream every frame
         p.seed_lo = seed_lo; p.seed_hi = seed_hi;
         p.light_position[0] = light_position.x; p.light_position[1] = light_position.y; p.light_position[2] = light_position.z;
         p.use_gi = use_gi; p.gi_bounces = gi_bounces; p.use_samples = use_samples;
@@ -420,6 +630,7 @@ struct RayCasterT {
         const vrt_camera c = camera.as_struct();
         vrt::check(vrt_render(svo.scene(), &c, &p, render_image.data(), colors.data(), &last_stats));
         if (use_samples) sample_count += uint32_t(p.spp);
+        else ++frame_index;
     }
     // The presentation step of the main loop (main.cpp:159-177): optional 3x3 / 5x5 median (res/median_3.frag,
     // res/median.frag) and the persistence blend of render_image into `display` (denoised_tex).
@@ -430,8 +641,21 @@ struct RayCasterT {
         p.width = render_size.x; p.height = render_size.y; p.median = median; p.old_value_conservation = old_value_conservation;
         vrt::check(vrt_present(vrt::default_context(), render_image.data(), display.data(), &p));
     }
-    void samples_to_image() {}                          // raycaster.hpp:94-103: done on the device by render()
+    // raycaster.hpp:94-103.  render() resolves on the device already; after renderRay() calls the queue is shaded first and the
+    // image is resolved here (the integer sums divide exactly like the reference's doubles).
+    void samples_to_image() {
+        const bool queued = !m_jobs.empty();
+        flush();
+        if (!queued && !m_resolve_on_host) return;
+        m_resolve_on_host = true;
+        for (size_t i = 0; i < colors.size() / 4; ++i) {
+            const uint32_t n = colors[4 * i + 3] ? colors[4 * i + 3] : 1u;
+            render_image[4 * i] = uint8_t(colors[4 * i] / n); render_image[4 * i + 1] = uint8_t(colors[4 * i + 1] / n);
+            render_image[4 * i + 2] = uint8_t(colors[4 * i + 2] / n); render_image[4 * i + 3] = 255;
+        }
+    }
     void resetSamples() {                               // raycaster.hpp:105-116
+        flush();
         std::fill(colors.begin(), colors.end(), 0u);
         sample_count = 0;
     }
@@ -456,7 +680,27 @@ struct RayCasterT {
     bool use_god_rays = false;
     int gi_bounces = 1;                                 // 2 = extension
     uint32_t seed_lo = 0x5EED, seed_hi = 0, sample_count = 0;
+    uint32_t frame_index = 0;                           // frames rendered in blend mode (selects the random stream)
     vrt_render_stats last_stats{};
+
+private:
+    vrt_render_params shade_params() const {
+        vrt_render_params p;
+        std::memset(&p, 0, sizeof(p));
+        p.width = render_size.x; p.height = render_size.y; p.row_end = render_size.y; p.spp = 1;
+        p.seed_lo = seed_lo; p.seed_hi = seed_hi;
+        p.light_position[0] = light_position.x; p.light_position[1] = light_position.y; p.light_position[2] = light_position.z;
+        p.use_gi = use_gi; p.gi_bounces = gi_bounces; p.use_samples = use_samples;
+        return p;
+    }
+    uint32_t pending_count(uint32_t pixel) {            // samples of this pixel already queued in this batch
+        if (m_pending.empty()) m_pending.assign(size_t(render_size.x) * render_size.y, 0);
+        return m_pending[pixel]++;
+    }
+    std::vector<vrt_shade_job> m_jobs;
+    std::vector<uint16_t> m_pending;
+    uint32_t m_cast_counter = 0;
+    bool m_resolve_on_host = false;
 };
 constexpr uint8_t SVO_DEPTH = 9u;                       // raycaster.hpp:42
 using RayCaster = RayCasterT<SVO_DEPTH>;

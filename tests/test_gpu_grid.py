@@ -151,3 +151,46 @@ def test_grid_frame_rejects_gi(vrt, ctx, textures):
     rc.use_samples, rc.use_gi = True, True
     with pytest.raises(vrt.VrtError):
         rc.render(vrt.Camera(position=(4, 20, 4)), spp=1)
+
+
+def test_bordered_grid_dda_equals_the_generic_loops(vrt, ctx, port):
+    """The default DDA (one linear bit index on the bordered grid, no bounds tests: vrt_context_set_option grid_variant 0)
+    against the generic loops (grid_variant 1: flat, and with the fetch-skipping pyramid) and the oracle — random scene,
+    origins inside and outside, axis-parallel directions; and a grid long enough for the 2048-iteration cap of
+    grid_3d.hpp:70 to bind (a solid cell behind 2100 empty ones is NOT hit)."""
+    rng = np.random.default_rng(9)
+    cells = (rng.random((40, 24, 56)) < 0.01).astype(np.uint8)
+    n = 60000
+    o = rng.uniform(-3, 60, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d[:300, 2] = 0.0
+    d[300:600, 0] = -0.0
+    o[:600] = np.floor(o[:600])
+    want, steps = port.grid_cast(cells, o, d, threads=8)
+    for make in (lambda: vrt.Grid3D(ctx, cells), lambda: vrt.MipmapGrid3D(ctx, cells, mip_levels=3)):
+        scene = make()
+        records = []
+        for variant in (0, 1):
+            ctx.set_option("grid_variant", variant)
+            got = scene.cast_rays(o, d)
+            assert_hits_equal(got, want, hit_flag(got), "grid_variant %d" % variant)
+            assert scene.last_complexity() == int(steps.sum())
+            records.append(got.view(np.uint8).copy())
+        assert np.array_equal(records[0], records[1])
+        scene.close()
+    ctx.set_option("grid_variant", 0)
+    long_grid = np.zeros((4, 4, 2200), np.uint8)
+    long_grid[1, 1, 2100] = 1
+    long_grid[2, 2, 2000] = 1
+    oo = np.float32([[1.5, 1.5, 0.5], [2.5, 2.5, 0.5], [1.5, 1.5, 100.5]])
+    dd = np.float32([[0, 0, 1], [0, 0, 1], [0, 0, 1]])
+    want, steps = port.grid_cast(long_grid, oo, dd)
+    assert list(want["hit"]) == [0, 1, 1] and int(steps[0]) == 2048
+    for variant in (0, 1):
+        ctx.set_option("grid_variant", variant)
+        s = vrt.Grid3D(ctx, long_grid)
+        got = s.cast_rays(oo, dd)
+        assert_hits_equal(got, want, hit_flag(got), "cap, grid_variant %d" % variant)
+        assert s.last_complexity() == int(steps.sum())
+        s.close()
+    ctx.set_option("grid_variant", 0)

@@ -135,7 +135,7 @@ def test_checkerboard_frames(vrt, scene9, port, terrain9_nodes, textures, W, H, 
     for frame in range(4):
         rc.checker_board_offset = 1 - (frame & 1)
         img = rc.render(cam, spp=2 if use_samples else 1).copy()
-        p = port_params(W, H, 9, cam, default_light(), 1, 1, use_samples, 2 if use_samples else 1, offset=2 * frame if use_samples else 0)
+        p = port_params(W, H, 9, cam, default_light(), 1, 1, use_samples, 2 if use_samples else 1, offset=2 * frame if use_samples else frame)   # blend mode: frame k draws sample stream k
         p.checker, p.checker_area_height = 1 + (1 - (frame & 1)), area_height
         a, want, _ = port.render(terrain9_nodes, p, *textures, prev_rgba=prev)
         if use_samples:
