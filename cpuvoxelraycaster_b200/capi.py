@@ -28,7 +28,7 @@ class RenderParams(C.Structure):
                 ("light_position", C.c_float * 3), ("use_gi", C.c_int32), ("gi_bounces", C.c_int32),
                 ("use_samples", C.c_int32), ("accum_in", C.c_int32), ("tile_step", C.c_int32), ("tile_index", C.c_int32),
                 ("roughness", C.c_float), ("max_bounds", C.c_int32),
-                ("checker", C.c_int32), ("checker_area_height", C.c_int32), ("autofocus", C.c_int32)]
+                ("checker", C.c_int32), ("checker_area_height", C.c_int32), ("mirror_y1", C.c_int32), ("autofocus", C.c_int32)]
 
 
 class PresentParams(C.Structure):

@@ -614,6 +614,12 @@ int check_render_args(const vrt_scene* sc, const vrt_camera* cam, const vrt_rend
     if (p->tile_step > 1 && (p->tile_index < 0 || p->tile_index >= p->tile_step)) return fail(VRT_ERR_INVALID, std::string(who) + ": tile_index must be in [0, tile_step)");
     if (cam && !sc->has_tex) return fail(VRT_ERR_INVALID, std::string(who) + ": call vrt_scene_set_textures first (raycaster.hpp:53-54)");
     if (p->checker < 0 || p->checker > 2 || p->checker_area_height < 0) return fail(VRT_ERR_INVALID, std::string(who) + ": checker must be 0, 1 or 2 and checker_area_height >= 0");
+    if (cam && sc->kind == VRT_SCENE_LSVO && p->mirror_y1 != 0) {
+        if (p->mirror_y1 < 0 || p->mirror_y1 > (1 << sc->depth) || p->max_bounds < 0 || p->max_bounds > 16)
+            return fail(VRT_ERR_INVALID, std::string(who) + ": mirror_y1 must be 0..2^depth and max_bounds 0..16");
+        if (sc->use_compact || sc->ctx->render_variant == 1 || sc->ctx->render_variant == 3)
+            return fail(VRT_ERR_UNSUPPORTED, std::string(who) + ": mirror reflections need the reference node layout and render_variant 0, 2 or 4");
+    }
     if (cam && p->autofocus && sc->kind != VRT_SCENE_LSVO) return fail(VRT_ERR_UNSUPPORTED, std::string(who) + ": autofocus needs an LSVO scene");
     if (cam && p->checker && sc->kind == VRT_SCENE_LSVO && (sc->ctx->render_variant == 1 || sc->ctx->render_variant >= 3))
         return fail(VRT_ERR_UNSUPPORTED, std::string(who) + ": the checkerboard needs render_variant 0 or 2");
@@ -638,6 +644,7 @@ vrt::RenderLaunch make_launch(const vrt_scene* sc, const vrt_camera* cam, const 
     L.sort_bins1 = sc->ctx->sort_bins1; L.sort_bins2 = sc->ctx->sort_bins2;
     L.roughness = p->roughness;
     L.max_bounds = p->max_bounds;
+    L.mirror_y1 = sc->kind == VRT_SCENE_LSVO ? p->mirror_y1 : 0;
     L.checker = p->checker; L.checker_area_height = p->checker_area_height;
     L.focal = p->autofocus ? reinterpret_cast<const float*>(sc->d_counters + kFocalSlot) : nullptr;
     L.tile_step = p->tile_step > 1 ? p->tile_step : 1;

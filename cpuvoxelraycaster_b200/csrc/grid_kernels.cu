@@ -301,8 +301,8 @@ __device__ __forceinline__ void grid_dda_fast(const GridLevels& g, float ox, flo
         const bool xy = tmx < tmy;                                                             // :73-99
         p0 = xy && (tmx < tmz);
         p1 = !xy && (tmy < tmz);
-        if (p0) idx += dix; else if (p1) idx += diy; else idx += diz;
-        if ((__ldg(bits + (idx >> 5)) >> (idx & 31u)) & 1u) { stopped = true; break; }         // :103-104, or the border
+        idx += p0 ? dix : (p1 ? diy : diz);
+        if (__ldg(bits + (idx >> 5)) & (1u << (idx & 31u))) { stopped = true; break; }         // :103-104, or the border
         // t_max += t_d AFTER the exit test: when the loop stops, the un-incremented t_max of the stepped axis is the hit distance
         if (p0) tmx += tdx; else if (p1) tmy += tdy; else tmz += tdz;                          // :78,86,94
     }

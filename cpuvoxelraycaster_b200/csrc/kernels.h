@@ -61,7 +61,8 @@ struct RenderLaunch {
     const uint8_t* tex_top;    // 16x16 RGB, device
     const uint8_t* tex_side;
     float roughness;           // grid frames: blur of mirror reflections
-    int max_bounds;            // grid frames: reflection depth (RayCaster::max_bounds, raycaster.hpp:277)
+    int max_bounds;            // reflection depth (RayCaster::max_bounds, raycaster.hpp:277)
+    int mirror_y1;             // LSVO frames: 1 + y of the voxel layer whose top faces are Cell::Mirror; 0 = none
     const float* focal;        // device: focal length computed by the autofocus kernel, or null = cam.focal_length
     int checker;               // 0 = every pixel, 1 / 2 = checkerboard with offset 0 / 1 (main.cpp:137,143)
     int checker_area_height;   // thread-area height the checkerboard phase restarts at (0 = never)

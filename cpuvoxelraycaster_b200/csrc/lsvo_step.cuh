@@ -216,7 +216,8 @@ struct Trav2 {
         if (fabsf(dy_) < kEps) dy_ = copysignf(kEps, dy_);
         if (fabsf(dz_) < kEps) dz_ = copysignf(kEps, dz_);
         dx = dx_; dy = dy_; dz = dz_;
-        tcx = -1.0f / fabsf(dx); tcy = -1.0f / fabsf(dy); tcz = -1.0f / fabsf(dz);   // :47
+        // :47 — -1/|d| correctly rounded == -(correctly rounded 1/|d|): the reciprocal intrinsic is the shorter sequence
+        tcx = -__frcp_rn(fabsf(dx)); tcy = -__frcp_rn(fabsf(dy)); tcz = -__frcp_rn(fabsf(dz));
         tox = ox_ * tcx; toy = oy_ * tcy; toz = oz_ * tcz;                  // :48
         mirror = finite ? 7u : 15u;
         if (dx > 0.0f) { mirror ^= 1u; tox = 3.0f * tcx - tox; }           // :50-52

@@ -28,6 +28,9 @@ struct ChainState {
     uint32_t rnd_z, rnd_w;           // Philox words of dimensions 2,3 (GI bounce 1)
     uint8_t tex_r, tex_g, tex_b;     // albedo texel
     bool have_hit, gi0_hit, gi1_hit;
+    // mirror reflections (extension, kMirror kernels only): reflections so far, and their accumulated tint
+    float tint;
+    int bounds;
 };
 
 struct NextRay {
@@ -52,6 +55,7 @@ __device__ __forceinline__ void chain_begin(const RenderLaunch& L, ChainState& c
     c.rnd_z = rnd0.z; c.rnd_w = rnd0.w;
     c.light = 0.f; c.irr0 = 0.f; c.irr1 = 0.f;
     c.have_hit = false; c.gi0_hit = false; c.gi1_hit = false;
+    c.tint = 1.0f; c.bounds = 0;
     const float u0 = lattice(rnd0.x, -0.5f, 0.5f), u1 = lattice(rnd0.y, -0.5f, 0.5f);    // camera_controller.hpp:40
     float fx = lens_x, fy = lens_y, fz = L.cam.fov;                                     // :37-39
     normalize3(fx, fy, fz);
@@ -77,12 +81,40 @@ __device__ __forceinline__ bool gi_noise(float nx, float ny, float nz, float c1,
     return false;
 }
 
+// Word `dim & 3` of Philox block `dim >> 2` of the sample's stream, on getRand's lattice
+__device__ __forceinline__ float lattice_dim(const RenderLaunch& L, uint32_t pixel, uint32_t sample, uint32_t dim, float lo, float hi) {
+    const uint4 w = philox4x32_10(pixel, sample, dim >> 2, 0u, L.seed_lo, L.seed_hi);
+    const uint32_t word = (dim & 3u) == 0u ? w.x : ((dim & 3u) == 1u ? w.y : ((dim & 3u) == 2u ? w.z : w.w));
+    return lattice(word, lo, hi);
+}
+
 // The ray of stage `stage` ended with result (r, h).  Returns the next stage and, unless it is kDone, the next ray.
+// kMirror: mirror reflections on LSVO frames (extension specified in oracle/port.c, shade_sample): the top faces of the voxel
+// layer y = L.mirror_y1 - 1 are Cell::Mirror; a mirror hit re-enters kPrimary with the reflected, roughness-jittered ray.
+template <bool kMirror = false>
 __device__ __forceinline__ int chain_advance(const RenderLaunch& L, ChainState& c, int stage, const LsvoResult& r, const LsvoHit& h,
                                              uint32_t pixel, uint32_t sample, float SCALE, float n_norm, NextRay& nr) {
     switch (stage) {
         case kPrimary: {                                                   // raycaster.hpp:131-145
             if (!r.hit) return kDone;
+            if (kMirror) {
+                const int vy = int((h.corner[1] - 1.0f) * float(1 << L.depth));
+                if (c.bounds < L.max_bounds && vy == L.mirror_y1 - 1 && h.normal[1] != 0.0f && h.normal[0] == 0.0f && h.normal[2] == 0.0f) {
+                    nr.ox = h.pos[0] + h.normal[0] * SCALE * 0.001f;
+                    nr.oy = h.pos[1] + h.normal[1] * SCALE * 0.001f;
+                    nr.oz = h.pos[2] + h.normal[2] * SCALE * 0.001f;
+                    const uint32_t b = uint32_t(c.bounds);
+                    const float r0 = lattice_dim(L, pixel, sample, 8u + 3u * b, -0.5f, 0.5f);
+                    const float r1 = lattice_dim(L, pixel, sample, 9u + 3u * b, -0.5f, 0.5f);
+                    const float r2 = lattice_dim(L, pixel, sample, 10u + 3u * b, -0.5f, 0.5f);
+                    nr.dx = nr.dx + L.roughness * r0; nr.dy = -nr.dy + L.roughness * r1; nr.dz = nr.dz + L.roughness * r2;
+                    normalize3(nr.dx, nr.dy, nr.dz);
+                    nr.coef = 0.0f;
+                    c.tint = c.tint * 0.8f;
+                    ++c.bounds;
+                    return kPrimary;
+                }
+            }
             c.have_hit = true;
             c.nx = h.normal[0]; c.ny = h.normal[1]; c.nz = h.normal[2];
             const uint8_t* tex = (c.ny != 0.0f) ? L.tex_top : L.tex_side;  // :211-215
@@ -149,6 +181,7 @@ __device__ __forceinline__ int chain_advance(const RenderLaunch& L, ChainState& 
 }
 
 // Adds the finished sample's colour (raycaster.hpp:161-163) to the pixel sums (:87-90).
+template <bool kMirror = false>
 __device__ __forceinline__ void chain_colour(const RenderLaunch& L, const ChainState& c, uint32_t& sum_r, uint32_t& sum_g, uint32_t& sum_b) {
     if (!c.have_hit) return;                                               // ColorResult stays Black, :38
     float gi = 0.0f;
@@ -158,7 +191,11 @@ __device__ __forceinline__ void chain_colour(const RenderLaunch& L, const ChainS
         gi = fmaxf(0.0f, 1000000.0f * fminf(0.5f, irr * c.dot_gi0) / 1.0f);   // :201,:206
     }
     const float f = fminf(1.0f, fmaxf(0.0f, c.light + gi));                // :163
-    sum_r += mul_u8(c.tex_r, f); sum_g += mul_u8(c.tex_g, f); sum_b += mul_u8(c.tex_b, f);
+    if (kMirror) {
+        sum_r += mul_u8(mul_u8(c.tex_r, f), c.tint); sum_g += mul_u8(mul_u8(c.tex_g, f), c.tint); sum_b += mul_u8(mul_u8(c.tex_b, f), c.tint);
+    } else {
+        sum_r += mul_u8(c.tex_r, f); sum_g += mul_u8(c.tex_g, f); sum_b += mul_u8(c.tex_b, f);
+    }
 }
 
 }  // namespace vrt

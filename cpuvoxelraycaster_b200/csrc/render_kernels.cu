@@ -24,7 +24,7 @@ namespace vrt {
 // kLive: the interactive-loop extras (checkerboard pixel mapping, focal length read from the autofocus kernel's output).
 // Compiled out of the plain instantiation so that they cost the many-sample frames nothing (register allocation of the
 // traversal loop is sensitive to every extra live value: 73.9 vs 75.6 ms on cfg 4).
-template <typename Nodes, bool kLive>
+template <typename Nodes, bool kLive, bool kMirror = false>
 __global__ void __launch_bounds__(128, VRT_K4_MIN_CTAS) render_accumulate_kernel(Nodes nodes, RenderLaunch L, uint32_t* __restrict__ accum,
                                                                 unsigned long long* __restrict__ counters) {
     extern __shared__ uint2 smem[];
@@ -90,9 +90,9 @@ __global__ void __launch_bounds__(128, VRT_K4_MIN_CTAS) render_accumulate_kernel
                     cnt[(6 + stage) * 128] += r.complexity;
                     LsvoHit h;
                     if (r.hit) lsvo_finish(r, nr.ox, nr.oy, nr.oz, L.depth, h);
-                    stage = chain_advance(L, c, stage, r, h, pixel, sample, SCALE, n_norm, nr);
+                    stage = chain_advance<kMirror>(L, c, stage, r, h, pixel, sample, SCALE, n_norm, nr);
                 }
-                chain_colour(L, c, sum_r, sum_g, sum_b);
+                chain_colour<kMirror>(L, c, sum_r, sum_g, sum_b);
             }
         }
         // the Q lanes of a pixel add up their sums; lane sub == 0 commits them
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(128) sort_samples_kernel(RenderLaunch L, SortP
 
 // kTrav: 0 = the first traversal loop (Trav), 1 = Trav2, 2 = Trav2 with the cone test compiled out of the primary / sun-shadow
 // casts (they are cast with coef = 0).  Same operations per ray, identical results.
-template <typename Nodes, int kTrav>
+template <typename Nodes, int kTrav, bool kMirror = false>
 __global__ void __launch_bounds__(128, VRT_K5_MIN_CTAS) render_rounds_kernel(Nodes nodes, RenderLaunch L, BlockGeometry G,
                                                                             const uint16_t* __restrict__ lists, uint32_t* meta,
                                                                             uint32_t* next_block, uint32_t* __restrict__ accum,
@@ -475,9 +475,9 @@ __global__ void __launch_bounds__(128, VRT_K5_MIN_CTAS) render_rounds_kernel(Nod
                     cnt[(6 + stage) * 128] += r.complexity;
                     LsvoHit h;
                     if (r.hit) lsvo_finish(r, nr.ox, nr.oy, nr.oz, L.depth, h);
-                    stage = chain_advance(L, cs, stage, r, h, pixel, sample, SCALE, n_norm, nr);
+                    stage = chain_advance<kMirror>(L, cs, stage, r, h, pixel, sample, SCALE, n_norm, nr);
                 }
-                chain_colour(L, cs, cr, cg, cb);
+                chain_colour<kMirror>(L, cs, cr, cg, cb);
             }
             __syncwarp();
             // one atomic per pixel and channel: the lanes holding samples of the same pixel add up first
@@ -710,6 +710,7 @@ cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const
             kernel<<<grid6, block, smem, stream>>>(view, L, P.G, lists, meta, next_block, d_accum, d_counters);
         };
         if (compact) launch6(render_rounds_kernel<CompactNodes, 0>, CompactNodes{nodes});
+        else if (L.mirror_y1 > 0) launch6(render_rounds_kernel<RefNodes, 2, true>, RefNodes{nodes});
         else switch (L.trav_policy) {
             case 0: launch6(render_rounds_kernel<RefNodes, 0>, RefNodes{nodes}); break;
             case 1: launch6(render_rounds_kernel<RefNodes, 1>, RefNodes{nodes}); break;
@@ -764,7 +765,10 @@ cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const
     Lc.samples_per_warp = q;
     const unsigned grid = unsigned(tiles * chunks);
     const bool live = L.checker != 0 || L.focal != nullptr;
-    if (compact && live) render_accumulate_kernel<CompactNodes, true><<<grid, block, smem, stream>>>(CompactNodes{nodes}, Lc, d_accum, d_counters);
+    if (L.mirror_y1 > 0 && !compact) {
+        if (live) render_accumulate_kernel<RefNodes, true, true><<<grid, block, smem, stream>>>(RefNodes{nodes}, Lc, d_accum, d_counters);
+        else render_accumulate_kernel<RefNodes, false, true><<<grid, block, smem, stream>>>(RefNodes{nodes}, Lc, d_accum, d_counters);
+    } else if (compact && live) render_accumulate_kernel<CompactNodes, true><<<grid, block, smem, stream>>>(CompactNodes{nodes}, Lc, d_accum, d_counters);
     else if (compact) render_accumulate_kernel<CompactNodes, false><<<grid, block, smem, stream>>>(CompactNodes{nodes}, Lc, d_accum, d_counters);
     else if (live) render_accumulate_kernel<RefNodes, true><<<grid, block, smem, stream>>>(RefNodes{nodes}, Lc, d_accum, d_counters);
     else render_accumulate_kernel<RefNodes, false><<<grid, block, smem, stream>>>(RefNodes{nodes}, Lc, d_accum, d_counters);

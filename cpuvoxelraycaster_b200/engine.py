@@ -449,7 +449,8 @@ class RayCaster:
         self.use_gi = False
         self.use_samples = False
         self.gi_bounces = 1
-        self.roughness = 0.0            # grid volumes: blur of Cell::Mirror reflections (extension)
+        self.roughness = 0.0            # blur of Cell::Mirror reflections (extension)
+        self.mirror_y = None            # LSVO volumes: voxel layer (castRay y) whose top faces are mirrors; None = no mirrors
         self.max_bounds = 4             # raycaster.hpp:277
         self.checker_board_offset = None   # None = every pixel; 0 / 1 = the checkerboard of main.cpp:137,143
         self.checker_area_height = 0       # RENDER_HEIGHT / area_count (main.cpp:132); 0 = one area
@@ -483,6 +484,7 @@ class RayCaster:
         p.roughness, p.max_bounds = float(self.roughness), int(self.max_bounds)
         p.checker = 0 if self.checker_board_offset is None else 1 + (int(self.checker_board_offset) & 1)
         p.checker_area_height = int(self.checker_area_height)
+        p.mirror_y1 = 0 if self.mirror_y is None else int(self.mirror_y) + 1
         p.autofocus = int(bool(self.autofocus))
         return p
 

@@ -122,6 +122,7 @@ class FrameRenderer:
         self.frames_done = 0
         self.use_gi, self.gi_bounces, self.use_samples = False, 1, True
         self.roughness, self.max_bounds = 0.0, 4
+        self.mirror_y = None                                              # LSVO frames: mirror layer (vrt_render_params::mirror_y1 - 1)
         self.checker_board_offset, self.checker_area_height = None, 0     # main.cpp:137,143 / :132
         self.display = None                                               # denoised_tex of main.cpp:159-177
         self.autofocus = False                                            # device-side centre-ray focus, main.cpp:114-121
@@ -147,6 +148,7 @@ class FrameRenderer:
         p.roughness, p.max_bounds = float(self.roughness), int(self.max_bounds)
         p.checker = 0 if self.checker_board_offset is None else 1 + (int(self.checker_board_offset) & 1)
         p.checker_area_height = int(self.checker_area_height)
+        p.mirror_y1 = 0 if self.mirror_y is None else int(self.mirror_y) + 1
         p.autofocus = int(bool(self.autofocus))
         return p
 

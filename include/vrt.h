@@ -213,13 +213,17 @@ typedef struct vrt_render_params {
     int32_t accum_in;            /* vrt_render: 1 = `accum` holds earlier sums and is added to (progressive frames) */
     int32_t tile_step;           /* > 1: only 4-row tiles t (counted from row_begin) with t % tile_step == tile_index */
     int32_t tile_index;          /*      are rendered/resolved — the balanced multi-GPU row partition */
-    float roughness;             /* grid scenes: blur of Cell::Mirror reflections (0 = perfect mirror) */
-    int32_t max_bounds;          /* grid scenes: reflection depth, RayCaster::max_bounds = 4 (raycaster.hpp:277) */
+    float roughness;             /* blur of Cell::Mirror reflections (0 = perfect mirror) */
+    int32_t max_bounds;          /* reflection depth, RayCaster::max_bounds = 4 (raycaster.hpp:277) */
     int32_t checker;             /* 0 = every pixel; 1 / 2 = the checkerboard of main.cpp:137,143 with
                                   * checker_board_offset 0 / 1: pixel (x,y) is rendered iff
                                   * (y - area_start(y)) % 2 == (x + offset) % 2; other pixels keep their value */
     int32_t checker_area_height; /* height of the reference's thread areas (RENDER_HEIGHT / area_count, main.cpp:132;
                                   * 135 in the demo): area_start(y) = y - y % area_height.  0 = one area (start 0) */
+    int32_t mirror_y1;           /* LSVO scenes: 1 + y (castRay voxel coordinates) of the voxel layer whose TOP faces are
+                                  * Cell::Mirror (cell.hpp:8) — the LSVO has one shared cell (lsvo.hpp:21-23), so mirrors are a rule:
+                                  * e.g. the flat valley floors of the demo terrain.  A mirror hit reflects like on grid scenes
+                                  * (roughness, max_bounds, tint 0.8 per bounce).  0 = no mirrors */
     int32_t autofocus;           /* 1 = LSVO scenes: focal length from the centre ray, cast on the device in front of the
                                   * frame (Camera::getClosestPoint camera_controller.hpp:56-60 + main.cpp:114-121:
                                   * distance * 2^depth, or 100 on a miss); cam->focal_length is ignored.  No host

@@ -625,6 +625,7 @@ struct RayCasterT : vrt::PendingFlush {
         p.accum_in = use_samples ? 1 : 0;
         p.checker = checker_board_offset < 0 ? 0 : 1 + (checker_board_offset & 1);
         p.checker_area_height = checker_area_height;
+        p.mirror_y1 = mirror_y < 0 ? 0 : mirror_y + 1; p.roughness = roughness; p.max_bounds = int32_t(max_bounds);
         p.autofocus = autofocus ? 1 : 0;
         if (!use_samples) std::fill(colors.begin(), colors.end(), 0u);
         const vrt_camera c = camera.as_struct();
@@ -670,6 +671,8 @@ struct RayCasterT : vrt::PendingFlush {
     std::vector<uint8_t> display;                       // RGBA8: denoised_tex of main.cpp:168-172, made by present()
     int checker_board_offset = -1;                      // -1 = every pixel; 0 / 1 = the checkerboard of main.cpp:137,143
     int checker_area_height = 0;                        // RENDER_HEIGHT / area_count (main.cpp:132); 0 = one area
+    int mirror_y = -1;                                  // voxel layer (castRay y) whose top faces are Cell::Mirror; -1 = none (extension)
+    float roughness = 0.0f;                             // blur of mirror reflections
     bool autofocus = false;                             // focal length from the centre ray on the device (main.cpp:114-121)
     const LSVO<SVO_DEPTH_>& svo;
     const vrt::Vector2i render_size;
@@ -691,6 +694,7 @@ private:
         p.seed_lo = seed_lo; p.seed_hi = seed_hi;
         p.light_position[0] = light_position.x; p.light_position[1] = light_position.y; p.light_position[2] = light_position.z;
         p.use_gi = use_gi; p.gi_bounces = gi_bounces; p.use_samples = use_samples;
+        p.max_bounds = int32_t(max_bounds);
         return p;
     }
     uint32_t pending_count(uint32_t pixel) {            // samples of this pixel already queued in this batch

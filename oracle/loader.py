@@ -32,7 +32,7 @@ class PortRenderParams(C.Structure):
                 ("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32), ("sample_offset", C.c_int32),
                 ("row_begin", C.c_int32), ("row_end", C.c_int32), ("threads", C.c_int32),
                 ("tile_step", C.c_int32), ("tile_index", C.c_int32), ("roughness", C.c_float), ("max_bounds", C.c_int32),
-                ("checker", C.c_int32), ("checker_area_height", C.c_int32)]
+                ("checker", C.c_int32), ("checker_area_height", C.c_int32), ("mirror_y1", C.c_int32)]
 
 
 class PortRenderStats(C.Structure):

@@ -645,11 +645,34 @@ static void shade_sample(const shade_ctx* c, int32_t x, int32_t y, int32_t sampl
     float o[3], d[3];
     vo_camera_ray(p, x, y, sample, o, d);
     vo_hit h;
-    lsvo_cast_one(c->nodes, p->depth, p->guard, o, d, 0.0f, 0.0f, &h);                              /* :131 */
-    st->rays[0]++; st->complexity[0] += h.complexity;
-    rgb[0] = rgb[1] = rgb[2] = 0;                                                                   /* ColorResult: Black, :38 */
-    if (!h.hit) return;
     const float SCALE = 1.0f / (float)(1 << p->depth);                                              /* :123-124 */
+    rgb[0] = rgb[1] = rgb[2] = 0;                                                                   /* ColorResult: Black, :38 */
+    /* Mirror reflections on LSVO frames — an EXTENSION ("parity unpinned": Cell::Mirror cell.hpp:8, RayContext::bounds and
+     * max_bounds = 4 raycaster.hpp:13,127,277 exist, no code reflects).  The LSVO carries one shared Solid/Grass cell
+     * (lsvo.hpp:21-23), so mirrors are given by a rule: with mirror_y1 > 0 the TOP faces (normal along y only) of the voxels
+     * of layer y = mirror_y1 - 1 (castRay coordinates; the flat valley floors of the demo terrain are such a layer) are
+     * Cell::Mirror.  A mirror hit with bounds < max_bounds continues from hit + normal * SCALE * 0.001 (the shadow-ray
+     * offset of :139) with d.y negated, jittered by roughness * (r0, r1, r2) from dimensions 8+3b..10+3b of the sample's
+     * Philox stream and re-normalised, tint *= 0.8 — the rule of vo_grid_render.  Reflection rays count as class 0. */
+    float tint = 1.0f;
+    int bounds = 0;
+    for (;;) {
+        lsvo_cast_one(c->nodes, p->depth, p->guard, o, d, 0.0f, 0.0f, &h);                          /* :131 */
+        st->rays[0]++; st->complexity[0] += h.complexity;
+        if (!h.hit) return;
+        if (!(p->mirror_y1 > 0 && bounds < p->max_bounds && h.voxel[1] == p->mirror_y1 - 1 && h.normal[1] != 0.0f && h.normal[0] == 0.0f &&
+              h.normal[2] == 0.0f))
+            break;
+        for (int a = 0; a < 3; ++a) o[a] = h.position[a] + h.normal[a] * SCALE * 0.001f;
+        d[1] = -d[1];
+        const float r0 = lattice_rand(p, pixel, (uint32_t)sample, 8u + 3u * (uint32_t)bounds, -0.5f, 0.5f);
+        const float r1 = lattice_rand(p, pixel, (uint32_t)sample, 9u + 3u * (uint32_t)bounds, -0.5f, 0.5f);
+        const float r2 = lattice_rand(p, pixel, (uint32_t)sample, 10u + 3u * (uint32_t)bounds, -0.5f, 0.5f);
+        const v3 nd = norm3(v3_(d[0] + p->roughness * r0, d[1] + p->roughness * r1, d[2] + p->roughness * r2));
+        d[0] = nd.x; d[1] = nd.y; d[2] = nd.z;
+        tint = tint * 0.8f;
+        ++bounds;
+    }
     const v3 n = v3_(h.normal[0], h.normal[1], h.normal[2]);
     const v3 hp = v3_(h.position[0] + n.x * SCALE * 0.001f, h.position[1] + n.y * SCALE * 0.001f, h.position[2] + n.z * SCALE * 0.001f);   /* :139 */
     /* albedo: :141-145, :209-240 — the LSVO's single cell is Solid/Grass (lsvo.hpp:21-23) */
@@ -669,7 +692,7 @@ static void shade_sample(const shade_ctx* c, int32_t x, int32_t y, int32_t sampl
     float gi = 0.0f;
     if (p->use_gi) gi = maxf_(0.0f, 1000000.0f * gi_estimate(c, &h, pixel, (uint32_t)sample, 0, st) / 1.0f);   /* :161, :201, :206 */
     const float f = minf_(1.0f, maxf_(0.0f, light + gi));                                           /* :163 */
-    rgb[0] = mulc(texel[0], f); rgb[1] = mulc(texel[1], f); rgb[2] = mulc(texel[2], f);
+    rgb[0] = mulc(mulc(texel[0], f), tint); rgb[1] = mulc(mulc(texel[1], f), tint); rgb[2] = mulc(mulc(texel[2], f), tint);   /* tint = 1: identity */
 }
 
 static void render_range(void* c_, uint64_t b, uint64_t e) {

@@ -82,6 +82,7 @@ typedef struct vo_render_params {
     int32_t max_bounds;            /* vo_grid_render: reflection depth, RayCaster::max_bounds = 4 (raycaster.hpp:277) */
     int32_t checker;               /* 0 = all pixels; 1 / 2 = checker_board_offset 0 / 1 of main.cpp:137,143 */
     int32_t checker_area_height;   /* RENDER_HEIGHT / area_count (main.cpp:132); 0 = a single area */
+    int32_t mirror_y1;             /* vo_render: 1 + y of the voxel layer whose top faces are Cell::Mirror (extension, see port.c); 0 = none */
 } vo_render_params;
 
 typedef struct vo_render_stats {

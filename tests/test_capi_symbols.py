@@ -23,13 +23,31 @@ def test_library_exports_every_symbol(vrt):
     assert b"sm_100a" in lib.vrt_build_info()
 
 
-def test_struct_sizes(vrt):
+def test_struct_sizes(vrt, tmp_path):
+    """The ctypes mirrors have the layout of the C structs in include/vrt.h (sizes and the offsets of the last fields, taken
+    from a C program compiled against the header)."""
     import ctypes as C
-    assert vrt.HIT.itemsize == 64 and vrt.LNODE.itemsize == 8
-    assert C.sizeof(vrt.capi.Camera) == 15 * 4
-    assert C.sizeof(vrt.capi.RenderParams) == 22 * 4
-    assert C.sizeof(vrt.capi.PresentParams) == 4 * 4
-    assert C.sizeof(vrt.capi.RenderStats) == 12 * 8
+    import subprocess
+    src = tmp_path / "sizes.c"
+    src.write_text('''#include <stdio.h>
+#include <stddef.h>
+#include <vrt.h>
+int main(void) {
+    printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(vrt_hit), sizeof(vrt_lnode), sizeof(vrt_camera), sizeof(vrt_render_params),
+           offsetof(vrt_render_params, mirror_y1), offsetof(vrt_render_params, autofocus), sizeof(vrt_present_params), sizeof(vrt_render_stats),
+           sizeof(vrt_shade_job), sizeof(vrt_shade_result), offsetof(vrt_shade_job, direction));
+    return 0;
+}
+''')
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    RP = vrt.capi.RenderParams
+    want = [vrt.HIT.itemsize, vrt.LNODE.itemsize, C.sizeof(vrt.capi.Camera), C.sizeof(RP), RP.mirror_y1.offset, RP.autofocus.offset,
+            C.sizeof(vrt.capi.PresentParams), C.sizeof(vrt.capi.RenderStats), vrt.capi.SHADE_JOB.itemsize, vrt.capi.SHADE_RESULT.itemsize,
+            vrt.capi.SHADE_JOB.fields["direction"][1]]
+    assert got == want
+    assert vrt.HIT.itemsize == 64 and vrt.LNODE.itemsize == 8 and C.sizeof(RP) == 23 * 4
 
 
 def test_no_cpu_fallback_without_device(vrt):

@@ -300,3 +300,30 @@ def test_lane_mapping_is_exact(vrt, port, terrain9_nodes, textures, q, chunks, s
     assert np.array_equal(rc.colors, accum) and np.array_equal(img, rgba)
     assert rc.last_stats["rays"] == list(stats.rays) and rc.last_stats["complexity"] == list(stats.complexity)
     c.close()
+
+
+@pytest.mark.parametrize("spp,use_gi,bounces,roughness", [(2, 1, 2, 0.05), (16, 1, 2, 0.05), (16, 0, 1, 0.0), (3, 1, 1, 0.2)])
+def test_lsvo_mirror_reflections_match_oracle(vrt, scene9, port, terrain9_nodes, textures, spp, use_gi, bounces, roughness):
+    """Blurry mirror reflections on LSVO frames (extension specified in oracle/port.c shade_sample: the top faces of voxel layer
+    y = 240 — the flat valley floors of T(9) — are Cell::Mirror): accumulators, image and ray / loop-trip counts exact against
+    the oracle, through K4 (few samples) and K6 (>= 8 samples), with GI and depth of field on top."""
+    W, H = 192, 108
+    cam = vrt.Camera(position=(256, 200, 256), view_angle=(0.0, -0.6), aperture=0.3, focal_length=80.0)
+    rc = vrt.RayCaster(scene9, (W, H))
+    rc.setLightPosition(default_light())
+    rc.use_samples, rc.use_gi, rc.gi_bounces = True, bool(use_gi), bounces
+    rc.mirror_y, rc.roughness, rc.max_bounds = 240, roughness, 4
+    img = rc.render(cam, spp=spp)
+    p = port_params(W, H, 9, cam, default_light(), use_gi, bounces, True, spp)
+    p.mirror_y1, p.roughness, p.max_bounds = 241, roughness, 4
+    accum, rgba, stats = port.render(terrain9_nodes, p, *textures)
+    assert np.array_equal(rc.colors, accum)
+    assert np.array_equal(img, rgba)
+    assert rc.last_stats["rays"] == list(stats.rays) and rc.last_stats["complexity"] == list(stats.complexity)
+    assert stats.rays[0] > 1.05 * W * H * spp                    # reflection rays were cast (they count as class 0)
+    # without the rule the same call is the plain frame
+    plain = vrt.RayCaster(scene9, (W, H))
+    plain.setLightPosition(default_light())
+    plain.use_samples, plain.use_gi, plain.gi_bounces = True, bool(use_gi), bounces
+    plain.render(cam, spp=spp)
+    assert plain.last_stats["rays"][0] == W * H * spp and not np.array_equal(plain.render_image, img)

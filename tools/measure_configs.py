@@ -57,7 +57,7 @@ def measure(ctx, stream, want, iters=5, cfg5_rays=100_000_000, emit=None):
     tex = np.load(os.path.join(ROOT, "tests", "golden", "textures.npz"))
     results = []
 
-    def out(d):
+    def emit_line(d):
         results.append(d)
         if emit:
             emit(d)
@@ -71,7 +71,7 @@ def measure(ctx, stream, want, iters=5, cfg5_rays=100_000_000, emit=None):
         ms = timed(stream, lambda: fr.render_device(cam, 1), a.iters)
         st = fr.stats()
         rays = sum(st["rays"])
-        out(dict(cfg=1, what="T(9) LSVO, 1280x720, 1 spp, primary + sun shadow (K4 + resolve)", ms_per_frame=round(ms, 4),
+        emit_line(dict(cfg=1, what="T(9) LSVO, 1280x720, 1 spp, primary + sun shadow (K4 + resolve)", ms_per_frame=round(ms, 4),
                               rays=st["rays"][:2], mrays_s=round(rays / ms / 1e3, 1),
                               algo_GBs=round((8 * sum(st["complexity"]) + 64 * rays + 16 * 1280 * 720) / ms / 1e6, 1)))
         scene.close()
@@ -99,7 +99,7 @@ def measure(ctx, stream, want, iters=5, cfg5_rays=100_000_000, emit=None):
                 ms_flat = timed(stream, lambda: flat.cast_rays_device(do, dd, n, out2), a.iters)
                 line.update(ms_flat_grid=round(ms_flat, 4), identical_to_flat=bool(torch.equal(out, out2)))
                 flat.close()
-            out(line)
+            emit_line(line)
             scene.close()
             if cfg == 3:
                 # the configuration's frame: primary + sun shadow + blurry reflections off a Cell::Mirror lake that floods
@@ -121,7 +121,7 @@ def measure(ctx, stream, want, iters=5, cfg5_rays=100_000_000, emit=None):
                     ms = timed(stream, lambda: fr.render_device(cam, spp), a.iters)
                     st = fr.stats()
                     rays, steps = sum(st["rays"][:3]), sum(st["complexity"][:3])
-                    out(dict(cfg=3, what="T(%d) mip grid %d^3 with a mirror lake, %dx%d frame: primary + sun shadow + blurry reflections "
+                    emit_line(dict(cfg=3, what="T(%d) mip grid %d^3 with a mirror lake, %dx%d frame: primary + sun shadow + blurry reflections "
                                           "(roughness 0.06, max_bounds 4), %d spp" % (D, size, W, H, spp), ms_per_frame=round(ms, 4),
                                           rays=dict(primary=st["rays"][0], shadow=st["rays"][1], reflection=st["rays"][2]),
                                           mirror_cells=int(len(xs)), mrays_s=round(rays / ms / 1e3, 1), mean_steps=round(steps / max(rays, 1), 1),
@@ -151,7 +151,7 @@ def measure(ctx, stream, want, iters=5, cfg5_rays=100_000_000, emit=None):
             res[variant] = ms
         cx = scene.last_complexity()
         hits = int((out.view(n, 16)[:, 10] & 1).sum())
-        out(dict(cfg=5, what="T(12) LSVO 4096^3, %d random rays" % n, device_build_s=round(tb, 3), slots=n_slots,
+        emit_line(dict(cfg=5, what="T(12) LSVO 4096^3, %d random rays" % n, device_build_s=round(tb, 3), slots=n_slots,
                               ms_persistent_adaptive=round(res[1], 3), ms_one_thread_per_ray=round(res[0], 3),
                               mrays_s=round(n / res[1] / 1e3, 1), hit_fraction=round(hits / n, 4), mean_complexity=round(cx / n, 2),
                               algo_GBs=round((8 * cx + 64 * n) / res[1] / 1e6, 1)))
