@@ -132,7 +132,6 @@ int vrt_context_set_option(vrt_context* ctx, const char* key, int value) {
     else if (k == "samples_per_warp" && value >= 0 && value <= 32 && (value & (value - 1)) == 0) ctx->samples_per_warp = value;
     else if (k == "time_frame_kernels" && (value == 0 || value == 1)) ctx->time_frame_kernels = value != 0;
     else if (k == "grid_variant" && (value == 0 || value == 1)) ctx->grid_variant = value;
-    else if (k == "smem_top_nodes" && value >= 0 && value <= 20000) ctx->smem_top_nodes = value;
     else if (k == "refill_cast" && value >= 0 && value <= 32) ctx->refill_cast = value;
     else if (k == "refill_render" && value >= 1 && value <= 32) ctx->refill_render = value;
     else return fail(VRT_ERR_INVALID, "vrt_context_set_option: unknown key or value out of range: " + k);
@@ -555,8 +554,7 @@ int vrt_cast_rays_device(vrt_scene* sc, const float* d_origin, const float* d_di
                                                    sc->d_counters, ctx->stream));
             else
                 VRT_CUDA(vrt::launch_lsvo_cast_persistent(sc->use_compact ? sc->d_compact : sc->d_nodes, sc->use_compact, int(sc->depth), sc->guard, d_origin, d_dir, coef, bias, n,
-                                                          d_out, sc->d_counters, ctx->refill_cast, ctx->stream,
-                                                          sc->use_compact ? uint32_t(std::min<uint64_t>(uint64_t(ctx->smem_top_nodes), sc->n_compact)) : 0u));
+                                                          d_out, sc->d_counters, ctx->refill_cast, ctx->stream));
             ctx->launches += 1;
             return VRT_OK;
         case VRT_SCENE_GRID:

@@ -52,7 +52,6 @@ struct vrt_context {
     int samples_per_warp = 0;                  // K4: lanes sharing a pixel (power of two), 0 = automatic
     int refill_cast = 0, refill_render = 16;   // parked lanes that trigger a refill (1..32); cast: 0 = warp-adaptive
     DeviceBuffer scratch_in, scratch_out;   // host-variant staging
-    int smem_top_nodes = 0;                 // K1p on the compact layout: first nodes (top levels) staged in shared memory; 0 = off
     int grid_variant = 0;                   // 0 = bordered-grid DDA, 1 = generic loop (flat / fetch-skipping pyramid)
     bool time_frame_kernels = false;        // "time_frame_kernels": bracket the frame kernels of every accumulate call with events
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> frame_events;   // recorded, not yet taken (vrt_context_take_timings)

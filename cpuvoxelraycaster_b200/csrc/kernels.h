@@ -100,7 +100,7 @@ namespace vrt {
 // d_counters: cast: [0] Σ complexity, [1] work counter; render: [0..11] stats, [12] work counter — zeroed by the caller.
 cudaError_t launch_lsvo_cast_persistent(const uint2* nodes, bool compact, int depth, int guard, const float* d_origin, const float* d_dir,
                                         float coef, float bias, uint64_t n, vrt_hit* d_out, unsigned long long* d_counters,
-                                        int refill, cudaStream_t stream, uint32_t smem_top_nodes = 0);
+                                        int refill, cudaStream_t stream);
 cudaError_t launch_render_persistent(const uint2* nodes, const RenderLaunch& L, uint32_t* d_accum, unsigned long long* d_counters,
                                      int refill, cudaStream_t stream);
 // Grid frames: camera rays, DDA, mirror reflections, texture + sun shadow, accumulation (grid_kernels.cu)

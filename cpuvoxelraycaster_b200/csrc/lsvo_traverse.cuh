@@ -44,25 +44,6 @@ struct CompactNodes {
     }
 };
 
-// Compact layout with its first n_top nodes — the top octree levels: the array is breadth first — staged in shared memory
-// (north_star (1) "top octree levels staged in shared memory").  A/B'd on the incoherent-ray workload in tools/probe_cfg5.py.
-struct CompactTopNodes {
-    const uint2* __restrict__ slots;
-    const uint2* top;      // shared memory copy of slots[0 .. n_top)
-    uint32_t n_top;
-    __device__ __forceinline__ NodeView fetch(uint32_t id) const {
-        const uint2 w = id < n_top ? top[id] : __ldg(slots + id);
-        NodeView v;
-        v.raw = w.x;
-        v.child_base = w.y;
-        return v;
-    }
-    __device__ __forceinline__ uint32_t child(const NodeView& v, uint32_t slot) const {
-        const uint32_t interior = (v.raw >> 8) & ~(v.raw >> 16) & 0xffu;
-        return v.child_base + __popc(interior & ((1u << slot) - 1u));
-    }
-};
-
 // Traversal state at termination (what the epilogue needs).
 struct LsvoResult {
     float px, py, pz;      // cell low corner in the mirrored frame (un-mirrored by lsvo_finish)

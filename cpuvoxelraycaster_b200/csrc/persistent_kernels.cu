@@ -7,8 +7,6 @@
 // their next rays (shadow / GI / next sample / next pixel, or the next ray of the buffer) and resumes.
 // Every lane's arithmetic is exactly that of LSVO<D>::castRay / RayCaster::castRay in the reference
 // (see lsvo_step.cuh, render_kernels.cu), so results do not depend on the scheduling.
-#include <type_traits>
-
 #include "lsvo_step.cuh"
 #include "render_chain.cuh"
 
@@ -55,12 +53,6 @@ __global__ void __launch_bounds__(128, 4) lsvo_cast_persistent_kernel(Nodes node
                                                                       uint64_t n, vrt_hit* __restrict__ out,
                                                                       unsigned long long* __restrict__ counters, int refill) {
     extern __shared__ uint2 smem[];
-    if constexpr (std::is_same<Nodes, CompactTopNodes>::value) {          // stage the top of the tree behind the stacks
-        uint2* top = smem + (depth + 1) * 128;
-        for (uint32_t i = threadIdx.x; i < nodes.n_top; i += blockDim.x) top[i] = __ldg(nodes.slots + i);
-        nodes.top = top;
-        __syncthreads();
-    }
     nodes.slots = pin(nodes.slots);
     guard = pin(guard);
     Stack64s<128> stack = Stack64s<128>::make(smem + threadIdx.x, pin(kSvoMaxDepth - depth));
@@ -283,14 +275,9 @@ static int resident_blocks(K kernel, int block, size_t smem) {
 
 template <typename Nodes>
 static cudaError_t cast_persistent(Nodes nv, int depth, int guard, const float* d_origin, const float* d_dir, float coef, float bias,
-                                   uint64_t n, vrt_hit* d_out, unsigned long long* d_counters, int refill, cudaStream_t stream,
-                                   size_t extra_smem = 0) {
+                                   uint64_t n, vrt_hit* d_out, unsigned long long* d_counters, int refill, cudaStream_t stream) {
     const int block = 128;
-    const size_t smem = size_t(depth + 1) * block * 8 + extra_smem;
-    if (smem > 48 * 1024) {
-        cudaFuncSetAttribute(lsvo_cast_persistent_kernel<Nodes, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        cudaFuncSetAttribute(lsvo_cast_persistent_kernel<Nodes, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    }
+    const size_t smem = size_t(depth + 1) * block * 8;
     auto launch = [&](auto kernel) {
         uint64_t grid = uint64_t(resident_blocks(kernel, block, smem));
         const uint64_t need = (n + block - 1) / block;
@@ -305,11 +292,8 @@ static cudaError_t cast_persistent(Nodes nv, int depth, int guard, const float* 
 
 cudaError_t launch_lsvo_cast_persistent(const uint2* nodes, bool compact, int depth, int guard, const float* d_origin, const float* d_dir,
                                         float coef, float bias, uint64_t n, vrt_hit* d_out, unsigned long long* d_counters,
-                                        int refill, cudaStream_t stream, uint32_t smem_top_nodes) {
+                                        int refill, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    if (compact && smem_top_nodes)
-        return cast_persistent(CompactTopNodes{nodes, nullptr, smem_top_nodes}, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_counters,
-                               refill, stream, size_t(smem_top_nodes) * sizeof(uint2));
     return compact ? cast_persistent(CompactNodes{nodes}, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_counters, refill, stream)
                    : cast_persistent(RefNodes{nodes}, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_counters, refill, stream);
 }

@@ -177,13 +177,6 @@ def test_compact_layout_gives_identical_results(vrt, port, terrain9_nodes, textu
     assert s.info()["device_bytes"] < 1.2 * terrain9_nodes.nbytes       # reference copy + ~1/8
     compact = s.cast_rays(o, d, 0.25, 0.0)
     assert np.array_equal(ref_layout.view(np.uint8), compact.view(np.uint8))
-    for top in (1, 300, 4096, 20000):                                    # top of the tree staged in shared memory (K1p)
-        c.set_option("smem_top_nodes", top)
-        staged = s.cast_rays(o, d, 0.25, 0.0)
-        assert np.array_equal(ref_layout.view(np.uint8), staged.view(np.uint8)), top
-        staged0 = s.cast_rays(o[:5000], d[:5000])                        # the cone-free instantiation
-        assert np.array_equal(s.cast_rays(o[:5000], d[:5000]).view(np.uint8), staged0.view(np.uint8))
-    c.set_option("smem_top_nodes", 0)
     want = port.lsvo_cast(terrain9_nodes, 9, o[:50000], d[:50000], 0.25, 0.0, threads=8)
     assert_hits_equal(compact[:50000], want, hit_flag(compact[:50000]), "compact")
     # a frame through the compact layout

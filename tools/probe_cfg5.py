@@ -1,8 +1,9 @@
 """cfg 5 (LSVO 4096^3, incoherent random rays — the one memory-latency-visible workload): A/B of the node-memory design
 points north_star (1) names, all with identical hit records (checked by hash):
   layout 0 = the reference's LNode array (8 slots of 8 B per node), layout 1 = compact breadth-first array of live nodes
-  (8 B per node), + an L2 access-policy window over its front, + its first N nodes (the top octree levels) staged in shared
-  memory (vrt_context_set_option "smem_top_nodes"); kernels K1p (persistent, regenerating), K1 and K1b (one thread per ray).
+  (8 B per node), + an L2 access-policy window over its front; kernels K1p (persistent, regenerating), K1 and K1b (one
+  thread per ray).  The variant with the top octree levels staged in shared memory (option "smem_top_nodes", removed again)
+  was measured with this script at commit 71c5298: profiles/r02_probe_cfg5.txt, profiles/r02_summary.md.
 One JSON line per variant.  PROBE_RAYS overrides the ray count (default 1e8)."""
 import hashlib
 import json
@@ -31,14 +32,12 @@ def main():
     d /= d.norm(dim=1, keepdim=True)
     out = torch.empty(n * 16, dtype=torch.int32, device="cuda")
     torch.cuda.synchronize()
-    variants = [(0, 0, 0, 1), (1, 0, 0, 1), (1, 1, 0, 1), (1, 0, 512, 1), (1, 0, 2048, 1), (1, 0, 4096, 1), (1, 0, 8192, 1), (1, 1, 4096, 1),
-                (0, 0, 0, 0), (0, 0, 0, 2), (1, 0, 0, 0)]
+    variants = [(0, 0, 0, 1), (1, 0, 0, 1), (1, 1, 0, 1), (0, 0, 0, 0), (0, 0, 0, 2), (1, 0, 0, 0)]
     if only:
         variants = [tuple(int(x) for x in only.split(","))]
     ref = None
     for layout, l2, top, variant in variants:
         scene.set_layout(layout, l2)
-        ctx.set_option("smem_top_nodes", top)
         ctx.set_option("cast_variant", variant)
         reps = 1 if only else 3
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
@@ -55,7 +54,6 @@ def main():
         ref = ref or h
         print(json.dumps(dict(layout=layout, l2_window=l2, smem_top_nodes=top, cast_variant=variant, ms=round(ms, 3), grays_s=round(n / ms / 1e6, 3),
                               same_records=h == ref, trips=scene.last_complexity())), flush=True)
-    ctx.set_option("smem_top_nodes", 0)
     ctx.set_option("cast_variant", 1)
 
 
