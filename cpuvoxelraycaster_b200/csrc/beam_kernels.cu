@@ -1,0 +1,137 @@
+// Beam floors: a conservative start distance for the primary rays of every screen tile.
+//
+// Primary rays are 41 % of all loop trips of the headline frame (42 trips per ray): most of them walk through the empty air
+// between the camera and the terrain.  LSVO<D>::castRay (lsvo.hpp:33-172) starts at t_min = max(0, entry into the root cube)
+// (:54-57); starting it at any t_floor <= (the ray's hit distance) gives the SAME HitPoint — position, distance, normal,
+// voxel_coord are functions of the hit cell and of the plane through which the ray enters it, not of the path that led
+// there — as long as nothing solid lies before t_floor.  Only HitPoint::complexity (the trip count) gets smaller.
+//
+// So for every 8x8-pixel tile this kernel computes a RIGOROUS lower bound of the hit distance of every primary ray of the
+// tile (every pixel of the tile, every lens sample): the distance from the camera to the nearest non-empty octree node that
+// intersects the tile's frustum — a front-to-back search of the octree against the four side planes of the frustum.
+//   * a ray can only hit voxels, every voxel lies in the non-empty nodes of every level, and the ray stays inside the
+//     frustum of its tile, so the node it hits is among those the search sees (box-vs-plane tests only ever err towards
+//     "intersects");
+//   * depth of field: a lens sample starts at camera + r, |r| <= aperture / sqrt(2), and aims at the focal point of its
+//     pixel (camera_controller.hpp:37-42); at distance t it is within |r| * (1 + t / focal_length) of the pixel's centre
+//     ray, so the planes are moved outwards by that amount (evaluated at the node's far corner);
+//   * the search stops descending at nodes smaller than half the tile's footprint at their distance (a finer bound buys
+//     little) and the floor is the nearest such node's box distance minus the lens radius and one voxel of slack.
+// Unlike the cone-marching beam optimisation of Laine & Karras (which follows only the tile's corner rays and can step over
+// geometry that pokes into the beam between them), this bound holds for arbitrary voxel sets: frames are byte-identical with
+// and without it (tests/test_gpu_render.py::test_beam_floors_do_not_change_frames).
+#include "lsvo_traverse.cuh"
+#include "kernels.h"
+
+namespace vrt {
+
+namespace {
+
+struct BeamFrame {
+    int x, y, z;       // low corner of the node's cube, voxel units, castRay space
+    uint32_t node;     // slot index of the node
+    int level;         // cube edge = 1 << level
+};
+
+}  // namespace
+
+// One thread per tile.  floor[ty * tiles_x + tx] = t (normalised units, as castRay measures it) below which no primary ray of
+// the tile can hit anything.
+__global__ void __launch_bounds__(64) beam_floor_kernel(const uint2* __restrict__ slots, RenderLaunch L, int tile, int tiles_x, int tiles_y,
+                                                        int tile_y0, float* __restrict__ floor) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= tiles_x * tiles_y) return;
+    const int tx = id % tiles_x, ty = tile_y0 + id / tiles_x;
+    const float S = float(1 << L.depth);
+    // camera centre in voxel units of the castRay cube: (position * SCALE + 1 - 1) * S = position
+    const float cx = L.cam.position[0], cy = L.cam.position[1], cz = L.cam.position[2];
+    const float aspect = float(L.width) / float(L.height);
+    // the four corner directions of the tile in world space (not normalised): pixel (x, y) looks along (x/H - aspect/2, y/H - 1/2, fov)
+    float dir[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float px = float(tx * tile + ((k & 1) ? tile : 0)), py = float(ty * tile + ((k & 2) ? tile : 0));
+        const float lx = px / float(L.height) - aspect * 0.5f, ly = py / float(L.height) - 0.5f, lz = L.cam.fov;
+        const float* m = L.cam.rot_mat;
+        dir[k][0] = (m[0] * lx + m[1] * ly) + m[2] * lz;
+        dir[k][1] = (m[3] * lx + m[4] * ly) + m[5] * lz;
+        dir[k][2] = (m[6] * lx + m[7] * ly) + m[8] * lz;
+    }
+    // inward unit normals of the side planes: left (00,01), right (11,10), top (10,00), bottom (01,11), oriented by the opposite corner
+    float pn[4][3];
+    const int pa[4] = {0, 3, 1, 2}, pb[4] = {2, 1, 0, 3}, inside[4] = {1, 0, 2, 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float* a = dir[pa[k]];
+        const float* b = dir[pb[k]];
+        float nx = a[1] * b[2] - a[2] * b[1], ny = a[2] * b[0] - a[0] * b[2], nz = a[0] * b[1] - a[1] * b[0];
+        const float* q = dir[inside[k]];
+        if (nx * q[0] + ny * q[1] + nz * q[2] < 0.0f) { nx = -nx; ny = -ny; nz = -nz; }
+        const float inv = rsqrtf(nx * nx + ny * ny + nz * nz);
+        pn[k][0] = nx * inv; pn[k][1] = ny * inv; pn[k][2] = nz * inv;
+    }
+    // lens radius (voxels) and its growth with distance, with a little slack for the rounding of everything above
+    const float lens = fabsf(L.cam.aperture) * 0.70710678f * 1.01f + 0.01f;
+    const float focal = fmaxf(L.focal ? __ldg(L.focal) : L.cam.focal_length, 1e-3f);
+    const float lens_growth = lens / focal;
+    // footprint of the tile per unit distance (voxels per voxel): its diagonal
+    const float spread = float(tile) * 1.4142136f / float(L.height);
+
+    BeamFrame stack[96];
+    int sp = 0;
+    stack[sp++] = BeamFrame{0, 0, 0, 0u, L.depth};
+    float best = 3.0e9f;                                   // nearest qualifying node so far (voxels)
+    while (sp > 0) {
+        const BeamFrame f = stack[--sp];
+        const uint2 w = __ldg(slots + f.node);
+        const uint32_t child_mask = (w.x >> 8) & 0xffu, leaf_mask = (w.x >> 16) & 0xffu;
+        const int half = 1 << (f.level - 1);
+        // front to back: the octant on the camera's side first.  The stack is LIFO, so the octants are visited farthest first
+        // and the nearest is pushed last (terminal nodes update `best` at once, whatever the order).
+        const uint32_t near_upper = (cx >= float(f.x + half) ? 1u : 0u) | (cy >= float(f.y + half) ? 2u : 0u) | (cz >= float(f.z + half) ? 4u : 0u);
+#pragma unroll 1
+        for (int k = 7; k >= 0; --k) {
+            const uint32_t upper = uint32_t(k) ^ near_upper;
+            const uint32_t s = ~upper & 7u;                // slot bit clear = upper half (the tree stores the mirrored octant, lsvo.hpp:79)
+            if (!((child_mask >> s) & 1u)) continue;
+            const int bx = f.x + ((upper & 1u) ? half : 0), by = f.y + ((upper & 2u) ? half : 0), bz = f.z + ((upper & 4u) ? half : 0);
+            const float x0 = float(bx) - cx, y0 = float(by) - cy, z0 = float(bz) - cz, e = float(half);
+            // distance from the camera to the box (0 inside) and to its far corner
+            const float nxd = fmaxf(fmaxf(x0, -(x0 + e)), 0.0f), nyd = fmaxf(fmaxf(y0, -(y0 + e)), 0.0f), nzd = fmaxf(fmaxf(z0, -(z0 + e)), 0.0f);
+            const float d_min = sqrtf(nxd * nxd + nyd * nyd + nzd * nzd);
+            if (d_min >= best) continue;
+            const float fx = fmaxf(fabsf(x0), fabsf(x0 + e)), fy = fmaxf(fabsf(y0), fabsf(y0 + e)), fz = fmaxf(fabsf(z0), fabsf(z0 + e));
+            const float d_far = sqrtf(fx * fx + fy * fy + fz * fz);
+            const float slack = lens + lens_growth * d_far + 1e-3f * e + 1e-4f * d_far;
+            bool outside = false;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                // the box corner farthest along the inward normal
+                const float qx = pn[k][0] >= 0.0f ? x0 + e : x0, qy = pn[k][1] >= 0.0f ? y0 + e : y0, qz = pn[k][2] >= 0.0f ? z0 + e : z0;
+                if (pn[k][0] * qx + pn[k][1] * qy + pn[k][2] * qz < -slack) outside = true;
+            }
+            if (outside) continue;
+            const bool leaf = (leaf_mask >> s) & 1u;
+            if (leaf || f.level - 1 == 0 || e <= 0.5f * spread * d_min) {
+                best = d_min;                              // d_min < best here
+            } else if (sp < 96) {
+                stack[sp++] = BeamFrame{bx, by, bz, f.node + w.y + s, f.level - 1};
+            } else {
+                best = d_min;                              // stack full (cannot happen for depth <= 12): stay conservative
+            }
+        }
+    }
+    const float t = (best - lens - 1.0f) / S;              // castRay's t is distance in the unit cube's units
+    floor[id] = best > 2.9e9f ? 3.0f : fmaxf(0.0f, t - 1e-5f * fabsf(t));   // empty frustum: beyond the cube's diagonal
+}
+
+cudaError_t launch_beam_floor(const uint2* nodes, const RenderLaunch& L, int tile, float* d_floor, cudaStream_t stream) {
+    const int tiles_x = (L.width + tile - 1) / tile;
+    const int ty0 = L.row_begin / tile, ty1 = (L.row_end + tile - 1) / tile;
+    const int n = tiles_x * (ty1 - ty0);
+    if (n <= 0) return cudaSuccess;
+    beam_floor_kernel<<<(n + 63) / 64, 64, 0, stream>>>(nodes, L, tile, tiles_x, ty1 - ty0, ty0, d_floor + size_t(ty0) * tiles_x);
+    return cudaGetLastError();
+}
+
+}  // namespace vrt

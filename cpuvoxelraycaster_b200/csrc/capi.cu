@@ -132,6 +132,7 @@ int vrt_context_set_option(vrt_context* ctx, const char* key, int value) {
     else if (k == "samples_per_warp" && value >= 0 && value <= 32 && (value & (value - 1)) == 0) ctx->samples_per_warp = value;
     else if (k == "time_frame_kernels" && (value == 0 || value == 1)) ctx->time_frame_kernels = value != 0;
     else if (k == "grid_variant" && (value == 0 || value == 1)) ctx->grid_variant = value;
+    else if (k == "beam_tile" && value >= 0 && value <= 64) ctx->beam_tile = value;
     else if (k == "refill_cast" && value >= 0 && value <= 32) ctx->refill_cast = value;
     else if (k == "refill_render" && value >= 1 && value <= 32) ctx->refill_render = value;
     else return fail(VRT_ERR_INVALID, "vrt_context_set_option: unknown key or value out of range: " + k);
@@ -523,6 +524,7 @@ int vrt_scene_destroy(vrt_scene* sc) {
     sc->frame_accum.release();
     sc->frame_rgba.release();
     sc->frame_lists.release();
+    sc->beam_floor.release();
     delete sc;
     return VRT_OK;
 }
@@ -640,6 +642,7 @@ vrt::RenderLaunch make_launch(const vrt_scene* sc, const vrt_camera* cam, const 
     L.samples_per_warp = sc->ctx->samples_per_warp;
     L.mapping = sc->ctx->render_variant == 1 ? 0 : sc->ctx->render_variant;
     L.scratch = nullptr; L.scratch_bytes = 0;
+    L.beam_floor = nullptr; L.beam_shift = 0; L.beam_tiles_x = 0;
     L.trav_policy = sc->ctx->trav_policy;
     L.grid_variant = sc->ctx->grid_variant;
     L.sort_bins1 = sc->ctx->sort_bins1; L.sort_bins2 = sc->ctx->sort_bins2;
@@ -694,6 +697,21 @@ int vrt_render_accumulate_device(vrt_scene* sc, const vrt_camera* cam, const vrt
                                          ctx->stream));
     else if (ctx->render_variant != 1) {
         vrt::RenderLaunch L = make_launch(sc, cam, p);
+        // beam floors (beam_kernels.cu): conservative start distances of the camera rays, per screen tile.  Frames are
+        // identical with and without them; only the trip counts of the primary rays shrink.
+        if (ctx->beam_tile > 0 && !sc->use_compact && (ctx->render_variant == 0 || ctx->render_variant == 2 || ctx->render_variant == 4)) {
+            int shift = 0;
+            while ((1 << (shift + 1)) <= ctx->beam_tile) ++shift;
+            const int tile = 1 << shift, tiles_x = (p->width + tile - 1) / tile, tiles_y = (p->height + tile - 1) / tile;
+            const size_t bytes = size_t(tiles_x) * tiles_y * sizeof(float);
+            if (bytes > sc->beam_floor.bytes) VRT_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (sc->beam_floor.reserve(bytes) != cudaSuccess) return fail(VRT_ERR_OOM, "vrt_render_accumulate_device: beam floor allocation failed");
+            VRT_CUDA(vrt::launch_beam_floor(sc->d_nodes, L, tile, static_cast<float*>(sc->beam_floor.ptr), ctx->stream));
+            ctx->launches += 1;
+            L.beam_floor = static_cast<const float*>(sc->beam_floor.ptr);
+            L.beam_shift = shift;
+            L.beam_tiles_x = tiles_x;
+        }
         const size_t need = vrt::render_scratch_bytes(L);
         if (need) {
             if (need > sc->frame_lists.bytes) VRT_CUDA(cudaStreamSynchronize(ctx->stream));     // an earlier frame may still read the old buffer

@@ -52,6 +52,7 @@ struct vrt_context {
     int samples_per_warp = 0;                  // K4: lanes sharing a pixel (power of two), 0 = automatic
     int refill_cast = 0, refill_render = 16;   // parked lanes that trigger a refill (1..32); cast: 0 = warp-adaptive
     DeviceBuffer scratch_in, scratch_out;   // host-variant staging
+    int beam_tile = 8;                      // LSVO frames: edge of the screen tiles that get a beam floor (beam_kernels.cu); 0 = off
     int grid_variant = 0;                   // 0 = bordered-grid DDA, 1 = generic loop (flat / fetch-skipping pyramid)
     bool time_frame_kernels = false;        // "time_frame_kernels": bracket the frame kernels of every accumulate call with events
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> frame_events;   // recorded, not yet taken (vrt_context_take_timings)
@@ -78,6 +79,7 @@ struct vrt_scene {
     bool has_tex = false;
     DeviceBuffer frame_accum, frame_rgba;       // vrt_render staging
     DeviceBuffer frame_lists;                   // K6: sorted sample lists of the frame in flight
+    DeviceBuffer beam_floor;                    // per-tile start distances of the camera rays of the frame in flight
     // Grid3D / MipmapGrid3D / SVO: bit-packed occupancy pyramid
     vrt::GridLevels grid{};
     uint32_t* d_grid_bits = nullptr;

@@ -53,6 +53,8 @@ struct RenderLaunch {
     void* scratch;               // K6: device scratch for the sorted sample lists (render_scratch_bytes)
     size_t scratch_bytes;
     int mapping;                 // 0 = automatic (K5 for many-sample GI frames, else K4), 2 = K4, 3 = K5
+    const float* beam_floor;     // LSVO frames: per-tile start distance of the camera rays (beam_kernels.cu), or null
+    int beam_shift, beam_tiles_x;  // tile edge = 1 << beam_shift pixels; tiles per row
     int grid_variant;            // grid frames: 0 = bordered-grid DDA (default), 1 = generic loop
     int trav_policy;             // K6 traversal loop: 0 = Trav, 1 = Trav2, 2 = Trav2 without the cone test on coef-0 rays (default)
     uint32_t seed_lo, seed_hi;
@@ -80,6 +82,8 @@ __host__ __device__ inline int checker_x_parity(int checker, int area_height, in
 size_t render_scratch_bytes(const RenderLaunch& L);
 cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const RenderLaunch& L, uint32_t* d_accum,
                                          unsigned long long* d_counters, cudaStream_t stream);
+// per-tile conservative start distances of the camera rays of rows [row_begin, row_end) (beam_kernels.cu); tile = 4, 8, 16 ...
+cudaError_t launch_beam_floor(const uint2* nodes, const RenderLaunch& L, int tile, float* d_floor, cudaStream_t stream);
 // RayCaster::castRay for explicit rays (vrt_shade_rays)
 cudaError_t launch_shade_rays(const uint2* nodes, bool compact, const RenderLaunch& L, uint64_t n, const vrt_shade_job* d_jobs,
                               vrt_shade_result* d_out, cudaStream_t stream);

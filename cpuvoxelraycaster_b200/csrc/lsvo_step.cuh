@@ -208,7 +208,10 @@ struct Trav2 {
     uint32_t parent, child, mirror, face;
     bool hit;
 
-    __device__ __forceinline__ void init(float ox_, float oy_, float oz_, float dx_, float dy_, float dz_, float coef_, float bias_) {
+    // t_floor: the walk starts at max(t_floor, entry into the root cube) instead of max(0, ...) (:57).  Any t_floor below the
+    // ray's hit distance leaves the HitPoint unchanged except for its complexity (beam_kernels.cu); 0 = the reference.
+    __device__ __forceinline__ void init(float ox_, float oy_, float oz_, float dx_, float dy_, float dz_, float coef_, float bias_,
+                                         float t_floor = 0.0f) {
         const bool finite = (((ox_ * 0.0f + oy_ * 0.0f) + oz_ * 0.0f) + ((dx_ * 0.0f + dy_ * 0.0f) + dz_ * 0.0f)) == 0.0f;
         if (!finite) { ox_ = 3.0f; oy_ = 3.0f; oz_ = 3.0f; dx_ = 1.0f; dy_ = 1.0f; dz_ = 1.0f; }
         coef = coef_; bias = bias_;
@@ -226,7 +229,7 @@ struct Trav2 {
         t_min = fmaxf(2.0f * tcx - tox, fmaxf(2.0f * tcy - toy, 2.0f * tcz - toz));   // :54
         t_max = fminf(tcx - tox, fminf(tcy - toy, tcz - toz));                         // :55
         h = t_max;
-        t_min = fmaxf(0.0f, t_min);
+        t_min = fmaxf(t_floor, t_min);                                     // :57 with t_floor = 0
         t_max = fminf(1.0f, t_max);
         parent = 0u; child = 0u; face = 0u;
         sf = 0.5f;                                                         // scale = 22
@@ -312,9 +315,9 @@ struct Trav2 {
 
 template <bool kCone, typename Nodes, typename Stack>
 __device__ __forceinline__ void lsvo_cast_ray2(const Nodes& nodes, Stack& stack, int guard, float guard_sf, float ox, float oy, float oz,
-                                               float dx, float dy, float dz, float coef, float bias, LsvoResult& r) {
+                                               float dx, float dy, float dz, float coef, float bias, LsvoResult& r, float t_floor = 0.0f) {
     Trav2<kCone> t;
-    t.init(ox, oy, oz, dx, dy, dz, coef, bias);
+    t.init(ox, oy, oz, dx, dy, dz, coef, bias, t_floor);
     while (t.step(nodes, stack, guard, guard_sf)) {}
     t.result(r);
 }

@@ -35,7 +35,13 @@ struct ChainState {
 
 struct NextRay {
     float ox, oy, oz, dx, dy, dz, coef;
+    float t_floor;   // conservative start distance (beam_kernels.cu): primary rays only, 0 for every other ray
 };
+
+// the beam floor of pixel (x, y), or 0 when the launch has none
+__device__ __forceinline__ float beam_floor_of(const RenderLaunch& L, int x, int y) {
+    return L.beam_floor ? __ldg(L.beam_floor + (y >> L.beam_shift) * L.beam_tiles_x + (x >> L.beam_shift)) : 0.0f;
+}
 
 __device__ __forceinline__ uint8_t mul_u8(uint8_t c, float f) {       // mult(sf::Color&, float), utils.cpp:43-48
     return uint8_t(fminf(255.0f, float(c) * f));
@@ -70,6 +76,7 @@ __device__ __forceinline__ void chain_begin(const RenderLaunch& L, ChainState& c
     nr.oy = (L.cam.position[1] + wy) * SCALE + 1.0f;
     nr.oz = (L.cam.position[2] + wz) * SCALE + 1.0f;
     nr.coef = 0.0f;
+    nr.t_floor = 0.0f;
 }
 
 // tangent-plane noise of getGlobalIllumination (raycaster.hpp:178-190); false when the normal is all zero
@@ -94,6 +101,7 @@ __device__ __forceinline__ float lattice_dim(const RenderLaunch& L, uint32_t pix
 template <bool kMirror = false>
 __device__ __forceinline__ int chain_advance(const RenderLaunch& L, ChainState& c, int stage, const LsvoResult& r, const LsvoHit& h,
                                              uint32_t pixel, uint32_t sample, float SCALE, float n_norm, NextRay& nr) {
+    nr.t_floor = 0.0f;                                                     // only camera rays have a beam floor
     switch (stage) {
         case kPrimary: {                                                   // raycaster.hpp:131-145
             if (!r.hit) return kDone;

@@ -81,10 +81,11 @@ __global__ void __launch_bounds__(128, VRT_K4_MIN_CTAS) render_accumulate_kernel
                 ChainState c;
                 NextRay nr;
                 chain_begin(L, c, pixel, sample, lens_x, lens_y, SCALE, focal_length, nr);
+                nr.t_floor = beam_floor_of(L, x, y);
                 int stage = kPrimary;
                 while (stage != kDone) {
                     LsvoResult r;
-                    if (stage < kGi0) lsvo_cast_ray2<false>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, 0.0f, 0.0f, r);
+                    if (stage < kGi0) lsvo_cast_ray2<false>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, 0.0f, 0.0f, r, nr.t_floor);
                     else lsvo_cast_ray2<true>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
                     cnt[stage * 128] += 1u;
                     cnt[(6 + stage) * 128] += r.complexity;
@@ -460,6 +461,7 @@ __global__ void __launch_bounds__(128, VRT_K5_MIN_CTAS) render_rounds_kernel(Nod
                 ChainState cs;
                 NextRay nr;
                 chain_begin(L, cs, pixel, sample, lens_x, lens_y, SCALE, focal_length, nr);
+                if constexpr (kTrav == 2) nr.t_floor = beam_floor_of(L, x, y);
                 int stage = kPrimary;
                 while (stage != kDone) {
                     LsvoResult r;
@@ -468,7 +470,7 @@ __global__ void __launch_bounds__(128, VRT_K5_MIN_CTAS) render_rounds_kernel(Nod
                     } else if constexpr (kTrav == 1) {
                         lsvo_cast_ray2<true>(nodes, stack2, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
                     } else {
-                        if (stage < kGi0) lsvo_cast_ray2<false>(nodes, stack2, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, 0.0f, 0.0f, r);
+                        if (stage < kGi0) lsvo_cast_ray2<false>(nodes, stack2, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, 0.0f, 0.0f, r, nr.t_floor);
                         else lsvo_cast_ray2<true>(nodes, stack2, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
                     }
                     cnt[stage * 128] += 1u;
@@ -560,6 +562,7 @@ __global__ void __launch_bounds__(128) shade_rays_kernel(Nodes nodes, RenderLaun
     nr.ox = job.start[0]; nr.oy = job.start[1]; nr.oz = job.start[2];
     nr.dx = job.direction[0]; nr.dy = job.direction[1]; nr.dz = job.direction[2];
     nr.coef = 0.0f;
+    nr.t_floor = 0.0f;
     int stage = kPrimary;
     float distance = 0.0f;
     uint32_t complexity = 0u;

@@ -100,6 +100,12 @@ int vrt_context_set_stream(vrt_context* ctx, void* stream);
  *   "samples_per_warp"  frame kernel: lanes of a warp sharing one pixel, power of two <= 32 (0 = automatic)
  *   "trav_policy" (default 2): traversal loop of the K6 frame kernel — 0 = Trav (round-1 loop), 1 = Trav2 (bookkeeping moved
  *                    off the ALU pipe), 2 = Trav2 with the cone test compiled out of the coef-0 casts; results identical
+ *   "beam_tile" (default 8): LSVO frames — edge in pixels (power of two) of the screen tiles for which a conservative start
+ *                    distance of the camera rays is computed in front of the frame (a front-to-back search of the octree
+ *                    against each tile's frustum, cpuvoxelraycaster_b200/csrc/beam_kernels.cu).  Frames are byte-identical
+ *                    with and without it; the trip counts (complexity) of the primary rays shrink.  0 = off: every ray
+ *                    starts where the reference starts it (lsvo.hpp:54-57) and vrt_render_stats equals the reference's counts
+ *   "grid_variant" (default 0): dense grids — 0 = DDA on the bordered bit grid, 1 = the generic loop / fetch-skipping pyramid
  *   "time_frame_kernels"  see vrt_context_take_timings */
 int vrt_context_set_option(vrt_context* ctx, const char* key, int value);
 /* number of kernel launches this context has enqueued so far (bench.py's gpu_launches) */

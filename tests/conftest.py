@@ -93,6 +93,10 @@ def ctx(vrt):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     c = vrt.Context(0)
+    # The shared context renders frames WITHOUT beam floors, so that vrt_render_stats carries the reference's own loop-trip
+    # counts (HitPoint::complexity) and can be compared with the oracle's; the beam floors (on by default in the product) are
+    # tested on their own: tests/test_gpu_render.py::test_beam_floors_do_not_change_frames and the full-size tests.
+    c.set_option("beam_tile", 0)
     yield c
     c.close()
 

@@ -110,6 +110,7 @@ def test_cfg4_headline_frame_is_kernel_independent(vrt, textures):
     for variant in (0, 2, 3):
         c = vrt.Context(0)
         c.set_option("render_variant", variant)
+        c.set_option("beam_tile", 0)                     # K5 has no beam floors: compare the reference trip counts
         s = vrt.LSVO.from_terrain(c, 11)
         s.set_textures(*textures)
         cam = vrt.Camera(position=(S / 2, S / 2 - 56, S / 2), view_angle=(0, 0), aperture=0.5)
@@ -204,6 +205,17 @@ def test_cfg4_headline_frame_crop_vs_oracle(vrt, ctx, port, textures, rows):
     assert not r.colors[:y0].any() and not r.colors[y1:].any()
     assert r.last_stats["rays"] == list(want_st.rays) and r.last_stats["complexity"] == list(want_st.complexity)
     assert r.last_stats["rays"][0] == W * (y1 - y0) * spp and r.last_stats["rays"][4] > 0
+    # the product default: beam floors on — same pixels and ray counts, fewer loop trips on the primary rays only
+    for tile in (8, 4):
+        ctx.set_option("beam_tile", tile)
+        b = vrt.RayCaster(s, (W, H))
+        b.setLightPosition(light)
+        b.use_samples, b.use_gi, b.gi_bounces = True, True, 2
+        b.render(cam, spp, rows[0], rows[1])
+        assert np.array_equal(b.colors, r.colors) and np.array_equal(b.render_image, r.render_image)
+        assert b.last_stats["rays"] == r.last_stats["rays"] and b.last_stats["complexity"][1:] == r.last_stats["complexity"][1:]
+        assert b.last_stats["complexity"][0] < 0.8 * r.last_stats["complexity"][0]
+    ctx.set_option("beam_tile", 0)
     s.close()
 
 

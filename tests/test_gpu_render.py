@@ -327,3 +327,60 @@ def test_lsvo_mirror_reflections_match_oracle(vrt, scene9, port, terrain9_nodes,
     plain.use_samples, plain.use_gi, plain.gi_bounces = True, bool(use_gi), bounces
     plain.render(cam, spp=spp)
     assert plain.last_stats["rays"][0] == W * H * spp and not np.array_equal(plain.render_image, img)
+
+
+def _frame(vrt, scene, size, cam, light, spp, use_gi=True, bounces=2, mirror_y=None):
+    rc = vrt.RayCaster(scene, size)
+    rc.setLightPosition(light)
+    rc.use_samples, rc.use_gi, rc.gi_bounces = True, use_gi, bounces
+    rc.mirror_y, rc.roughness = mirror_y, 0.05
+    rc.render(cam, spp=spp)
+    return rc.colors.copy(), rc.last_stats
+
+
+@pytest.mark.parametrize("position,view,aperture,focal", [((256, 200, 256), (0.3, -0.35), 0.5, 60.0), ((256, 200, 256), (0.0, 0.0), 0.0, 100.0),
+                                                          ((256, 200, 256), (0.0, -0.6), 2.0, 30.0), ((300, 230, 120), (2.1, -0.1), 0.5, 200.0),
+                                                          ((256, 262, 256), (0.5, 0.2), 0.5, 80.0), ((256, 200, 256), (0.0, 1.2), 1.0, 5.0)])
+def test_beam_floors_do_not_change_frames(vrt, ctx, scene9, position, view, aperture, focal):
+    """The per-tile start distances of the camera rays (beam_kernels.cu; on by default in the product, off in this test
+    context) must be conservative for every pixel and every lens sample: accumulators, ray counts and the trip counts of all
+    secondary rays are identical with tiles of 4, 8, 16 and 32 pixels and without; only the primary rays' trip count shrinks.
+    Cameras: the demo's, grazing, looking down / up, wide aperture with a short focal length, close to the ground, under it."""
+    cam = vrt.Camera(position=position, view_angle=view, aperture=aperture, focal_length=focal)
+    for size, spp in (((200, 113), 3), ((128, 72), 16)):          # K4 and K6
+        ctx.set_option("beam_tile", 0)
+        want, st0 = _frame(vrt, scene9, size, cam, default_light(), spp, mirror_y=240)
+        for tile in (4, 8, 16, 32):
+            ctx.set_option("beam_tile", tile)
+            got, st = _frame(vrt, scene9, size, cam, default_light(), spp, mirror_y=240)
+            assert np.array_equal(got, want), (size, tile)
+            assert st["rays"] == st0["rays"] and st["complexity"][1:] == st0["complexity"][1:]
+            assert st["complexity"][0] <= st0["complexity"][0]
+        ctx.set_option("beam_tile", 0)
+
+
+def test_beam_floors_on_a_random_voxel_scene(vrt, ctx, textures):
+    """Thin, scattered geometry (6000 random voxels at depth 6, and a depth-9 scene of isolated voxels and 1-voxel columns): the
+    case in which a corner-ray beam optimisation steps over geometry.  Frames identical with and without the floors."""
+    g = golden("lsvo_random6.npz")
+    rng = np.random.default_rng(3)
+    sparse = np.concatenate([rng.integers(0, 512, (3000, 3)), np.stack([np.full(400, 100), np.arange(400), np.full(400, 300)], 1),
+                             np.stack([np.arange(60, 460), np.full(400, 250), np.full(400, 257)], 1)]).astype(np.uint32)
+    for depth, nodes, cams in ((6, g["nodes"], [((120, 100, -40), (0.3, 0.2)), ((32, 32, 32), (1.0, 0.4)), ((-30, 20, 10), (0.9, 0.1))]),
+                               (9, vrt.host_build_lsvo_from_voxels(9, sparse), [((256, 256, -100), (0.0, 0.0)), ((20, 20, 20), (0.7, 0.5))])):
+        s = vrt.LSVO(ctx, nodes, depth)
+        s.set_textures(*textures)
+        light = np.float32([-200, -1000, -300]) * np.float32(1.0 / (1 << depth)) + np.float32(1.0)
+        for position, view in cams:
+            cam = vrt.Camera(position=position, view_angle=view, aperture=0.7, focal_length=40.0)
+            for size, spp in (((160, 90), 2), ((96, 54), 16)):
+                ctx.set_option("beam_tile", 0)
+                want, st0 = _frame(vrt, s, size, cam, light, spp)
+                assert st0["rays"][1] > 0                      # something is hit
+                for tile in (4, 8, 16):
+                    ctx.set_option("beam_tile", tile)
+                    got, st = _frame(vrt, s, size, cam, light, spp)
+                    assert np.array_equal(got, want), (depth, position, size, tile)
+                    assert st["rays"] == st0["rays"] and st["complexity"][1:] == st0["complexity"][1:]
+        ctx.set_option("beam_tile", 0)
+        s.close()

@@ -17,6 +17,7 @@ import cpuvoxelraycaster_b200 as vrt  # noqa: E402
 from cpuvoxelraycaster_b200.frame import FrameRenderer  # noqa: E402
 
 TAG = os.environ.get("PROBE_TAG", "current")
+BEAMS = [int(x) for x in os.environ.get("PROBE_BEAMS", "0,4,8,16,32").split(",")]
 
 
 def time_frame(fr, cs, p, stream, reps=3):
@@ -64,11 +65,16 @@ def main():
             for pol in policies:
                 if pol is not None:
                     ctx.set_option("trav_policy", pol)
-                ms = time_frame(fr, cs, p, stream)
-                st = fr.stats()
-                h = hashlib.sha256(fr.accum.cpu().numpy().tobytes()).hexdigest()[:16]
-                print(json.dumps(dict(tag=TAG, what="K6 frame", world=world, gi=gi, bounces=bounces, policy=pol, ms=round(ms, 3),
-                                      rays=sum(st["rays"]), trips=sum(st["complexity"]), hash=h)), flush=True)
+                for beam in (BEAMS if pol in (2, None) else [0]):
+                    have_beam = set_opt(ctx, "beam_tile", beam)
+                    if beam and not have_beam:
+                        continue
+                    ms = time_frame(fr, cs, p, stream)
+                    st = fr.stats()
+                    h = hashlib.sha256(fr.accum.cpu().numpy().tobytes()).hexdigest()[:16]
+                    print(json.dumps(dict(tag=TAG, what="K6 frame", world=world, gi=gi, bounces=bounces, policy=pol, beam_tile=beam, ms=round(ms, 3),
+                                          rays=sum(st["rays"]), trips=sum(st["complexity"]), primary_trips=st["complexity"][0], hash=h)), flush=True)
+            set_opt(ctx, "beam_tile", 8)
     if policies[0] is not None:
         ctx.set_option("trav_policy", 2)
     # batched casts
