@@ -83,6 +83,7 @@ _SIGNATURES = {
     "vrt_render": (C.c_int, [_vp, C.POINTER(Camera), C.POINTER(RenderParams), _vp, _vp, C.POINTER(RenderStats)]),
     "vrt_scene_last_render_stats": (C.c_int, [_vp, C.POINTER(RenderStats)]),
     "vrt_shade_rays": (C.c_int, [_vp, C.POINTER(RenderParams), _u64, _vp, _vp]),
+    "vrt_beam_floors": (C.c_int, [_vp, C.POINTER(Camera), C.POINTER(RenderParams), _i32, _vp]),
     "vrt_autofocus": (C.c_int, [_vp, C.POINTER(Camera), C.POINTER(_f)]),
     "vrt_lsvo_create_from_voxels": (C.c_int, [_vp, _u32, _vp, _u64, _i32, C.POINTER(_vp)]),
     "vrt_scene_set_cells": (C.c_int, [_vp, _vp, _u64, _i32]),

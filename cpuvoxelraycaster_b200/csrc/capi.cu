@@ -769,6 +769,26 @@ int vrt_shade_rays(vrt_scene* sc, const vrt_render_params* p, uint64_t n, const 
     return VRT_OK;
 }
 
+int vrt_beam_floors(vrt_scene* sc, const vrt_camera* cam, const vrt_render_params* p, int32_t tile, float* out) {
+    if (!sc || !cam || !p || !out) return fail(VRT_ERR_INVALID, "vrt_beam_floors: NULL argument");
+    if (sc->kind != VRT_SCENE_LSVO || sc->use_compact) return fail(VRT_ERR_UNSUPPORTED, "vrt_beam_floors: needs an LSVO scene in the reference layout");
+    if (tile < 1 || tile > 64 || (tile & (tile - 1))) return fail(VRT_ERR_INVALID, "vrt_beam_floors: tile must be a power of two, 1..64");
+    if (p->width <= 0 || p->height <= 0 || p->width > 65536 || p->height > 65536) return fail(VRT_ERR_INVALID, "vrt_beam_floors: bad frame size");
+    vrt_context* ctx = sc->ctx;
+    if (int s = use_device(ctx)) return s;
+    const int tiles_x = (p->width + tile - 1) / tile, tiles_y = (p->height + tile - 1) / tile;
+    const size_t bytes = size_t(tiles_x) * tiles_y * sizeof(float);
+    if (bytes > sc->beam_floor.bytes) VRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (sc->beam_floor.reserve(bytes) != cudaSuccess) return fail(VRT_ERR_OOM, "vrt_beam_floors: device allocation failed");
+    vrt_render_params q = *p;
+    q.row_begin = 0; q.row_end = p->height; q.autofocus = 0;
+    VRT_CUDA(vrt::launch_beam_floor(sc->d_nodes, make_launch(sc, cam, &q), tile, static_cast<float*>(sc->beam_floor.ptr), ctx->stream));
+    ctx->launches += 1;
+    VRT_CUDA(cudaMemcpyAsync(out, sc->beam_floor.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    VRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VRT_OK;
+}
+
 int vrt_scene_last_render_stats(vrt_scene* sc, vrt_render_stats* stats) {
     if (!sc || !stats) return fail(VRT_ERR_INVALID, "vrt_scene_last_render_stats: NULL argument");
     if (int s = use_device(sc->ctx)) return s;

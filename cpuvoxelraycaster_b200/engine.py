@@ -507,6 +507,14 @@ class RayCaster:
         self.last_stats = dict(rays=list(stats.rays), complexity=list(stats.complexity))
         return self.render_image
 
+    def beam_floors(self, camera, tile=8):
+        """Diagnostic (vrt_beam_floors): per-tile start distances of the camera rays, float32 [tiles_y, tiles_x]."""
+        W, H = self.render_size
+        tx, ty = (W + tile - 1) // tile, (H + tile - 1) // tile
+        out = np.zeros((ty, tx), np.float32)
+        check(lib().vrt_beam_floors(self.svo.handle, C.byref(camera.as_struct()), C.byref(self.params(1)), int(tile), ptr(out)))
+        return out
+
     def present(self, median=0, old_value_conservation=None):
         """The presentation step of the main loop (src/main.cpp:159-177): optional 3x3 / 5x5 median
         (res/median_3.frag, res/median.frag) and the persistence blend into `display`."""

@@ -260,6 +260,10 @@ int vrt_render_resolve_device(vrt_scene* scene, const vrt_render_params* p, cons
 int vrt_render(vrt_scene* scene, const vrt_camera* cam, const vrt_render_params* p, uint8_t* rgba, uint32_t* accum,
                vrt_render_stats* stats);
 int vrt_scene_last_render_stats(vrt_scene* scene, vrt_render_stats* stats);
+/* Diagnostic: the beam floors a frame with these parameters would use (context option "beam_tile"): out[ty * tiles_x + tx],
+ * tiles_x = ceil(width / tile), for every tile of the frame — the distance (castRay units) below which no camera ray of the
+ * tile (any pixel, any lens sample) can hit anything; 3.0 = nothing in the tile's frustum.  No reference counterpart. */
+int vrt_beam_floors(vrt_scene* scene, const vrt_camera* cam, const vrt_render_params* p, int32_t tile, float* out);
 
 /* RayCaster::castRay (raycaster.hpp:118-167) for explicit rays — the call the reference's per-pixel loop makes through
  * renderRay (raycaster.hpp:67-92) with the ray Camera::getRay produced (main.cpp:147-149): start and direction in the

@@ -84,6 +84,18 @@ def textures():
 def vrt():
     import cpuvoxelraycaster_b200 as v
     v.capi.lib()   # raises if libvrt.so is missing: no fallback
+    # Every context a test creates renders frames WITHOUT beam floors unless the test turns them on: vrt_render_stats then
+    # carries the reference's own loop-trip counts (HitPoint::complexity) and can be compared with the oracle's.  The beam
+    # floors (on by default in the product — the C++ test programs run with them) are tested on their own:
+    # tests/test_gpu_render.py::test_beam_floors_*, tests/test_gpu_fullsize.py.
+    if not getattr(v.Context, "_tests_patched", False):
+        plain_init = v.Context.__init__
+
+        def init_without_beam(self, *a, **k):
+            plain_init(self, *a, **k)
+            self.set_option("beam_tile", 0)
+        v.Context.__init__ = init_without_beam
+        v.Context._tests_patched = True
     return v
 
 
@@ -92,11 +104,7 @@ def ctx(vrt):
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
-    c = vrt.Context(0)
-    # The shared context renders frames WITHOUT beam floors, so that vrt_render_stats carries the reference's own loop-trip
-    # counts (HitPoint::complexity) and can be compared with the oracle's; the beam floors (on by default in the product) are
-    # tested on their own: tests/test_gpu_render.py::test_beam_floors_do_not_change_frames and the full-size tests.
-    c.set_option("beam_tile", 0)
+    c = vrt.Context(0)          # beam floors off, see the `vrt` fixture
     yield c
     c.close()
 

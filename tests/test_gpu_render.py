@@ -384,3 +384,32 @@ def test_beam_floors_on_a_random_voxel_scene(vrt, ctx, textures):
                     assert st["rays"] == st0["rays"] and st["complexity"][1:] == st0["complexity"][1:]
         ctx.set_option("beam_tile", 0)
         s.close()
+
+
+@pytest.mark.parametrize("aperture,focal,view", [(0.0, 100.0, (0.3, -0.35)), (0.5, 60.0, (0.3, -0.35)), (2.0, 20.0, (0.0, -0.1))])
+def test_beam_floors_are_below_every_primary_hit(vrt, ctx, scene9, port, terrain9_nodes, aperture, focal, view):
+    """The invariant itself: for every tile, floor <= the hit distance of every camera ray of the tile — checked against the
+    ORACLE's primary hits for all pixels and 20 lens samples each — and the floors are
+    not trivial: on average they skip more than a third of the way to the nearest hit of the tile."""
+    W, H = 160, 90
+    cam = vrt.Camera(position=(256, 200, 256), view_angle=view, aperture=aperture, focal_length=focal)
+    rc = vrt.RayCaster(scene9, (W, H))
+    rc.setLightPosition(default_light())
+    p = port_params(W, H, 9, cam, default_light(), 0, 1, True, 1)
+    # the oracle's camera rays, sample by sample (Philox lattice)
+    o, d = [], []
+    for y in range(H):
+        for x in range(W):
+            for smp in range(20):
+                oo, dd = port.camera_ray(p, x, y, smp)
+                o.append(oo)
+                d.append(dd)
+    o, d = np.array(o, np.float32), np.array(d, np.float32)
+    hits = port.lsvo_cast(terrain9_nodes, 9, o, d, threads=8)
+    t_hit = np.where(hits["hit"] != 0, hits["distance"], np.float32(10.0)).reshape(H, W, 20).min(-1)
+    for tile in (4, 8, 16):
+        fl = rc.beam_floors(cam, tile)
+        per_pixel = np.repeat(np.repeat(fl, tile, 0), tile, 1)[:H, :W]
+        assert (per_pixel <= t_hit).all(), (tile, float((per_pixel - t_hit).max()))
+        tight = per_pixel[t_hit < 10] / t_hit[t_hit < 10]
+        assert tight.mean() > 0.35, (tile, float(tight.mean()))

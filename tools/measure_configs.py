@@ -151,9 +151,17 @@ def measure(ctx, stream, want, iters=5, cfg5_rays=100_000_000, emit=None):
             res[variant] = ms
         cx = scene.last_complexity()
         hits = int((out.view(n, 16)[:, 10] & 1).sum())
+        # end to end through vrt_cast_rays with HOST buffers: 24 B per ray in, 64 B per hit record out over PCIe (pageable numpy)
+        ne = min(n, 10_000_000)
+        ho, hd = o[:ne].cpu().numpy(), d[:ne].cpu().numpy()
+        scene.cast_rays(ho[:1000], hd[:1000])
+        t0 = time.time()
+        scene.cast_rays(ho, hd)
+        e2e_s = time.time() - t0
         emit_line(dict(cfg=5, what="T(12) LSVO 4096^3, %d random rays" % n, device_build_s=round(tb, 3), slots=n_slots,
                               ms_persistent_adaptive=round(res[1], 3), ms_one_thread_per_ray=round(res[0], 3),
                               mrays_s=round(n / res[1] / 1e3, 1), hit_fraction=round(hits / n, 4), mean_complexity=round(cx / n, 2),
+                              e2e_host_buffers=dict(rays=ne, ms=round(e2e_s * 1e3, 1), mrays_s=round(ne / e2e_s / 1e6, 1), bytes_per_ray=88),
                               algo_GBs=round((8 * cx + 64 * n) / res[1] / 1e6, 1)))
         scene.close()
         ctx.set_option("cast_variant", 1)
