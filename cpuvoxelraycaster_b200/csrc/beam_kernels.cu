@@ -70,6 +70,14 @@ __global__ void __launch_bounds__(64) beam_floor_kernel(const uint2* __restrict_
         const float inv = rsqrtf(nx * nx + ny * ny + nz * nz);
         pn[k][0] = nx * inv; pn[k][1] = ny * inv; pn[k][2] = nz * inv;
     }
+    // fifth plane: in front of the camera.  Without it a box BEHIND the camera passes the side-plane tests whenever the frustum
+    // there is narrower than the lens slack (small tiles): sky tiles would "see" the ground behind the camera and lose their skip
+    float fwd[3] = {dir[0][0] + dir[1][0] + dir[2][0] + dir[3][0], dir[0][1] + dir[1][1] + dir[2][1] + dir[3][1],
+                    dir[0][2] + dir[1][2] + dir[2][2] + dir[3][2]};
+    {
+        const float inv = rsqrtf(fwd[0] * fwd[0] + fwd[1] * fwd[1] + fwd[2] * fwd[2]);
+        fwd[0] *= inv; fwd[1] *= inv; fwd[2] *= inv;
+    }
     // lens radius (voxels) and its growth with distance, with a little slack for the rounding of everything above
     const float lens = fabsf(L.cam.aperture) * 0.70710678f * 1.01f + 0.01f;
     const float focal = fmaxf(L.focal ? __ldg(L.focal) : L.cam.focal_length, 1e-3f);
@@ -109,6 +117,10 @@ __global__ void __launch_bounds__(64) beam_floor_kernel(const uint2* __restrict_
                 // the box corner farthest along the inward normal
                 const float qx = pn[k][0] >= 0.0f ? x0 + e : x0, qy = pn[k][1] >= 0.0f ? y0 + e : y0, qz = pn[k][2] >= 0.0f ? z0 + e : z0;
                 if (pn[k][0] * qx + pn[k][1] * qy + pn[k][2] * qz < -slack) outside = true;
+            }
+            {   // every ray point is r + t * u with t >= 0 and u within the tile: dot(fwd, p) >= -|r| for all of them
+                const float qx = fwd[0] >= 0.0f ? x0 + e : x0, qy = fwd[1] >= 0.0f ? y0 + e : y0, qz = fwd[2] >= 0.0f ? z0 + e : z0;
+                if (fwd[0] * qx + fwd[1] * qy + fwd[2] * qz < -slack) outside = true;
             }
             if (outside) continue;
             const bool leaf = (leaf_mask >> s) & 1u;

@@ -366,22 +366,24 @@ def test_beam_floors_on_a_random_voxel_scene(vrt, ctx, textures):
     rng = np.random.default_rng(3)
     sparse = np.concatenate([rng.integers(0, 512, (3000, 3)), np.stack([np.full(400, 100), np.arange(400), np.full(400, 300)], 1),
                              np.stack([np.arange(60, 460), np.full(400, 250), np.full(400, 257)], 1)]).astype(np.uint32)
-    for depth, nodes, cams in ((6, g["nodes"], [((120, 100, -40), (0.3, 0.2)), ((32, 32, 32), (1.0, 0.4)), ((-30, 20, 10), (0.9, 0.1))]),
+    for depth, nodes, cams in ((6, g["nodes"], [((32, 32, -60), (0.0, 0.0)), ((32, 30, -20), (0.2, 0.1)), ((10, 20, 5), (0.7, 0.3))]),
                                (9, vrt.host_build_lsvo_from_voxels(9, sparse), [((256, 256, -100), (0.0, 0.0)), ((20, 20, 20), (0.7, 0.5))])):
         s = vrt.LSVO(ctx, nodes, depth)
         s.set_textures(*textures)
         light = np.float32([-200, -1000, -300]) * np.float32(1.0 / (1 << depth)) + np.float32(1.0)
+        seen = 0
         for position, view in cams:
             cam = vrt.Camera(position=position, view_angle=view, aperture=0.7, focal_length=40.0)
             for size, spp in (((160, 90), 2), ((96, 54), 16)):
                 ctx.set_option("beam_tile", 0)
                 want, st0 = _frame(vrt, s, size, cam, light, spp)
-                assert st0["rays"][1] > 0                      # something is hit
+                seen += st0["rays"][1]
                 for tile in (4, 8, 16):
                     ctx.set_option("beam_tile", tile)
                     got, st = _frame(vrt, s, size, cam, light, spp)
                     assert np.array_equal(got, want), (depth, position, size, tile)
                     assert st["rays"] == st0["rays"] and st["complexity"][1:] == st0["complexity"][1:]
+        assert seen > 1000, depth                              # the cameras do look at the voxels
         ctx.set_option("beam_tile", 0)
         s.close()
 
