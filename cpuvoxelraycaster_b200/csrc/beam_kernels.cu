@@ -16,7 +16,9 @@
 //     pixel (camera_controller.hpp:37-42); at distance t it is within |r| * (1 + t / focal_length) of the pixel's centre
 //     ray, so the planes are moved outwards by that amount (evaluated at the node's far corner);
 //   * the search stops descending at nodes smaller than half the tile's footprint at their distance (a finer bound buys
-//     little) and the floor is the nearest such node's box distance minus the lens radius and one voxel of slack.
+//     little) and the floor is the nearest such node's box distance minus the lens radius and two voxels of slack; every ray
+//     lowers it further by the stretch over which its own plane crossings are numerically uncertain (render_chain.cuh,
+//     beam_floor_of).
 // Unlike the cone-marching beam optimisation of Laine & Karras (which follows only the tile's corner rays and can step over
 // geometry that pokes into the beam between them), this bound holds for arbitrary voxel sets: frames are byte-identical with
 // and without it (tests/test_gpu_render.py::test_beam_floors_do_not_change_frames).
@@ -42,6 +44,13 @@ __global__ void __launch_bounds__(64) beam_floor_kernel(const uint2* __restrict_
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= tiles_x * tiles_y) return;
     const int tx = id % tiles_x, ty = tile_y0 + id / tiles_x;
+    if (L.tile_step > 1) {                                 // multi-GPU tile split: only tiles that contain rows this rank renders
+        bool mine = false;
+        for (int row = ty * tile; row < ty * tile + tile; row += 4)
+            mine = mine || (((row - L.row_begin) >> 2) % L.tile_step == L.tile_index);
+        if (tile < 4) mine = ((ty * tile - L.row_begin) >> 2) % L.tile_step == L.tile_index;
+        if (!mine) return;
+    }
     const float S = float(1 << L.depth);
     // camera centre in voxel units of the castRay cube: (position * SCALE + 1 - 1) * S = position
     const float cx = L.cam.position[0], cy = L.cam.position[1], cz = L.cam.position[2];
@@ -133,7 +142,7 @@ __global__ void __launch_bounds__(64) beam_floor_kernel(const uint2* __restrict_
             }
         }
     }
-    const float t = (best - lens - 1.0f) / S;              // castRay's t is distance in the unit cube's units
+    const float t = (best - lens - 2.0f) / S;              // castRay's t is distance in the unit cube's units; two voxels of slack
     floor[id] = best > 2.9e9f ? 3.0f : fmaxf(0.0f, t - 1e-5f * fabsf(t));   // empty frustum: beyond the cube's diagonal
 }
 

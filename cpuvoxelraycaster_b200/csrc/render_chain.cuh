@@ -38,9 +38,19 @@ struct NextRay {
     float t_floor;   // conservative start distance (beam_kernels.cu): primary rays only, 0 for every other ray
 };
 
-// the beam floor of pixel (x, y), or 0 when the launch has none
-__device__ __forceinline__ float beam_floor_of(const RenderLaunch& L, int x, int y) {
-    return L.beam_floor ? __ldg(L.beam_floor + (y >> L.beam_shift) * L.beam_tiles_x + (x >> L.beam_shift)) : 0.0f;
+// The beam floor of a camera ray of pixel (x, y) with direction d, or 0 when the launch has none.
+// The tile's floor is lowered per ray by kPlaneSlack / min|d|: castRay computes the time at which a ray crosses a cell plane as
+// p * (-1/|d|) - o * (-1/|d|) (lsvo.hpp:47-48,76) — for a direction component near zero the two products are huge and cancel, so
+// which side of a plane the walk believes the ray to be on is uncertain within ~4e-7 of the plane, and a ray that runs
+// nearly parallel to a plane stays inside that band for a stretch of 4e-7 / |d| in t.  Inside the band a walk that starts at
+// t_floor can take the other side than the walk from 0 did, and then reports the hit cell's other face (measured on the
+// oracle: ~1e-6 of the horizon rays at |d| < 1e-3, none once the start lies a band length before the hit —
+// profiles/r02_summary.md).  Rays with a zero component get no floor at all.
+constexpr float kPlaneSlack = 1.6e-5f;
+__device__ __forceinline__ float beam_floor_of(const RenderLaunch& L, int x, int y, float dx, float dy, float dz) {
+    if (!L.beam_floor) return 0.0f;
+    const float tile_floor = __ldg(L.beam_floor + (y >> L.beam_shift) * L.beam_tiles_x + (x >> L.beam_shift));
+    return fmaxf(0.0f, tile_floor - kPlaneSlack / fminf(fabsf(dx), fminf(fabsf(dy), fabsf(dz))));
 }
 
 __device__ __forceinline__ uint8_t mul_u8(uint8_t c, float f) {       // mult(sf::Color&, float), utils.cpp:43-48

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(128, VRT_K4_MIN_CTAS) render_accumulate_kernel
                 ChainState c;
                 NextRay nr;
                 chain_begin(L, c, pixel, sample, lens_x, lens_y, SCALE, focal_length, nr);
-                nr.t_floor = beam_floor_of(L, x, y);
+                nr.t_floor = beam_floor_of(L, x, y, nr.dx, nr.dy, nr.dz);
                 int stage = kPrimary;
                 while (stage != kDone) {
                     LsvoResult r;
@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(128, VRT_K5_MIN_CTAS) render_rounds_kernel(Nod
                 ChainState cs;
                 NextRay nr;
                 chain_begin(L, cs, pixel, sample, lens_x, lens_y, SCALE, focal_length, nr);
-                if constexpr (kTrav == 2) nr.t_floor = beam_floor_of(L, x, y);
+                if constexpr (kTrav == 2) nr.t_floor = beam_floor_of(L, x, y, nr.dx, nr.dy, nr.dz);
                 int stage = kPrimary;
                 while (stage != kDone) {
                     LsvoResult r;
