@@ -28,6 +28,29 @@ using vrt::fail;
 using vrt::use_device;
 
 
+namespace {
+// (re)computes the bounds of the solid voxels of an LSVO scene from its node array (reference layout) — after creation and
+// after every edit.  Synchronises the stream.
+int update_bounds(vrt_scene* sc, const char* who) {
+    vrt_context* ctx = sc->ctx;
+    void* work = nullptr;
+    float* d_bounds = nullptr;
+    cudaError_t e = cudaMalloc(&work, vrt::bounds_work_bytes());
+    if (e == cudaSuccess) e = cudaMalloc(&d_bounds, 6 * sizeof(float));
+    if (e == cudaSuccess) e = vrt::device_scene_bounds(sc->d_nodes, int(sc->depth), 2.0f, d_bounds, work, ctx->stream);
+    float host[6];
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host, d_bounds, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (work) cudaFree(work);
+    if (d_bounds) cudaFree(d_bounds);
+    ctx->launches += 2 * sc->depth + 1;
+    if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? fail(VRT_ERR_OOM, std::string(who) + ": device allocation failed (scene bounds)") : cuda_fail(e, who);
+    for (int a = 0; a < 3; ++a) { sc->bounds.lo[a] = host[a]; sc->bounds.hi[a] = host[3 + a]; }
+    return VRT_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int vrt_abi_version(void) { return VRT_ABI_VERSION; }
@@ -133,6 +156,7 @@ int vrt_context_set_option(vrt_context* ctx, const char* key, int value) {
     else if (k == "time_frame_kernels" && (value == 0 || value == 1)) ctx->time_frame_kernels = value != 0;
     else if (k == "grid_variant" && (value == 0 || value == 1)) ctx->grid_variant = value;
     else if (k == "beam_tile" && value >= 0 && value <= 64) ctx->beam_tile = value;
+    else if (k == "bounds_exit" && (value == 0 || value == 1)) ctx->bounds_exit = value;
     else if (k == "refill_cast" && value >= 0 && value <= 32) ctx->refill_cast = value;
     else if (k == "refill_render" && value >= 1 && value <= 32) ctx->refill_render = value;
     else return fail(VRT_ERR_INVALID, "vrt_context_set_option: unknown key or value out of range: " + k);
@@ -227,6 +251,7 @@ int vrt_lsvo_create(vrt_context* ctx, const vrt_lnode* nodes, uint64_t n_nodes, 
                                               : cuda_fail(e, "vrt_lsvo_create");
     }
     sc->device_bytes = n_nodes * sizeof(uint2);
+    if (int s = update_bounds(sc, "vrt_lsvo_create")) { vrt_scene_destroy(sc); return s; }
     *out = sc;
     return VRT_OK;
 }
@@ -252,6 +277,7 @@ int vrt_lsvo_create_terrain(vrt_context* ctx, uint32_t depth, int32_t guard, vrt
                                               : cuda_fail(e, "vrt_lsvo_create_terrain");
     }
     sc->device_bytes = sc->n_nodes * sizeof(uint2);
+    if (int s = update_bounds(sc, "vrt_lsvo_create_terrain")) { vrt_scene_destroy(sc); return s; }
     *out = sc;
     return VRT_OK;
 }
@@ -284,6 +310,7 @@ int vrt_lsvo_create_heightfield(vrt_context* ctx, uint32_t depth, const int32_t*
                                               : cuda_fail(e, "vrt_lsvo_create_heightfield");
     }
     sc->device_bytes = sc->n_nodes * sizeof(uint2) + columns * sizeof(int32_t);
+    if (int s = update_bounds(sc, "vrt_lsvo_create_heightfield")) { vrt_scene_destroy(sc); return s; }
     *out = sc;
     return VRT_OK;
 }
@@ -325,6 +352,7 @@ int vrt_scene_edit_heights(vrt_scene* sc, uint32_t x0, uint32_t z0, uint32_t nx,
     sc->device_bytes -= sc->n_nodes * sizeof(uint2);
     sc->d_nodes = d_new;
     sc->n_nodes = n_new;
+    if (int s = update_bounds(sc, "vrt_scene_edit_heights")) return s;
     if (sc->d_compact) {                                    // the compact copy is rebuilt from the new array
         cudaFree(sc->d_compact);
         sc->device_bytes -= sc->n_compact * sizeof(uint2);
@@ -370,6 +398,7 @@ int rebuild_from_keys(vrt_scene* sc, const uint64_t* d_keys, uint32_t n_keys, co
     sc->device_bytes -= sc->n_nodes * sizeof(uint2);
     sc->d_nodes = d_new;
     sc->n_nodes = n_new;
+    if (int s = update_bounds(sc, who)) return s;
     if (sc->d_compact) {
         cudaFree(sc->d_compact);
         sc->device_bytes -= sc->n_compact * sizeof(uint2);
@@ -643,6 +672,8 @@ vrt::RenderLaunch make_launch(const vrt_scene* sc, const vrt_camera* cam, const 
     L.mapping = sc->ctx->render_variant == 1 ? 0 : sc->ctx->render_variant;
     L.scratch = nullptr; L.scratch_bytes = 0;
     L.beam_floor = nullptr; L.beam_shift = 0; L.beam_tiles_x = 0;
+    if (sc->kind == VRT_SCENE_LSVO && sc->ctx->bounds_exit) L.bounds = sc->bounds;
+    else L.bounds = vrt::SceneBounds{{1.0f, 1.0f, 1.0f}, {2.0f, 2.0f, 2.0f}};
     L.trav_policy = sc->ctx->trav_policy;
     L.grid_variant = sc->ctx->grid_variant;
     L.sort_bins1 = sc->ctx->sort_bins1; L.sort_bins2 = sc->ctx->sort_bins2;

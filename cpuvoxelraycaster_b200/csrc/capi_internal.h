@@ -52,6 +52,7 @@ struct vrt_context {
     int samples_per_warp = 0;                  // K4: lanes sharing a pixel (power of two), 0 = automatic
     int refill_cast = 0, refill_render = 16;   // parked lanes that trigger a refill (1..32); cast: 0 = warp-adaptive
     DeviceBuffer scratch_in, scratch_out;   // host-variant staging
+    int bounds_exit = 1;                    // LSVO frames: walks end when the ray leaves the scene's bounds (1) or the root cube (0, the reference)
     int beam_tile = 8;                      // LSVO frames: edge of the screen tiles that get a beam floor (beam_kernels.cu); 0 = off
     int grid_variant = 0;                   // 0 = bordered-grid DDA, 1 = generic loop (flat / fetch-skipping pyramid)
     bool time_frame_kernels = false;        // "time_frame_kernels": bracket the frame kernels of every accumulate call with events
@@ -69,6 +70,7 @@ struct vrt_scene {
     uint64_t n_nodes = 0;
     uint64_t device_bytes = 0;
     unsigned long long* d_counters = nullptr;   // [0] Σ complexity of the last cast; [2..13] render rays/complexity per class
+    vrt::SceneBounds bounds{{1.0f, 1.0f, 1.0f}, {2.0f, 2.0f, 2.0f}};   // LSVO: bounds of the solid voxels (scene_device.cu), castRay coordinates
     uint2* d_compact = nullptr;                 // optional compact breadth-first copy (vrt_scene_set_layout)
     uint64_t n_compact = 0;
     bool use_compact = false;

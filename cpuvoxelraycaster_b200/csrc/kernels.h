@@ -40,6 +40,11 @@ cudaError_t launch_grid_cast(const GridLevels& g, bool use_mip, int variant, con
 cudaError_t launch_svo_cast(const GridLevels& g, int depth, const float* d_origin, const float* d_dir, uint32_t max_iter,
                             uint64_t n, vrt_hit* d_out, unsigned long long* d_counters, cudaStream_t stream);
 
+// Bounds of everything solid in an LSVO scene, castRay coordinates (see lsvo_step.cuh, Trav2 kBounds)
+struct SceneBounds {
+    float lo[3], hi[3];
+};
+
 // Everything one render launch needs, passed by value (constant bank).
 struct RenderLaunch {
     int width, height, row_begin, row_end;
@@ -53,6 +58,7 @@ struct RenderLaunch {
     void* scratch;               // K6: device scratch for the sorted sample lists (render_scratch_bytes)
     size_t scratch_bytes;
     int mapping;                 // 0 = automatic (K5 for many-sample GI frames, else K4), 2 = K4, 3 = K5
+    SceneBounds bounds;          // LSVO frames: walks end when the ray leaves this box (the whole cube [1,2]^3 = the reference's walk)
     const float* beam_floor;     // LSVO frames: per-tile start distance of the camera rays (beam_kernels.cu), or null
     int beam_shift, beam_tiles_x;  // tile edge = 1 << beam_shift pixels; tiles per row
     int grid_variant;            // grid frames: 0 = bordered-grid DDA (default), 1 = generic loop
@@ -82,6 +88,10 @@ __host__ __device__ inline int checker_x_parity(int checker, int area_height, in
 size_t render_scratch_bytes(const RenderLaunch& L);
 cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const RenderLaunch& L, uint32_t* d_accum,
                                          unsigned long long* d_counters, cudaStream_t stream);
+// bounds of the solid voxels of an LSVO in the reference layout, enlarged by `margin_voxels`, into d_bounds (6 floats: lo xyz, hi xyz);
+// d_work: scratch of bounds_work_bytes() bytes (scene_device.cu)
+size_t bounds_work_bytes();
+cudaError_t device_scene_bounds(const uint2* d_nodes, int depth, float margin_voxels, float* d_bounds, void* d_work, cudaStream_t stream);
 // per-tile conservative start distances of the camera rays of rows [row_begin, row_end) (beam_kernels.cu); tile = 4, 8, 16 ...
 cudaError_t launch_beam_floor(const uint2* nodes, const RenderLaunch& L, int tile, float* d_floor, cudaStream_t stream);
 // RayCaster::castRay for explicit rays (vrt_shade_rays)

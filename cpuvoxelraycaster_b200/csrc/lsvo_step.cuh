@@ -15,6 +15,7 @@
 //   * the node base pointer and the loop guard are pinned in registers (they were re-read from the constant
 //     bank on every trip, in the dependent chain in front of the node fetch).
 #pragma once
+#include "kernels.h"
 #include "lsvo_traverse.cuh"
 
 namespace vrt {
@@ -198,20 +199,25 @@ struct Stack64s {
     }
 };
 
-template <bool kCone>
+// Bounds of everything solid in the scene (castRay's [1,2]^3 coordinates, a little enlarged): a ray that has left this box
+// cannot hit anything any more.  kBounds walks stop there instead of at the root cube's far side (lsvo.hpp:72) — a shadow ray
+// that has climbed out of the terrain no longer pays for the empty half of the world.  Misses stay misses; only their trip
+// count shrinks, so this is for frames (like the beam floors), not for the batched casts that report HitPoint::complexity.
+template <bool kCone, bool kBounds = false>
 struct Trav2 {
     float dx, dy, dz, coef, bias;
     float tcx, tcy, tcz, tox, toy, toz;
     float px, py, pz;
     float t_min, t_max, h;
     float sf, iters_f;
+    float t_limit;       // kBounds: the time at which the ray leaves the scene bounds
     uint32_t parent, child, mirror, face;
     bool hit;
 
     // t_floor: the walk starts at max(t_floor, entry into the root cube) instead of max(0, ...) (:57).  Any t_floor below the
     // ray's hit distance leaves the HitPoint unchanged except for its complexity (beam_kernels.cu); 0 = the reference.
     __device__ __forceinline__ void init(float ox_, float oy_, float oz_, float dx_, float dy_, float dz_, float coef_, float bias_,
-                                         float t_floor = 0.0f) {
+                                         float t_floor = 0.0f, const SceneBounds* bounds = nullptr) {
         const bool finite = (((ox_ * 0.0f + oy_ * 0.0f) + oz_ * 0.0f) + ((dx_ * 0.0f + dy_ * 0.0f) + dz_ * 0.0f)) == 0.0f;
         if (!finite) { ox_ = 3.0f; oy_ = 3.0f; oz_ = 3.0f; dx_ = 1.0f; dy_ = 1.0f; dz_ = 1.0f; }
         coef = coef_; bias = bias_;
@@ -231,6 +237,14 @@ struct Trav2 {
         h = t_max;
         t_min = fmaxf(t_floor, t_min);                                     // :57 with t_floor = 0
         t_max = fminf(1.0f, t_max);
+        if (kBounds) {
+            // exit from the bounds box, with the expressions of :55 (in the mirrored frame every direction is negative, so the
+            // exit planes are the low ones: lo on an unmirrored axis, 3 - hi on a mirrored one)
+            const float bx = (mirror & 1u) ? bounds->lo[0] : 3.0f - bounds->hi[0];
+            const float by = (mirror & 2u) ? bounds->lo[1] : 3.0f - bounds->hi[1];
+            const float bz = (mirror & 4u) ? bounds->lo[2] : 3.0f - bounds->hi[2];
+            t_limit = fminf(bx * tcx - tox, fminf(by * tcy - toy, bz * tcz - toz));
+        }
         parent = 0u; child = 0u; face = 0u;
         sf = 0.5f;                                                         // scale = 22
         px = 1.0f; py = 1.0f; pz = 1.0f;
@@ -277,6 +291,7 @@ struct Trav2 {
         if (sy) step_mask ^= 2u;
         if (sz) step_mask ^= 4u;
         t_min = tc_max;
+        if (kBounds) { if (t_min > t_limit) return false; }                 // outside everything solid: a miss, whatever follows
         child ^= step_mask;
         face = step_mask;
         if (child & step_mask) {                                             // :124-145, see Trav::step
@@ -313,11 +328,12 @@ struct Trav2 {
     }
 };
 
-template <bool kCone, typename Nodes, typename Stack>
+template <bool kCone, bool kBounds = false, typename Nodes, typename Stack>
 __device__ __forceinline__ void lsvo_cast_ray2(const Nodes& nodes, Stack& stack, int guard, float guard_sf, float ox, float oy, float oz,
-                                               float dx, float dy, float dz, float coef, float bias, LsvoResult& r, float t_floor = 0.0f) {
-    Trav2<kCone> t;
-    t.init(ox, oy, oz, dx, dy, dz, coef, bias, t_floor);
+                                               float dx, float dy, float dz, float coef, float bias, LsvoResult& r, float t_floor = 0.0f,
+                                               const SceneBounds* bounds = nullptr) {
+    Trav2<kCone, kBounds> t;
+    t.init(ox, oy, oz, dx, dy, dz, coef, bias, t_floor, bounds);
     while (t.step(nodes, stack, guard, guard_sf)) {}
     t.result(r);
 }

@@ -388,4 +388,82 @@ cudaError_t device_compact_lsvo(const uint2* d_ref, uint64_t n_ref, int depth, u
     return cudaSuccess;
 }
 
+
+// ---- bounds of the solid voxels (for Trav2's kBounds walks) ------------------------------------------------------------
+// A breadth-first sweep of the reference-layout array from the root: one queue entry per non-empty node (slot index + low
+// corner in voxel units), expanded level by level on the device until the cubes are 8 voxels wide (or a level would not fit
+// the queue): the min / max corners of those cubes are the bounds, at most 8 voxels loose — plenty for "the ray has left
+// everything solid".  Scene construction, not the hot path: a handful of small launches.
+namespace {
+constexpr uint32_t kBoundsQueue = 1u << 19;                 // entries per queue (8 MB each)
+struct BoundsEntry { uint32_t node, x, y, z; };
+
+__global__ void bounds_expand_kernel(const uint2* __restrict__ slots, const BoundsEntry* __restrict__ in, const uint32_t* __restrict__ n_in_ptr,
+                                     int level, int stop_level, BoundsEntry* __restrict__ out, uint32_t* __restrict__ n_out,
+                                     int* __restrict__ box /* lo xyz (min), hi xyz (max) in voxels */) {
+    const uint32_t n_in = *n_in_ptr;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += gridDim.x * blockDim.x) {
+        const BoundsEntry e = in[i];
+        const uint2 w = __ldg(slots + e.node);
+        const uint32_t child_mask = (w.x >> 8) & 0xffu, leaf_mask = (w.x >> 16) & 0xffu;
+        const uint32_t half = 1u << (level - 1);
+        for (uint32_t s = 0; s < 8; ++s) {
+            if (!((child_mask >> s) & 1u)) continue;
+            // slot bit clear = upper half (the tree stores the mirrored octant, lsvo.hpp:79)
+            const uint32_t x = e.x + ((s & 1u) ? 0u : half), y = e.y + ((s & 2u) ? 0u : half), z = e.z + ((s & 4u) ? 0u : half);
+            bool terminal = ((leaf_mask >> s) & 1u) || level - 1 <= stop_level;
+            if (!terminal) {
+                const uint32_t at = atomicAdd(n_out, 1u);
+                if (at < kBoundsQueue) out[at] = BoundsEntry{e.node + w.y + s, x, y, z};
+                else terminal = true;                        // queue full: take the whole cube (still a bound)
+            }
+            if (terminal) {
+                atomicMin(box + 0, int(x)); atomicMin(box + 1, int(y)); atomicMin(box + 2, int(z));
+                atomicMax(box + 3, int(x + half)); atomicMax(box + 4, int(y + half)); atomicMax(box + 5, int(z + half));
+            }
+        }
+    }
+}
+__global__ void bounds_clamp_count_kernel(uint32_t* n) { if (*n > kBoundsQueue) *n = kBoundsQueue; }
+__global__ void bounds_finish_kernel(const int* __restrict__ box, int depth, float margin, float* __restrict__ out) {
+    const float S = float(1 << depth);
+    if (box[0] > box[3]) {                                  // nothing solid: an empty box in front of every ray
+        for (int a = 0; a < 3; ++a) { out[a] = 1.5f; out[3 + a] = 1.5f; }
+        return;
+    }
+    for (int a = 0; a < 3; ++a) {
+        out[a] = fmaxf(1.0f, 1.0f + (float(box[a]) - margin) / S);
+        out[3 + a] = fminf(2.0f, 1.0f + (float(box[3 + a]) + margin) / S);
+    }
+}
+}  // namespace
+
+size_t bounds_work_bytes() { return 2 * size_t(kBoundsQueue) * sizeof(BoundsEntry) + 64; }
+
+cudaError_t device_scene_bounds(const uint2* d_nodes, int depth, float margin_voxels, float* d_bounds, void* d_work, cudaStream_t stream) {
+    char* base = static_cast<char*>(d_work);
+    BoundsEntry* q[2] = {reinterpret_cast<BoundsEntry*>(base), reinterpret_cast<BoundsEntry*>(base + size_t(kBoundsQueue) * sizeof(BoundsEntry))};
+    uint32_t* counts = reinterpret_cast<uint32_t*>(base + 2 * size_t(kBoundsQueue) * sizeof(BoundsEntry));   // [0], [1]: queue sizes
+    int* box = reinterpret_cast<int*>(counts + 2);
+    const BoundsEntry root{0u, 0u, 0u, 0u};
+    const uint32_t one = 1u;
+    const int init_box[6] = {1 << 30, 1 << 30, 1 << 30, -1, -1, -1};
+    cudaError_t e = cudaMemcpyAsync(q[0], &root, sizeof(root), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(counts, &one, sizeof(one), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(box, init_box, sizeof(init_box), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
+    const int stop_level = depth > 3 ? 3 : 0;               // cubes of 8 voxels
+    int cur = 0;
+    for (int level = depth; level >= 1; --level) {
+        e = cudaMemsetAsync(counts + (cur ^ 1), 0, sizeof(uint32_t), stream);
+        if (e != cudaSuccess) return e;
+        bounds_expand_kernel<<<296, 256, 0, stream>>>(d_nodes, q[cur], counts + cur, level, stop_level, q[cur ^ 1], counts + (cur ^ 1), box);
+        bounds_clamp_count_kernel<<<1, 1, 0, stream>>>(counts + (cur ^ 1));
+        cur ^= 1;
+        if (level - 1 <= stop_level) break;
+    }
+    bounds_finish_kernel<<<1, 1, 0, stream>>>(box, depth, margin_voxels, d_bounds);
+    return cudaGetLastError();
+}
+
 }  // namespace vrt

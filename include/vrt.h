@@ -105,6 +105,9 @@ int vrt_context_set_stream(vrt_context* ctx, void* stream);
  *                    against each tile's frustum, cpuvoxelraycaster_b200/csrc/beam_kernels.cu).  Frames are byte-identical
  *                    with and without it; the trip counts (complexity) of the primary rays shrink.  0 = off: every ray
  *                    starts where the reference starts it (lsvo.hpp:54-57) and vrt_render_stats equals the reference's counts
+ *   "bounds_exit" (default 1): LSVO frames — a walk ends as soon as its ray has left the bounding box of the solid voxels
+ *                    (computed on the device when the scene is created or edited) instead of at the far side of the root cube
+ *                    (lsvo.hpp:72): misses stay misses, only their trip counts shrink.  0 = the reference's walk
  *   "grid_variant" (default 0): dense grids — 0 = DDA on the bordered bit grid, 1 = the generic loop / fetch-skipping pyramid
  *   "time_frame_kernels"  see vrt_context_take_timings */
 int vrt_context_set_option(vrt_context* ctx, const char* key, int value);

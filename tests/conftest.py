@@ -84,9 +84,9 @@ def textures():
 def vrt():
     import cpuvoxelraycaster_b200 as v
     v.capi.lib()   # raises if libvrt.so is missing: no fallback
-    # Every context a test creates renders frames WITHOUT beam floors unless the test turns them on: vrt_render_stats then
-    # carries the reference's own loop-trip counts (HitPoint::complexity) and can be compared with the oracle's.  The beam
-    # floors (on by default in the product — the C++ test programs run with them) are tested on their own:
+    # Every context a test creates renders frames WITHOUT beam floors and bounds exits unless the test turns them on:
+    # vrt_render_stats then carries the reference's own loop-trip counts (HitPoint::complexity) and can be compared with the
+    # oracle's.  Both shortcuts (on by default in the product — the C++ test programs run with them) are tested on their own:
     # tests/test_gpu_render.py::test_beam_floors_*, tests/test_gpu_fullsize.py.
     if not getattr(v.Context, "_tests_patched", False):
         plain_init = v.Context.__init__
@@ -94,6 +94,7 @@ def vrt():
         def init_without_beam(self, *a, **k):
             plain_init(self, *a, **k)
             self.set_option("beam_tile", 0)
+            self.set_option("bounds_exit", 0)
         v.Context.__init__ = init_without_beam
         v.Context._tests_patched = True
     return v

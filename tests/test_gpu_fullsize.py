@@ -110,7 +110,8 @@ def test_cfg4_headline_frame_is_kernel_independent(vrt, textures):
     for variant in (0, 2, 3):
         c = vrt.Context(0)
         c.set_option("render_variant", variant)
-        c.set_option("beam_tile", 0)                     # K5 has no beam floors: compare the reference trip counts
+        c.set_option("beam_tile", 0)                     # K5 has no beam floors / bounds exits: compare the reference trip counts
+        c.set_option("bounds_exit", 0)
         s = vrt.LSVO.from_terrain(c, 11)
         s.set_textures(*textures)
         cam = vrt.Camera(position=(S / 2, S / 2 - 56, S / 2), view_angle=(0, 0), aperture=0.5)
@@ -206,16 +207,21 @@ def test_cfg4_headline_frame_crop_vs_oracle(vrt, ctx, port, textures, rows):
     assert r.last_stats["rays"] == list(want_st.rays) and r.last_stats["complexity"] == list(want_st.complexity)
     assert r.last_stats["rays"][0] == W * (y1 - y0) * spp and r.last_stats["rays"][4] > 0
     # the product default: beam floors on — same pixels and ray counts, fewer loop trips on the primary rays only
-    for tile in (8, 4):
+    for tile, bounds in ((8, 0), (4, 0), (8, 1)):
         ctx.set_option("beam_tile", tile)
+        ctx.set_option("bounds_exit", bounds)
         b = vrt.RayCaster(s, (W, H))
         b.setLightPosition(light)
         b.use_samples, b.use_gi, b.gi_bounces = True, True, 2
         b.render(cam, spp, rows[0], rows[1])
         assert np.array_equal(b.colors, r.colors) and np.array_equal(b.render_image, r.render_image)
-        assert b.last_stats["rays"] == r.last_stats["rays"] and b.last_stats["complexity"][1:] == r.last_stats["complexity"][1:]
+        assert b.last_stats["rays"] == r.last_stats["rays"]
+        if not bounds:
+            assert b.last_stats["complexity"][1:] == r.last_stats["complexity"][1:]
+        assert all(x <= y for x, y in zip(b.last_stats["complexity"], r.last_stats["complexity"]))
         assert b.last_stats["complexity"][0] < 0.8 * r.last_stats["complexity"][0]
     ctx.set_option("beam_tile", 0)
+    ctx.set_option("bounds_exit", 0)
     s.close()
 
 

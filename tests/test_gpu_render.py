@@ -356,6 +356,15 @@ def test_beam_floors_do_not_change_frames(vrt, ctx, scene9, position, view, aper
             assert np.array_equal(got, want), (size, tile)
             assert st["rays"] == st0["rays"] and st["complexity"][1:] == st0["complexity"][1:]
             assert st["complexity"][0] <= st0["complexity"][0]
+        # ... and with the walks ending at the scene's bounds instead of the root cube (the product default: both on)
+        for tile in (0, 8):
+            ctx.set_option("beam_tile", tile)
+            ctx.set_option("bounds_exit", 1)
+            got, st = _frame(vrt, scene9, size, cam, default_light(), spp, mirror_y=240)
+            ctx.set_option("bounds_exit", 0)
+            assert np.array_equal(got, want), (size, tile, "bounds")
+            assert st["rays"] == st0["rays"] and all(a <= b for a, b in zip(st["complexity"], st0["complexity"]))
+            assert sum(st["complexity"]) < sum(st0["complexity"])
         ctx.set_option("beam_tile", 0)
 
 
@@ -383,6 +392,11 @@ def test_beam_floors_on_a_random_voxel_scene(vrt, ctx, textures):
                     got, st = _frame(vrt, s, size, cam, light, spp)
                     assert np.array_equal(got, want), (depth, position, size, tile)
                     assert st["rays"] == st0["rays"] and st["complexity"][1:] == st0["complexity"][1:]
+                ctx.set_option("bounds_exit", 1)
+                got, st = _frame(vrt, s, size, cam, light, spp)
+                ctx.set_option("bounds_exit", 0)
+                assert np.array_equal(got, want) and st["rays"] == st0["rays"], (depth, position, size, "bounds")
+                assert all(a <= b for a, b in zip(st["complexity"], st0["complexity"]))
         assert seen > 1000, depth                              # the cameras do look at the voxels
         ctx.set_option("beam_tile", 0)
         s.close()

@@ -66,7 +66,8 @@ def main():
                 if pol is not None:
                     ctx.set_option("trav_policy", pol)
                 for beam in (BEAMS if pol in (2, None) else [0]):
-                    have_beam = set_opt(ctx, "beam_tile", beam)
+                    have_beam = set_opt(ctx, "beam_tile", 0 if beam < 0 else beam)
+                    set_opt(ctx, "bounds_exit", 0 if beam <= 0 and beam != -1 else 1)      # -1 = bounds only; > 0 = beam + bounds; 0 = neither
                     if beam and not have_beam:
                         continue
                     ms = time_frame(fr, cs, p, stream)
@@ -75,6 +76,7 @@ def main():
                     print(json.dumps(dict(tag=TAG, what="K6 frame", world=world, gi=gi, bounces=bounces, policy=pol, beam_tile=beam, ms=round(ms, 3),
                                           rays=sum(st["rays"]), trips=sum(st["complexity"]), primary_trips=st["complexity"][0], hash=h)), flush=True)
             set_opt(ctx, "beam_tile", 8)
+            set_opt(ctx, "bounds_exit", 1)
     if policies[0] is not None:
         ctx.set_option("trav_policy", 2)
     # batched casts
