@@ -203,6 +203,9 @@ struct Stack64s {
 // cannot hit anything any more.  kBounds walks stop there instead of at the root cube's far side (lsvo.hpp:72) — a shadow ray
 // that has climbed out of the terrain no longer pays for the empty half of the world.  Misses stay misses; only their trip
 // count shrinks, so this is for frames (like the beam floors), not for the batched casts that report HitPoint::complexity.
+// Only for rays without a cone (coef = bias = 0: camera and sun-shadow rays): a cone ray "hits" the first NON-EMPTY NODE it
+// finds smaller than its cone (lsvo.hpp:82-85), and such a node reaches far beyond the voxels it contains — measured: with the
+// bound applied to the GI rays 0.4 % of them lose their hit.
 template <bool kCone, bool kBounds = false>
 struct Trav2 {
     float dx, dy, dz, coef, bias;

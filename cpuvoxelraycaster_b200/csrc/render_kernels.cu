@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(128, VRT_K4_MIN_CTAS) render_accumulate_kernel
                 while (stage != kDone) {
                     LsvoResult r;
                     if (stage < kGi0) lsvo_cast_ray2<false, true>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, 0.0f, 0.0f, r, nr.t_floor, &L.bounds);
-                    else lsvo_cast_ray2<true, true>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r, 0.0f, &L.bounds);
+                    else lsvo_cast_ray2<true>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
                     cnt[stage * 128] += 1u;
                     cnt[(6 + stage) * 128] += r.complexity;
                     LsvoHit h;
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(128, VRT_K5_MIN_CTAS) render_rounds_kernel(Nod
                         lsvo_cast_ray2<true>(nodes, stack2, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
                     } else {
                         if (stage < kGi0) lsvo_cast_ray2<false, true>(nodes, stack2, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, 0.0f, 0.0f, r, nr.t_floor, &L.bounds);
-                        else lsvo_cast_ray2<true, true>(nodes, stack2, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r, 0.0f, &L.bounds);
+                        else lsvo_cast_ray2<true>(nodes, stack2, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
                     }
                     cnt[stage * 128] += 1u;
                     cnt[(6 + stage) * 128] += r.complexity;
