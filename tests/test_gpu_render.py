@@ -364,7 +364,7 @@ def test_beam_floors_do_not_change_frames(vrt, ctx, scene9, position, view, aper
             ctx.set_option("bounds_exit", 0)
             assert np.array_equal(got, want), (size, tile, "bounds")
             assert st["rays"] == st0["rays"] and all(a <= b for a, b in zip(st["complexity"], st0["complexity"]))
-            assert sum(st["complexity"]) < sum(st0["complexity"])
+            assert sum(st["complexity"]) <= sum(st0["complexity"])
         ctx.set_option("beam_tile", 0)
 
 
