@@ -730,7 +730,9 @@ int vrt_render_accumulate_device(vrt_scene* sc, const vrt_camera* cam, const vrt
         vrt::RenderLaunch L = make_launch(sc, cam, p);
         // beam floors (beam_kernels.cu): conservative start distances of the camera rays, per screen tile.  Frames are
         // identical with and without them; only the trip counts of the primary rays shrink.
-        if (ctx->beam_tile > 0 && !sc->use_compact && (ctx->render_variant == 0 || ctx->render_variant == 2 || ctx->render_variant == 4)) {
+        // Worth its own launch (~0.15 ms: one thread per tile, a latency-bound tree search) only when every floor is used by many
+        // rays: frames with >= 8 samples per pixel.  The interactive 1-sample frames (0.2 ms in all) go without.
+        if (ctx->beam_tile > 0 && p->spp >= 8 && !sc->use_compact && (ctx->render_variant == 0 || ctx->render_variant == 2 || ctx->render_variant == 4)) {
             int shift = 0;
             while ((1 << (shift + 1)) <= ctx->beam_tile) ++shift;
             const int tile = 1 << shift, tiles_x = (p->width + tile - 1) / tile, tiles_y = (p->height + tile - 1) / tile;

@@ -100,7 +100,7 @@ int vrt_context_set_stream(vrt_context* ctx, void* stream);
  *   "samples_per_warp"  frame kernel: lanes of a warp sharing one pixel, power of two <= 32 (0 = automatic)
  *   "trav_policy" (default 2): traversal loop of the K6 frame kernel — 0 = Trav (round-1 loop), 1 = Trav2 (bookkeeping moved
  *                    off the ALU pipe), 2 = Trav2 with the cone test compiled out of the coef-0 casts; results identical
- *   "beam_tile" (default 8): LSVO frames — edge in pixels (power of two) of the screen tiles for which a conservative start
+ *   "beam_tile" (default 8): LSVO frames with >= 8 samples per pixel — edge in pixels (power of two) of the screen tiles for which a conservative start
  *                    distance of the camera rays is computed in front of the frame (a front-to-back search of the octree
  *                    against each tile's frustum, cpuvoxelraycaster_b200/csrc/beam_kernels.cu).  Frames are byte-identical
  *                    with and without it; the trip counts (complexity) of the primary rays shrink.  0 = off: every ray

@@ -347,7 +347,8 @@ def test_beam_floors_do_not_change_frames(vrt, ctx, scene9, position, view, aper
     secondary rays are identical with tiles of 4, 8, 16 and 32 pixels and without; only the primary rays' trip count shrinks.
     Cameras: the demo's, grazing, looking down / up, wide aperture with a short focal length, close to the ground, under it."""
     cam = vrt.Camera(position=position, view_angle=view, aperture=aperture, focal_length=focal)
-    for size, spp in (((200, 113), 3), ((128, 72), 16)):          # K4 and K6
+    for size, spp, variant in (((200, 113), 8, 2), ((128, 72), 16, 0)):          # K4 (forced) and K6
+        ctx.set_option("render_variant", variant)
         ctx.set_option("beam_tile", 0)
         want, st0 = _frame(vrt, scene9, size, cam, default_light(), spp, mirror_y=240)
         for tile in (4, 8, 16, 32):
@@ -366,6 +367,7 @@ def test_beam_floors_do_not_change_frames(vrt, ctx, scene9, position, view, aper
             assert st["rays"] == st0["rays"] and all(a <= b for a, b in zip(st["complexity"], st0["complexity"]))
             assert sum(st["complexity"]) <= sum(st0["complexity"])
         ctx.set_option("beam_tile", 0)
+    ctx.set_option("render_variant", 0)
 
 
 def test_beam_floors_on_a_random_voxel_scene(vrt, ctx, textures):
@@ -383,7 +385,8 @@ def test_beam_floors_on_a_random_voxel_scene(vrt, ctx, textures):
         seen = 0
         for position, view in cams:
             cam = vrt.Camera(position=position, view_angle=view, aperture=0.7, focal_length=40.0)
-            for size, spp in (((160, 90), 2), ((96, 54), 16)):
+            for size, spp, variant in (((160, 90), 8, 2), ((96, 54), 16, 0)):
+                ctx.set_option("render_variant", variant)
                 ctx.set_option("beam_tile", 0)
                 want, st0 = _frame(vrt, s, size, cam, light, spp)
                 seen += st0["rays"][1]
@@ -399,6 +402,7 @@ def test_beam_floors_on_a_random_voxel_scene(vrt, ctx, textures):
                 assert all(a <= b for a, b in zip(st["complexity"], st0["complexity"]))
         assert seen > 1000, depth                              # the cameras do look at the voxels
         ctx.set_option("beam_tile", 0)
+        ctx.set_option("render_variant", 0)
         s.close()
 
 
