@@ -56,9 +56,9 @@ __global__ void __launch_bounds__(128) lsvo_cast2_kernel(Nodes nodes, int depth,
                                                          vrt_hit* __restrict__ out, unsigned long long* __restrict__ total_complexity) {
     extern __shared__ uint2 smem[];
     nodes.slots = pin(nodes.slots);
-    guard = pin(guard);
-    Stack64s<128> stack = Stack64s<128>::make(smem + threadIdx.x, pin(kSvoMaxDepth - depth));
-    const float guard_sf = pin(guard_scale_f(guard));
+    const float guard_sf = keep_in_register(guard_scale_f(guard), smem + threadIdx.x);
+    guard = keep_in_register(guard, smem + threadIdx.x);
+    Stack64s<128> stack = Stack64s<128>::make(smem + threadIdx.x, kSvoMaxDepth - depth);
     const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     uint32_t iters = 0u;
     if (i < n) {

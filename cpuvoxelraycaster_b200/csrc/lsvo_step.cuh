@@ -42,6 +42,15 @@ __device__ __forceinline__ const uint2* pin(const uint2* p) {
     return reinterpret_cast<const uint2*>(reinterpret_cast<uintptr_t>(p) + blockIdx.y + threadIdx.z);
 }
 __device__ __forceinline__ int pin(int v) { return v + int(blockIdx.y); }
+// A value ptxas cannot re-derive: written to and read back from the thread's own shared-memory slot (volatile), once per
+// kernel.  For loop invariants that must live in a register across the traversal loop — ptxas re-materialises anything it can
+// trace to kernel parameters or special registers, every trip, when registers are scarce.
+__device__ __forceinline__ uint32_t keep_in_register(uint32_t v, const void* own_shared_slot) {
+    asm volatile("st.volatile.shared.b32 [%1], %0;\n\tld.volatile.shared.b32 %0, [%1];" : "+r"(v) : "r"(uint32_t(__cvta_generic_to_shared(own_shared_slot))) : "memory");
+    return v;
+}
+__device__ __forceinline__ int keep_in_register(int v, const void* slot) { return int(keep_in_register(uint32_t(v), slot)); }
+__device__ __forceinline__ float keep_in_register(float v, const void* slot) { return __uint_as_float(keep_in_register(__float_as_uint(v), slot)); }
 
 struct Trav {
     // ray (direction after the |d| >= 2^-23 clamp) and cone
@@ -179,23 +188,28 @@ __device__ __forceinline__ void lsvo_cast_ray(const Nodes& nodes, Stack& stack, 
 //   * addresses the stack from the bits of sf (push) / with one IMAD from the scale (pop).
 template <int kThreads>
 struct Stack64s {
-    uint2* base_scale;   // entry of scale s at base_scale[s * kThreads]          (s = octree scale, 23 - depth .. 22)
+    uint32_t addr;       // shared-memory byte address of the entry of scale 0 (entry of scale s at addr + s * kThreads * 8)
+    // `thread_base` is the thread's first stack slot.  The address is passed through a volatile shared-memory round trip: ptxas
+    // otherwise re-derives it from %tid / %ctaid and the kernel parameters on every push and pop (11 of the 14 instructions of a
+    // push in the round-2 capture) instead of keeping one register alive across the loop.
     __device__ __forceinline__ static Stack64s make(uint2* thread_base, int depth_offset) {
         Stack64s st;
-        st.base_scale = thread_base - depth_offset * kThreads;
+        uint32_t a = uint32_t(__cvta_generic_to_shared(thread_base)) - uint32_t(depth_offset * kThreads * 8);
+        asm volatile("st.volatile.shared.b32 [%1], %0;\n\tld.volatile.shared.b32 %0, [%1];" : "+r"(a) : "r"(uint32_t(__cvta_generic_to_shared(thread_base))) : "memory");
+        st.addr = a;
         return st;
     }
-    // sf = 2^(scale - 23): bits = (scale + 104) << 23, so (bits >> 23) - 104 = scale and bits >> 16 = (scale + 104) * 128
+    // sf = 2^(scale - 23): bits = (scale + 104) << 23, so byte offset (scale + 104) * 128 * 8 = bits >> 13 (the low 23 bits of a
+    // power of two are zero: no masking needed)
     __device__ __forceinline__ void push_sf(float sf, uint32_t p, float t) {
         static_assert(kThreads == 128, "the shift below assumes 128 threads per block");
-        // byte offset (scale + 104) * 128 * 8 = bits >> 13 (the low 23 bits of a power of two are zero: no masking needed)
-        char* a = reinterpret_cast<char*>(base_scale - 104 * kThreads) + (__float_as_uint(sf) >> 13);
-        *reinterpret_cast<uint2*>(a) = make_uint2(p, __float_as_uint(t));
+        const uint32_t a = addr + (__float_as_uint(sf) >> 13);
+        asm volatile("st.shared.v2.b32 [%0 + -106496], {%1, %2};" :: "r"(a), "r"(p), "r"(__float_as_uint(t)) : "memory");
     }
     __device__ __forceinline__ void pop(int scale, uint32_t& p, float& t) const {
-        const uint2 e = base_scale[scale * kThreads];
-        p = e.x;
-        t = __uint_as_float(e.y);
+        uint32_t ty;
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(p), "=r"(ty) : "r"(addr + uint32_t(scale) * uint32_t(kThreads * 8)) : "memory");
+        t = __uint_as_float(ty);
     }
 };
 

@@ -47,16 +47,16 @@ __device__ __forceinline__ void store_hit_record(vrt_hit* out, const LsvoResult&
 constexpr int kRayChunk = 64;
 
 template <typename Nodes, bool kCone>
-__global__ void __launch_bounds__(128, 4) lsvo_cast_persistent_kernel(Nodes nodes, int depth, int guard,
+__global__ void __launch_bounds__(128, 8) lsvo_cast_persistent_kernel(Nodes nodes, int depth, int guard,
                                                                       const float* __restrict__ origin,
                                                                       const float* __restrict__ dir, float coef, float bias,
                                                                       uint64_t n, vrt_hit* __restrict__ out,
                                                                       unsigned long long* __restrict__ counters, int refill) {
     extern __shared__ uint2 smem[];
     nodes.slots = pin(nodes.slots);
-    guard = pin(guard);
-    Stack64s<128> stack = Stack64s<128>::make(smem + threadIdx.x, pin(kSvoMaxDepth - depth));
-    const float guard_sf = pin(guard_scale_f(guard));
+    const float guard_sf = keep_in_register(guard_scale_f(guard), smem + threadIdx.x);
+    guard = keep_in_register(guard, smem + threadIdx.x);
+    Stack64s<128> stack = Stack64s<128>::make(smem + threadIdx.x, kSvoMaxDepth - depth);
     const int lane = threadIdx.x & 31;
     const unsigned lt = lanemask_lt();
     const bool adaptive = refill <= 0;

@@ -29,9 +29,9 @@ __global__ void __launch_bounds__(128, VRT_K4_MIN_CTAS) render_accumulate_kernel
                                                                 unsigned long long* __restrict__ counters) {
     extern __shared__ uint2 smem[];
     nodes.slots = pin(nodes.slots);
-    const int guard = pin(L.guard);
-    Stack64s<128> stack = Stack64s<128>::make(smem + threadIdx.x, pin(kSvoMaxDepth - L.depth));
-    const float guard_sf = pin(guard_scale_f(L.guard));
+    const int guard = keep_in_register(L.guard, smem + threadIdx.x);
+    Stack64s<128> stack = Stack64s<128>::make(smem + threadIdx.x, kSvoMaxDepth - L.depth);
+    const float guard_sf = keep_in_register(guard_scale_f(L.guard), smem + threadIdx.x);
 
     // 8x4 pixel tile per warp, 4 tiles side by side per block: coherent primary rays share nodes
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -412,8 +412,17 @@ __global__ void __launch_bounds__(128) sort_samples_kernel(RenderLaunch L, SortP
 
 // kTrav: 0 = the first traversal loop (Trav), 1 = Trav2, 2 = Trav2 with the cone test compiled out of the primary / sun-shadow
 // casts (they are cast with coef = 0).  Same operations per ray, identical results.
+//
+// 8 CTAs per SM (64 registers): with the loop invariants held in registers (keep_in_register, lsvo_step.cuh) the four traversal
+// loops compile without spills at 64 registers — the ~270 bytes of spills sit in the chain code between the casts — and the
+// kernel, which was waiting on instruction latency at 20 warps per SM (issue slots 74 % busy, 1.75 eligible warps per scheduler),
+// gains from every step: 5 / 6 / 7 / 8 CTAs per SM = 45.06 / 42.83 / 41.69 / 41.15 ms on the headline frame, same box
+// (profiles/r02_ab_keepreg.txt).
+#ifndef VRT_K6_MIN_CTAS
+#define VRT_K6_MIN_CTAS 8
+#endif
 template <typename Nodes, int kTrav, bool kMirror = false>
-__global__ void __launch_bounds__(128, VRT_K5_MIN_CTAS) render_rounds_kernel(Nodes nodes, RenderLaunch L, BlockGeometry G,
+__global__ void __launch_bounds__(128, VRT_K6_MIN_CTAS) render_rounds_kernel(Nodes nodes, RenderLaunch L, BlockGeometry G,
                                                                             const uint16_t* __restrict__ lists, uint32_t* meta,
                                                                             uint32_t* next_block, uint32_t* __restrict__ accum,
                                                                             unsigned long long* __restrict__ counters) {
@@ -421,10 +430,11 @@ __global__ void __launch_bounds__(128, VRT_K5_MIN_CTAS) render_rounds_kernel(Nod
     __shared__ int s_block;
     Stack64<128> stack{smem + threadIdx.x};
     nodes.slots = pin(nodes.slots);
-    const int guard = pin(L.guard);
+    // kTrav 0 keeps the first loop's recipe (blockIdx.y sums); the Trav2 loops hold their invariants in registers
+    const int guard = kTrav == 0 ? pin(L.guard) : keep_in_register(L.guard, smem + threadIdx.x);
     const int depth_offset = pin(kSvoMaxDepth - L.depth);
-    Stack64s<128> stack2 = Stack64s<128>::make(smem + threadIdx.x, depth_offset);
-    const float guard_sf = pin(guard_scale_f(L.guard));
+    Stack64s<128> stack2 = Stack64s<128>::make(smem + threadIdx.x, kSvoMaxDepth - L.depth);
+    const float guard_sf = keep_in_register(guard_scale_f(L.guard), smem + threadIdx.x);
     (void)stack; (void)stack2; (void)guard_sf;
     const int lane = threadIdx.x & 31;
     uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + (L.depth + 1) * 128) + threadIdx.x;
@@ -499,27 +509,38 @@ __global__ void __launch_bounds__(128, VRT_K5_MIN_CTAS) render_rounds_kernel(Nod
         }
     };
 
-    // ---- own blocks: the CTA takes a block, its warps share the block's rounds ----
+    // One call site for trace_block (it holds four inlined traversal loops: two copies of it do not fit the instruction cache).
+    // Phase 0 — own blocks: the CTA takes a block, its warps share the block's rounds (`work >= n_blocks` is CTA-uniform, so all
+    // warps leave the phase together and the barriers stay matched).  Phase 1 — help: blocks are started in order, so unfinished
+    // ones are among the last started; every warp scans backwards, 32 blocks per look, and joins whatever still has rounds.
+    bool helping = false;
+    int base = n_blocks - 1;
+    unsigned open_mask = 0u;
     for (;;) {
-        if (threadIdx.x == 0) s_block = int(atomicAdd(next_block, 1u));
-        __syncthreads();
-        const int work = s_block;
-        __syncthreads();
-        if (work >= n_blocks) break;
-        trace_block(work);
-    }
-    // ---- help: blocks are started in order, so unfinished ones are among the last started ----
-    for (int base = n_blocks - 1; base >= 0; base -= 32) {
-        const int work = base - lane;
-        bool open = false;
-        if (work >= 0) open = *reinterpret_cast<volatile uint32_t*>(meta + 2 * work + 1) * 32u < meta[2 * work];
-        unsigned m = __ballot_sync(0xffffffffu, open);
-        if (!m && base < n_blocks - 1 - 32 * 256) break;                           // far behind the frontier: everything is done
-        while (m) {
-            const int l = __ffs(m) - 1;
-            m &= m - 1;
-            trace_block(base - l);
+        int work;
+        if (!helping) {
+            if (threadIdx.x == 0) s_block = int(atomicAdd(next_block, 1u));
+            __syncthreads();
+            work = s_block;
+            __syncthreads();
+            if (work >= n_blocks) { helping = true; base = n_blocks - 1 + 32; continue; }
+        } else {
+            if (!open_mask) {
+                base -= 32;
+                if (base < 0) break;
+                const int w = base - lane;
+                bool open = false;
+                if (w >= 0) open = *reinterpret_cast<volatile uint32_t*>(meta + 2 * w + 1) * 32u < meta[2 * w];
+                open_mask = __ballot_sync(0xffffffffu, open);
+                if (!open_mask) {
+                    if (base < n_blocks - 1 - 32 * 256) break;                       // far behind the frontier: everything is done
+                    continue;
+                }
+            }
+            work = base - (__ffs(open_mask) - 1);
+            open_mask &= open_mask - 1;
         }
+        trace_block(work);
     }
     __syncthreads();
 #pragma unroll
@@ -545,9 +566,9 @@ __global__ void __launch_bounds__(128) shade_rays_kernel(Nodes nodes, RenderLaun
                                                          vrt_shade_result* __restrict__ out) {
     extern __shared__ uint2 smem[];
     nodes.slots = pin(nodes.slots);
-    const int guard = pin(L.guard);
-    Stack64s<128> stack = Stack64s<128>::make(smem + threadIdx.x, pin(kSvoMaxDepth - L.depth));
-    const float guard_sf = pin(guard_scale_f(L.guard));
+    const int guard = keep_in_register(L.guard, smem + threadIdx.x);
+    Stack64s<128> stack = Stack64s<128>::make(smem + threadIdx.x, kSvoMaxDepth - L.depth);
+    const float guard_sf = keep_in_register(guard_scale_f(L.guard), smem + threadIdx.x);
     const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const vrt_shade_job job = jobs[i];

@@ -1,7 +1,7 @@
 """Static view of a kernel's traversal loop in SASS (no GPU needed): finds the innermost loop around the 8-byte node
 fetch (LDG.E.64) and prints its instructions with the pipe each one issues on (B300_MICROARCH.md: FFMA/FMUL/FADD/IMAD/
 HFMA2 = FMA pipe, full rate; integer add / logic / shift / compare / select / min-max / MOV = ALU pipe, half rate).
-   python tools/sass_loop.py <object or .so> <kernel-name-substring> [-q]"""
+   python tools/sass_loop.py <object or .so> <kernel-name-substring> [-q] [-a]"""
 import re
 import subprocess
 import sys
@@ -51,15 +51,26 @@ def main():
         # innermost loop containing an LDG.E.64: smallest backward branch span around it
         ldg = [i for i, (_, _, t) in enumerate(ins) if t.startswith("LDG.E.64")]
         best = None
+        loops = []
         for i, (a, p, t) in enumerate(ins):
             m = re.match(r"BRA(?:\.U)?\s+(?:!?U?P\d+,\s*)?(0x[0-9a-f]+)", t)
             if m and int(m.group(1), 16) in addr and addr[int(m.group(1), 16)] <= i:
                 lo = addr[int(m.group(1), 16)]
-                if any(lo <= k <= i for k in ldg) and (best is None or i - lo < best[1] - best[0]):
-                    best = (lo, i)
+                if any(lo <= k <= i for k in ldg):
+                    loops.append((lo, i))
+                    if best is None or i - lo < best[1] - best[0]:
+                        best = (lo, i)
         if best is None:
             print(fname, ": no loop found")
             continue
+        if "-a" in sys.argv:      # every innermost loop around a node fetch (a frame kernel has one per ray class)
+            inner = [l for l in loops if not any(o != l and l[0] <= o[0] and o[1] <= l[1] for o in loops)]
+            for lo, hi in inner:
+                c2 = {}
+                for a, p, t in ins[lo:hi + 1]:
+                    k = pipe(t.split()[0])
+                    c2[k] = c2.get(k, 0) + 1
+                print("  loop %04x..%04x: %d instructions %s" % (ins[lo][0], ins[hi][0], hi - lo + 1, dict(sorted(c2.items()))))
         lo, hi = best
         cnt = {}
         for a, p, t in ins[lo:hi + 1]:
