@@ -8,7 +8,8 @@
 //
 // So for every 8x8-pixel tile this kernel computes a RIGOROUS lower bound of the hit distance of every primary ray of the
 // tile (every pixel of the tile, every lens sample): the distance from the camera to the nearest non-empty octree node that
-// intersects the tile's frustum — a front-to-back search of the octree against the four side planes of the frustum.
+// intersects the tile's frustum — a front-to-back search of the octree against the four side planes of the frustum (and a
+// fifth plane in front of the camera).
 //   * a ray can only hit voxels, every voxel lies in the non-empty nodes of every level, and the ray stays inside the
 //     frustum of its tile, so the node it hits is among those the search sees (box-vs-plane tests only ever err towards
 //     "intersects");
@@ -29,19 +30,22 @@ namespace vrt {
 
 namespace {
 
-struct BeamFrame {
-    int x, y, z;       // low corner of the node's cube, voxel units, castRay space
-    uint32_t node;     // slot index of the node
-    int level;         // cube edge = 1 << level
-};
+constexpr int kBeamThreads = 128;                 // 16 tiles per block: 8 lanes per tile
+constexpr int kBeamStack = 88;                    // <= 7 pushes per level, depth <= 12
 
 }  // namespace
 
-// One thread per tile.  floor[ty * tiles_x + tx] = t (normalised units, as castRay measures it) below which no primary ray of
-// the tile can hit anything.
-__global__ void __launch_bounds__(64) beam_floor_kernel(const uint2* __restrict__ slots, RenderLaunch L, int tile, int tiles_x, int tiles_y,
-                                                        int tile_y0, float* __restrict__ floor) {
-    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+// Eight lanes per tile: lane `sub` of a group tests child `sub` of the node the group has popped, so the eight box-vs-frustum
+// tests of a node run side by side instead of one after the other (one thread per tile took 0.30 ms on the headline frame whatever
+// the number of tiles: the time of the longest search, one dependent test after the other).  The group's stack lives in shared
+// memory; the children that have to be searched are pushed farthest first, so the nearest is popped next (front to back).
+// floor[ty * tiles_x + tx] = t (normalised units, as castRay measures it) below which no primary ray of the tile can hit anything.
+__global__ void __launch_bounds__(kBeamThreads) beam_floor_kernel(const uint2* __restrict__ slots, RenderLaunch L, int tile, int tiles_x,
+                                                                  int tiles_y, int tile_y0, float* __restrict__ floor) {
+    __shared__ uint4 stacks[kBeamThreads / 8][kBeamStack];      // x | y << 16, z | level << 16, node, bits of d_min
+    const int group = threadIdx.x >> 3, sub = threadIdx.x & 7, lane = threadIdx.x & 31;
+    const unsigned gmask = 0xffu << (lane & 24);
+    const int id = blockIdx.x * (kBeamThreads / 8) + group;
     if (id >= tiles_x * tiles_y) return;
     const int tx = id % tiles_x, ty = tile_y0 + id / tiles_x;
     if (L.tile_step > 1) {                                 // multi-GPU tile split: only tiles that contain rows this rank renders
@@ -67,7 +71,7 @@ __global__ void __launch_bounds__(64) beam_floor_kernel(const uint2* __restrict_
         dir[k][2] = (m[6] * lx + m[7] * ly) + m[8] * lz;
     }
     // inward unit normals of the side planes: left (00,01), right (11,10), top (10,00), bottom (01,11), oriented by the opposite corner
-    float pn[4][3];
+    float pn[5][3];
     const int pa[4] = {0, 3, 1, 2}, pb[4] = {2, 1, 0, 3}, inside[4] = {1, 0, 2, 0};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -80,12 +84,13 @@ __global__ void __launch_bounds__(64) beam_floor_kernel(const uint2* __restrict_
         pn[k][0] = nx * inv; pn[k][1] = ny * inv; pn[k][2] = nz * inv;
     }
     // fifth plane: in front of the camera.  Without it a box BEHIND the camera passes the side-plane tests whenever the frustum
-    // there is narrower than the lens slack (small tiles): sky tiles would "see" the ground behind the camera and lose their skip
-    float fwd[3] = {dir[0][0] + dir[1][0] + dir[2][0] + dir[3][0], dir[0][1] + dir[1][1] + dir[2][1] + dir[3][1],
-                    dir[0][2] + dir[1][2] + dir[2][2] + dir[3][2]};
+    // there is narrower than the lens slack (small tiles): sky tiles would "see" the ground behind the camera and lose their skip.
+    // Every ray point is r + t * u with t >= 0 and u within the tile: dot(fwd, p) >= -|r| for all of them.
     {
-        const float inv = rsqrtf(fwd[0] * fwd[0] + fwd[1] * fwd[1] + fwd[2] * fwd[2]);
-        fwd[0] *= inv; fwd[1] *= inv; fwd[2] *= inv;
+        const float fx = dir[0][0] + dir[1][0] + dir[2][0] + dir[3][0], fy = dir[0][1] + dir[1][1] + dir[2][1] + dir[3][1],
+                    fz = dir[0][2] + dir[1][2] + dir[2][2] + dir[3][2];
+        const float inv = rsqrtf(fx * fx + fy * fy + fz * fz);
+        pn[4][0] = fx * inv; pn[4][1] = fy * inv; pn[4][2] = fz * inv;
     }
     // lens radius (voxels) and its growth with distance, with a little slack for the rounding of everything above
     const float lens = fabsf(L.cam.aperture) * 0.70710678f * 1.01f + 0.01f;
@@ -94,56 +99,76 @@ __global__ void __launch_bounds__(64) beam_floor_kernel(const uint2* __restrict_
     // footprint of the tile per unit distance (voxels per voxel): its diagonal
     const float spread = float(tile) * 1.4142136f / float(L.height);
 
-    BeamFrame stack[96];
-    int sp = 0;
-    stack[sp++] = BeamFrame{0, 0, 0, 0u, L.depth};
-    float best = 3.0e9f;                                   // nearest qualifying node so far (voxels)
+    uint4* stack = stacks[group];
+    int sp = 1;
+    if (sub == 0) stack[0] = make_uint4(0u, uint32_t(L.depth) << 16, 0u, 0u);
+    __syncwarp(gmask);
+    float best = 3.0e9f;                                   // nearest qualifying node so far (voxels); the same in all lanes of a group
     while (sp > 0) {
-        const BeamFrame f = stack[--sp];
-        const uint2 w = __ldg(slots + f.node);
+        const uint4 f = stack[--sp];
+        __syncwarp(gmask);                                 // everyone has read the frame before anyone overwrites its slot
+        if (__uint_as_float(f.w) >= best) continue;        // something nearer was found since this node was pushed
+        const int fx = int(f.x & 0xffffu), fy = int(f.x >> 16), fz = int(f.y & 0xffffu), level = int(f.y >> 16);
+        const uint2 w = __ldg(slots + f.z);
         const uint32_t child_mask = (w.x >> 8) & 0xffu, leaf_mask = (w.x >> 16) & 0xffu;
-        const int half = 1 << (f.level - 1);
-        // front to back: the octant on the camera's side first.  The stack is LIFO, so the octants are visited farthest first
-        // and the nearest is pushed last (terminal nodes update `best` at once, whatever the order).
-        const uint32_t near_upper = (cx >= float(f.x + half) ? 1u : 0u) | (cy >= float(f.y + half) ? 2u : 0u) | (cz >= float(f.z + half) ? 4u : 0u);
-#pragma unroll 1
-        for (int k = 7; k >= 0; --k) {
-            const uint32_t upper = uint32_t(k) ^ near_upper;
-            const uint32_t s = ~upper & 7u;                // slot bit clear = upper half (the tree stores the mirrored octant, lsvo.hpp:79)
-            if (!((child_mask >> s) & 1u)) continue;
-            const int bx = f.x + ((upper & 1u) ? half : 0), by = f.y + ((upper & 2u) ? half : 0), bz = f.z + ((upper & 4u) ? half : 0);
+        const int half = 1 << (level - 1);
+        // front to back: lane 0 takes the octant on the camera's side, lane 7 the opposite one
+        const uint32_t near_upper = (cx >= float(fx + half) ? 1u : 0u) | (cy >= float(fy + half) ? 2u : 0u) | (cz >= float(fz + half) ? 4u : 0u);
+        const uint32_t upper = uint32_t(sub) ^ near_upper;
+        const uint32_t s = ~upper & 7u;                    // slot bit clear = upper half (the tree stores the mirrored octant, lsvo.hpp:79)
+        const int bx = fx + ((upper & 1u) ? half : 0), by = fy + ((upper & 2u) ? half : 0), bz = fz + ((upper & 4u) ? half : 0);
+        float d_min = 3.0e9f;
+        bool search = false, terminal = false;
+        if ((child_mask >> s) & 1u) {
             const float x0 = float(bx) - cx, y0 = float(by) - cy, z0 = float(bz) - cz, e = float(half);
             // distance from the camera to the box (0 inside) and to its far corner
             const float nxd = fmaxf(fmaxf(x0, -(x0 + e)), 0.0f), nyd = fmaxf(fmaxf(y0, -(y0 + e)), 0.0f), nzd = fmaxf(fmaxf(z0, -(z0 + e)), 0.0f);
-            const float d_min = sqrtf(nxd * nxd + nyd * nyd + nzd * nzd);
-            if (d_min >= best) continue;
-            const float fx = fmaxf(fabsf(x0), fabsf(x0 + e)), fy = fmaxf(fabsf(y0), fabsf(y0 + e)), fz = fmaxf(fabsf(z0), fabsf(z0 + e));
-            const float d_far = sqrtf(fx * fx + fy * fy + fz * fz);
-            const float slack = lens + lens_growth * d_far + 1e-3f * e + 1e-4f * d_far;
-            bool outside = false;
+            d_min = sqrtf(nxd * nxd + nyd * nyd + nzd * nzd);
+            if (d_min < best) {
+                const float ax = fmaxf(fabsf(x0), fabsf(x0 + e)), ay = fmaxf(fabsf(y0), fabsf(y0 + e)), az = fmaxf(fabsf(z0), fabsf(z0 + e));
+                const float d_far = sqrtf(ax * ax + ay * ay + az * az);
+                const float slack = lens + lens_growth * d_far + 1e-3f * e + 1e-4f * d_far;
+                bool outside = false;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                // the box corner farthest along the inward normal
-                const float qx = pn[k][0] >= 0.0f ? x0 + e : x0, qy = pn[k][1] >= 0.0f ? y0 + e : y0, qz = pn[k][2] >= 0.0f ? z0 + e : z0;
-                if (pn[k][0] * qx + pn[k][1] * qy + pn[k][2] * qz < -slack) outside = true;
-            }
-            {   // every ray point is r + t * u with t >= 0 and u within the tile: dot(fwd, p) >= -|r| for all of them
-                const float qx = fwd[0] >= 0.0f ? x0 + e : x0, qy = fwd[1] >= 0.0f ? y0 + e : y0, qz = fwd[2] >= 0.0f ? z0 + e : z0;
-                if (fwd[0] * qx + fwd[1] * qy + fwd[2] * qz < -slack) outside = true;
-            }
-            if (outside) continue;
-            const bool leaf = (leaf_mask >> s) & 1u;
-            if (leaf || f.level - 1 == 0 || e <= 0.5f * spread * d_min) {
-                best = d_min;                              // d_min < best here
-            } else if (sp < 96) {
-                stack[sp++] = BeamFrame{bx, by, bz, f.node + w.y + s, f.level - 1};
-            } else {
-                best = d_min;                              // stack full (cannot happen for depth <= 12): stay conservative
+                for (int k = 0; k < 5; ++k) {
+                    // the box corner farthest along the inward normal
+                    const float qx = pn[k][0] >= 0.0f ? x0 + e : x0, qy = pn[k][1] >= 0.0f ? y0 + e : y0, qz = pn[k][2] >= 0.0f ? z0 + e : z0;
+                    if (pn[k][0] * qx + pn[k][1] * qy + pn[k][2] * qz < -slack) outside = true;
+                }
+                if (!outside) {
+                    const bool leaf = (leaf_mask >> s) & 1u;
+                    terminal = leaf || level - 1 == 0 || e <= 0.5f * spread * d_min;
+                    search = !terminal;
+                }
             }
         }
+        // the nearest terminal child bounds everything else
+        float cand = terminal ? d_min : 3.0e9f;
+        cand = fminf(cand, __shfl_xor_sync(gmask, cand, 1));
+        cand = fminf(cand, __shfl_xor_sync(gmask, cand, 2));
+        cand = fminf(cand, __shfl_xor_sync(gmask, cand, 4));
+        best = fminf(best, cand);
+        search = search && d_min < best;
+        const unsigned pushing = (__ballot_sync(gmask, search) >> (lane & 24)) & 0xffu;
+        const int n_push = __popc(pushing);
+        if (sp + n_push > kBeamStack) {                    // cannot happen for depth <= 12: stay conservative
+            float m = search ? d_min : 3.0e9f;
+            m = fminf(m, __shfl_xor_sync(gmask, m, 1));
+            m = fminf(m, __shfl_xor_sync(gmask, m, 2));
+            m = fminf(m, __shfl_xor_sync(gmask, m, 4));
+            best = fminf(best, m);
+        } else {
+            // farthest first: lane `sub` goes below every pushing lane nearer than itself
+            if (search) stack[sp + __popc(pushing >> (sub + 1))] = make_uint4(uint32_t(bx) | uint32_t(by) << 16, uint32_t(bz) | uint32_t(level - 1) << 16,
+                                                                             f.z + w.y + s, __float_as_uint(d_min));
+            sp += n_push;
+        }
+        __syncwarp(gmask);
     }
-    const float t = (best - lens - 2.0f) / S;              // castRay's t is distance in the unit cube's units; two voxels of slack
-    floor[id] = best > 2.9e9f ? 3.0f : fmaxf(0.0f, t - 1e-5f * fabsf(t));   // empty frustum: beyond the cube's diagonal
+    if (sub == 0) {
+        const float t = (best - lens - 2.0f) / S;          // castRay's t is distance in the unit cube's units; two voxels of slack
+        floor[id] = best > 2.9e9f ? 3.0f : fmaxf(0.0f, t - 1e-5f * fabsf(t));   // empty frustum: beyond the cube's diagonal
+    }
 }
 
 cudaError_t launch_beam_floor(const uint2* nodes, const RenderLaunch& L, int tile, float* d_floor, cudaStream_t stream) {
@@ -151,7 +176,8 @@ cudaError_t launch_beam_floor(const uint2* nodes, const RenderLaunch& L, int til
     const int ty0 = L.row_begin / tile, ty1 = (L.row_end + tile - 1) / tile;
     const int n = tiles_x * (ty1 - ty0);
     if (n <= 0) return cudaSuccess;
-    beam_floor_kernel<<<(n + 63) / 64, 64, 0, stream>>>(nodes, L, tile, tiles_x, ty1 - ty0, ty0, d_floor + size_t(ty0) * tiles_x);
+    const int per_block = kBeamThreads / 8;
+    beam_floor_kernel<<<(n + per_block - 1) / per_block, kBeamThreads, 0, stream>>>(nodes, L, tile, tiles_x, ty1 - ty0, ty0, d_floor + size_t(ty0) * tiles_x);
     return cudaGetLastError();
 }
 

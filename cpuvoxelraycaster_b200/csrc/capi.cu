@@ -148,6 +148,7 @@ int vrt_context_set_option(vrt_context* ctx, const char* key, int value) {
     const std::string k(key);
     if (k == "cast_variant" && value >= 0 && value <= 2) ctx->cast_variant = value;
     else if (k == "render_variant" && value >= 0 && value <= 4) ctx->render_variant = value;
+    else if (k == "help_window" && value >= 0 && value <= 4096) ctx->help_window = value;
     else if (k == "sort_bins1" && value >= 0 && value <= 256) ctx->sort_bins1 = value;
     else if (k == "sort_bins2" && value >= 0 && value <= 256) ctx->sort_bins2 = value;
     else if (k == "spp_chunks" && value >= 0 && value <= 4096) ctx->spp_chunks = value;
@@ -677,6 +678,7 @@ vrt::RenderLaunch make_launch(const vrt_scene* sc, const vrt_camera* cam, const 
     L.trav_policy = sc->ctx->trav_policy;
     L.grid_variant = sc->ctx->grid_variant;
     L.sort_bins1 = sc->ctx->sort_bins1; L.sort_bins2 = sc->ctx->sort_bins2;
+    L.help_window = sc->ctx->help_window;
     L.roughness = p->roughness;
     L.max_bounds = p->max_bounds;
     L.mirror_y1 = sc->kind == VRT_SCENE_LSVO ? p->mirror_y1 : 0;
@@ -730,7 +732,7 @@ int vrt_render_accumulate_device(vrt_scene* sc, const vrt_camera* cam, const vrt
         vrt::RenderLaunch L = make_launch(sc, cam, p);
         // beam floors (beam_kernels.cu): conservative start distances of the camera rays, per screen tile.  Frames are
         // identical with and without them; only the trip counts of the primary rays shrink.
-        // Worth its own launch (~0.15 ms: one thread per tile, a latency-bound tree search) only when every floor is used by many
+        // Worth its own launch (a latency-bound tree search, eight lanes per tile) only when every floor is used by many
         // rays: frames with >= 8 samples per pixel.  The interactive 1-sample frames (0.2 ms in all) go without.
         if (ctx->beam_tile > 0 && p->spp >= 8 && !sc->use_compact && (ctx->render_variant == 0 || ctx->render_variant == 2 || ctx->render_variant == 4)) {
             int shift = 0;

@@ -55,6 +55,7 @@ struct RenderLaunch {
     int spp_chunks;              // K4: runs the samples are cut into (0 = chosen by the launcher)
     int samples_per_warp;        // K4: lanes sharing a pixel, power of two 1..32 (0 = chosen by the launcher)
     int sort_bins1, sort_bins2;  // K5: angle bins per GI bounce (0 = chosen by the launcher; product <= 256)
+    int help_window;             // K6: groups of 32 blocks, counted from the last started, over which helping CTAs spread (0 = all start at the last)
     void* scratch;               // K6: device scratch for the sorted sample lists (render_scratch_bytes)
     size_t scratch_bytes;
     int mapping;                 // 0 = automatic (K5 for many-sample GI frames, else K4), 2 = K4, 3 = K5

@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(128) sort_samples_kernel(RenderLaunch L, SortP
 template <typename Nodes, int kTrav, bool kMirror = false>
 __global__ void __launch_bounds__(128, VRT_K6_MIN_CTAS) render_rounds_kernel(Nodes nodes, RenderLaunch L, BlockGeometry G,
                                                                             const uint16_t* __restrict__ lists, uint32_t* meta,
-                                                                            uint32_t* next_block, uint32_t* __restrict__ accum,
+                                                                            uint32_t* __restrict__ accum,
                                                                             unsigned long long* __restrict__ counters) {
     extern __shared__ uint2 smem[];
     __shared__ int s_block;
@@ -445,6 +445,8 @@ __global__ void __launch_bounds__(128, VRT_K6_MIN_CTAS) render_rounds_kernel(Nod
     const float aspect = float(L.width) / float(L.height);                    // main.cpp:133
     const float focal_length = L.focal ? __ldg(L.focal) : L.cam.focal_length;
     const int n_blocks = G.tiles_x * G.tiles_y * G.runs;
+    // the next block to start: a counter behind the blocks' (samples, next round) pairs, addressed from `meta` on the spot (a pointer
+    // of its own would be one more value alive across the traversal loops)
 
     // all rounds this warp can get of block `work`
     auto trace_block = [&](int work) {
@@ -513,32 +515,51 @@ __global__ void __launch_bounds__(128, VRT_K6_MIN_CTAS) render_rounds_kernel(Nod
     // Phase 0 — own blocks: the CTA takes a block, its warps share the block's rounds (`work >= n_blocks` is CTA-uniform, so all
     // warps leave the phase together and the barriers stay matched).  Phase 1 — help: blocks are started in order, so unfinished
     // ones are among the last started; every warp scans backwards, 32 blocks per look, and joins whatever still has rounds.
-    bool helping = false;
-    int base = n_blocks - 1;
+    // Helping CTAs spread out (L.help_window = W > 0): CTA c starts its scan at group (last - c mod W) of the W highest groups of 32
+    // blocks and, inside a group, at a block picked by c / W; it goes round the window until a whole turn finds nothing open, then
+    // continues below it as before.  Its four warps make the same choices, so they join the same block and share its nodes in L1.
+    // W = 0: every warp starts at the last block (all helpers work their way down through the same blocks together).
+    bool helping = false, below = false;
+    const int groups = (n_blocks + 31) >> 5;
+    const int W = L.help_window > groups ? groups : L.help_window;
+    const int rot = W > 0 ? int(blockIdx.x / unsigned(W)) & 31 : 0;
+    int g = groups - 1, looked = 0, cur = 0;
     unsigned open_mask = 0u;
     for (;;) {
         int work;
         if (!helping) {
-            if (threadIdx.x == 0) s_block = int(atomicAdd(next_block, 1u));
+            if (threadIdx.x == 0) s_block = int(atomicAdd(meta + 2 * n_blocks, 1u));
             __syncthreads();
             work = s_block;
             __syncthreads();
-            if (work >= n_blocks) { helping = true; base = n_blocks - 1 + 32; continue; }
+            if (work >= n_blocks) {
+                helping = true;
+                below = W == 0;
+                g = W > 0 ? groups - 1 - int(blockIdx.x % unsigned(W)) : groups - 1;
+                continue;
+            }
         } else {
             if (!open_mask) {
-                base -= 32;
-                if (base < 0) break;
-                const int w = base - lane;
+                // (a global count of the blocks handed out completely, read here to leave at once when nothing is left, measured
+                // slower: 40.85 vs 40.51 ms on the headline frame, profiles/r02_ab_exh.txt)
+                if (!below && looked == W) { below = true; g = groups - 1 - W; }
+                if (below && (g < 0 || g < groups - 1 - 256)) break;                  // far behind the frontier: everything is done
+                cur = g * 32 + 31;
+                const int w = cur - lane;
                 bool open = false;
-                if (w >= 0) open = *reinterpret_cast<volatile uint32_t*>(meta + 2 * w + 1) * 32u < meta[2 * w];
+                if (w < n_blocks) open = *reinterpret_cast<volatile uint32_t*>(meta + 2 * w + 1) * 32u < meta[2 * w];
                 open_mask = __ballot_sync(0xffffffffu, open);
-                if (!open_mask) {
-                    if (base < n_blocks - 1 - 32 * 256) break;                       // far behind the frontier: everything is done
-                    continue;
+                if (below) --g;
+                else {
+                    looked = open_mask ? 0 : looked + 1;
+                    g = g == groups - W ? groups - 1 : g - 1;
                 }
+                if (!open_mask) continue;
             }
-            work = base - (__ffs(open_mask) - 1);
-            open_mask &= open_mask - 1;
+            const unsigned turned = __funnelshift_r(open_mask, open_mask, rot);
+            const int bit = (__ffs(turned) - 1 + rot) & 31;
+            open_mask &= ~(1u << bit);
+            work = cur - bit;
         }
         trace_block(work);
     }
@@ -673,6 +694,7 @@ RoundsPlan plan_rounds(const RenderLaunch& L) {
     if (P.G.tiles_y < 0) P.G.tiles_y = 0;
     int runs = 1;
     while ((L.spp + runs - 1) / runs > 64) runs *= 2;                               // <= 8192 samples per list (16-bit entries)
+    while (runs < L.spp_chunks && runs * 2 <= L.spp) runs *= 2;                     // explicit override: more, shorter lists
     P.G.runs = runs;
     P.G.cap = 128 * ((L.spp + runs - 1) / runs);
     const int n = 128 * (L.spp / runs);
@@ -731,7 +753,7 @@ cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem);
             unsigned grid6 = unsigned(per_sm > 0 ? per_sm : 1) * unsigned(sms);
             if (grid6 > blocks) grid6 = blocks;
-            kernel<<<grid6, block, smem, stream>>>(view, L, P.G, lists, meta, next_block, d_accum, d_counters);
+            kernel<<<grid6, block, smem, stream>>>(view, L, P.G, lists, meta, d_accum, d_counters);
         };
         if (compact) launch6(render_rounds_kernel<CompactNodes, 0>, CompactNodes{nodes});
         else if (L.mirror_y1 > 0) launch6(render_rounds_kernel<RefNodes, 2, true>, RefNodes{nodes});

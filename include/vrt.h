@@ -98,6 +98,8 @@ int vrt_context_set_stream(vrt_context* ctx, void* stream);
  *                    refill_cast 0 = warp-adaptive (default)
  *   "spp_chunks"     frame kernel: number of runs a pixel's samples are cut into (0 = automatic)
  *   "samples_per_warp"  frame kernel: lanes of a warp sharing one pixel, power of two <= 32 (0 = automatic)
+ *   "help_window" (default 64): K6 frame kernel — CTAs that have run out of blocks of their own help with unfinished ones; they spread
+ *                    over the last `help_window` groups of 32 blocks instead of all starting at the last block (0).  Results identical
  *   "trav_policy" (default 2): traversal loop of the K6 frame kernel — 0 = Trav (round-1 loop), 1 = Trav2 (bookkeeping moved
  *                    off the ALU pipe), 2 = Trav2 with the cone test compiled out of the coef-0 casts; results identical
  *   "beam_tile" (default 8): LSVO frames with >= 8 samples per pixel — edge in pixels (power of two) of the screen tiles for which a conservative start

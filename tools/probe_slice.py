@@ -1,5 +1,8 @@
-"""Times K4 on the slice one of N GPUs would own (4-row tiles t % N == 0 of the cfg-4 frame) for combinations of
-spp_chunks / samples_per_warp — tuning aid for the launcher's automatic choice."""
+"""What one rank of an N-GPU tile split costs, measured on ONE GPU: the cfg-4 frame's slice of rank r of `world` (4-row tiles dealt
+round-robin) is rendered alone and timed with CUDA events; slice_ms * world / full_ms - 1 is the scaling loss that comes from the
+frame kernels themselves (fixed costs, tails), as opposed to the exchange.  PROBE_SLICE_ONE=world,rank renders only that slice, once
+warmed up — for an ncu launch list; PROBE_CASES="1,0;8,3" picks the (world, rank) cases; PROBE_OPTS="key=value,..." sets context
+options first.  One JSON line per measurement."""
 import json
 import os
 import sys
@@ -12,8 +15,24 @@ import cpuvoxelraycaster_b200 as vrt  # noqa: E402
 from cpuvoxelraycaster_b200.frame import FrameRenderer  # noqa: E402
 
 
+def time_frame(fr, cs, p, stream, reps=5):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            fr.accum.zero_()
+            fr.accumulate(cs, p)
+        for i in range(reps):
+            fr.accum.zero_()
+            ev[i].record(stream)
+            fr.accumulate(cs, p)
+        ev[reps].record(stream)
+    stream.synchronize()
+    return float(np.median([ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]))
+
+
 def main():
-    D, S = 11, 2048.0
+    D = int(os.environ.get("PROBE_DEPTH", "11"))
+    S = float(1 << D)
     stream = torch.cuda.Stream()
     ctx = vrt.Context(0, stream.cuda_stream)
     scene = vrt.LSVO.from_terrain(ctx, D)
@@ -21,26 +40,30 @@ def main():
     scene.set_textures(t["top"], t["side"])
     cam = vrt.Camera(position=(S / 2, S / 2 - 56, S / 2), view_angle=(0, 0), aperture=0.5)
     cam.autofocus(scene)
-    for world in (1, 8):
-        fr = FrameRenderer(scene, 1920, 1080, 0, world, None, None, stream)
-        fr.use_gi, fr.gi_bounces = True, 2
+    cs = cam.as_struct()
+    for kv in filter(None, os.environ.get("PROBE_OPTS", "").split(",")):          # context options, e.g. PROBE_OPTS=beam_overlap=0
+        k, v = kv.split("=")
+        try:
+            ctx.set_option(k, int(v))
+        except Exception as e:                                                       # an older library build: say so, carry on
+            print(json.dumps(dict(option=k, error=str(e)[:80])), flush=True)
+    one = os.environ.get("PROBE_SLICE_ONE")
+    cases = [tuple(int(x) for x in one.split(","))] if one else [tuple(int(x) for x in c.split(",")) for c in os.environ["PROBE_CASES"].split(";")] if os.environ.get("PROBE_CASES") else [(1, 0), (2, 0), (2, 1), (4, 0), (4, 3), (8, 0), (8, 3), (8, 7)]
+    full = None
+    for world, rank in cases:
+        fr = FrameRenderer(scene, 1920, 1080, rank, world, None, None, stream, exchange="nccl")
         fr.light = np.float32([-200, -1000, -300]) * np.float32(1.0 / S) + np.float32(1.0)
-        p, cs = fr.params(64), cam.as_struct()
-        for chunks, q in ((0, 0), (1, 32), (2, 32), (4, 16), (8, 8), (16, 4), (32, 2), (64, 1), (29, 1), (4, 1), (16, 1), (32, 1)):
-            ctx.set_option("spp_chunks", chunks)
-            ctx.set_option("samples_per_warp", q)
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-            with torch.cuda.stream(stream):
-                fr.accum.zero_()
-                fr.accumulate(cs, p)
-                for i in range(4):
-                    fr.accum.zero_()
-                    ev[i].record(stream)
-                    fr.accumulate(cs, p)
-                ev[4].record(stream)
-            stream.synchronize()
-            ms = float(np.median([ev[i].elapsed_time(ev[i + 1]) for i in range(3)]))
-            print(json.dumps(dict(world=world, spp_chunks=chunks, samples_per_warp=q, ms=round(ms, 3))), flush=True)
+        fr.use_gi, fr.gi_bounces = True, 2
+        p = fr.params(64)
+        ctx.set_option("time_frame_kernels", 1)
+        ms = time_frame(fr, cs, p, stream, reps=1 if one else 5)
+        kt = ctx.take_kernel_timings()
+        ctx.set_option("time_frame_kernels", 0)
+        if world == 1:
+            full = ms
+        st = fr.stats()
+        print(json.dumps(dict(world=world, rank=rank, ms=round(ms, 3), sort_and_trace_ms=round(float(np.median(kt)), 3) if len(kt) else None,
+                              rays=sum(st["rays"]), trips=sum(st["complexity"]), loss_pct=round(100 * (ms * world / full - 1), 2) if full else None)), flush=True)
 
 
 if __name__ == "__main__":
