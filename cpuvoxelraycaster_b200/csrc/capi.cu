@@ -146,7 +146,7 @@ int vrt_context_take_timings(vrt_context* ctx, float* ms, int32_t cap, int32_t* 
 int vrt_context_set_option(vrt_context* ctx, const char* key, int value) {
     if (!ctx || !key) return fail(VRT_ERR_INVALID, "vrt_context_set_option: NULL argument");
     const std::string k(key);
-    if (k == "cast_variant" && value >= 0 && value <= 2) ctx->cast_variant = value;
+    if (k == "cast_variant" && value >= 0 && value <= 3) ctx->cast_variant = value;
     else if (k == "render_variant" && value >= 0 && value <= 4) ctx->render_variant = value;
     else if (k == "help_window" && value >= 0 && value <= 4096) ctx->help_window = value;
     else if (k == "sort_bins1" && value >= 0 && value <= 256) ctx->sort_bins1 = value;
@@ -568,6 +568,7 @@ int vrt_scene_info(const vrt_scene* sc, int32_t* kind, uint32_t* depth, uint64_t
 }
 
 // ---- batched traversal -----------------------------------------------------------------------------
+constexpr int kGateSlot = 14;        // d_counters[14]: verdict of the ray classifier (automatic cast variant)
 int vrt_cast_rays_device(vrt_scene* sc, const float* d_origin, const float* d_dir, float coef, float bias, uint64_t n,
                          vrt_hit* d_out) {
     if (!sc) return fail(VRT_ERR_INVALID, "vrt_cast_rays_device: scene is NULL");
@@ -579,7 +580,21 @@ int vrt_cast_rays_device(vrt_scene* sc, const float* d_origin, const float* d_di
     if (n == 0) return VRT_OK;
     switch (sc->kind) {
         case VRT_SCENE_LSVO:
-            if (ctx->cast_variant == 2 && !sc->use_compact)
+            if (ctx->cast_variant == 3 && !sc->use_compact) {
+                // automatic: cone rays are short — one thread per ray wins whatever their order; small batches are not worth a
+                // look; otherwise a classifier kernel decides on the device and both kernels are enqueued, gated on its verdict
+                // (no host round trip: the call stays asynchronous)
+                if (fabsf(coef) >= 0.05f || n < 65536) {
+                    VRT_CUDA(vrt::launch_lsvo_cast2(sc->d_nodes, int(sc->depth), sc->guard, d_origin, d_dir, coef, bias, n, d_out, sc->d_counters, ctx->stream));
+                } else {
+                    unsigned long long* gate = sc->d_counters + kGateSlot;
+                    VRT_CUDA(vrt::launch_classify_rays(d_origin, d_dir, n, gate, ctx->stream));
+                    VRT_CUDA(vrt::launch_lsvo_cast2(sc->d_nodes, int(sc->depth), sc->guard, d_origin, d_dir, coef, bias, n, d_out, sc->d_counters, ctx->stream, gate, 1ull));
+                    VRT_CUDA(vrt::launch_lsvo_cast_persistent(sc->d_nodes, false, int(sc->depth), sc->guard, d_origin, d_dir, coef, bias, n, d_out, sc->d_counters,
+                                                              ctx->refill_cast, ctx->stream, gate, 0ull));
+                    ctx->launches += 2;
+                }
+            } else if ((ctx->cast_variant == 2 || ctx->cast_variant == 3) && !sc->use_compact)
                 VRT_CUDA(vrt::launch_lsvo_cast2(sc->d_nodes, int(sc->depth), sc->guard, d_origin, d_dir, coef, bias, n, d_out, sc->d_counters, ctx->stream));
             else if (ctx->cast_variant == 0 || ctx->cast_variant == 2)
                 VRT_CUDA(vrt::launch_lsvo_cast_ref(sc->use_compact ? sc->d_compact : sc->d_nodes, sc->use_compact, int(sc->depth), sc->guard, d_origin, d_dir, coef, bias, n, d_out,

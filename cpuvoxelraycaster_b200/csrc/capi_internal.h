@@ -45,7 +45,7 @@ struct vrt_context {
     // 1 = persistent threads with per-lane ray regeneration; 0 = one thread per ray / pixel.
     // Defaults follow the measurements in profiles/r01_summary.md: batched casts regenerate (warp-adaptive),
     // frames keep one lane per pixel (coherent primary/shadow rays lose more from de-phasing than GI rays gain).
-    int cast_variant = 1, render_variant = 0;
+    int cast_variant = 3, render_variant = 0;
     int help_window = 64;                       // K6: see RenderLaunch::help_window (0/8/32/64/256: 5.53/5.41/5.36/5.35/5.34 ms on a 1/8 slice)
     int sort_bins1 = 0, sort_bins2 = 0;         // K5: angle bins of the two GI bounces (0 = automatic)
     int spp_chunks = 0;                        // K4: 0 = automatic

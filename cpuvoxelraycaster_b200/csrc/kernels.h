@@ -10,9 +10,12 @@ namespace vrt {
 cudaError_t launch_lsvo_cast_ref(const uint2* nodes, bool compact, int depth, int guard, const float* d_origin, const float* d_dir,
                                  float coef, float bias, uint64_t n, vrt_hit* d_out, unsigned long long* d_complexity,
                                  cudaStream_t stream);
-// K1b: the same on Trav2 (lsvo_step.cuh), reference layout
+// K1b: the same on Trav2 (lsvo_step.cuh), reference layout.  d_gate != NULL: the kernel runs only if *d_gate == want.
 cudaError_t launch_lsvo_cast2(const uint2* nodes, int depth, int guard, const float* d_origin, const float* d_dir, float coef, float bias,
-                              uint64_t n, vrt_hit* d_out, unsigned long long* d_complexity, cudaStream_t stream);
+                              uint64_t n, vrt_hit* d_out, unsigned long long* d_complexity, cudaStream_t stream,
+                              const unsigned long long* d_gate = nullptr, unsigned long long want = 0);
+// *d_gate = 1 if the batch's rays are coherent in groups of 32 consecutive rays (n >= 1024), else 0
+cudaError_t launch_classify_rays(const float* d_origin, const float* d_dir, uint64_t n, unsigned long long* d_gate, cudaStream_t stream);
 
 // Bit-packed occupancy pyramid of a dense grid: level l holds cubes of edge 2^l, z-contiguous like
 // Grid3D::m_cells[x][y][z] (grid_3d.hpp:26); bit i of the level = word i>>5, bit i&31.
@@ -115,7 +118,8 @@ namespace vrt {
 // d_counters: cast: [0] Σ complexity, [1] work counter; render: [0..11] stats, [12] work counter — zeroed by the caller.
 cudaError_t launch_lsvo_cast_persistent(const uint2* nodes, bool compact, int depth, int guard, const float* d_origin, const float* d_dir,
                                         float coef, float bias, uint64_t n, vrt_hit* d_out, unsigned long long* d_counters,
-                                        int refill, cudaStream_t stream);
+                                        int refill, cudaStream_t stream, const unsigned long long* d_gate = nullptr,
+                                        unsigned long long want = 0);
 cudaError_t launch_render_persistent(const uint2* nodes, const RenderLaunch& L, uint32_t* d_accum, unsigned long long* d_counters,
                                      int refill, cudaStream_t stream);
 // Grid frames: camera rays, DDA, mirror reflections, texture + sun shadow, accumulation (grid_kernels.cu)

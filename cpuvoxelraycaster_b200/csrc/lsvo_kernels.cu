@@ -49,19 +49,22 @@ __global__ void __launch_bounds__(128) lsvo_cast_kernel(Nodes nodes, int depth, 
     if ((threadIdx.x & 31) == 0 && iters) atomicAdd(total_complexity, (unsigned long long)iters);
 }
 
-// K1b: the same kernel on Trav2 (bookkeeping off the ALU pipe, cone test compiled out for coef = bias = 0)
+// K1b: the same kernel on Trav2 (bookkeeping off the ALU pipe, cone test compiled out for coef = bias = 0).  Grid-stride, so that a
+// gated launch (below) can use a bounded grid; with one CTA per 128 rays the loop body runs once.
+// gate != nullptr: the kernel runs only if *gate == want (the automatic choice between K1b and K1p, made on the device).
 template <typename Nodes, bool kCone>
 __global__ void __launch_bounds__(128) lsvo_cast2_kernel(Nodes nodes, int depth, int guard, const float* __restrict__ origin,
                                                          const float* __restrict__ dir, float coef, float bias, uint64_t n,
-                                                         vrt_hit* __restrict__ out, unsigned long long* __restrict__ total_complexity) {
+                                                         vrt_hit* __restrict__ out, unsigned long long* __restrict__ total_complexity,
+                                                         const unsigned long long* __restrict__ gate, unsigned long long want) {
     extern __shared__ uint2 smem[];
+    if (gate && *gate != want) return;
     nodes.slots = pin(nodes.slots);
     const float guard_sf = keep_in_register(guard_scale_f(guard), smem + threadIdx.x);
     guard = keep_in_register(guard, smem + threadIdx.x);
     Stack64s<128> stack = Stack64s<128>::make(smem + threadIdx.x, kSvoMaxDepth - depth);
-    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     uint32_t iters = 0u;
-    if (i < n) {
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
         const float ox = origin[3 * i], oy = origin[3 * i + 1], oz = origin[3 * i + 2];
         const float dx = dir[3 * i], dy = dir[3 * i + 1], dz = dir[3 * i + 2];
         LsvoResult r;
@@ -69,22 +72,67 @@ __global__ void __launch_bounds__(128) lsvo_cast2_kernel(Nodes nodes, int depth,
         LsvoHit h;
         if (r.hit) lsvo_finish(r, ox, oy, oz, depth, h);
         store_hit(out + i, r, h, depth);
-        iters = r.complexity;
+        iters += r.complexity;
     }
+    __syncwarp();
     for (int o = 16; o > 0; o >>= 1) iters += __shfl_xor_sync(0xffffffffu, iters, o);
     if ((threadIdx.x & 31) == 0 && iters) atomicAdd(total_complexity, (unsigned long long)iters);
 }
 
+// Are the rays of a batch coherent the way the reference's are (32 consecutive rays = neighbouring pixels of one camera)?  32 groups
+// of 32 consecutive rays, spread over the batch, are looked at: a group is coherent when its directions (normalised) and its origins
+// stay close to those of the group's first ray.  *gate = 1 when at least 3/4 of the groups are: one thread per ray (K1b) then beats
+// the regenerating persistent kernel (8.6 vs 6.5 Grays/s on 1080p camera rays; 4.5 vs 6.5 on random rays — profiles/r02_probe_bounds.txt).
+// The choice only decides which kernel runs; both return the same bytes.
+__global__ void __launch_bounds__(1024) classify_rays_kernel(const float* __restrict__ origin, const float* __restrict__ dir, uint64_t n,
+                                                            unsigned long long* __restrict__ gate) {
+    __shared__ int votes;
+    if (threadIdx.x == 0) votes = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, group = threadIdx.x >> 5;
+    const uint64_t groups = n / 32;                        // n >= 1024 (the launcher's rule)
+    const uint64_t i = (groups * uint64_t(group) / 32) * 32 + uint64_t(lane);
+    float dx = dir[3 * i], dy = dir[3 * i + 1], dz = dir[3 * i + 2];
+    const float inv = rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-30f));
+    dx *= inv; dy *= inv; dz *= inv;
+    const float ox = origin[3 * i], oy = origin[3 * i + 1], oz = origin[3 * i + 2];
+    float spread = fmaxf(fmaxf(fabsf(dx - __shfl_sync(0xffffffffu, dx, 0)), fabsf(dy - __shfl_sync(0xffffffffu, dy, 0))),
+                         fabsf(dz - __shfl_sync(0xffffffffu, dz, 0)));
+    float apart = fmaxf(fmaxf(fabsf(ox - __shfl_sync(0xffffffffu, ox, 0)), fabsf(oy - __shfl_sync(0xffffffffu, oy, 0))),
+                        fabsf(oz - __shfl_sync(0xffffffffu, oz, 0)));
+    if (!(spread == spread) || !(apart == apart)) spread = 1e9f;          // NaN rays: not coherent
+    for (int o = 16; o > 0; o >>= 1) {
+        spread = fmaxf(spread, __shfl_xor_sync(0xffffffffu, spread, o));
+        apart = fmaxf(apart, __shfl_xor_sync(0xffffffffu, apart, o));
+    }
+    if (lane == 0 && spread < 0.25f && apart < 0.05f) atomicAdd(&votes, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) *gate = votes >= 24 ? 1ull : 0ull;
+}
+
+cudaError_t launch_classify_rays(const float* d_origin, const float* d_dir, uint64_t n, unsigned long long* d_gate, cudaStream_t stream) {
+    classify_rays_kernel<<<1, 1024, 0, stream>>>(d_origin, d_dir, n, d_gate);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_lsvo_cast2(const uint2* nodes, int depth, int guard, const float* d_origin, const float* d_dir, float coef, float bias,
-                              uint64_t n, vrt_hit* d_out, unsigned long long* d_complexity, cudaStream_t stream) {
+                              uint64_t n, vrt_hit* d_out, unsigned long long* d_complexity, cudaStream_t stream,
+                              const unsigned long long* d_gate, unsigned long long want) {
     if (n == 0) return cudaSuccess;
     const int block = 128;
     const size_t smem = size_t(depth + 1) * block * 8;
-    const uint64_t grid = (n + block - 1) / block;
+    uint64_t grid = (n + block - 1) / block;
+    if (d_gate) {                                          // bounded grid: a launch that turns out not to be wanted must cost nothing
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const uint64_t cap = uint64_t(sms) * 16 * 8;       // 8 rounds of 16 CTAs per SM: dynamic enough to stay balanced
+        if (grid > cap) grid = cap;
+    }
     if (coef == 0.0f && bias == 0.0f)
-        lsvo_cast2_kernel<RefNodes, false><<<unsigned(grid), block, smem, stream>>>(RefNodes{nodes}, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_complexity);
+        lsvo_cast2_kernel<RefNodes, false><<<unsigned(grid), block, smem, stream>>>(RefNodes{nodes}, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_complexity, d_gate, want);
     else
-        lsvo_cast2_kernel<RefNodes, true><<<unsigned(grid), block, smem, stream>>>(RefNodes{nodes}, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_complexity);
+        lsvo_cast2_kernel<RefNodes, true><<<unsigned(grid), block, smem, stream>>>(RefNodes{nodes}, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_complexity, d_gate, want);
     return cudaGetLastError();
 }
 

@@ -51,8 +51,10 @@ __global__ void __launch_bounds__(128, 8) lsvo_cast_persistent_kernel(Nodes node
                                                                       const float* __restrict__ origin,
                                                                       const float* __restrict__ dir, float coef, float bias,
                                                                       uint64_t n, vrt_hit* __restrict__ out,
-                                                                      unsigned long long* __restrict__ counters, int refill) {
+                                                                      unsigned long long* __restrict__ counters, int refill,
+                                                                      const unsigned long long* __restrict__ gate, unsigned long long want) {
     extern __shared__ uint2 smem[];
+    if (gate && *gate != want) return;                     // the automatic K1b / K1p choice (lsvo_kernels.cu, classify_rays_kernel)
     nodes.slots = pin(nodes.slots);
     const float guard_sf = keep_in_register(guard_scale_f(guard), smem + threadIdx.x);
     guard = keep_in_register(guard, smem + threadIdx.x);
@@ -275,14 +277,15 @@ static int resident_blocks(K kernel, int block, size_t smem) {
 
 template <typename Nodes>
 static cudaError_t cast_persistent(Nodes nv, int depth, int guard, const float* d_origin, const float* d_dir, float coef, float bias,
-                                   uint64_t n, vrt_hit* d_out, unsigned long long* d_counters, int refill, cudaStream_t stream) {
+                                   uint64_t n, vrt_hit* d_out, unsigned long long* d_counters, int refill, cudaStream_t stream,
+                                   const unsigned long long* d_gate, unsigned long long want) {
     const int block = 128;
     const size_t smem = size_t(depth + 1) * block * 8;
     auto launch = [&](auto kernel) {
         uint64_t grid = uint64_t(resident_blocks(kernel, block, smem));
         const uint64_t need = (n + block - 1) / block;
         if (need < grid) grid = need;
-        kernel<<<unsigned(grid), block, smem, stream>>>(nv, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_counters, refill);
+        kernel<<<unsigned(grid), block, smem, stream>>>(nv, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_counters, refill, d_gate, want);
     };
     // the cone test is compiled out when it cannot fire (coef = bias = 0: lsvo_step.cuh, Trav2)
     if (coef == 0.0f && bias == 0.0f) launch(lsvo_cast_persistent_kernel<Nodes, false>);
@@ -292,10 +295,10 @@ static cudaError_t cast_persistent(Nodes nv, int depth, int guard, const float* 
 
 cudaError_t launch_lsvo_cast_persistent(const uint2* nodes, bool compact, int depth, int guard, const float* d_origin, const float* d_dir,
                                         float coef, float bias, uint64_t n, vrt_hit* d_out, unsigned long long* d_counters,
-                                        int refill, cudaStream_t stream) {
+                                        int refill, cudaStream_t stream, const unsigned long long* d_gate, unsigned long long want) {
     if (n == 0) return cudaSuccess;
-    return compact ? cast_persistent(CompactNodes{nodes}, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_counters, refill, stream)
-                   : cast_persistent(RefNodes{nodes}, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_counters, refill, stream);
+    return compact ? cast_persistent(CompactNodes{nodes}, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_counters, refill, stream, d_gate, want)
+                   : cast_persistent(RefNodes{nodes}, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_counters, refill, stream, d_gate, want);
 }
 
 cudaError_t launch_render_persistent(const uint2* nodes, const RenderLaunch& L, uint32_t* d_accum, unsigned long long* d_counters,

@@ -88,8 +88,10 @@ int vrt_context_destroy(vrt_context* ctx);
 int vrt_context_synchronize(vrt_context* ctx);
 int vrt_context_set_stream(vrt_context* ctx, void* stream);
 /* Tuning knobs (no reference counterpart):
- *   "cast_variant" (default 1): 1 = persistent threads with per-lane ray regeneration (K1p), 0 = one thread per ray (K1),
- *                    2 = one thread per ray on the Trav2 loop (K1b)
+ *   "cast_variant" (default 3): 3 = automatic — a classifier kernel looks at the batch (are 32 consecutive rays neighbours, like the
+ *                    reference's pixel rays?) and gates K1b (coherent) or K1p (incoherent) on the device, no host round trip;
+ *                    1 = persistent threads with per-lane ray regeneration (K1p), 0 = one thread per ray (K1),
+ *                    2 = one thread per ray on the Trav2 loop (K1b).  Results identical
  *   "render_variant" (default 0): 0 = automatic (K6 for frames with >= 8 samples, else K4), 1 = K4p persistent
  *                    regenerating warps, 2 = K4 one lane per pixel/sample group, 3 = K5 samples of a pixel block
  *                    regrouped by GI direction inside the CTA, 4 = K6 the same lists in global memory traced by

@@ -287,7 +287,7 @@ def test_cfg5_lsvo4096_prefix_1e6_vs_oracle(vrt, port):
     nodes = port.build_terrain(12)
     want = port.lsvo_cast(nodes, 12, o, d, guard=0, threads=16)
     del nodes
-    for variant in (1, 0):
+    for variant in (3, 1, 0, 2):                                       # 3 = automatic (the default): the classifier sends these to K1p
         c.set_option("cast_variant", variant)
         a = s.cast_rays(o, d)
         assert_hits_equal(a, want, hit_flag(a), "cfg5 10^6 prefix, cast_variant %d" % variant)
@@ -328,7 +328,7 @@ def test_cfg1_full_frame_known_answers(vrt, ctx, textures):
     d = normalize((normalize(lens) * f32(g["focal_length"])).astype(np.float32))
     assert np.array_equal(cam.rot_mat, np.eye(3, dtype=np.float32).ravel())
     o = np.broadcast_to(np.float32(g["cam_position"]) * np.float32(1 / 512.0) + np.float32(1), d.shape).copy()
-    for variant in (0, 1):
+    for variant in (0, 1, 2, 3):                                       # 3 = automatic (the default): the classifier sends these to K1b
         ctx.set_option("cast_variant", variant)
         hits = s.cast_rays(o, d)
         hf = hit_flag(hits)
@@ -336,5 +336,5 @@ def test_cfg1_full_frame_known_answers(vrt, ctx, textures):
         assert hashlib.sha256(hf.astype(np.uint8).tobytes()).hexdigest() == g["sha256_hit_flags"]
         assert hashlib.sha256(hits["complexity"].astype(np.uint32).tobytes()).hexdigest() == g["sha256_complexity"]
         assert hashlib.sha256(hits["distance"][hf].astype(np.float32).tobytes()).hexdigest() == g["sha256_distance_of_hits"]
-    ctx.set_option("cast_variant", 1)
+    ctx.set_option("cast_variant", 3)
     s.close()

@@ -85,7 +85,7 @@ def test_edge_cases(vrt, ctx, port):
     assert hit_flag(got)[0] and got["distance"][0] == 0.5 and not np.any(got["normal"][0])
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_non_finite_rays_are_misses(vrt, port, terrain9_nodes, variant):
     """The reference's loop never ends on a NaN / infinite ray; engine and oracle define a miss of complexity 0."""
     c = vrt.Context(0)
@@ -109,7 +109,7 @@ def test_non_finite_rays_are_misses(vrt, port, terrain9_nodes, variant):
     c.close()
 
 
-@pytest.mark.parametrize("variant,refill", [(0, 8), (1, 0), (1, 1), (1, 8), (1, 20), (1, 32)])
+@pytest.mark.parametrize("variant,refill", [(0, 8), (1, 0), (1, 1), (1, 8), (1, 20), (1, 32), (2, 0), (3, 0)])
 def test_kernel_variants_agree(vrt, port, terrain9_nodes, variant, refill):
     """One-thread-per-ray and persistent/regenerating kernels give byte-identical hit records for every refill
     threshold (scheduling must not change results)."""

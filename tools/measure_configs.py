@@ -145,7 +145,7 @@ def measure(ctx, stream, want, iters=5, cfg5_rays=100_000_000, emit=None):
         d /= d.norm(dim=1, keepdim=True)
         out = torch.empty(n * 16, dtype=torch.int32, device="cuda")
         res = {}
-        for variant in (1, 0):
+        for variant in (3, 1, 0):                                    # 3 = automatic (the default): classifier + gated K1b / K1p
             ctx.set_option("cast_variant", variant)
             ms = timed(stream, lambda: scene.cast_rays_device(o, d, n, out), max(2, a.iters // 2))
             res[variant] = ms
@@ -159,12 +159,12 @@ def measure(ctx, stream, want, iters=5, cfg5_rays=100_000_000, emit=None):
         scene.cast_rays(ho, hd)
         e2e_s = time.time() - t0
         emit_line(dict(cfg=5, what="T(12) LSVO 4096^3, %d random rays" % n, device_build_s=round(tb, 3), slots=n_slots,
-                              ms_persistent_adaptive=round(res[1], 3), ms_one_thread_per_ray=round(res[0], 3),
-                              mrays_s=round(n / res[1] / 1e3, 1), hit_fraction=round(hits / n, 4), mean_complexity=round(cx / n, 2),
+                              ms_automatic=round(res[3], 3), ms_persistent_adaptive=round(res[1], 3), ms_one_thread_per_ray=round(res[0], 3),
+                              mrays_s=round(n / res[3] / 1e3, 1), hit_fraction=round(hits / n, 4), mean_complexity=round(cx / n, 2),
                               e2e_host_buffers=dict(rays=ne, ms=round(e2e_s * 1e3, 1), mrays_s=round(ne / e2e_s / 1e6, 1), bytes_per_ray=88),
-                              algo_GBs=round((8 * cx + 64 * n) / res[1] / 1e6, 1)))
+                              algo_GBs=round((8 * cx + 64 * n) / res[3] / 1e6, 1)))
         scene.close()
-        ctx.set_option("cast_variant", 1)
+        ctx.set_option("cast_variant", 3)
     return results
 
 
