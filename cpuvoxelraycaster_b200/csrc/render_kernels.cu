@@ -417,7 +417,9 @@ __global__ void __launch_bounds__(128) sort_samples_kernel(RenderLaunch L, SortP
 // loops compile without spills at 64 registers — the ~270 bytes of spills sit in the chain code between the casts — and the
 // kernel, which was waiting on instruction latency at 20 warps per SM (issue slots 74 % busy, 1.75 eligible warps per scheduler),
 // gains from every step: 5 / 6 / 7 / 8 CTAs per SM = 45.06 / 42.83 / 41.69 / 41.15 ms on the headline frame, same box
-// (profiles/r02_ab_keepreg.txt).
+// (profiles/r02_ab_keepreg.txt).  Beyond 8 it loses again although the loops still hold at 56 / 48 / 40 registers: 9 / 10 / 12 CTAs =
+// 42.1 / 42.0 / 43.8 ms against 40.3 (profiles/r02_ab_ctas2.txt; L1 shrinks and the chain code spills 260-420 bytes), and per-warp
+// statistics counters (6 KB of shared memory less per CTA, redux + two shared atomics per cast) cost 0.3 ms instead of gaining.
 #ifndef VRT_K6_MIN_CTAS
 #define VRT_K6_MIN_CTAS 8
 #endif
