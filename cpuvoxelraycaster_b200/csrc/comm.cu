@@ -37,14 +37,18 @@ constexpr int kMaxWorld = 16;
 
 // Counters at the start of every window; only the ones in the ROOT's window (and, for deliver_all, in each window) are used.
 struct Flags {
-    unsigned long long arrived;    // += 1 per rank and frame when its tiles are in this window's frame buffer
+    unsigned long long unused0;
     unsigned long long consumed;   // frames of this window's buffers that have been handed to the consumer (host copy done)
     unsigned long long acc_done;   // sample split: += 1 per rank and frame when its accumulator is complete
     unsigned long long reduced;    // sample split: += 1 per rank and frame when it has finished reading the peers' accumulators
     unsigned long long error;      // != 0: a wait timed out
     unsigned long long pad[3];
+    // arrived_from[r] = 1 + ordinal of the latest frame whose tiles rank r has stored into this window's frame buffer.  One slot
+    // per SOURCE: a shared arrival count cannot tell a fast rank's next frame from a slow rank's current one (with three or more
+    // ranks the consumer then takes a frame before its last tiles are in — found by tests/multigpu_frame_check.py on 4 GPUs).
+    unsigned long long arrived_from[kMaxWorld];
 };
-static_assert(sizeof(Flags) == 64, "Flags layout");
+static_assert(sizeof(Flags) == 64 + 8 * kMaxWorld && sizeof(Flags) <= 256, "Flags layout (the window header is 256 bytes)");
 
 struct Blob {                      // what vrt_comm_export writes: VRT_COMM_HANDLE_BYTES
     uint32_t magic, rank, world, device;
@@ -68,7 +72,6 @@ struct vrt_comm {
     bool connected = false;
     uint64_t frame_no = 0;                  // frames started
     uint64_t sample_frames = 0;             // frames rendered with the sample split so far (orders acc_done / reduced)
-    uint64_t expect_arrived = 0;            // tile pushes this rank's window must have received once all frames so far are in
     long long last_in_buf[kMaxWorld][2];    // frame ordinal last delivered into buffer b of rank t's window (-1: none); identical on all ranks
     cudaStream_t copy_stream = nullptr;     // root: device-to-host copies overlap the next frame
     cudaEvent_t frame_ready = nullptr, copy_done[2] = {nullptr, nullptr};
@@ -97,6 +100,20 @@ __global__ void signal_kernel(unsigned long long* counter, unsigned long long ad
 __global__ void set_kernel(unsigned long long* counter, unsigned long long value) {
     __threadfence_system();
     atomicMax_system(counter, value);
+}
+// spins until counter[0..n) are all >= want
+__global__ void wait_all_kernel(const unsigned long long* counter, int n, unsigned long long want, unsigned long long* err) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int r = 0; r < n; ++r)
+        while (ld_acquire_sys(counter + r) < want) {
+            __nanosleep(200);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > 4000000000ull) {
+                atomicAdd_system(err, 1ull);
+                return;
+            }
+        }
 }
 // spins until *counter >= want (at most ~4 s of globaltimer), else records an error in `err`
 __global__ void wait_kernel(const unsigned long long* counter, unsigned long long want, unsigned long long* err) {
@@ -373,15 +390,14 @@ int vrt_render_distributed(vrt_comm* c, vrt_scene* sc, const vrt_camera* cam, co
     // publish: this rank's tiles are in the targets' buffers
     for (int t = 0; t < W; ++t)
         if (deliver_all || t == root) {
-            signal_kernel<<<1, 1, 0, st>>>(&c->flags(t)->arrived, 1ull);
+            set_kernel<<<1, 1, 0, st>>>(&c->flags(t)->arrived_from[c->rank], f + 1);
             ctx->launches += 1;
         }
     // consumer side: wait for everybody's tiles, then hand the frame over
     if (deliver_all || c->rank == root) {
         Flags* mine = c->flags(c->rank);
-        c->expect_arrived += uint64_t(W);
         if (W > 1) {
-            wait_kernel<<<1, 1, 0, st>>>(&mine->arrived, c->expect_arrived, &mine->error);
+            wait_all_kernel<<<1, 1, 0, st>>>(mine->arrived_from, W, f + 1, &mine->error);
             ctx->launches += 1;
         }
         if (host_rgba) {

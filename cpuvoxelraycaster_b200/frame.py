@@ -112,10 +112,15 @@ class FrameRenderer:
         self.stream = stream if stream is not None else torch.cuda.Stream(self.device)
         scene.ctx.set_stream(self.stream.cuda_stream)      # libvrt re-applies an installed L2 access-policy window to it
         scene.ctx.torch_stream = self.stream               # keeps the cudaStream_t alive as long as the context uses it
-        self.exchange = TileExchange(self.W, self.H, self.rank, self.world, self.device, group)
-        self.H_pad, self.row_bytes = self.exchange.H_pad, self.exchange.row_bytes
-        self.accum = torch.zeros(self.H_pad * self.W * 4, dtype=torch.int32, device=self.device)   # r,g,b,count sums
-        self.rgba = torch.zeros(self.H_pad * self.W * 4, dtype=torch.uint8, device=self.device)
+        # Device buffers are created ON the render stream: their zero fills are then ordered before the first frame (on torch's
+        # current stream — the default one, behind whatever collective is still pending there — a fill could land between a frame's
+        # trace and its resolve and wipe the accumulator: seen as all-zero tiles of one rank in the first frame on 4 GPUs), and the
+        # caching allocator ties the blocks to the stream that uses them.
+        with torch.cuda.stream(self.stream):
+            self.exchange = TileExchange(self.W, self.H, self.rank, self.world, self.device, group)
+            self.H_pad, self.row_bytes = self.exchange.H_pad, self.exchange.row_bytes
+            self.accum = torch.zeros(self.H_pad * self.W * 4, dtype=torch.int32, device=self.device)   # r,g,b,count sums
+            self.rgba = torch.zeros(self.H_pad * self.W * 4, dtype=torch.uint8, device=self.device)
         # two pinned host frames: frame i is copied out while frame i+1 renders (render_pipelined)
         self.host_frames = [torch.empty(self.H * self.row_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
         self.host_frame = self.host_frames[0]
@@ -192,7 +197,8 @@ class FrameRenderer:
         """main.cpp:159-177 on the device: optional median, then the persistence blend of `frame` (a device uint8
         [H, W, 4] view such as render_device returns) into the display surface, which is returned."""
         if self.display is None:
-            self.display = torch.zeros(self.H * self.W * 4, dtype=torch.uint8, device=self.device)
+            with torch.cuda.stream(self.stream):             # fill ordered before the first use (see __init__)
+                self.display = torch.zeros(self.H * self.W * 4, dtype=torch.uint8, device=self.device)
         p = capi.PresentParams(self.W, self.H, int(median), float(old_value_conservation))
         with torch.cuda.stream(self.stream):
             check(lib().vrt_present_device(self.scene.ctx.handle, ptr(frame), ptr(self.display), C.byref(p)))

@@ -23,8 +23,8 @@ def test_frame_identical_across_world_sizes():
 
 
 @pytest.mark.gpu
-def test_cpp_host_drives_two_gpus_through_the_c_abi():
-    """tests/cpp/multigpu_test.cpp: one C++ process, vrt_comm_create_local + vrt_render_distributed on 2 GPUs, tile and sample
+def test_cpp_host_drives_several_gpus_through_the_c_abi():
+    """tests/cpp/multigpu_test.cpp: one C++ process, vrt_comm_create_local + vrt_render_distributed on 2-4 GPUs, tile and sample
     splits, three pipelined frames each, compared byte for byte with vrt_render on one GPU."""
     import torch
     from conftest import golden
@@ -36,5 +36,6 @@ def test_cpp_host_drives_two_gpus_through_the_c_abi():
                     "-o", exe, "-L" + lib_dir, "-lvrt", "-Wl,-rpath," + lib_dir], check=True)
     t = golden("textures.npz")
     open(tex, "wb").write(t["top"].tobytes() + t["side"].tobytes())
-    r = subprocess.run([exe, tex, "2"], capture_output=True, text=True, timeout=300)
+    # three or more GPUs when the box has them: that is where an arrival protocol can go wrong (a fast rank overtaking a slow one)
+    r = subprocess.run([exe, tex, str(min(4, torch.cuda.device_count()))], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "multigpu_test: OK" in r.stdout and "MISMATCH" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

@@ -433,3 +433,39 @@ def test_beam_floors_are_below_every_primary_hit(vrt, ctx, scene9, port, terrain
         assert (per_pixel <= t_hit).all(), (tile, float((per_pixel - t_hit).max()))
         tight = per_pixel[t_hit < 10] / t_hit[t_hit < 10]
         assert tight.mean() > 0.35, (tile, float(tight.mean()))
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_tile_split_slices_add_up_with_product_defaults(vrt, ctx, scene9, world):
+    """What the ranks of a multi-GPU tile split render, rendered one after the other on ONE GPU with the product defaults (beam
+    floors, bounds exit, K6): the slices' accumulators and ray counts add up to the single-GPU frame's.  Ragged frame (330x187:
+    the last 4-row tile and the last 8-pixel beam tile are cut), 8 samples per pixel — the configuration
+    tests/multigpu_frame_check.py runs on 4 GPUs."""
+    import torch
+    from cpuvoxelraycaster_b200.frame import FrameRenderer
+    W, H, spp = 330, 187, 8
+    cam = vrt.Camera(position=(256, 200, 256), view_angle=(0.3, -0.35), aperture=0.5, focal_length=60.0)
+    cs = cam.as_struct()
+    ctx.set_option("beam_tile", 8)
+    ctx.set_option("bounds_exit", 1)
+    try:
+        def accumulate(rank, n):
+            fr = FrameRenderer(scene9, W, H, rank, n, None, None, None, exchange="nccl")
+            fr.use_gi, fr.gi_bounces, fr.light = True, 2, default_light()
+            fr.accum.zero_()
+            fr.accumulate(cs, fr.params(spp))
+            torch.cuda.synchronize()
+            return fr.accum.cpu().numpy().astype(np.int64)[: H * W * 4], fr.stats()
+        want, st1 = accumulate(0, 1)
+        total = np.zeros_like(want)
+        rays = [0] * 6
+        for r in range(world):
+            a, st = accumulate(r, world)
+            total += a
+            rays = [x + y for x, y in zip(rays, st["rays"])]
+        bad = np.flatnonzero((total != want).reshape(-1, 4).any(axis=1))
+        assert bad.size == 0, "world %d: %d pixels differ, first at (x, y) = %s" % (world, bad.size, [(int(i % W), int(i // W)) for i in bad[:8]])
+        assert rays == list(st1["rays"])
+    finally:
+        ctx.set_option("beam_tile", 0)
+        ctx.set_option("bounds_exit", 0)

@@ -54,7 +54,7 @@ def main():
         fr = FrameRenderer(scene, 1920, 1080, rank, world, None, None, stream, exchange="nccl")
         fr.light = np.float32([-200, -1000, -300]) * np.float32(1.0 / S) + np.float32(1.0)
         fr.use_gi, fr.gi_bounces = True, 2
-        p = fr.params(64)
+        p = fr.params(int(os.environ.get("PROBE_SPP", "64")))
         ctx.set_option("time_frame_kernels", 1)
         ms = time_frame(fr, cs, p, stream, reps=1 if one else 5)
         kt = ctx.take_kernel_timings()
