@@ -367,8 +367,14 @@ __global__ void __launch_bounds__(256) grid_cast_fast_kernel(GridLevels g, const
 
 __device__ __forceinline__ uint8_t mul_u8g(uint8_t c, float f) { return uint8_t(fminf(255.0f, float(c) * f)); }   // utils.cpp:43-48
 
+// 12 CTAs per SM (40 registers): the DDA loops need few registers and the kernel waits on instruction latency — left to itself
+// ptxas takes 72 registers (7 CTAs per SM) and still spills 24 bytes.  cfg-3 frame (4K, mirror lake), same box: unbounded / 8 / 10 / 12
+// CTAs per SM = 13.4 / 9.46 / 8.61 / 8.48 ms (profiles/r02_ab_grid_k4.txt).
+#ifndef VRT_GRID_RENDER_MIN_CTAS
+#define VRT_GRID_RENDER_MIN_CTAS 12
+#endif
 template <int kMode>
-__global__ void __launch_bounds__(128) grid_render_kernel(GridLevels g, RenderLaunch L, uint32_t* __restrict__ accum,
+__global__ void __launch_bounds__(128, VRT_GRID_RENDER_MIN_CTAS) grid_render_kernel(GridLevels g, RenderLaunch L, uint32_t* __restrict__ accum,
                                                           unsigned long long* __restrict__ counters) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tiles_x = (L.width + 31) / 32;

@@ -17,9 +17,13 @@
 
 namespace vrt {
 
-// 4 CTAs per SM (128 registers): more resident warps at fewer registers measured slower (profiles/r01_summary.md)
+// 8 CTAs per SM (64 registers).  Round 1 ran K4 at 4 (128 registers: more warps at fewer registers spilled into the loop and
+// measured slower); with the Trav2 loop and its invariants held in registers (lsvo_step.cuh) the loops compile spill-free at 64
+// registers (~200 bytes of spills in the chain code) and the extra warps pay: 4 / 6 / 8 CTAs per SM = 0.201 / 0.180 / 0.172 ms on
+// the 720p 1-sample frame, 4.19 / 3.72 / 3.62 ms on a 1080p 4-sample GI frame, 1.38 / 1.20 / 1.15 ms on the 4K interactive frame
+// (profiles/r02_ab_k4.txt).
 #ifndef VRT_K4_MIN_CTAS
-#define VRT_K4_MIN_CTAS 4
+#define VRT_K4_MIN_CTAS 8
 #endif
 // kLive: the interactive-loop extras (checkerboard pixel mapping, focal length read from the autofocus kernel's output).
 // Compiled out of the plain instantiation so that they cost the many-sample frames nothing (register allocation of the
@@ -585,7 +589,7 @@ __global__ void __launch_bounds__(128, VRT_K6_MIN_CTAS) render_rounds_kernel(Nod
 // ray, the same sample chain as the frame kernels (sun shadow, GI with the Philox numbers of (pixel, sample)), so a ray
 // that equals the frame kernels' primary ray of (pixel, sample) gives exactly that sample's colour.
 template <typename Nodes>
-__global__ void __launch_bounds__(128) shade_rays_kernel(Nodes nodes, RenderLaunch L, uint64_t n, const vrt_shade_job* __restrict__ jobs,
+__global__ void __launch_bounds__(128, 8) shade_rays_kernel(Nodes nodes, RenderLaunch L, uint64_t n, const vrt_shade_job* __restrict__ jobs,
                                                          vrt_shade_result* __restrict__ out) {
     extern __shared__ uint2 smem[];
     nodes.slots = pin(nodes.slots);
