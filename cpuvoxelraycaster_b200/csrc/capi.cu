@@ -33,16 +33,13 @@ namespace {
 // after every edit.  Synchronises the stream.
 int update_bounds(vrt_scene* sc, const char* who) {
     vrt_context* ctx = sc->ctx;
-    void* work = nullptr;
-    float* d_bounds = nullptr;
-    cudaError_t e = cudaMalloc(&work, vrt::bounds_work_bytes());
-    if (e == cudaSuccess) e = cudaMalloc(&d_bounds, 6 * sizeof(float));
-    if (e == cudaSuccess) e = vrt::device_scene_bounds(sc->d_nodes, int(sc->depth), 2.0f, d_bounds, work, ctx->stream);
+    // work memory + 6 result floats, kept with the scene (an edit must not pay for cudaMalloc / cudaFree)
+    cudaError_t e = sc->bounds_work.reserve(vrt::bounds_work_bytes() + 256);
+    float* d_bounds = e == cudaSuccess ? reinterpret_cast<float*>(static_cast<char*>(sc->bounds_work.ptr) + vrt::bounds_work_bytes()) : nullptr;
+    if (e == cudaSuccess) e = vrt::device_scene_bounds(sc->d_nodes, int(sc->depth), 2.0f, d_bounds, sc->bounds_work.ptr, ctx->stream);
     float host[6];
     if (e == cudaSuccess) e = cudaMemcpyAsync(host, d_bounds, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (work) cudaFree(work);
-    if (d_bounds) cudaFree(d_bounds);
     ctx->launches += 2 * sc->depth + 1;
     if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? fail(VRT_ERR_OOM, std::string(who) + ": device allocation failed (scene bounds)") : cuda_fail(e, who);
     for (int a = 0; a < 3; ++a) { sc->bounds.lo[a] = host[a]; sc->bounds.hi[a] = host[3 + a]; }
@@ -325,34 +322,37 @@ int vrt_scene_edit_heights(vrt_scene* sc, uint32_t x0, uint32_t z0, uint32_t nx,
     vrt_context* ctx = sc->ctx;
     if (int s = use_device(ctx)) return s;
     // the edit is staged: the old rectangle is kept until the new node array exists, and put back if the rebuild fails,
-    // so that the resident heights always describe the world that is being rendered
-    int32_t* d_old = nullptr;
-    VRT_CUDA(cudaMalloc(&d_old, size_t(nx) * nz * sizeof(int32_t)));
+    // so that the resident heights always describe the world that is being rendered.  All device memory involved is kept with
+    // the scene (work arrays, the staged rectangle, and the node array this edit replaces: the next edit builds into it).
+    if (sc->edit_old.reserve(size_t(nx) * nz * sizeof(int32_t)) != cudaSuccess) return fail(VRT_ERR_OOM, "vrt_scene_edit_heights: device allocation failed (scene unchanged)");
+    int32_t* d_old = static_cast<int32_t*>(sc->edit_old.ptr);
     cudaError_t e = cudaMemcpy2DAsync(d_old, size_t(nz) * sizeof(int32_t), sc->d_heights + size_t(x0) * S + z0, S * sizeof(int32_t),
                                       size_t(nz) * sizeof(int32_t), nx, cudaMemcpyDeviceToDevice, ctx->stream);
     if (e == cudaSuccess)
         e = cudaMemcpy2DAsync(sc->d_heights + size_t(x0) * S + z0, S * sizeof(int32_t), heights, size_t(nz) * sizeof(int32_t),
                               size_t(nz) * sizeof(int32_t), nx, cudaMemcpyHostToDevice, ctx->stream);
     uint2* d_new = nullptr;
-    uint64_t n_new = 0;
-    if (e == cudaSuccess) e = vrt::device_build_terrain_lsvo(int(sc->depth), &d_new, &n_new, nullptr, ctx->stream, sc->d_heights);
+    uint64_t n_new = 0, cap_new = 0;
+    if (e == cudaSuccess) e = vrt::device_build_terrain_lsvo(int(sc->depth), &d_new, &n_new, nullptr, ctx->stream, sc->d_heights, &sc->build_pool, &cap_new);
     ctx->launches += 7 + 9 * sc->depth;
     if (e != cudaSuccess) {
         cudaGetLastError();
         cudaMemcpy2DAsync(sc->d_heights + size_t(x0) * S + z0, S * sizeof(int32_t), d_old, size_t(nz) * sizeof(int32_t),
                           size_t(nz) * sizeof(int32_t), nx, cudaMemcpyDeviceToDevice, ctx->stream);
         cudaStreamSynchronize(ctx->stream);
-        cudaFree(d_old);
         return e == cudaErrorMemoryAllocation ? fail(VRT_ERR_OOM, "vrt_scene_edit_heights: device allocation failed (scene unchanged)")
                                               : cuda_fail(e, "vrt_scene_edit_heights (scene unchanged)");
     }
-    cudaFree(d_old);
-    // the builder synchronised the stream: nothing in flight reads the old arrays any more
-    cudaFree(sc->d_nodes);
+    // the replaced array stays alive as the pool's spare: frames already enqueued on the stream still read it, and the next edit —
+    // enqueued behind them on the same stream — builds into it
+    if (sc->build_pool.spare) cudaFree(sc->build_pool.spare);
+    sc->build_pool.spare = sc->d_nodes;
+    sc->build_pool.spare_slots = sc->nodes_capacity ? sc->nodes_capacity : sc->n_nodes;
     sc->device_bytes += n_new * sizeof(uint2);
     sc->device_bytes -= sc->n_nodes * sizeof(uint2);
     sc->d_nodes = d_new;
     sc->n_nodes = n_new;
+    sc->nodes_capacity = cap_new;
     if (int s = update_bounds(sc, "vrt_scene_edit_heights")) return s;
     if (sc->d_compact) {                                    // the compact copy is rebuilt from the new array
         cudaFree(sc->d_compact);
@@ -555,6 +555,9 @@ int vrt_scene_destroy(vrt_scene* sc) {
     sc->frame_rgba.release();
     sc->frame_lists.release();
     sc->beam_floor.release();
+    sc->build_pool.release();
+    sc->edit_old.release();
+    sc->bounds_work.release();
     delete sc;
     return VRT_OK;
 }

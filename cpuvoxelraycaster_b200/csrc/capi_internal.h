@@ -76,6 +76,9 @@ struct vrt_scene {
     uint64_t n_compact = 0;
     bool use_compact = false;
     int32_t* d_heights = nullptr;               // heightfield scenes: column heights [S*S], resident for edits
+    vrt::BuildPool build_pool;                  // heightfield scenes: work arrays + spare node array kept between edits
+    uint64_t nodes_capacity = 0;                // slots d_nodes can hold (>= n_nodes once an edit has built it from the pool)
+    DeviceBuffer edit_old, bounds_work;         // staged rectangle of an edit; work memory of the scene-bounds sweep
     uint64_t* d_voxel_keys = nullptr;           // voxel-set scenes: sorted distinct path keys, resident for edits
     uint32_t n_voxel_keys = 0;
     uint8_t* d_tex = nullptr;                   // top (768 B) then side (768 B)

@@ -1,6 +1,7 @@
 // Kernel launchers of libvrt (implemented in the .cu files, called by capi.cu).
 #pragma once
 #include <cstdint>
+#include <vector>
 #include <cuda_runtime.h>
 #include "../../include/vrt.h"
 
@@ -128,8 +129,26 @@ cudaError_t launch_grid_render(const GridLevels& g, bool use_mip, const RenderLa
 // Scene construction on the device (scene_device.cu): T(depth) in the reference's LNode layout, nothing crosses PCIe.
 // *d_slots is cudaMalloc'ed (the caller frees it); d_heights_out may be null.
 // d_heights_in (device, [S*S] int32, index x*S+z): build from these column heights instead of the FastNoise terrain.
+// Device memory a scene keeps between rebuilds (edits re-flatten the world: without this every edit pays cudaMalloc / cudaFree of the
+// node array and of ~40 work arrays — most of the 11-14 ms an edit took at 2048^3).  Work arrays are handed out in call order and
+// grow on demand; the node array that an edit replaces becomes the spare the next edit builds into.
+struct BuildPool {
+    std::vector<void*> ptr;
+    std::vector<size_t> bytes;
+    size_t next = 0;               // next work array to hand out (reset per build)
+    uint2* spare = nullptr;        // a node array of spare_slots slots, free to build into
+    uint64_t spare_slots = 0;
+    void release() {
+        for (void* p : ptr) cudaFree(p);
+        ptr.clear(); bytes.clear(); next = 0;
+        if (spare) cudaFree(spare);
+        spare = nullptr; spare_slots = 0;
+    }
+};
+// pool != NULL: work arrays and the node array come from the pool (the array may be larger than *n_slots: *capacity_slots), and the
+// call returns without waiting for the device (the caller keeps the replaced array alive as the pool's spare instead of freeing it).
 cudaError_t device_build_terrain_lsvo(int depth, uint2** d_slots, uint64_t* n_slots, int32_t* d_heights_out, cudaStream_t stream,
-                                      const int32_t* d_heights_in = nullptr);
+                                      const int32_t* d_heights_in = nullptr, BuildPool* pool = nullptr, uint64_t* capacity_slots = nullptr);
 // Reference layout → compact breadth-first array of live nodes, on the device (scene_device.cu); caller frees *d_out.
 // voxel_build.cu: arbitrary voxel sets on the device (sorted path keys → LNode array) and voxel edits
 cudaError_t device_voxel_keys(const uint32_t* d_xyz, uint64_t n, int depth, uint64_t** d_keys, uint32_t* n_keys, cudaStream_t stream);
