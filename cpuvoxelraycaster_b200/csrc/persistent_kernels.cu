@@ -46,8 +46,11 @@ __device__ __forceinline__ void store_hit_record(vrt_hit* out, const LsvoResult&
 // (ncu: 4.7 of 32 lanes active on random rays without regeneration), probing coherent mode again now and then.
 constexpr int kRayChunk = 64;
 
+#ifndef VRT_K1P_MIN_CTAS
+#define VRT_K1P_MIN_CTAS 8
+#endif
 template <typename Nodes, bool kCone>
-__global__ void __launch_bounds__(128, 8) lsvo_cast_persistent_kernel(Nodes nodes, int depth, int guard,
+__global__ void __launch_bounds__(128, VRT_K1P_MIN_CTAS) lsvo_cast_persistent_kernel(Nodes nodes, int depth, int guard,
                                                                       const float* __restrict__ origin,
                                                                       const float* __restrict__ dir, float coef, float bias,
                                                                       uint64_t n, vrt_hit* __restrict__ out,
