@@ -53,11 +53,12 @@ extern "C" {
 int vrt_abi_version(void) { return VRT_ABI_VERSION; }
 const char* vrt_last_error(void) { return g_last_error.c_str(); }
 const char* vrt_build_info(void) {
-    return "libvrt sm_100a --fmad=false -prec-div=true -prec-sqrt=true -ftz=false; kernels: lsvo_cast_kernel (K1), "
-           "lsvo_cast_persistent_kernel (K1p, default), render_accumulate_kernel (K4, interactive frames), render_sorted_kernel (K5), "
-           "sort_samples_kernel + render_rounds_kernel (K6, default for >= 8 samples per pixel), render_persistent_kernel (K4p), "
-           "autofocus_kernel, resolve_kernel, present_kernel, grid_cast_kernel<mip> (K2/K2m), svo_cast_kernel (K3), "
-           "grid_render_kernel<mip>, terrain / heightfield / voxel-set builders";
+    return "libvrt sm_100a --fmad=false -prec-div=true -prec-sqrt=true -ftz=false; kernels: lsvo_cast_kernel (K1), lsvo_cast2_kernel (K1b), "
+           "lsvo_cast_persistent_kernel (K1p), classify_rays_kernel (default: gates K1b / K1p per batch), render_accumulate_kernel (K4, "
+           "interactive frames), render_sorted_kernel (K5), beam_floor_kernel + sort_samples_kernel + render_rounds_kernel (K6, default for "
+           ">= 8 samples per pixel), render_persistent_kernel (K4p), shade_rays_kernel, autofocus_kernel, resolve_kernel, "
+           "resolve_push_kernel (multi-GPU), present_kernel, grid_cast_fast_kernel (K2f, default), grid_cast_kernel<mip> (K2/K2m), "
+           "svo_cast_kernel (K3), grid_render_kernel<mode>, terrain / heightfield / voxel-set builders";
 }
 
 int vrt_context_create(int device, void* stream, vrt_context** out) {

@@ -719,7 +719,7 @@ RoundsPlan plan_rounds(const RenderLaunch& L) {
 }  // namespace
 
 // 2 = K4, 3 = K5, 4 = K6.  Automatic: K6 for many-sample frames (with or without a GI pass: without one the lists stay
-// in pixel order and K6 still wins through 5 CTAs per SM and its even finish), K4 for the interactive loop.
+// in pixel order and K6 still wins through its even finish), K4 for the interactive loop.
 static int choose_mapping(const RenderLaunch& L) {
     if (L.checker) return 2;
     if (L.mapping >= 2) return L.mapping;
