@@ -370,7 +370,8 @@ int vrt_scene_edit_heights(vrt_scene* sc, uint32_t x0, uint32_t z0, uint32_t nx,
 
 namespace {
 // uploads a host voxel list and turns it into sorted distinct path keys on the device
-int upload_voxel_keys(vrt_context* ctx, uint32_t depth, const uint32_t* xyz, uint64_t n, uint64_t** d_keys, uint32_t* n_keys, const char* who) {
+int upload_voxel_keys(vrt_context* ctx, uint32_t depth, const uint32_t* xyz, uint64_t n, uint64_t** d_keys, uint32_t* n_keys, const char* who,
+                      vrt::BuildPool* pool = nullptr) {
     if (n && !xyz) return fail(VRT_ERR_INVALID, std::string(who) + ": NULL voxel list");
     if (n > 0xffffffffull) return fail(VRT_ERR_INVALID, std::string(who) + ": too many voxels");
     const uint32_t S = 1u << depth;
@@ -379,7 +380,7 @@ int upload_voxel_keys(vrt_context* ctx, uint32_t depth, const uint32_t* xyz, uin
     uint32_t* d_xyz = nullptr;
     cudaError_t e = cudaMalloc(&d_xyz, (n ? n : 1) * 3 * sizeof(uint32_t));
     if (e == cudaSuccess && n) e = cudaMemcpyAsync(d_xyz, xyz, n * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = vrt::device_voxel_keys(d_xyz, n, int(depth), d_keys, n_keys, ctx->stream);
+    if (e == cudaSuccess) e = vrt::device_voxel_keys(d_xyz, n, int(depth), d_keys, n_keys, ctx->stream, pool);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (d_xyz) cudaFree(d_xyz);
     ctx->launches += 4;
@@ -388,18 +389,28 @@ int upload_voxel_keys(vrt_context* ctx, uint32_t depth, const uint32_t* xyz, uin
 }
 
 // re-flattens a voxel-set scene from its resident keys and swaps the node array in
-int rebuild_from_keys(vrt_scene* sc, const uint64_t* d_keys, uint32_t n_keys, const char* who) {
+// pooled: an edit (the scene keeps work arrays and the replaced node array for the next one); else the arrays are freed
+int rebuild_from_keys(vrt_scene* sc, const uint64_t* d_keys, uint32_t n_keys, const char* who, bool pooled = false) {
     vrt_context* ctx = sc->ctx;
     uint2* d_new = nullptr;
-    uint64_t n_new = 0;
-    cudaError_t e = vrt::device_build_lsvo_from_keys(int(sc->depth), d_keys, n_keys, &d_new, &n_new, ctx->stream);
+    uint64_t n_new = 0, cap_new = 0;
+    cudaError_t e = vrt::device_build_lsvo_from_keys(int(sc->depth), d_keys, n_keys, &d_new, &n_new, ctx->stream, pooled ? &sc->build_pool : nullptr, &cap_new);
     ctx->launches += 2 + 4 * sc->depth;
     if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? fail(VRT_ERR_OOM, std::string(who) + ": device allocation failed") : cuda_fail(e, who);
-    if (sc->d_nodes) cudaFree(sc->d_nodes);                 // the builder synchronised the stream
+    if (sc->d_nodes) {                                      // the builder synchronised the stream: nothing reads the old array any more
+        if (pooled) {
+            if (sc->build_pool.spare) cudaFree(sc->build_pool.spare);
+            sc->build_pool.spare = sc->d_nodes;
+            sc->build_pool.spare_slots = sc->nodes_capacity ? sc->nodes_capacity : sc->n_nodes;
+        } else {
+            cudaFree(sc->d_nodes);
+        }
+    }
     sc->device_bytes += n_new * sizeof(uint2);
     sc->device_bytes -= sc->n_nodes * sizeof(uint2);
     sc->d_nodes = d_new;
     sc->n_nodes = n_new;
+    sc->nodes_capacity = cap_new;
     if (int s = update_bounds(sc, who)) return s;
     if (sc->d_compact) {
         cudaFree(sc->d_compact);
@@ -452,17 +463,17 @@ int vrt_scene_set_cells(vrt_scene* sc, const uint32_t* xyz, uint64_t n, int32_t 
     VRT_CUDA(cudaStreamSynchronize(ctx->stream));           // nothing in flight may still read the arrays replaced below
     uint64_t* d_edit = nullptr;
     uint32_t n_edit = 0;
-    if (int s = upload_voxel_keys(ctx, sc->depth, xyz, n, &d_edit, &n_edit, "vrt_scene_set_cells")) return s;
+    if (int s = upload_voxel_keys(ctx, sc->depth, xyz, n, &d_edit, &n_edit, "vrt_scene_set_cells", &sc->build_pool)) return s;
     uint64_t* d_merged = nullptr;
     uint32_t n_merged = 0;
     cudaError_t e = vrt::device_edit_voxel_keys(sc->d_voxel_keys, sc->n_voxel_keys, d_edit, n_edit, solid != 0, int(sc->depth), &d_merged,
-                                                &n_merged, ctx->stream);
+                                                &n_merged, ctx->stream, &sc->build_pool);
     cudaFree(d_edit);
     ctx->launches += 3;
     if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? fail(VRT_ERR_OOM, "vrt_scene_set_cells: device allocation failed")
                                                                 : cuda_fail(e, "vrt_scene_set_cells");
     // staged: the node array is rebuilt from the candidate key set first; the resident keys are replaced only when that worked
-    if (int s = rebuild_from_keys(sc, d_merged, n_merged, "vrt_scene_set_cells")) {
+    if (int s = rebuild_from_keys(sc, d_merged, n_merged, "vrt_scene_set_cells", true)) {
         cudaFree(d_merged);
         return s;
     }

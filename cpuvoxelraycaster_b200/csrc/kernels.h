@@ -145,16 +145,45 @@ struct BuildPool {
         spare = nullptr; spare_slots = 0;
     }
 };
+// Work arrays of one build: from the pool (call order, grown on demand, kept) or cudaMalloc'ed and freed on destruction.
+struct PoolScratch {
+    BuildPool* pool;
+    std::vector<void*> owned;
+    explicit PoolScratch(BuildPool* p) : pool(p) { if (pool) pool->next = 0; }
+    ~PoolScratch() { for (void* q : owned) cudaFree(q); }
+    template <typename T> cudaError_t alloc(T** q, size_t n) {
+        const size_t want = (n ? n : 1) * sizeof(T);
+        if (!pool) {
+            cudaError_t e = cudaMalloc(reinterpret_cast<void**>(q), want);
+            if (e == cudaSuccess) owned.push_back(*q);
+            return e;
+        }
+        const size_t i = pool->next++;
+        if (i >= pool->ptr.size()) { pool->ptr.push_back(nullptr); pool->bytes.push_back(0); }
+        if (pool->bytes[i] < want) {                       // grow with some slack: edits change the counts a little
+            if (pool->ptr[i]) cudaFree(pool->ptr[i]);
+            pool->ptr[i] = nullptr; pool->bytes[i] = 0;
+            const size_t cap = want + want / 8 + 256;
+            cudaError_t e = cudaMalloc(&pool->ptr[i], cap);
+            if (e != cudaSuccess) return e;
+            pool->bytes[i] = cap;
+        }
+        *q = static_cast<T*>(pool->ptr[i]);
+        return cudaSuccess;
+    }
+};
 // pool != NULL: work arrays and the node array come from the pool (the array may be larger than *n_slots: *capacity_slots), and the
 // call returns without waiting for the device (the caller keeps the replaced array alive as the pool's spare instead of freeing it).
 cudaError_t device_build_terrain_lsvo(int depth, uint2** d_slots, uint64_t* n_slots, int32_t* d_heights_out, cudaStream_t stream,
                                       const int32_t* d_heights_in = nullptr, BuildPool* pool = nullptr, uint64_t* capacity_slots = nullptr);
 // Reference layout → compact breadth-first array of live nodes, on the device (scene_device.cu); caller frees *d_out.
 // voxel_build.cu: arbitrary voxel sets on the device (sorted path keys → LNode array) and voxel edits
-cudaError_t device_voxel_keys(const uint32_t* d_xyz, uint64_t n, int depth, uint64_t** d_keys, uint32_t* n_keys, cudaStream_t stream);
+// pool (optional): work arrays — and, for the node array, the spare — are taken from / kept in the scene's BuildPool (edits)
+cudaError_t device_voxel_keys(const uint32_t* d_xyz, uint64_t n, int depth, uint64_t** d_keys, uint32_t* n_keys, cudaStream_t stream,
+                              BuildPool* pool = nullptr);
 cudaError_t device_edit_voxel_keys(const uint64_t* d_keys, uint32_t n_keys, const uint64_t* d_edit, uint32_t n_edit, int add, int depth,
-                                   uint64_t** d_out, uint32_t* n_out, cudaStream_t stream);
+                                   uint64_t** d_out, uint32_t* n_out, cudaStream_t stream, BuildPool* pool = nullptr);
 cudaError_t device_build_lsvo_from_keys(int depth, const uint64_t* d_keys, uint32_t n_keys, uint2** d_slots, uint64_t* n_slots,
-                                        cudaStream_t stream);
+                                        cudaStream_t stream, BuildPool* pool = nullptr, uint64_t* capacity_slots = nullptr);
 cudaError_t device_compact_lsvo(const uint2* d_ref, uint64_t n_ref, int depth, uint2** d_out, uint64_t* n_out, cudaStream_t stream);
 }  // namespace vrt

@@ -223,32 +223,7 @@ __global__ void root_kernel(Level root) {                  // the root: slot 0, 
     root.cpos[0] = 1u;
 }
 
-struct Scratch {
-    BuildPool* pool;
-    std::vector<void*> ptrs;                               // owned (no pool)
-    explicit Scratch(BuildPool* p) : pool(p) { if (pool) pool->next = 0; }
-    ~Scratch() { for (void* p : ptrs) cudaFree(p); }
-    template <typename T> cudaError_t alloc(T** p, size_t n) {
-        const size_t want = (n ? n : 1) * sizeof(T);
-        if (!pool) {
-            cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), want);
-            if (e == cudaSuccess) ptrs.push_back(*p);
-            return e;
-        }
-        const size_t i = pool->next++;
-        if (i >= pool->ptr.size()) { pool->ptr.push_back(nullptr); pool->bytes.push_back(0); }
-        if (pool->bytes[i] < want) {                       // grow with some slack: edits change the node counts a little
-            if (pool->ptr[i]) cudaFree(pool->ptr[i]);
-            pool->ptr[i] = nullptr; pool->bytes[i] = 0;
-            const size_t cap = want + want / 8 + 256;
-            cudaError_t e = cudaMalloc(&pool->ptr[i], cap);
-            if (e != cudaSuccess) return e;
-            pool->bytes[i] = cap;
-        }
-        *p = static_cast<T*>(pool->ptr[i]);
-        return cudaSuccess;
-    }
-};
+using Scratch = PoolScratch;
 
 #define VRT_TRY(call)                          \
     do {                                       \

@@ -38,15 +38,7 @@ struct PrefixLevels {
     int depth;
 };
 
-struct Scratch {
-    std::vector<void*> ptrs;
-    ~Scratch() { for (void* q : ptrs) cudaFree(q); }
-    template <typename T> cudaError_t alloc(T** q, size_t n) {
-        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(q), (n ? n : 1) * sizeof(T));
-        if (e == cudaSuccess) ptrs.push_back(*q);
-        return e;
-    }
-};
+using Scratch = PoolScratch;
 
 #define VRT_TRY(call)                          \
     do {                                       \
@@ -152,11 +144,12 @@ cudaError_t sort_unique(uint64_t* d_in, uint32_t n, int bits, uint64_t* d_sorted
 }  // namespace
 
 // xyz (device, n triples, coordinates < 2^depth) → sorted distinct voxel keys.  *d_keys is cudaMalloc'ed (caller frees).
-cudaError_t device_voxel_keys(const uint32_t* d_xyz, uint64_t n, int depth, uint64_t** d_keys, uint32_t* n_keys, cudaStream_t stream) {
+cudaError_t device_voxel_keys(const uint32_t* d_xyz, uint64_t n, int depth, uint64_t** d_keys, uint32_t* n_keys, cudaStream_t stream,
+                              BuildPool* pool) {
     *d_keys = nullptr;
     *n_keys = 0;
     if (n > 0xffffffffull) return cudaErrorInvalidValue;
-    Scratch sc;
+    Scratch sc(pool);
     uint64_t *raw = nullptr, *sorted = nullptr, *uniq = nullptr;
     VRT_TRY(sc.alloc(&raw, n));
     VRT_TRY(sc.alloc(&sorted, n));
@@ -175,10 +168,10 @@ cudaError_t device_voxel_keys(const uint32_t* d_xyz, uint64_t n, int depth, uint
 // Merges (add != 0) or removes the keys of `d_edit` (n_edit sorted distinct keys) into / from the scene's list.
 // *d_out is cudaMalloc'ed (caller frees).
 cudaError_t device_edit_voxel_keys(const uint64_t* d_keys, uint32_t n_keys, const uint64_t* d_edit, uint32_t n_edit, int add, int depth,
-                                   uint64_t** d_out, uint32_t* n_out, cudaStream_t stream) {
+                                   uint64_t** d_out, uint32_t* n_out, cudaStream_t stream, BuildPool* pool) {
     *d_out = nullptr;
     *n_out = 0;
-    Scratch sc;
+    Scratch sc(pool);
     const uint64_t total = uint64_t(n_keys) + (add ? n_edit : 0);
     if (total > 0xffffffffull) return cudaErrorInvalidValue;
     uint64_t* result = nullptr;
@@ -215,11 +208,12 @@ cudaError_t device_edit_voxel_keys(const uint64_t* d_keys, uint32_t n_keys, cons
 
 // Sorted distinct voxel keys → the reference's LNode array.  *d_slots is cudaMalloc'ed (caller frees).
 cudaError_t device_build_lsvo_from_keys(int depth, const uint64_t* d_keys, uint32_t n_keys, uint2** d_slots, uint64_t* n_slots,
-                                        cudaStream_t stream) {
+                                        cudaStream_t stream, BuildPool* pool, uint64_t* capacity_slots) {
     *d_slots = nullptr;
     *n_slots = 0;
+    if (capacity_slots) *capacity_slots = 0;
     if (depth < 1 || depth + 1 > kMaxLevels) return cudaErrorInvalidValue;
-    Scratch sc;
+    Scratch sc(pool);
     uint2* slots = nullptr;
     if (n_keys == 0) {                                                       // LSVO of an empty SVO: the root alone, child_offset 1
         VRT_TRY(cudaMalloc(&slots, sizeof(uint2)));
@@ -261,7 +255,17 @@ cudaError_t device_build_lsvo_from_keys(int depth, const uint64_t* d_keys, uint3
     }
     const uint64_t n = 1 + 8 * interior;                                     // root slot + one 8-slot block per interior node
     if (n > 0xffffffffull) return cudaErrorInvalidValue;
-    VRT_TRY(cudaMalloc(&slots, n * sizeof(uint2)));
+    uint64_t capacity = n;
+    if (pool && pool->spare && pool->spare_slots >= n) {                     // build into the array the previous edit replaced
+        slots = pool->spare;
+        capacity = pool->spare_slots;
+        pool->spare = nullptr;
+        pool->spare_slots = 0;
+    } else {
+        if (pool) capacity = n + n / 16 + 4096;
+        VRT_TRY(cudaMalloc(&slots, capacity * sizeof(uint2)));
+    }
+    if (capacity_slots) *capacity_slots = capacity;
     fill_default_slots_kernel<<<148 * 8, 256, 0, stream>>>(slots, n);
     std::vector<uint32_t*> cpos(depth, nullptr);
     cudaError_t e = cudaSuccess;
@@ -273,7 +277,11 @@ cudaError_t device_build_lsvo_from_keys(int depth, const uint64_t* d_keys, uint3
         emit_nodes_kernel<<<(P.n[l] + 127) / 128, 128, 0, stream>>>(P, l, cpos[l], l > 0 ? cpos[l - 1] : nullptr, slots);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    if (e != cudaSuccess) { cudaFree(slots); return e; }
+    if (e != cudaSuccess) {
+        if (pool) { if (pool->spare) cudaFree(pool->spare); pool->spare = slots; pool->spare_slots = capacity; }
+        else cudaFree(slots);
+        return e;
+    }
     *d_slots = slots;
     *n_slots = n;
     return cudaSuccess;
