@@ -293,19 +293,43 @@ __device__ __forceinline__ void grid_dda_fast(const GridLevels& g, float ox, flo
     // strides and the grid pointer pinned in registers (ptxas otherwise re-derives them from the constant bank every trip)
     const uint32_t dix = uint32_t(sx) * PY * PZ + blockIdx.y, diy = uint32_t(sy) * PZ + blockIdx.y, diz = uint32_t(sz) + blockIdx.y;
     const uint32_t* __restrict__ bits = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(g.pad_bits) + blockIdx.y + threadIdx.z);
-    float it = 0.0f;
-    bool p0 = false, p1 = false, stopped = false;
+    // The loop is bound by the half-rate ALU pipe (ncu: ALU 82 %, FMA 14 %): compares, selects, integer adds, shifts and logic all
+    // issue there.  The step is therefore written with explicit predication: the chosen axis' t_max grows by a predicated FADD and the
+    // cell index moves by a predicated IMAD (`stride * one + idx`, `one` an opaque 1: both FMA pipe) instead of selects and an add;
+    // the hit distance — the stepped axis' t_max before its increment (:77,85,93), which is the smallest of the three by the very
+    // comparisons that chose the axis (ties hold equal values) — is a min3; the axis of the last step is recovered after the loop
+    // from the index difference.  The fp32 operations are those of grid_3d.hpp:73-99, in order.
+    const uint32_t one = 1u + blockIdx.y;
+    float it = 0.0f, t_old = 0.0f;
+    uint32_t idx_prev = idx;
+    bool stopped = false;
     for (;;) {
         if (kCap) { if (!(it < 2048.0f)) break; }                                              // :70
         it += 1.0f;
-        const bool xy = tmx < tmy;                                                             // :73-99
-        p0 = xy && (tmx < tmz);
-        p1 = !xy && (tmy < tmz);
-        idx += p0 ? dix : (p1 ? diy : diz);
+        asm volatile(
+            "{\n\t"
+            ".reg .pred q, px, py, pn;\n\t"
+            ".reg .f32 m;\n\t"
+            "setp.lt.f32 q, %0, %1;\n\t"                  // t_max_x < t_max_y                               :73
+            "setp.lt.and.f32 px, %0, %2, q;\n\t"          //   ... and t_max_x < t_max_z: step x             :74
+            "setp.lt.and.f32 py, %1, %2, !q;\n\t"         // else t_max_y < t_max_z: step y                  :84
+            "or.pred pn, px, py;\n\t"                     // neither: step z
+            "min.f32 m, %1, %2;\n\t"
+            "min.f32 %4, %0, m;\n\t"                      // the stepped axis' t_max before its increment
+            "mov.u32 %5, %3;\n\t"
+            "@px add.f32 %0, %0, %6;\n\t"                 // :78
+            "@px mad.lo.u32 %3, %9, %12, %3;\n\t"
+            "@py add.f32 %1, %1, %7;\n\t"                 // :86
+            "@py mad.lo.u32 %3, %10, %12, %3;\n\t"
+            "@!pn add.f32 %2, %2, %8;\n\t"                // :94
+            "@!pn mad.lo.u32 %3, %11, %12, %3;\n\t"
+            "}"
+            : "+f"(tmx), "+f"(tmy), "+f"(tmz), "+r"(idx), "=f"(t_old), "=r"(idx_prev)
+            : "f"(tdx), "f"(tdy), "f"(tdz), "r"(dix), "r"(diy), "r"(diz), "r"(one));
         if (__ldg(bits + (idx >> 5)) & (1u << (idx & 31u))) { stopped = true; break; }         // :103-104, or the border
-        // t_max += t_d AFTER the exit test: when the loop stops, the un-incremented t_max of the stepped axis is the hit distance
-        if (p0) tmx += tdx; else if (p1) tmy += tdy; else tmz += tdz;                          // :78,86,94
     }
+    const uint32_t moved = idx - idx_prev;                                                     // strides differ: PY * PZ > PZ > 1
+    const bool p0 = moved == dix * one, p1 = moved == diy * one;
     r.steps = uint32_t(it);
     if (!stopped) return;
     const uint32_t pz = idx % PZ, q = idx / PZ, py = q % PY, px = q / PY;
@@ -313,7 +337,7 @@ __device__ __forceinline__ void grid_dda_fast(const GridLevels& g, float ox, flo
     if (cx < 0 || cy < 0 || cz < 0 || cx >= X || cy >= Y || cz >= Z) return;                   // left the grid: miss
     r.hit = true;
     r.side = p0 ? 0 : (p1 ? 1 : 2);
-    r.t = p0 ? tmx : (p1 ? tmy : tmz);                                                         // :77,85,93
+    r.t = t_old;                                                                               // :77,85,93
     r.cx = cx; r.cy = cy; r.cz = cz;
 }
 
