@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(128) lsvo_cast_kernel(Nodes nodes, int depth, 
 // K1b: the same kernel on Trav2 (bookkeeping off the ALU pipe, cone test compiled out for coef = bias = 0).  Grid-stride, so that a
 // gated launch (below) can use a bounded grid; with one CTA per 128 rays the loop body runs once.
 // gate != nullptr: the kernel runs only if *gate == want (the automatic choice between K1b and K1p, made on the device).
-template <typename Nodes, bool kCone>
+// kGuard = false: the loop guard cannot bind for this scene and is compiled out (lsvo_step.cuh, Trav2).
+template <typename Nodes, bool kCone, bool kGuard>
 __global__ void __launch_bounds__(128) lsvo_cast2_kernel(Nodes nodes, int depth, int guard, const float* __restrict__ origin,
                                                          const float* __restrict__ dir, float coef, float bias, uint64_t n,
                                                          vrt_hit* __restrict__ out, unsigned long long* __restrict__ total_complexity,
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(128) lsvo_cast2_kernel(Nodes nodes, int depth,
         const float ox = origin[3 * i], oy = origin[3 * i + 1], oz = origin[3 * i + 2];
         const float dx = dir[3 * i], dy = dir[3 * i + 1], dz = dir[3 * i + 2];
         LsvoResult r;
-        lsvo_cast_ray2<kCone>(nodes, stack, guard, guard_sf, ox, oy, oz, dx, dy, dz, coef, bias, r);
+        lsvo_cast_ray2<kCone, false, kGuard>(nodes, stack, guard, guard_sf, ox, oy, oz, dx, dy, dz, coef, bias, r);
         LsvoHit h;
         if (r.hit) lsvo_finish(r, ox, oy, oz, depth, h);
         store_hit(out + i, r, h, depth);
@@ -129,10 +130,12 @@ cudaError_t launch_lsvo_cast2(const uint2* nodes, int depth, int guard, const fl
         const uint64_t cap = uint64_t(sms) * 16 * 8;       // 8 rounds of 16 CTAs per SM: dynamic enough to stay balanced
         if (grid > cap) grid = cap;
     }
-    if (coef == 0.0f && bias == 0.0f)
-        lsvo_cast2_kernel<RefNodes, false><<<unsigned(grid), block, smem, stream>>>(RefNodes{nodes}, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_complexity, d_gate, want);
-    else
-        lsvo_cast2_kernel<RefNodes, true><<<unsigned(grid), block, smem, stream>>>(RefNodes{nodes}, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_complexity, d_gate, want);
+    auto launch = [&](auto kernel) {
+        kernel<<<unsigned(grid), block, smem, stream>>>(RefNodes{nodes}, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_complexity, d_gate, want);
+    };
+    const bool cone = !(coef == 0.0f && bias == 0.0f), guarded = guard >= kSvoMaxDepth - depth;   // can the loop guard ever bind?
+    if (cone) { if (guarded) launch(lsvo_cast2_kernel<RefNodes, true, true>); else launch(lsvo_cast2_kernel<RefNodes, true, false>); }
+    else { if (guarded) launch(lsvo_cast2_kernel<RefNodes, false, true>); else launch(lsvo_cast2_kernel<RefNodes, false, false>); }
     return cudaGetLastError();
 }
 

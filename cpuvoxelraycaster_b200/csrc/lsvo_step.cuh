@@ -220,7 +220,11 @@ struct Stack64s {
 // Only for rays without a cone (coef = bias = 0: camera and sun-shadow rays): a cone ray "hits" the first NON-EMPTY NODE it
 // finds smaller than its cone (lsvo.hpp:82-85), and such a node reaches far beyond the voxels it contains — measured: with the
 // bound applied to the GI rays 0.4 % of them lose their hit.
-template <bool kCone, bool kBounds = false>
+// kGuard = false compiles the loop guard `scale > MAX_DEPTH` (lsvo.hpp:72) out: with guard < 23 - depth it can never bind — the
+// deepest cells a walk can stand in are the voxels (scale 23 - depth: every child of a node of the level above is a leaf or
+// empty, which vrt_lsvo_create validates and the device builders guarantee), the test after a descent compares a scale
+// >= 23 - depth, and the one after a POP a scale larger than one that has passed already.  The launchers pick the variant.
+template <bool kCone, bool kBounds = false, bool kGuard = true>
 struct Trav2 {
     float dx, dy, dz, coef, bias;
     float tcx, tcy, tcz, tox, toy, toz;
@@ -229,7 +233,8 @@ struct Trav2 {
     float sf, iters_f;
     float t_limit;       // kBounds: the time at which the ray leaves the scene bounds
     uint32_t parent, child, mirror, face;
-    bool hit;
+    // There is no `hit` flag: a flag written inside the loop costs an instruction per trip on two of its three paths (ptxas sets
+    // it in front of the exits).  How the walk ended is read off the state it ended in, see hit().
 
     // t_floor: the walk starts at max(t_floor, entry into the root cube) instead of max(0, ...) (:57).  Any t_floor below the
     // ray's hit distance leaves the HitPoint unchanged except for its complexity (beam_kernels.cu); 0 = the reference.
@@ -269,7 +274,6 @@ struct Trav2 {
         if (1.5f * tcy - toy > t_min) { child ^= 2u; py = 1.5f; }
         if (1.5f * tcz - toz > t_min) { child ^= 4u; pz = 1.5f; }
         iters_f = 0.0f;
-        hit = false;
     }
 
     // one trip of the loop (:72-146); guard_sf = 2^(guard - 23)
@@ -280,15 +284,18 @@ struct Trav2 {
         const float cx = px * tcx - tox, cy = py * tcy - toy, cz = pz * tcz - toz;   // :76
         const float tc_max = fminf(cx, fminf(cy, cz));
         const uint32_t shift = child ^ mirror;                               // :79
-        const uint32_t child_bit = 0x100u << shift;
-        if ((nd.raw & child_bit) && t_min <= t_max) {                        // :80-81
-            if (kCone) {
-                if (tc_max * coef + bias >= sf) { hit = true; return false; }    // :82-85
-            }
+        const uint32_t masks = nd.raw >> shift;                              // bit 8: the child exists, bit 16: it is a leaf
+        if ((masks & 0x100u) && t_min <= t_max) {                            // :80-81
             const float tv_max = fminf(t_max, tc_max);
-            const float half = sf * 0.5f;
-            if (t_min <= tv_max) {                                           // :89
-                if (nd.raw & (child_bit << 8)) { hit = true; return false; }  // :90-95
+            const bool inside = t_min <= tv_max;                             // :89
+            // the two ways of ending on a hit — the cone is wider than the cell (:82-85, tested first in the reference), the child
+            // is a leaf (:90-95) — leave the same state behind: one exit for both
+            // (as a mask, not as a bool: ptxas turns the boolean form into a shift, an AND and an integer compare)
+            uint32_t ends = masks & (inside ? 0x10000u : 0u);
+            if (kCone) { if (tc_max * coef + bias >= sf) ends = 1u; }
+            if (ends) return false;
+            if (inside) {
+                const float half = sf * 0.5f;
                 if (tc_max < h) stack.push_sf(sf, parent, t_max);            // :97-100
                 h = tc_max;
                 parent = nodes.child(nd, shift);                             // :103
@@ -298,61 +305,77 @@ struct Trav2 {
                 if (half * tcy + cy > t_min) { child ^= 2u; py += half; }
                 if (half * tcz + cz > t_min) { child ^= 4u; pz += half; }
                 t_max = tv_max;
-                return sf > guard_sf;                                        // :72
+                return kGuard ? sf > guard_sf : true;                        // :72
             }
         }
-        // ADVANCE (:113-122).  The step is applied separately on the two continuations, so that POP can XOR the stepped
-        // position with the position still held in px/py/pz (no copies of the old position carried around the loop)
+        // ADVANCE (:113-122).  The step is applied once, for both continuations.  POP needs the position before the step as well:
+        // on a stepped axis that is exactly p + sf (grid-aligned values, exact subtraction and addition) — three FADDs on the FMA
+        // pipe inside the pop path instead of copies or selects on the ALU pipe, and popping lanes share the step with the others.
         const bool sx = cx <= tc_max, sy = cy <= tc_max, sz = cz <= tc_max;   // :115-118
         uint32_t step_mask = sx ? 1u : 0u;
         if (sy) step_mask ^= 2u;
         if (sz) step_mask ^= 4u;
         t_min = tc_max;
+        // (opaque to the compiler, here and below: without it t_min = tc_max is re-materialised behind the bounds test and twice
+        // inside the pop path, and the pop path reuses the differences p - sf: selects instead of predicated FADDs)
+        asm volatile("" : "+f"(t_min));
         if (kBounds) { if (t_min > t_limit) return false; }                 // outside everything solid: a miss, whatever follows
         child ^= step_mask;
         face = step_mask;
+        if (sx) px -= sf;
+        if (sy) py -= sf;
+        if (sz) pz -= sf;
+        asm volatile("" : "+f"(px), "+f"(py), "+f"(pz));
         if (child & step_mask) {                                             // :124-145, see Trav::step
-            // stepped axes only: step, and collect the bits the step changed (predicated FADD + LOP3 per axis, no selects)
-            uint32_t diff = 0u;
-            if (sx) { const float n = px - sf; diff |= __float_as_uint(n) ^ __float_as_uint(px); px = n; }
-            if (sy) { const float n = py - sf; diff |= __float_as_uint(n) ^ __float_as_uint(py); py = n; }
-            if (sz) { const float n = pz - sf; diff |= __float_as_uint(n) ^ __float_as_uint(pz); pz = n; }
+            uint32_t diff = 0u;                                              // the bits the step changed, stepped axes only
+            if (sx) diff |= __float_as_uint(px) ^ __float_as_uint(px + sf);
+            if (sy) diff |= __float_as_uint(py) ^ __float_as_uint(py + sf);
+            if (sz) diff |= __float_as_uint(pz) ^ __float_as_uint(pz + sf);
             const uint32_t ix = __float_as_uint(px), iy = __float_as_uint(py), iz = __float_as_uint(pz);
             int scale;                                                       // index of the highest differing bit (:132): FLO
             asm("bfind.u32 %0, %1;" : "=r"(scale) : "r"(diff));
-            if (scale >= kSvoMaxDepth) return false;                         // left the root cube: miss (the position is not read)
+            if (scale >= kSvoMaxDepth) return false;                         // left the root cube: a miss (a stepped p is < 1 now)
             stack.pop(scale, parent, t_max);                                 // :134-136
             sf = __uint_as_float(uint32_t(scale + 104) << 23);               // :133
-            const uint32_t keep = 0xffffffffu << scale;
+            const uint32_t bit = 1u << scale, keep = 0u - bit;               // (x >> s) << s == x & -(1 << s)
             px = __uint_as_float(ix & keep);                                 // :137-142
             py = __uint_as_float(iy & keep);
             pz = __uint_as_float(iz & keep);
-            child = ((ix >> scale) & 1u) | (((iy >> scale) & 1u) << 1) | (((iz >> scale) & 1u) << 2);   // :143
+            child = ((ix & bit) + 2u * (iy & bit) + 4u * (iz & bit)) >> scale;   // :143
             h = 0.0f;
-            return scale > guard;
+            return kGuard ? scale > guard : true;
         }
-        px = sx ? px - sf : px;
-        py = sy ? py - sf : py;
-        pz = sz ? pz - sf : pz;
         return true;
     }
 
-    __device__ __forceinline__ void result(LsvoResult& r) const {
+    // How the walk ended, read off its final state.  step() returns false (a) on a hit, with the state of the trip's start; (b) when
+    // the guard stops it: sf <= guard_sf, which no trip starts with; (c) on the bounds exit: t_min > t_limit — every ADVANCE
+    // that continues has t_min <= t_limit, and a walk that STARTS beyond its limit cannot hit without an ADVANCE (it would have to
+    // start inside a solid voxel, i.e. inside the bounds); (d) when a step leaves the root cube: only a step from p = 1 does
+    // that, and it leaves p = 1 - sf < 1 behind — no other state has a coordinate below 1.
+    __device__ __forceinline__ bool hit(float guard_sf) const {
+        bool miss = fminf(px, fminf(py, pz)) < 1.0f;
+        if (kGuard) miss = miss || !(sf > guard_sf);
+        if (kBounds) miss = miss || t_min > t_limit;
+        return !miss;
+    }
+
+    __device__ __forceinline__ void result(LsvoResult& r, float guard_sf) const {
         r.px = px; r.py = py; r.pz = pz;
         r.t_min = t_min; r.scale_f = sf; r.scale = int(__float_as_uint(sf) >> 23) - 104; r.face = face; r.mirror = mirror & 7u;
-        r.complexity = (mirror & 8u) ? 0u : uint32_t(iters_f); r.hit = hit;
+        r.complexity = (mirror & 8u) ? 0u : uint32_t(iters_f); r.hit = hit(guard_sf);
         r.dx = dx; r.dy = dy; r.dz = dz;
     }
 };
 
-template <bool kCone, bool kBounds = false, typename Nodes, typename Stack>
+template <bool kCone, bool kBounds = false, bool kGuard = true, typename Nodes, typename Stack>
 __device__ __forceinline__ void lsvo_cast_ray2(const Nodes& nodes, Stack& stack, int guard, float guard_sf, float ox, float oy, float oz,
                                                float dx, float dy, float dz, float coef, float bias, LsvoResult& r, float t_floor = 0.0f,
                                                const SceneBounds* bounds = nullptr) {
-    Trav2<kCone, kBounds> t;
+    Trav2<kCone, kBounds, kGuard> t;
     t.init(ox, oy, oz, dx, dy, dz, coef, bias, t_floor, bounds);
     while (t.step(nodes, stack, guard, guard_sf)) {}
-    t.result(r);
+    t.result(r, guard_sf);
 }
 __device__ __forceinline__ float guard_scale_f(int guard) { return __uint_as_float(uint32_t(guard + 104) << 23); }
 __device__ __forceinline__ float pin(float v) { return v + float(blockIdx.y); }

@@ -49,7 +49,7 @@ constexpr int kRayChunk = 64;
 #ifndef VRT_K1P_MIN_CTAS
 #define VRT_K1P_MIN_CTAS 8
 #endif
-template <typename Nodes, bool kCone>
+template <typename Nodes, bool kCone, bool kGuard>
 __global__ void __launch_bounds__(128, VRT_K1P_MIN_CTAS) lsvo_cast_persistent_kernel(Nodes nodes, int depth, int guard,
                                                                       const float* __restrict__ origin,
                                                                       const float* __restrict__ dir, float coef, float bias,
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(128, VRT_K1P_MIN_CTAS) lsvo_cast_persistent_ke
     int refills_since_probe = 0;
     bool sync_batch = false;                               // all 32 lanes were started in the same refill phase
 
-    Trav2<kCone> t;
+    Trav2<kCone, false, kGuard> t;
     bool alive = false, has_result = false, exhausted = false;
     uint64_t ray = 0, chunk_next = 0, chunk_end = 0;       // chunk_* are warp-uniform
     unsigned long long iter_sum = 0;
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(128, VRT_K1P_MIN_CTAS) lsvo_cast_persistent_ke
         }
         if (retiring) {
             LsvoResult r;
-            t.result(r);
+            t.result(r, guard_sf);
             LsvoHit h;
             if (r.hit) lsvo_finish(r, origin[3 * ray], origin[3 * ray + 1], origin[3 * ray + 2], depth, h);   // re-read, not carried in registers
             store_hit_record(out + ray, r, h, depth);
@@ -291,8 +291,10 @@ static cudaError_t cast_persistent(Nodes nv, int depth, int guard, const float* 
         kernel<<<unsigned(grid), block, smem, stream>>>(nv, depth, guard, d_origin, d_dir, coef, bias, n, d_out, d_counters, refill, d_gate, want);
     };
     // the cone test is compiled out when it cannot fire (coef = bias = 0: lsvo_step.cuh, Trav2)
-    if (coef == 0.0f && bias == 0.0f) launch(lsvo_cast_persistent_kernel<Nodes, false>);
-    else launch(lsvo_cast_persistent_kernel<Nodes, true>);
+    // ... and the loop guard when it cannot bind (guard below the voxels' own scale)
+    const bool cone = !(coef == 0.0f && bias == 0.0f), guarded = guard >= kSvoMaxDepth - depth;
+    if (cone) { if (guarded) launch(lsvo_cast_persistent_kernel<Nodes, true, true>); else launch(lsvo_cast_persistent_kernel<Nodes, true, false>); }
+    else { if (guarded) launch(lsvo_cast_persistent_kernel<Nodes, false, true>); else launch(lsvo_cast_persistent_kernel<Nodes, false, false>); }
     return cudaGetLastError();
 }
 

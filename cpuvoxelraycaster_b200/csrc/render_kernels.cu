@@ -17,6 +17,9 @@
 
 namespace vrt {
 
+// Can the loop guard `scale > guard` (lsvo.hpp:72) ever stop a walk?  Not when the voxels' own scale passes it (Trav2, kGuard).
+static bool guard_binds(const RenderLaunch& L) { return L.guard >= kSvoMaxDepth - L.depth; }
+
 // 8 CTAs per SM (64 registers).  Round 1 ran K4 at 4 (128 registers: more warps at fewer registers spilled into the loop and
 // measured slower); with the Trav2 loop and its invariants held in registers (lsvo_step.cuh) the loops compile spill-free at 64
 // registers (~200 bytes of spills in the chain code) and the extra warps pay: 4 / 6 / 8 CTAs per SM = 0.201 / 0.180 / 0.172 ms on
@@ -28,7 +31,8 @@ namespace vrt {
 // kLive: the interactive-loop extras (checkerboard pixel mapping, focal length read from the autofocus kernel's output).
 // Compiled out of the plain instantiation so that they cost the many-sample frames nothing (register allocation of the
 // traversal loop is sensitive to every extra live value: 73.9 vs 75.6 ms on cfg 4).
-template <typename Nodes, bool kLive, bool kMirror = false>
+// kGuard = false: the loop guard cannot bind for this scene and is compiled out (lsvo_step.cuh, Trav2).
+template <typename Nodes, bool kLive, bool kMirror = false, bool kGuard = true>
 __global__ void __launch_bounds__(128, VRT_K4_MIN_CTAS) render_accumulate_kernel(Nodes nodes, RenderLaunch L, uint32_t* __restrict__ accum,
                                                                 unsigned long long* __restrict__ counters) {
     extern __shared__ uint2 smem[];
@@ -89,8 +93,8 @@ __global__ void __launch_bounds__(128, VRT_K4_MIN_CTAS) render_accumulate_kernel
                 int stage = kPrimary;
                 while (stage != kDone) {
                     LsvoResult r;
-                    if (stage < kGi0) lsvo_cast_ray2<false, true>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, 0.0f, 0.0f, r, nr.t_floor, &L.bounds);
-                    else lsvo_cast_ray2<true>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
+                    if (stage < kGi0) lsvo_cast_ray2<false, true, kGuard>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, 0.0f, 0.0f, r, nr.t_floor, &L.bounds);
+                    else lsvo_cast_ray2<true, false, kGuard>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
                     cnt[stage * 128] += 1u;
                     cnt[(6 + stage) * 128] += r.complexity;
                     LsvoHit h;
@@ -427,7 +431,7 @@ __global__ void __launch_bounds__(128) sort_samples_kernel(RenderLaunch L, SortP
 #ifndef VRT_K6_MIN_CTAS
 #define VRT_K6_MIN_CTAS 8
 #endif
-template <typename Nodes, int kTrav, bool kMirror = false>
+template <typename Nodes, int kTrav, bool kMirror = false, bool kGuard = true>
 __global__ void __launch_bounds__(128, VRT_K6_MIN_CTAS) render_rounds_kernel(Nodes nodes, RenderLaunch L, BlockGeometry G,
                                                                             const uint16_t* __restrict__ lists, uint32_t* meta,
                                                                             uint32_t* __restrict__ accum,
@@ -488,8 +492,8 @@ __global__ void __launch_bounds__(128, VRT_K6_MIN_CTAS) render_rounds_kernel(Nod
                     } else if constexpr (kTrav == 1) {
                         lsvo_cast_ray2<true>(nodes, stack2, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
                     } else {
-                        if (stage < kGi0) lsvo_cast_ray2<false, true>(nodes, stack2, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, 0.0f, 0.0f, r, nr.t_floor, &L.bounds);
-                        else lsvo_cast_ray2<true>(nodes, stack2, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
+                        if (stage < kGi0) lsvo_cast_ray2<false, true, kGuard>(nodes, stack2, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, 0.0f, 0.0f, r, nr.t_floor, &L.bounds);
+                        else lsvo_cast_ray2<true, false, kGuard>(nodes, stack2, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
                     }
                     cnt[stage * 128] += 1u;
                     cnt[(6 + stage) * 128] += r.complexity;
@@ -588,7 +592,7 @@ __global__ void __launch_bounds__(128, VRT_K6_MIN_CTAS) render_rounds_kernel(Nod
 // reference's renderRay receives from Camera::getRay (main.cpp:147-149) — and gets the sample's colour back.  One thread per
 // ray, the same sample chain as the frame kernels (sun shadow, GI with the Philox numbers of (pixel, sample)), so a ray
 // that equals the frame kernels' primary ray of (pixel, sample) gives exactly that sample's colour.
-template <typename Nodes>
+template <typename Nodes, bool kGuard>
 __global__ void __launch_bounds__(128, 8) shade_rays_kernel(Nodes nodes, RenderLaunch L, uint64_t n, const vrt_shade_job* __restrict__ jobs,
                                                          vrt_shade_result* __restrict__ out) {
     extern __shared__ uint2 smem[];
@@ -616,8 +620,8 @@ __global__ void __launch_bounds__(128, 8) shade_rays_kernel(Nodes nodes, RenderL
     uint32_t complexity = 0u;
     while (stage != kDone) {
         LsvoResult r;
-        if (stage < kGi0) lsvo_cast_ray2<false>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, 0.0f, 0.0f, r);
-        else lsvo_cast_ray2<true>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
+        if (stage < kGi0) lsvo_cast_ray2<false, false, kGuard>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, 0.0f, 0.0f, r);
+        else lsvo_cast_ray2<true, false, kGuard>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
         if (stage == kPrimary) { complexity = r.complexity; if (r.hit) distance = r.t_min; }   // RayContext, raycaster.hpp:132-133,137
         LsvoHit h;
         if (r.hit) lsvo_finish(r, nr.ox, nr.oy, nr.oz, L.depth, h);
@@ -638,8 +642,9 @@ cudaError_t launch_shade_rays(const uint2* nodes, bool compact, const RenderLaun
     if (!n) return cudaSuccess;
     const size_t smem = size_t(L.depth + 1) * 128 * 8;
     const unsigned grid = unsigned((n + 127) / 128);
-    if (compact) shade_rays_kernel<CompactNodes><<<grid, 128, smem, stream>>>(CompactNodes{nodes}, L, n, d_jobs, d_out);
-    else shade_rays_kernel<RefNodes><<<grid, 128, smem, stream>>>(RefNodes{nodes}, L, n, d_jobs, d_out);
+    if (compact) shade_rays_kernel<CompactNodes, true><<<grid, 128, smem, stream>>>(CompactNodes{nodes}, L, n, d_jobs, d_out);
+    else if (guard_binds(L)) shade_rays_kernel<RefNodes, true><<<grid, 128, smem, stream>>>(RefNodes{nodes}, L, n, d_jobs, d_out);
+    else shade_rays_kernel<RefNodes, false><<<grid, 128, smem, stream>>>(RefNodes{nodes}, L, n, d_jobs, d_out);
     return cudaGetLastError();
 }
 
@@ -762,11 +767,16 @@ cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const
             kernel<<<grid6, block, smem, stream>>>(view, L, P.G, lists, meta, d_accum, d_counters);
         };
         if (compact) launch6(render_rounds_kernel<CompactNodes, 0>, CompactNodes{nodes});
-        else if (L.mirror_y1 > 0) launch6(render_rounds_kernel<RefNodes, 2, true>, RefNodes{nodes});
-        else switch (L.trav_policy) {
+        else if (L.mirror_y1 > 0) {
+            if (guard_binds(L)) launch6(render_rounds_kernel<RefNodes, 2, true, true>, RefNodes{nodes});
+            else launch6(render_rounds_kernel<RefNodes, 2, true, false>, RefNodes{nodes});
+        } else switch (L.trav_policy) {
             case 0: launch6(render_rounds_kernel<RefNodes, 0>, RefNodes{nodes}); break;
             case 1: launch6(render_rounds_kernel<RefNodes, 1>, RefNodes{nodes}); break;
-            default: launch6(render_rounds_kernel<RefNodes, 2>, RefNodes{nodes}); break;
+            default:
+                if (guard_binds(L)) launch6(render_rounds_kernel<RefNodes, 2, false, true>, RefNodes{nodes});
+                else launch6(render_rounds_kernel<RefNodes, 2, false, false>, RefNodes{nodes});
+                break;
         }
         return cudaGetLastError();
     }
@@ -817,13 +827,18 @@ cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const
     Lc.samples_per_warp = q;
     const unsigned grid = unsigned(tiles * chunks);
     const bool live = L.checker != 0 || L.focal != nullptr;
-    if (L.mirror_y1 > 0 && !compact) {
-        if (live) render_accumulate_kernel<RefNodes, true, true><<<grid, block, smem, stream>>>(RefNodes{nodes}, Lc, d_accum, d_counters);
-        else render_accumulate_kernel<RefNodes, false, true><<<grid, block, smem, stream>>>(RefNodes{nodes}, Lc, d_accum, d_counters);
-    } else if (compact && live) render_accumulate_kernel<CompactNodes, true><<<grid, block, smem, stream>>>(CompactNodes{nodes}, Lc, d_accum, d_counters);
-    else if (compact) render_accumulate_kernel<CompactNodes, false><<<grid, block, smem, stream>>>(CompactNodes{nodes}, Lc, d_accum, d_counters);
-    else if (live) render_accumulate_kernel<RefNodes, true><<<grid, block, smem, stream>>>(RefNodes{nodes}, Lc, d_accum, d_counters);
-    else render_accumulate_kernel<RefNodes, false><<<grid, block, smem, stream>>>(RefNodes{nodes}, Lc, d_accum, d_counters);
+    auto launch4 = [&](auto kernel, auto view) { kernel<<<grid, block, smem, stream>>>(view, Lc, d_accum, d_counters); };
+    const bool guarded = guard_binds(L);
+    if (compact) {
+        if (live) launch4(render_accumulate_kernel<CompactNodes, true>, CompactNodes{nodes});
+        else launch4(render_accumulate_kernel<CompactNodes, false>, CompactNodes{nodes});
+    } else if (L.mirror_y1 > 0) {
+        if (live) { if (guarded) launch4(render_accumulate_kernel<RefNodes, true, true, true>, RefNodes{nodes}); else launch4(render_accumulate_kernel<RefNodes, true, true, false>, RefNodes{nodes}); }
+        else { if (guarded) launch4(render_accumulate_kernel<RefNodes, false, true, true>, RefNodes{nodes}); else launch4(render_accumulate_kernel<RefNodes, false, true, false>, RefNodes{nodes}); }
+    } else {
+        if (live) { if (guarded) launch4(render_accumulate_kernel<RefNodes, true, false, true>, RefNodes{nodes}); else launch4(render_accumulate_kernel<RefNodes, true, false, false>, RefNodes{nodes}); }
+        else { if (guarded) launch4(render_accumulate_kernel<RefNodes, false, false, true>, RefNodes{nodes}); else launch4(render_accumulate_kernel<RefNodes, false, false, false>, RefNodes{nodes}); }
+    }
     return cudaGetLastError();
 }
 
