@@ -233,6 +233,7 @@ struct Trav2 {
     float sf, iters_f;
     float t_limit;       // kBounds: the time at which the ray leaves the scene bounds
     uint32_t parent, child, mirror, face;
+    uint2 nd_;           // the two words of node `parent`, loaded when parent changes (a descent, a POP) instead of on every trip
     // There is no `hit` flag: a flag written inside the loop costs an instruction per trip on two of its three paths (ptxas sets
     // it in front of the exits).  How the walk ended is read off the state it ended in, see hit().
 
@@ -275,16 +276,18 @@ struct Trav2 {
         if (1.5f * tcz - toz > t_min) { child ^= 4u; pz = 1.5f; }
         iters_f = 0.0f;
     }
+    // the root node, before the first trip
+    template <typename Nodes> __device__ __forceinline__ void prime(const Nodes& nodes) { nd_ = nodes.load(0u); }
 
     // one trip of the loop (:72-146); guard_sf = 2^(guard - 23)
     template <typename Nodes, typename Stack>
     __device__ __forceinline__ bool step(const Nodes& nodes, Stack& stack, int guard, float guard_sf) {
         iters_f += 1.0f;
-        const NodeView nd = nodes.fetch(parent);                             // :74
+        const uint32_t nd_raw = nd_.x;                                       // :74
         const float cx = px * tcx - tox, cy = py * tcy - toy, cz = pz * tcz - toz;   // :76
         const float tc_max = fminf(cx, fminf(cy, cz));
         const uint32_t shift = child ^ mirror;                               // :79
-        const uint32_t masks = nd.raw >> shift;                              // bit 8: the child exists, bit 16: it is a leaf
+        const uint32_t masks = nd_raw >> shift;                              // bit 8: the child exists, bit 16: it is a leaf
         if ((masks & 0x100u) && t_min <= t_max) {                            // :80-81
             const float tv_max = fminf(t_max, tc_max);
             const bool inside = t_min <= tv_max;                             // :89
@@ -298,7 +301,8 @@ struct Trav2 {
                 const float half = sf * 0.5f;
                 if (tc_max < h) stack.push_sf(sf, parent, t_max);            // :97-100
                 h = tc_max;
-                parent = nodes.child(nd, shift);                             // :103
+                parent = nodes.child_of(parent, nd_, shift);                 // :103
+                nd_ = nodes.load(parent);
                 child = 0u;
                 sf = half;                                                   // --scale
                 if (half * tcx + cx > t_min) { child ^= 1u; px += half; }    // :88,107-109
@@ -336,6 +340,7 @@ struct Trav2 {
             asm("bfind.u32 %0, %1;" : "=r"(scale) : "r"(diff));
             if (scale >= kSvoMaxDepth) return false;                         // left the root cube: a miss (a stepped p is < 1 now)
             stack.pop(scale, parent, t_max);                                 // :134-136
+            nd_ = nodes.load(parent);
             sf = __uint_as_float(uint32_t(scale + 104) << 23);               // :133
             const uint32_t bit = 1u << scale, keep = 0u - bit;               // (x >> s) << s == x & -(1 << s)
             px = __uint_as_float(ix & keep);                                 // :137-142
@@ -374,6 +379,7 @@ __device__ __forceinline__ void lsvo_cast_ray2(const Nodes& nodes, Stack& stack,
                                                const SceneBounds* bounds = nullptr) {
     Trav2<kCone, kBounds, kGuard> t;
     t.init(ox, oy, oz, dx, dy, dz, coef, bias, t_floor, bounds);
+    t.prime(nodes);
     while (t.step(nodes, stack, guard, guard_sf)) {}
     t.result(r, guard_sf);
 }

@@ -23,6 +23,10 @@ struct RefNodes {
         return v;
     }
     __device__ __forceinline__ uint32_t child(const NodeView& v, uint32_t slot) const { return v.child_base + slot; }
+    // the same in two halves, for a walk that keeps the node's two words across trips (Trav2): nothing is computed from the
+    // loaded words until a descent needs the child's index, so no instruction waits for the load at the end of a trip
+    __device__ __forceinline__ uint2 load(uint32_t id) const { return __ldg(slots + id); }
+    __device__ __forceinline__ uint32_t child_of(uint32_t id, const uint2& w, uint32_t slot) const { return id + w.y + slot; }
 };
 
 // Compact layout (built on the device by scene_device.cu): only nodes that own a child block are stored, level by
@@ -41,6 +45,11 @@ struct CompactNodes {
     __device__ __forceinline__ uint32_t child(const NodeView& v, uint32_t slot) const {
         const uint32_t interior = (v.raw >> 8) & ~(v.raw >> 16) & 0xffu;       // child_mask & ~leaf_mask
         return v.child_base + __popc(interior & ((1u << slot) - 1u));
+    }
+    __device__ __forceinline__ uint2 load(uint32_t id) const { return __ldg(slots + id); }
+    __device__ __forceinline__ uint32_t child_of(uint32_t, const uint2& w, uint32_t slot) const {
+        const uint32_t interior = (w.x >> 8) & ~(w.x >> 16) & 0xffu;
+        return w.y + __popc(interior & ((1u << slot) - 1u));
     }
 };
 

@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(128, VRT_K1P_MIN_CTAS) lsvo_cast_persistent_ke
                 ray = chunk_next + rank;
                 t.init(origin[3 * ray], origin[3 * ray + 1], origin[3 * ray + 2], dir[3 * ray], dir[3 * ray + 1], dir[3 * ray + 2],
                        coef, bias);
+                t.prime(nodes);
                 alive = true;
                 has_result = true;
             }
