@@ -1,6 +1,7 @@
 // C ABI of libvrt (include/vrt.h).  Thin: argument checks, device memory, kernel launches.
 // There is no CPU fallback — every compute entry point needs a CUDA device.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -676,6 +677,9 @@ int check_render_args(const vrt_scene* sc, const vrt_camera* cam, const vrt_rend
     if (cam && (p->spp <= 0 || p->gi_bounces < 0 || p->gi_bounces > 2)) return fail(VRT_ERR_INVALID, std::string(who) + ": spp must be > 0 and gi_bounces in 0..2");
     if (p->tile_step > 1 && (p->tile_index < 0 || p->tile_index >= p->tile_step)) return fail(VRT_ERR_INVALID, std::string(who) + ": tile_index must be in [0, tile_step)");
     if (cam && !sc->has_tex) return fail(VRT_ERR_INVALID, std::string(who) + ": call vrt_scene_set_textures first (raycaster.hpp:53-54)");
+    if (cam)    // a rotation (camera_controller.hpp:27-32): the frame kernels rely on |ray direction| staying near 1 (Trav2, kUnit)
+        for (int i = 0; i < 9; ++i)
+            if (!(std::fabs(cam->rot_mat[i]) <= 1024.0f)) return fail(VRT_ERR_INVALID, std::string(who) + ": rot_mat is not a rotation matrix");
     if (p->checker < 0 || p->checker > 2 || p->checker_area_height < 0) return fail(VRT_ERR_INVALID, std::string(who) + ": checker must be 0, 1 or 2 and checker_area_height >= 0");
     if (cam && sc->kind == VRT_SCENE_LSVO && p->mirror_y1 != 0) {
         if (p->mirror_y1 < 0 || p->mirror_y1 > (1 << sc->depth) || p->max_bounds < 0 || p->max_bounds > 16)

@@ -211,6 +211,22 @@ struct Stack64s {
         asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(p), "=r"(ty) : "r"(addr + uint32_t(scale) * uint32_t(kThreads * 8)) : "memory");
         t = __uint_as_float(ty);
     }
+    // Per-thread statistics pairs behind the stack, addressed from the same register: the stack's slots are the scales
+    // 23 - depth .. 23, so whatever the depth the 8-byte slot of "scale" 24 + k is the k-th pair behind the thread's stack
+    // column (the frame kernels reserve six: rays and loop trips per ray class).  One LDS.64 / STS.64 and an IMAD per ray; the
+    // plain array form re-derived the address from %tid and the kernel parameters every time (20 instructions per ray).
+    __device__ __forceinline__ void stat_zero(int k) const {
+        asm volatile("st.shared.v2.b32 [%0], {%1, %1};" :: "r"(addr + uint32_t(kSvoMaxDepth + 1 + k) * uint32_t(kThreads * 8)), "r"(0u) : "memory");
+    }
+    __device__ __forceinline__ void stat_add(int k, uint32_t a, uint32_t b) const {
+        const uint32_t at = addr + uint32_t(kSvoMaxDepth + 1 + k) * uint32_t(kThreads * 8);
+        uint32_t x, y;
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(at) : "memory");
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" :: "r"(at), "r"(x + a), "r"(y + b) : "memory");
+    }
+    __device__ __forceinline__ void stat_get(int k, uint32_t& a, uint32_t& b) const {
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr + uint32_t(kSvoMaxDepth + 1 + k) * uint32_t(kThreads * 8)) : "memory");
+    }
 };
 
 // Bounds of everything solid in the scene (castRay's [1,2]^3 coordinates, a little enlarged): a ray that has left this box
@@ -224,12 +240,16 @@ struct Stack64s {
 // deepest cells a walk can stand in are the voxels (scale 23 - depth: every child of a node of the level above is a leaf or
 // empty, which vrt_lsvo_create validates and the device builders guarantee), the test after a descent compares a scale
 // >= 23 - depth, and the one after a POP a scale larger than one that has passed already.  The launchers pick the variant.
-template <bool kCone, bool kBounds = false, bool kGuard = true>
+// kUnit = true promises |d| <= 2^100 or so (the frame kernels: their directions are normalised, or a normalised vector times the
+// camera's rotation matrix, which vrt_render* checks): the child selection of a descent may then use one FFMA per axis for
+// half * tc + c.  That is the reference's FMUL + FADD bit for bit — half is a power of two and |tc| = 1 / |d| is far from the
+// denormals, so the product is exact and the only rounding is the sum's, as in the two-instruction form.
+template <bool kCone, bool kBounds = false, bool kGuard = true, bool kUnit = false>
 struct Trav2 {
     float dx, dy, dz, coef, bias;
     float tcx, tcy, tcz, tox, toy, toz;
     float px, py, pz;
-    float t_min, t_max, h;
+    float t_min, t_max;
     float sf, iters_f;
     float t_limit;       // kBounds: the time at which the ray leaves the scene bounds
     uint32_t parent, child, mirror, face;
@@ -256,8 +276,7 @@ struct Trav2 {
         if (dy > 0.0f) { mirror ^= 2u; toy = 3.0f * tcy - toy; }
         if (dz > 0.0f) { mirror ^= 4u; toz = 3.0f * tcz - toz; }
         t_min = fmaxf(2.0f * tcx - tox, fmaxf(2.0f * tcy - toy, 2.0f * tcz - toz));   // :54
-        t_max = fminf(tcx - tox, fminf(tcy - toy, tcz - toz));                         // :55
-        h = t_max;
+        t_max = fminf(tcx - tox, fminf(tcy - toy, tcz - toz));                         // :55 (h = t_max, :56: see the push in step())
         t_min = fmaxf(t_floor, t_min);                                     // :57 with t_floor = 0
         t_max = fminf(1.0f, t_max);
         if (kBounds) {
@@ -299,15 +318,24 @@ struct Trav2 {
             if (ends) return false;
             if (inside) {
                 const float half = sf * 0.5f;
-                if (tc_max < h) stack.push_sf(sf, parent, t_max);            // :97-100
-                h = tc_max;
+                // :97-100 push unconditionally.  The reference skips the write when the child's exit time equals `h` (the exit time
+                // of the cell it is in, or 0 right after a POP).  Skipped or not, the slot of a level only ever holds (P, t_max(P))
+                // for the node P the walk is inside at that level — t_max changes on descents and POPs only, so every write made
+                // while inside P writes the same pair — and the reference skips exactly the writes that are redundant (after a
+                // POP: the slot was just read) or never read (equal exit times: the POP that leaves the child leaves P too).  The
+                // walk therefore reads the same pairs with or without `h`; without it the loop has three instructions and one
+                // live register less.
+                stack.push_sf(sf, parent, t_max);
                 parent = nodes.child_of(parent, nd_, shift);                 // :103
                 nd_ = nodes.load(parent);
                 child = 0u;
                 sf = half;                                                   // --scale
-                if (half * tcx + cx > t_min) { child ^= 1u; px += half; }    // :88,107-109
-                if (half * tcy + cy > t_min) { child ^= 2u; py += half; }
-                if (half * tcz + cz > t_min) { child ^= 4u; pz += half; }
+                const float mx = kUnit ? fmaf(half, tcx, cx) : half * tcx + cx;   // the centre planes' crossing times, :88
+                const float my = kUnit ? fmaf(half, tcy, cy) : half * tcy + cy;
+                const float mz = kUnit ? fmaf(half, tcz, cz) : half * tcz + cz;
+                if (mx > t_min) { child ^= 1u; px += half; }                 // :107-109
+                if (my > t_min) { child ^= 2u; py += half; }
+                if (mz > t_min) { child ^= 4u; pz += half; }
                 t_max = tv_max;
                 return kGuard ? sf > guard_sf : true;                        // :72
             }
@@ -347,7 +375,6 @@ struct Trav2 {
             py = __uint_as_float(iy & keep);
             pz = __uint_as_float(iz & keep);
             child = ((ix & bit) + 2u * (iy & bit) + 4u * (iz & bit)) >> scale;   // :143
-            h = 0.0f;
             return kGuard ? scale > guard : true;
         }
         return true;
@@ -373,11 +400,11 @@ struct Trav2 {
     }
 };
 
-template <bool kCone, bool kBounds = false, bool kGuard = true, typename Nodes, typename Stack>
+template <bool kCone, bool kBounds = false, bool kGuard = true, bool kUnit = false, typename Nodes, typename Stack>
 __device__ __forceinline__ void lsvo_cast_ray2(const Nodes& nodes, Stack& stack, int guard, float guard_sf, float ox, float oy, float oz,
                                                float dx, float dy, float dz, float coef, float bias, LsvoResult& r, float t_floor = 0.0f,
                                                const SceneBounds* bounds = nullptr) {
-    Trav2<kCone, kBounds, kGuard> t;
+    Trav2<kCone, kBounds, kGuard, kUnit> t;
     t.init(ox, oy, oz, dx, dy, dz, coef, bias, t_floor, bounds);
     t.prime(nodes);
     while (t.step(nodes, stack, guard, guard_sf)) {}

@@ -63,10 +63,9 @@ __global__ void __launch_bounds__(128, VRT_K4_MIN_CTAS) render_accumulate_kernel
     const int sub = lane & (Q - 1);                        // which of the pixel's Q concurrent samples
     const int runs = (s_end - s_begin) / Q;                // launcher guarantees divisibility
 
-    // ray statistics per class: private shared-memory counters (12 registers less across the traversal loop)
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + (L.depth + 1) * 128) + threadIdx.x;
+    // ray statistics per class: private shared-memory pairs behind the stack (12 registers less across the traversal loop)
 #pragma unroll
-    for (int k = 0; k < 12; ++k) cnt[k * 128] = 0u;
+    for (int k = 0; k < 6; ++k) stack.stat_zero(k);
     const float SCALE = 1.0f / float(1 << L.depth);                           // raycaster.hpp:123-124 / main.cpp:82
     const float n_norm = SCALE * 0.0078125f * 2.0f;                           // raycaster.hpp:171-172
     const float aspect = float(L.width) / float(L.height);                    // main.cpp:133
@@ -93,10 +92,9 @@ __global__ void __launch_bounds__(128, VRT_K4_MIN_CTAS) render_accumulate_kernel
                 int stage = kPrimary;
                 while (stage != kDone) {
                     LsvoResult r;
-                    if (stage < kGi0) lsvo_cast_ray2<false, true, kGuard>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, 0.0f, 0.0f, r, nr.t_floor, &L.bounds);
-                    else lsvo_cast_ray2<true, false, kGuard>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
-                    cnt[stage * 128] += 1u;
-                    cnt[(6 + stage) * 128] += r.complexity;
+                    if (stage < kGi0) lsvo_cast_ray2<false, true, kGuard, true>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, 0.0f, 0.0f, r, nr.t_floor, &L.bounds);
+                    else lsvo_cast_ray2<true, false, kGuard, true>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
+                    stack.stat_add(stage, 1u, r.complexity);
                     LsvoHit h;
                     if (r.hit) lsvo_finish(r, nr.ox, nr.oy, nr.oz, L.depth, h);
                     stage = chain_advance<kMirror>(L, c, stage, r, h, pixel, sample, SCALE, n_norm, nr);
@@ -126,7 +124,8 @@ __global__ void __launch_bounds__(128, VRT_K4_MIN_CTAS) render_accumulate_kernel
     // statistics: rays and Σ complexity per ray class (warp reduce, one atomic per warp and class)
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-        uint32_t a = cnt[k * 128], b = cnt[(6 + k) * 128];
+        uint32_t a, b;
+        stack.stat_get(k, a, b);
         for (int o = 16; o > 0; o >>= 1) {
             a += __shfl_xor_sync(0xffffffffu, a, o);
             b += __shfl_xor_sync(0xffffffffu, b, o);
@@ -156,7 +155,7 @@ __device__ __forceinline__ float noise_angle(uint32_t w1, uint32_t w2) {
     const float x = float(int(w1 % 100u) - 50), y = float(int(w2 % 100u) - 50);
     const float s = fabsf(x) + fabsf(y);
     if (s == 0.0f) return 0.0f;
-    const float t = y / s;                                                     // -1..1
+    const float t = __fdividef(y, s);                                          // -1..1; a sort key only: no need for the IEEE quotient
     return x >= 0.0f ? (y >= 0.0f ? t : 4.0f + t) : 2.0f - t;
 }
 
@@ -349,6 +348,10 @@ __device__ __forceinline__ void block_origin(const RenderLaunch& L, const BlockG
     s_begin = (run * L.spp) / G.runs;
     n_s = ((run + 1) * L.spp) / G.runs - s_begin;
 }
+// list entry c = pixel j of the block, sample s of the run: c = j * n_s + s.  Runs are powers of two except for odd sample
+// counts: a shift instead of the ~25-instruction integer division (log2 < 0: divide).
+__device__ __forceinline__ int run_log2(int n_s) { return (n_s & (n_s - 1)) == 0 ? 31 - __clz(n_s) : -1; }
+__device__ __forceinline__ int entry_pixel(int c, int n_s, int log2) { return log2 >= 0 ? c >> log2 : c / n_s; }
 __device__ __forceinline__ void block_pixel(int x0, int y0, int j, int& x, int& y) {     // 8x4 sub-tile by sub-tile
     x = x0 + (j >> 5) * 8 + (j & 7);
     y = y0 + ((j >> 3) & 3);
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(128) sort_samples_kernel(RenderLaunch L, SortP
     const int lane = threadIdx.x & 31, work = blockIdx.x;
     int x0, y0, s_begin, n_s;
     block_origin(L, G, work, x0, y0, s_begin, n_s);
-    const int n_chains = 128 * n_s, n_keys = plan.bins1 * plan.bins2;
+    const int n_chains = 128 * n_s, n_keys = plan.bins1 * plan.bins2, n_s_log2 = run_log2(n_s);
     uint16_t* ids = lists + size_t(work) * G.cap;
     for (int i = threadIdx.x; i < 257; i += 128) hist[i] = 0u;
     __syncthreads();
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(128) sort_samples_kernel(RenderLaunch L, SortP
     for (int c = threadIdx.x; c < n_padded; c += 128) {
         uint32_t key = 255u;
         if (c < n_chains) {
-            const int j = c / n_s, s = s_begin + (c - j * n_s);
+            const int j = entry_pixel(c, n_s, n_s_log2), s = s_begin + (c - j * n_s);
             int x, y;
             block_pixel(x0, y0, j, x, y);
             if (x < L.width && y < L.row_end) {
@@ -447,9 +450,8 @@ __global__ void __launch_bounds__(128, VRT_K6_MIN_CTAS) render_rounds_kernel(Nod
     const float guard_sf = keep_in_register(guard_scale_f(L.guard), smem + threadIdx.x);
     (void)stack; (void)stack2; (void)guard_sf;
     const int lane = threadIdx.x & 31;
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + (L.depth + 1) * 128) + threadIdx.x;
 #pragma unroll
-    for (int k = 0; k < 12; ++k) cnt[k * 128] = 0u;
+    for (int k = 0; k < 6; ++k) stack2.stat_zero(k);                          // rays and loop trips per ray class, behind the stack
     const float SCALE = 1.0f / float(1 << L.depth);                           // raycaster.hpp:123-124 / main.cpp:82
     const float n_norm = SCALE * 0.0078125f * 2.0f;                           // raycaster.hpp:171-172
     const float aspect = float(L.width) / float(L.height);                    // main.cpp:133
@@ -492,11 +494,10 @@ __global__ void __launch_bounds__(128, VRT_K6_MIN_CTAS) render_rounds_kernel(Nod
                     } else if constexpr (kTrav == 1) {
                         lsvo_cast_ray2<true>(nodes, stack2, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
                     } else {
-                        if (stage < kGi0) lsvo_cast_ray2<false, true, kGuard>(nodes, stack2, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, 0.0f, 0.0f, r, nr.t_floor, &L.bounds);
-                        else lsvo_cast_ray2<true, false, kGuard>(nodes, stack2, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
+                        if (stage < kGi0) lsvo_cast_ray2<false, true, kGuard, true>(nodes, stack2, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, 0.0f, 0.0f, r, nr.t_floor, &L.bounds);
+                        else lsvo_cast_ray2<true, false, kGuard, true>(nodes, stack2, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
                     }
-                    cnt[stage * 128] += 1u;
-                    cnt[(6 + stage) * 128] += r.complexity;
+                    stack2.stat_add(stage, 1u, r.complexity);
                     LsvoHit h;
                     if (r.hit) lsvo_finish(r, nr.ox, nr.oy, nr.oz, L.depth, h);
                     stage = chain_advance<kMirror>(L, cs, stage, r, h, pixel, sample, SCALE, n_norm, nr);
@@ -576,7 +577,8 @@ __global__ void __launch_bounds__(128, VRT_K6_MIN_CTAS) render_rounds_kernel(Nod
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-        uint32_t a = cnt[k * 128], b = cnt[(6 + k) * 128];
+        uint32_t a, b;
+        stack2.stat_get(k, a, b);
         for (int o = 16; o > 0; o >>= 1) {
             a += __shfl_xor_sync(0xffffffffu, a, o);
             b += __shfl_xor_sync(0xffffffffu, b, o);
@@ -621,7 +623,7 @@ __global__ void __launch_bounds__(128, 8) shade_rays_kernel(Nodes nodes, RenderL
     while (stage != kDone) {
         LsvoResult r;
         if (stage < kGi0) lsvo_cast_ray2<false, false, kGuard>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, 0.0f, 0.0f, r);
-        else lsvo_cast_ray2<true, false, kGuard>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
+        else lsvo_cast_ray2<true, false, kGuard, true>(nodes, stack, guard, guard_sf, nr.ox, nr.oy, nr.oz, nr.dx, nr.dy, nr.dz, nr.coef, 0.0f, r);
         if (stage == kPrimary) { complexity = r.complexity; if (r.hit) distance = r.t_min; }   // RayContext, raycaster.hpp:132-133,137
         LsvoHit h;
         if (r.hit) lsvo_finish(r, nr.ox, nr.oy, nr.oz, L.depth, h);
