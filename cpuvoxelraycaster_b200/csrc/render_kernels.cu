@@ -330,8 +330,8 @@ __global__ void __launch_bounds__(128, VRT_K5_MIN_CTAS) render_sorted_kernel(Nod
 // global memory (16 KB per block), `render_rounds_kernel` runs one persistent CTA set that takes blocks from a global
 // counter — the CTA's warps pull rounds of 32 list entries from the block's own counter, so a block still has the L1 of one
 // SM to itself — and, once no blocks are left, every warp looks for blocks that still have rounds and helps with them.
-// A round commits its colours with one warp-aggregated atomic per pixel (match_any + redux), so several CTAs can work
-// on one block.  Same samples, same numbers, integer sums: the frame cannot change.
+// A round commits its colours itself, with RED operations on the pixels' accumulators in global memory, so several CTAs can
+// work on one block.  Same samples, same numbers, integer sums: the frame cannot change.
 
 struct BlockGeometry {
     int tiles_x, tiles_y;      // 32x4-pixel blocks owned by this launch
@@ -505,19 +505,19 @@ __global__ void __launch_bounds__(128, VRT_K6_MIN_CTAS) render_rounds_kernel(Nod
                 chain_colour<kMirror>(L, cs, cr, cg, cb);
             }
             __syncwarp();
-            // one atomic per pixel and channel: the lanes holding samples of the same pixel add up first
-            const unsigned peers = __match_any_sync(0xffffffffu, key);
-            cr = __reduce_add_sync(peers, cr);
-            cg = __reduce_add_sync(peers, cg);
-            cb = __reduce_add_sync(peers, cb);
-            if (key != 0xffffffffu && lane == __ffs(peers) - 1) {
+            // Every lane adds its own sample to the pixel's accumulator (Sample, raycaster.hpp:18-24,87-90) with RED operations —
+            // no return value, the L2 merges the adds of a pixel.  Several CTAs may work on one block, so the sums live in
+            // global memory.  (Adding up the lanes of a pixel first — match_any + three reduce_add, one atomic per pixel and
+            // channel — costs ~170 instructions per round for the loops ptxas makes of a reduction over a partial mask:
+            // 36.74 vs 36.0 ms on the headline frame, profiles/r02_ab_commit.txt.)
+            if (key != 0xffffffffu) {
                 int x, y;
                 block_pixel(x0, y0, int(key), x, y);
-                uint32_t* w = accum + 4 * (size_t(y) * size_t(L.width) + size_t(x));   // Sample, raycaster.hpp:18-24,87-90
+                uint32_t* w = accum + 4 * (size_t(y) * size_t(L.width) + size_t(x));
                 if (cr) atomicAdd(w, cr);
                 if (cg) atomicAdd(w + 1, cg);
                 if (cb) atomicAdd(w + 2, cb);
-                atomicAdd(w + 3, uint32_t(__popc(peers)));
+                atomicAdd(w + 3, 1u);
             }
         }
     };
