@@ -62,7 +62,7 @@ def config_json(w, n_gpus):
                         "camera C(%d)" % (w["size"], w["depth"], w["width"], w["height"], w["spp"], w["gi_bounces"], w["aperture"], w["depth"]),
             "depth": w["depth"], "width": w["width"], "height": w["height"], "spp": w["spp"], "gi_bounces": w["gi_bounces"],
             "aperture": w["aperture"], "n_gpus": n_gpus, "rng": "Philox4x32-10 on getRand's 100-level lattice, key 0x5EED",
-            "ray_definition": "distinct castRay calls (the reference's 4 identical shadow samples count once)",
+            "ray_definition": "distinct castRay calls of the frame (the reference's 4 identical shadow samples count once); camera rays of beam tiles with an empty frustum are answered by the beam search without a walk and are counted — primary_rays_answered_by_beam_search says how many, value_walked_rays_only leaves them out",
             "l2": "inputs larger than L2: 1.35 GB node array + 33 MB accumulator vs 126 MB L2"}
 
 
@@ -288,7 +288,7 @@ def run_ours(args):
     kernel_ms = float(np.mean(kernel_times)) if kernel_times else float("nan")
     st = fr.stats()                                          # this rank's share, last frame
     t = torch.tensor([ms_total, kernel_ms], dtype=torch.float64, device=device)
-    cnt = torch.tensor(st["rays"] + st["complexity"] + [launches], dtype=torch.int64, device=device)
+    cnt = torch.tensor(st["rays"] + st["complexity"] + [launches, st.get("culled_primary", 0)], dtype=torch.int64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         local_cnt = cnt.clone()
@@ -299,13 +299,16 @@ def run_ours(args):
     rays = [int(x) for x in cnt[:6].tolist()]
     cx = [int(x) for x in cnt[6:12].tolist()]
     launches = int(cnt[12])                                  # libvrt kernels launched in the timed region, all ranks
+    # primary rays of samples whose 8x8-pixel beam tile has nothing in its frustum: answered (a miss) by the beam search, counted
+    # in rays[0] like every castRay call the reference makes for the frame, but not walked — no node bytes, no ray / hit record
+    culled = int(cnt[13])
     total_rays = sum(rays)
     ms_per_step = ms_total / args.steps
     value = total_rays / (ms_per_step * 1e-3) / 1e6
 
     # roofline of the dominant kernel on this rank: algorithmic bytes = sum over its rays of (8 B node per
     # iteration + 64 B ray/hit record) + 16 B accumulator write per pixel
-    l_rays, l_cx = int(local_cnt[:6].sum()), int(local_cnt[6:12].sum())
+    l_rays, l_cx = int(local_cnt[:6].sum()) - int(local_cnt[13]), int(local_cnt[6:12].sum())   # walked rays only
     if args.split == "samples":
         my_pixels = w["height"] * w["width"]
     else:
@@ -407,6 +410,8 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_json(w, world),
                 "rays_per_frame": dict(zip(["primary", "shadow", "gi", "gi_shadow", "gi2", "gi2_shadow"], rays)),
+                "primary_rays_answered_by_beam_search": culled,
+                "value_walked_rays_only": round((total_rays - culled) / (ms_per_step * 1e-3) / 1e6, 2),
                 "mean_complexity": round(sum(cx) / max(1, total_rays), 2),
                 "ms_per_frame": round(ms_per_step, 4), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clocks, "frame_identity": identity, "extra": extra}

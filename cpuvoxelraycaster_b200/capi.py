@@ -82,6 +82,7 @@ _SIGNATURES = {
     "vrt_render_resolve_device": (C.c_int, [_vp, C.POINTER(RenderParams), _vp, _vp]),
     "vrt_render": (C.c_int, [_vp, C.POINTER(Camera), C.POINTER(RenderParams), _vp, _vp, C.POINTER(RenderStats)]),
     "vrt_scene_last_render_stats": (C.c_int, [_vp, C.POINTER(RenderStats)]),
+    "vrt_scene_last_render_culled": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "vrt_shade_rays": (C.c_int, [_vp, C.POINTER(RenderParams), _u64, _vp, _vp]),
     "vrt_beam_floors": (C.c_int, [_vp, C.POINTER(Camera), C.POINTER(RenderParams), _i32, _vp]),
     "vrt_autofocus": (C.c_int, [_vp, C.POINTER(Camera), C.POINTER(_f)]),

@@ -241,9 +241,9 @@ int vrt_lsvo_create(vrt_context* ctx, const vrt_lnode* nodes, uint64_t n_nodes, 
     sc->guard = guard > 0 ? guard : (guard < 0 ? 0 : int32_t(depth));   // 0 = reference, <0 = lifted
     sc->n_nodes = n_nodes;
     cudaError_t e = cudaMalloc(&sc->d_nodes, n_nodes * sizeof(uint2));
-    if (e == cudaSuccess) e = cudaMalloc(&sc->d_counters, 16 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&sc->d_counters, kCounterSlots * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemcpyAsync(sc->d_nodes, nodes, n_nodes * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(sc->d_counters, 0, 16 * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(sc->d_counters, 0, kCounterSlots * sizeof(unsigned long long), ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         vrt_scene_destroy(sc);
@@ -268,8 +268,8 @@ int vrt_lsvo_create_terrain(vrt_context* ctx, uint32_t depth, int32_t guard, vrt
     sc->guard = guard > 0 ? guard : (guard < 0 ? 0 : int32_t(depth));
     cudaError_t e = vrt::device_build_terrain_lsvo(int(depth), &sc->d_nodes, &sc->n_nodes, nullptr, ctx->stream);
     ctx->launches += 7 + 9 * depth;      // heights, pyramid, count/scan (4 per level), size/place/emit per level, fill, root
-    if (e == cudaSuccess) e = cudaMalloc(&sc->d_counters, 16 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemsetAsync(sc->d_counters, 0, 16 * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess) e = cudaMalloc(&sc->d_counters, kCounterSlots * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemsetAsync(sc->d_counters, 0, kCounterSlots * sizeof(unsigned long long), ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         vrt_scene_destroy(sc);
@@ -301,8 +301,8 @@ int vrt_lsvo_create_heightfield(vrt_context* ctx, uint32_t depth, const int32_t*
         e = vrt::device_build_terrain_lsvo(int(depth), &sc->d_nodes, &sc->n_nodes, heights ? nullptr : sc->d_heights, ctx->stream,
                                            heights ? sc->d_heights : nullptr);
     ctx->launches += 7 + 9 * depth;
-    if (e == cudaSuccess) e = cudaMalloc(&sc->d_counters, 16 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemsetAsync(sc->d_counters, 0, 16 * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess) e = cudaMalloc(&sc->d_counters, kCounterSlots * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemsetAsync(sc->d_counters, 0, kCounterSlots * sizeof(unsigned long long), ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         vrt_scene_destroy(sc);
@@ -440,8 +440,8 @@ int vrt_lsvo_create_from_voxels(vrt_context* ctx, uint32_t depth, const uint32_t
     int s = upload_voxel_keys(ctx, depth, xyz, n, &sc->d_voxel_keys, &sc->n_voxel_keys, "vrt_lsvo_create_from_voxels");
     if (s == VRT_OK) s = rebuild_from_keys(sc, sc->d_voxel_keys, sc->n_voxel_keys, "vrt_lsvo_create_from_voxels");
     if (s == VRT_OK) {
-        cudaError_t e = cudaMalloc(&sc->d_counters, 16 * sizeof(unsigned long long));
-        if (e == cudaSuccess) e = cudaMemsetAsync(sc->d_counters, 0, 16 * sizeof(unsigned long long), ctx->stream);
+        cudaError_t e = cudaMalloc(&sc->d_counters, kCounterSlots * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMemsetAsync(sc->d_counters, 0, kCounterSlots * sizeof(unsigned long long), ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) s = cuda_fail(e, "vrt_lsvo_create_from_voxels");
     }
@@ -663,7 +663,7 @@ int vrt_scene_last_complexity(vrt_scene* sc, uint64_t* total) {
 
 // ---- rendering -------------------------------------------------------------------------------------
 namespace {
-constexpr int kRenderCounters = 2;   // offset of the 12 render counters inside d_counters
+constexpr int kRenderCounters = 2;   // offset of the 12 render counters inside d_counters (+ kernels.h kCulledCounter = slot 16)
 constexpr int kFocalSlot = 15;       // d_counters[15] holds the float focal length of vrt_render_params::autofocus
 
 int check_render_args(const vrt_scene* sc, const vrt_camera* cam, const vrt_render_params* p, const char* who) {
@@ -742,6 +742,7 @@ int vrt_render_accumulate_device(vrt_scene* sc, const vrt_camera* cam, const vrt
     vrt_context* ctx = sc->ctx;
     if (int s = use_device(ctx)) return s;
     VRT_CUDA(cudaMemsetAsync(sc->d_counters + kRenderCounters, 0, 13 * sizeof(unsigned long long), ctx->stream));
+    VRT_CUDA(cudaMemsetAsync(sc->d_counters + kRenderCounters + vrt::kCulledCounter, 0, sizeof(unsigned long long), ctx->stream));
     if (p->row_end == p->row_begin) return VRT_OK;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     if (ctx->time_frame_kernels) {                           // device time of this call's frame kernels, on the launching stream
@@ -865,6 +866,16 @@ int vrt_scene_last_render_stats(vrt_scene* sc, vrt_render_stats* stats) {
     VRT_CUDA(cudaMemcpyAsync(v, sc->d_counters + kRenderCounters, sizeof(v), cudaMemcpyDeviceToHost, sc->ctx->stream));
     VRT_CUDA(cudaStreamSynchronize(sc->ctx->stream));
     for (int k = 0; k < 6; ++k) { stats->rays[k] = v[k]; stats->complexity[k] = v[6 + k]; }
+    return VRT_OK;
+}
+
+int vrt_scene_last_render_culled(vrt_scene* sc, uint64_t* primary_rays) {
+    if (!sc || !primary_rays) return fail(VRT_ERR_INVALID, "vrt_scene_last_render_culled: NULL argument");
+    if (int s = use_device(sc->ctx)) return s;
+    unsigned long long v = 0;
+    VRT_CUDA(cudaMemcpyAsync(&v, sc->d_counters + kRenderCounters + vrt::kCulledCounter, sizeof(v), cudaMemcpyDeviceToHost, sc->ctx->stream));
+    VRT_CUDA(cudaStreamSynchronize(sc->ctx->stream));
+    *primary_rays = v;
     return VRT_OK;
 }
 
@@ -1025,9 +1036,9 @@ int create_grid_scene(vrt_context* ctx, const uint8_t* cells, int X, int Y, int 
             }
     }
     cudaError_t e = cudaMalloc(&sc->d_grid_bits, words.size() * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&sc->d_counters, 16 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&sc->d_counters, kCounterSlots * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemcpyAsync(sc->d_grid_bits, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(sc->d_counters, 0, 16 * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(sc->d_counters, 0, kCounterSlots * sizeof(unsigned long long), ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { vrt_scene_destroy(sc); return cuda_fail(e, "grid scene upload"); }
     for (int l = 0; l < levels; ++l) sc->grid.level[l].bits = sc->d_grid_bits + offsets[l];

@@ -61,6 +61,8 @@ struct vrt_context {
     cudaAccessPolicyWindow l2_window{};     // installed by vrt_scene_set_layout(.., l2_persist); follows the stream (set_stream)
 };
 
+constexpr int kCounterSlots = 24;    // length of vrt_scene::d_counters
+
 struct vrt_scene {
     vrt_context* ctx = nullptr;
     int kind = 0;
@@ -70,7 +72,7 @@ struct vrt_scene {
     uint2* d_nodes = nullptr;
     uint64_t n_nodes = 0;
     uint64_t device_bytes = 0;
-    unsigned long long* d_counters = nullptr;   // [0] Σ complexity of the last cast; [2..13] render rays/complexity per class
+    unsigned long long* d_counters = nullptr;   // kCounterSlots: [0] Σ complexity of the last cast; [2..13] render rays/complexity per class; [14] gate / K4p work; [15] focal; [16] culled primaries
     vrt::SceneBounds bounds{{1.0f, 1.0f, 1.0f}, {2.0f, 2.0f, 2.0f}};   // LSVO: bounds of the solid voxels (scene_device.cu), castRay coordinates
     uint2* d_compact = nullptr;                 // optional compact breadth-first copy (vrt_scene_set_layout)
     uint64_t n_compact = 0;

@@ -89,6 +89,9 @@ __host__ __device__ inline int checker_x_parity(int checker, int area_height, in
 }
 
 // K0+K4: ray generation, traversal, shading and accumulation for rows [row_begin,row_end) (render_kernels.cu)
+// d_counters of the frame launchers: [0..5] rays per class, [6..11] loop trips per class, [12] K4p's work counter,
+// [kCulledCounter] primary rays answered by the beam search without a walk (K6: sort_samples_kernel)
+constexpr int kCulledCounter = 14;
 // device scratch launch_render_accumulate_ref needs for this launch (0 unless the K6 mapping is selected)
 size_t render_scratch_bytes(const RenderLaunch& L);
 cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const RenderLaunch& L, uint32_t* d_accum,

@@ -357,16 +357,23 @@ __device__ __forceinline__ void block_pixel(int x0, int y0, int j, int& x, int& 
     y = y0 + ((j >> 3) & 3);
 }
 
+// Samples whose pixel lies in a beam tile with NOTHING in its frustum (floor 3.0, beam_kernels.cu: no non-empty node meets
+// the tile's lens-widened frustum, so every camera ray of the tile misses) never enter a list: the sort counts them — one add to
+// the pixel's sample count per run, one to the primary-ray statistics (complexity 0) and one to `culled` per block — and K6 only
+// traces what can hit something.  Their colour is the reference's black (raycaster.hpp:38), i.e. nothing to add to the sums.
 __global__ void __launch_bounds__(128) sort_samples_kernel(RenderLaunch L, SortPlan plan, BlockGeometry G, uint16_t* __restrict__ lists,
-                                                           uint32_t* __restrict__ meta) {
+                                                           uint32_t* __restrict__ meta, uint32_t* __restrict__ accum,
+                                                           unsigned long long* __restrict__ counters, unsigned long long* __restrict__ culled) {
     __shared__ uint32_t hist[260];
-    __shared__ uint8_t keys[8192];                                             // one key per sample of the block (255 = off-frame)
+    __shared__ uint8_t keys[8192];                                             // one key per sample of the block (255 = not in the list)
+    __shared__ uint32_t s_culled;
     const int lane = threadIdx.x & 31, work = blockIdx.x;
     int x0, y0, s_begin, n_s;
     block_origin(L, G, work, x0, y0, s_begin, n_s);
     const int n_chains = 128 * n_s, n_keys = plan.bins1 * plan.bins2, n_s_log2 = run_log2(n_s);
     uint16_t* ids = lists + size_t(work) * G.cap;
     for (int i = threadIdx.x; i < 257; i += 128) hist[i] = 0u;
+    if (threadIdx.x == 0) s_culled = 0u;
     __syncthreads();
     // pass 1: keys and histogram.  Lanes of a warp holding the same key add up first (one shared-memory atomic per key
     // and warp instead of one per sample: with 16 sectors the plain version serialises 8 deep)
@@ -377,7 +384,17 @@ __global__ void __launch_bounds__(128) sort_samples_kernel(RenderLaunch L, SortP
             const int j = entry_pixel(c, n_s, n_s_log2), s = s_begin + (c - j * n_s);
             int x, y;
             block_pixel(x0, y0, j, x, y);
-            if (x < L.width && y < L.row_end) {
+            bool in_list = x < L.width && y < L.row_end;
+#ifndef VRT_NO_CULL                                                            // (A/B builds: make EXTRA=-DVRT_NO_CULL)
+            if (in_list && L.beam_floor && __ldg(L.beam_floor + (y >> L.beam_shift) * L.beam_tiles_x + (x >> L.beam_shift)) == 3.0f) {
+                in_list = false;                                               // answered by the beam search: a miss
+                if (c == j * n_s) {                                            // once per pixel and run
+                    atomicAdd(accum + 4 * (size_t(y) * size_t(L.width) + size_t(x)) + 3, uint32_t(n_s));
+                    atomicAdd(&s_culled, uint32_t(n_s));
+                }
+            }
+#endif
+            if (in_list) {
                 key = 0u;
                 if (n_keys > 1) {
                     const uint32_t pixel = uint32_t(y) * uint32_t(L.width) + uint32_t(x), sample = uint32_t(L.sample_offset + s);
@@ -418,6 +435,10 @@ __global__ void __launch_bounds__(128) sort_samples_kernel(RenderLaunch L, SortP
         if (key != 255u && lane == leader) first = atomicAdd(hist + key, uint32_t(__popc(peers)));
         first = __shfl_sync(0xffffffffu, first, leader);
         if (key != 255u) ids[first + uint32_t(__popc(peers & ((1u << lane) - 1u)))] = uint16_t(c);
+    }
+    if (threadIdx.x == 0 && s_culled) {                                        // (the barriers above order the block's adds before this read)
+        atomicAdd(counters + kPrimary, (unsigned long long)s_culled);
+        atomicAdd(culled, (unsigned long long)s_culled);
     }
 }
 
@@ -758,7 +779,7 @@ cudaError_t launch_render_accumulate_ref(const uint2* nodes, bool compact, const
         uint32_t* next_block = meta + 2 * size_t(blocks);
         cudaError_t e = cudaMemsetAsync(next_block, 0, sizeof(uint32_t), stream);
         if (e != cudaSuccess) return e;
-        sort_samples_kernel<<<blocks, 128, 0, stream>>>(L, P.sort, P.G, lists, meta);
+        sort_samples_kernel<<<blocks, 128, 0, stream>>>(L, P.sort, P.G, lists, meta, d_accum, d_counters, d_counters + kCulledCounter);
         int per_sm = 0, sms = 0, dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -504,7 +504,9 @@ class RayCaster:
             self.sample_count += int(spp)
         else:
             self.frame_index += 1
-        self.last_stats = dict(rays=list(stats.rays), complexity=list(stats.complexity))
+        culled = C.c_uint64(0)          # primary rays answered by the beam search instead of a walk (vrt_scene_last_render_culled)
+        check(lib().vrt_scene_last_render_culled(self.svo.handle, C.byref(culled)))
+        self.last_stats = dict(rays=list(stats.rays), complexity=list(stats.complexity), culled_primary=int(culled.value))
         return self.render_image
 
     def beam_floors(self, camera, tile=8):

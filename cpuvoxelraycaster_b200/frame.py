@@ -249,4 +249,6 @@ class FrameRenderer:
     def stats(self):
         st = capi.RenderStats()
         check(lib().vrt_scene_last_render_stats(self.scene.handle, C.byref(st)))
-        return dict(rays=list(st.rays), complexity=list(st.complexity))
+        culled = C.c_uint64(0)                      # primary rays answered by the beam search (counted in rays[0], no walk)
+        check(lib().vrt_scene_last_render_culled(self.scene.handle, C.byref(culled)))
+        return dict(rays=list(st.rays), complexity=list(st.complexity), culled_primary=int(culled.value))

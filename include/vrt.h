@@ -267,6 +267,11 @@ int vrt_render_resolve_device(vrt_scene* scene, const vrt_render_params* p, cons
 int vrt_render(vrt_scene* scene, const vrt_camera* cam, const vrt_render_params* p, uint8_t* rgba, uint32_t* accum,
                vrt_render_stats* stats);
 int vrt_scene_last_render_stats(vrt_scene* scene, vrt_render_stats* stats);
+/* How many of the last frame's primary rays (they are counted in vrt_render_stats::rays[0], with complexity 0) were answered by the
+ * beam search instead of a walk: samples of pixels whose beam tile has nothing in its frustum (context option "beam_tile",
+ * vrt_beam_floors: floor 3.0) — such a camera ray misses whatever its lens sample, so the frame kernels do not start its chain.
+ * No reference counterpart (there every castRay call walks, lsvo.hpp:72-146); 0 without beam floors. */
+int vrt_scene_last_render_culled(vrt_scene* scene, uint64_t* primary_rays);
 /* Diagnostic: the beam floors a frame with these parameters would use (context option "beam_tile"): out[ty * tiles_x + tx],
  * tiles_x = ceil(width / tile), for every tile of the frame — the distance (castRay units) below which no camera ray of the
  * tile (any pixel, any lens sample) can hit anything; 3.0 = nothing in the tile's frustum.  No reference counterpart. */

@@ -351,12 +351,16 @@ def test_beam_floors_do_not_change_frames(vrt, ctx, scene9, position, view, aper
         ctx.set_option("render_variant", variant)
         ctx.set_option("beam_tile", 0)
         want, st0 = _frame(vrt, scene9, size, cam, default_light(), spp, mirror_y=240)
+        assert st0["culled_primary"] == 0
         for tile in (4, 8, 16, 32):
             ctx.set_option("beam_tile", tile)
             got, st = _frame(vrt, scene9, size, cam, default_light(), spp, mirror_y=240)
             assert np.array_equal(got, want), (size, tile)
             assert st["rays"] == st0["rays"] and st["complexity"][1:] == st0["complexity"][1:]
             assert st["complexity"][0] <= st0["complexity"][0]
+            # K6 does not start the chains of samples whose tile has an empty frustum: they are counted (rays[0] above, the
+            # accumulator's sample counts in `got`), never more of them than camera rays that miss, and only K6 does it
+            assert st["culled_primary"] <= st0["rays"][0] and (variant == 0 or st["culled_primary"] == 0)
         # ... and with the walks ending at the scene's bounds instead of the root cube (the product default: both on)
         for tile in (0, 8):
             ctx.set_option("beam_tile", tile)
@@ -368,6 +372,34 @@ def test_beam_floors_do_not_change_frames(vrt, ctx, scene9, position, view, aper
             assert sum(st["complexity"]) <= sum(st0["complexity"])
         ctx.set_option("beam_tile", 0)
     ctx.set_option("render_variant", 0)
+
+
+def test_samples_of_empty_beam_tiles_are_answered_without_a_walk(vrt, ctx, scene9):
+    """K6 with beam floors: samples of pixels whose tile has nothing in its frustum do not enter the sample lists — the sort kernel
+    counts them.  Horizon view (half sky): the frame (sums AND per-pixel sample counts), the ray counts of every class are those of
+    the frame without floors; the culled rays are camera rays that miss (never more than rays[0] - rays[1], no mirrors here so
+    every primary hit casts one sun-shadow ray), most of the sky is culled, and their trips are gone from complexity[0]."""
+    cam = vrt.Camera(position=(256, 200, 256), view_angle=(0.0, 0.0), aperture=0.5, focal_length=100.0)
+    size, spp = (256, 144), 16
+    ctx.set_option("render_variant", 0)
+    ctx.set_option("beam_tile", 0)
+    want, st0 = _frame(vrt, scene9, size, cam, default_light(), spp)
+    misses = st0["rays"][0] - st0["rays"][1]
+    assert st0["rays"][0] == size[0] * size[1] * spp and misses > st0["rays"][0] // 4 and st0["culled_primary"] == 0
+    try:
+        for tile in (4, 8, 16):
+            ctx.set_option("beam_tile", tile)
+            got, st = _frame(vrt, scene9, size, cam, default_light(), spp)
+            assert np.array_equal(got, want), tile
+            assert (got[..., 3] == spp).all()
+            assert st["rays"] == st0["rays"] and st["complexity"][1:] == st0["complexity"][1:]
+            assert 0 < st["culled_primary"] <= misses, (tile, st["culled_primary"], misses)
+            assert st["culled_primary"] % spp == 0                       # whole pixels
+            if tile <= 8:
+                assert st["culled_primary"] > misses // 2, (tile, st["culled_primary"], misses)
+            assert st["complexity"][0] < st0["complexity"][0]
+    finally:
+        ctx.set_option("beam_tile", 0)
 
 
 def test_beam_floors_on_a_random_voxel_scene(vrt, ctx, textures):
