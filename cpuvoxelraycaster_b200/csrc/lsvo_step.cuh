@@ -185,7 +185,16 @@ __device__ __forceinline__ void lsvo_cast_ray(const Nodes& nodes, Stack& stack, 
 //   * drops the cone test `tc_max * coef + bias >= sf` (lsvo.hpp:82-85) at compile time for rays cast with coef = bias = 0
 //     (primary and sun-shadow rays: the test can never be true there — 0 >= sf is false for every sf > 0, and a NaN product,
 //     inf * 0, compares false as well);
-//   * addresses the stack from the bits of sf (push) / with one IMAD from the scale (pop).
+//   * addresses the stack from the bits of sf (push) / with one IMAD from the scale (pop);
+// and, after the per-instruction view of the 8-CTA frame kernel (profiles/r02_summary.md: most warp-trips execute all three
+// paths of the loop, so an instruction removed from any path is removed from most trips),
+//   * applies the ADVANCE step once for both continuations (POP rebuilds the old position as p + sf, exactly);
+//   * has one exit for both kinds of hit and no hit flag (how the walk ended is read off its final state, Trav2::hit);
+//   * compiles the loop guard out where it cannot bind (kGuard) and uses one FFMA per axis for the child selection where the
+//     product is exact (kUnit);
+//   * keeps the current node's two words in registers across trips (loaded when `parent` changes only);
+//   * pushes unconditionally (no `h`: the same pairs are read back, see step()).
+// 107 -> 86 instructions per loop in the frame kernels; every step with byte-identical frames and trip counts.
 template <int kThreads>
 struct Stack64s {
     uint32_t addr;       // shared-memory byte address of the entry of scale 0 (entry of scale s at addr + s * kThreads * 8)
