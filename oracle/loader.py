@@ -87,6 +87,8 @@ class Port:
         L.vo_terrain_heights.argtypes = [C.c_int32, C.c_void_p]
         L.vo_lsvo_cast.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                    C.c_uint64, C.c_void_p, C.c_int]
+        L.vo_lsvo_cast_restructured.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int,
+                                                C.c_uint64, C.c_void_p, C.c_int]
         L.vo_grid_cast.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64,
                                    C.c_void_p, C.c_void_p, C.c_int]
         L.vo_svo_cast.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p,
@@ -125,6 +127,14 @@ class Port:
         out = np.zeros(len(o), PORT_HIT)
         self.lib.vo_lsvo_cast(_p(nodes), depth, depth if guard is None else guard, _p(o), _p(d), coef, bias, len(o),
                               _p(out), threads)
+        return out
+
+    def lsvo_cast_restructured(self, nodes, depth, origin, direction, coef=0.0, bias=0.0, guard=None, unit=False, threads=1):
+        """The walk with the device loop's structural changes (port.c: lsvo_cast_one_restructured); must equal lsvo_cast."""
+        o, d = _f32(origin), _f32(direction)
+        out = np.zeros(len(o), PORT_HIT)
+        self.lib.vo_lsvo_cast_restructured(_p(nodes), depth, depth if guard is None else guard, _p(o), _p(d), coef, bias,
+                                           1 if unit else 0, len(o), _p(out), threads)
         return out
 
     def grid_cast(self, cells, origin, direction, threads=1):

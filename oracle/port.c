@@ -405,6 +405,138 @@ void vo_lsvo_cast(const vo_lnode* nodes, int depth, int guard, const float* orig
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* The same walk with the structural changes of the device loop (csrc/lsvo_step.cuh, Trav2) — a CPU cross-check of the
+ * arguments in DESIGN.md §4, NOT a second specification: tests/test_oracle_golden.py asserts that it returns exactly what
+ * lsvo_cast_one returns (records and trip counts) on terrain, random voxel sets and degenerate rays.
+ *   - the stack write of lsvo.hpp:97-100 is unconditional (no `h`);
+ *   - cone hit (:82-85) and leaf hit (:90-95) share one exit; there is no hit flag: how the walk ended is read off its
+ *     final state (a coordinate below 1 / the guard / otherwise a hit);
+ *   - the guard test is dropped where it cannot bind (guard < 23 - depth);
+ *   - the child selection uses fmaf(half, tc, c) when `unit` is set (exact product: half is a power of two);
+ *   - the node is fetched when `parent` changes only.                                                                    */
+static void lsvo_cast_one_restructured(const vo_lnode* nodes, int depth, int guard, const float o[3], const float din[3],
+                                       float coef, float bias, int unit, vo_hit* res) {
+    const float EPS = 1.0f / (float)(1 << 23);
+    const int depth_offset = 23 - depth;
+    const int guarded = guard >= 23 - depth;
+    const float guard_sf = u2f((uint32_t)(guard + 104) << 23);
+    uint32_t stack_parent[24]; float stack_tmax[24];
+    float d[3], tc[3], to[3], p[3];
+    uint32_t mirror = 7u;
+    memset(res, 0, sizeof(*res));
+    if ((((o[0] * 0.0f + o[1] * 0.0f) + o[2] * 0.0f) + ((din[0] * 0.0f + din[1] * 0.0f) + din[2] * 0.0f)) != 0.0f) return;
+    for (int a = 0; a < 3; ++a) {
+        d[a] = din[a];
+        if (fabsf(d[a]) < EPS) d[a] = copysignf(EPS, d[a]);
+        tc[a] = -1.0f / fabsf(d[a]);
+        to[a] = o[a] * tc[a];
+        if (d[a] > 0.0f) { mirror ^= 1u << a; to[a] = 3.0f * tc[a] - to[a]; }
+    }
+    float t_min = maxf_(2.0f * tc[0] - to[0], maxf_(2.0f * tc[1] - to[1], 2.0f * tc[2] - to[2]));
+    float t_max = minf_(tc[0] - to[0], minf_(tc[1] - to[1], tc[2] - to[2]));
+    t_min = maxf_(0.0f, t_min);
+    t_max = minf_(1.0f, t_max);
+    uint32_t parent = 0u, child = 0u, face = 0u;
+    float sf = 0.5f;
+    for (int a = 0; a < 3; ++a) {
+        p[a] = 1.0f;
+        if (1.5f * tc[a] - to[a] > t_min) { child ^= 1u << a; p[a] = 1.5f; }
+    }
+    uint32_t iters = 0;
+    vo_lnode nd = nodes[0];
+    if (guarded && !(sf > guard_sf)) { res->complexity = 0; return; }   /* the loop condition before the first trip (:72) */
+    for (;;) {
+        ++iters;
+        float corner[3];
+        for (int a = 0; a < 3; ++a) corner[a] = p[a] * tc[a] - to[a];
+        const float tc_max = minf_(corner[0], minf_(corner[1], corner[2]));
+        const uint32_t shift = child ^ mirror;
+        if (((nd.child_mask >> shift) & 1u) && t_min <= t_max) {
+            const float tv_max = minf_(t_max, tc_max);
+            const int inside = t_min <= tv_max;
+            int ends = inside && ((nd.leaf_mask >> shift) & 1u);
+            if (tc_max * coef + bias >= sf) ends = 1;
+            if (ends) break;
+            if (inside) {
+                const float half = sf * 0.5f;
+                int scale = (int)(f2u(sf) >> 23) - 104;
+                stack_parent[scale - depth_offset] = parent;
+                stack_tmax[scale - depth_offset] = t_max;
+                parent += nd.child_offset + shift;
+                nd = nodes[parent];
+                child = 0u;
+                sf = half;
+                for (int a = 0; a < 3; ++a) {
+                    const float t_half = unit ? fmaf(half, tc[a], corner[a]) : half * tc[a] + corner[a];
+                    if (t_half > t_min) { child ^= 1u << a; p[a] += half; }
+                }
+                t_max = tv_max;
+                if (guarded && !(sf > guard_sf)) break;
+                continue;
+            }
+        }
+        uint32_t step = 0u;
+        for (int a = 0; a < 3; ++a)
+            if (corner[a] <= tc_max) { step ^= 1u << a; p[a] -= sf; }
+        t_min = tc_max;
+        child ^= step;
+        face = step;
+        if (child & step) {
+            uint32_t diff = 0u, ip[3];
+            for (int a = 0; a < 3; ++a) {
+                ip[a] = f2u(p[a]);
+                if (step & (1u << a)) diff |= ip[a] ^ f2u(p[a] + sf);
+            }
+            int scale = 31 - __builtin_clz(diff);
+            if (scale >= 23) break;
+            parent = stack_parent[scale - depth_offset];
+            t_max = stack_tmax[scale - depth_offset];
+            nd = nodes[parent];
+            sf = u2f((uint32_t)(scale + 104) << 23);
+            const uint32_t bit = 1u << scale, keep = 0u - bit;
+            child = ((ip[0] & bit) + 2u * (ip[1] & bit) + 4u * (ip[2] & bit)) >> scale;
+            for (int a = 0; a < 3; ++a) p[a] = u2f(ip[a] & keep);
+            if (guarded && !(scale > guard)) break;
+        }
+    }
+    res->complexity = iters;
+    int miss = minf_(p[0], minf_(p[1], p[2])) < 1.0f;
+    if (guarded && !(sf > guard_sf)) miss = 1;
+    if (miss) return;
+    const int scale = (int)(f2u(sf) >> 23) - 104;
+    res->hit = 1;
+    res->scale = scale;
+    res->face = face;
+    for (int a = 0; a < 3; ++a) {
+        const float sg = (float)(0.0f < d[a]) - (float)(d[a] < 0.0f);
+        res->normal[a] = (-sg) * (float)(face & (1u << a));
+        if ((mirror & (1u << a)) == 0) p[a] = 3.0f - sf - p[a];
+        res->position[a] = minf_(maxf_(o[a] + t_min * d[a], p[a] + EPS), p[a] + sf - EPS);
+        res->voxel[a] = (int32_t)((p[a] - 1.0f) * (float)(1 << depth));
+    }
+    res->distance = t_min;
+    const float S = (float)(1 << depth);
+    if (res->normal[0] != 0.0f) {
+        res->voxel_coord[0] = fracf_(res->position[2] * S); res->voxel_coord[1] = fracf_(res->position[1] * S);
+    } else if (res->normal[1] != 0.0f) {
+        res->voxel_coord[0] = fracf_(res->position[0] * S); res->voxel_coord[1] = fracf_(res->position[2] * S);
+    } else if (res->normal[2] != 0.0f) {
+        res->voxel_coord[0] = fracf_(res->position[0] * S); res->voxel_coord[1] = fracf_(res->position[1] * S);
+    }
+}
+typedef struct { const vo_lnode* nodes; int depth, guard; const float *o, *d; float coef, bias; int unit; vo_hit* out; } lsvo2_ctx;
+static void lsvo2_range(void* c_, uint64_t b, uint64_t e) {
+    lsvo2_ctx* c = (lsvo2_ctx*)c_;
+    for (uint64_t i = b; i < e; ++i)
+        lsvo_cast_one_restructured(c->nodes, c->depth, c->guard, c->o + 3 * i, c->d + 3 * i, c->coef, c->bias, c->unit, c->out + i);
+}
+void vo_lsvo_cast_restructured(const vo_lnode* nodes, int depth, int guard, const float* origin, const float* dir, float coef,
+                               float bias, int unit, uint64_t n, vo_hit* out, int threads) {
+    lsvo2_ctx c = {nodes, depth, guard, origin, dir, coef, bias, unit, out};
+    par_for(lsvo2_range, &c, n, 4096, threads);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* Grid3D<X,Y,Z>::castRay, include/grid_3d.hpp:35-132                                          */
 /* ------------------------------------------------------------------------------------------ */
 static void grid_cast_one(const uint8_t* cells, int X, int Y, int Z, const float o[3], const float d[3], vo_hit* res,

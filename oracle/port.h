@@ -51,6 +51,12 @@ uint64_t vo_build_dense_lsvo(int depth, const uint8_t* occ, vo_lnode* out, uint6
 void vo_lsvo_cast(const vo_lnode* nodes, int depth, int guard, const float* origin, const float* dir,
                   float coef, float bias, uint64_t n, vo_hit* out, int threads);
 
+/* The LSVO walk restated with the structural changes of the device loop (unconditional push, one hit exit, hit read off the final
+ * state, guard dropped where it cannot bind, fmaf child selection with unit != 0, node fetched when the parent changes): must
+ * return exactly what vo_lsvo_cast returns — a CPU cross-check of DESIGN.md §4, not a second specification. */
+void vo_lsvo_cast_restructured(const vo_lnode* nodes, int depth, int guard, const float* origin, const float* dir, float coef,
+                               float bias, int unit, uint64_t n, vo_hit* out, int threads);
+
 /* Grid3D<X,Y,Z>::castRay, include/grid_3d.hpp:35-132; cells[(x*Y+y)*Z+z] = Cell::Type. */
 void vo_grid_cast(const uint8_t* cells, int X, int Y, int Z, const float* origin, const float* dir,
                   uint64_t n, vo_hit* out, uint32_t* steps, int threads);

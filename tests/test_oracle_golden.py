@@ -67,6 +67,73 @@ def test_lsvo_random_scene(port):
         assert_hits_equal(hits, g[key], hits["hit"] != 0, key)
 
 
+def _unit(v):
+    v = np.asarray(v, np.float32)
+    return (v / np.sqrt((v * v).sum(1, keepdims=True, dtype=np.float32))).astype(np.float32)
+
+
+def test_restructured_walk_equals_the_reference_walk(port):
+    """The device loop (csrc/lsvo_step.cuh, Trav2) differs from lsvo.hpp:72-146 in structure, not in arithmetic: unconditional
+    stack writes (no `h`), one exit for cone and leaf hits, the hit read off the final state instead of a flag, no loop guard where
+    it cannot bind, fmaf(half, tc, c) for the child selection of unit directions, the node fetched when the parent changes.
+    port.c restates exactly those changes on the CPU; here every field of every record AND the trip counts must equal the
+    reference-shaped walk's — on the T(9) terrain (camera-like, random, surface-skimming cone rays), on a random voxel set with
+    binding and lifted guards, and on degenerate rays (axis-parallel, zero components, origins on cell planes, inside solids,
+    outside the cube, huge and tiny direction magnitudes, non-finite)."""
+    rng = np.random.default_rng(11)
+    t9 = port.build_terrain(9)
+    g6 = golden("lsvo_random6.npz")
+    r6 = g6["nodes"].copy()
+
+    def check(nodes, depth, o, d, coef, guard=None, unit=False, label=""):
+        want = port.lsvo_cast(nodes, depth, o, d, coef=coef, guard=guard, threads=4)
+        got = port.lsvo_cast_restructured(nodes, depth, o, d, coef=coef, guard=guard, unit=unit, threads=4)
+        assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), (label, int((got["complexity"] != want["complexity"]).sum()),
+                                                                          int((got["hit"] != want["hit"]).sum()))
+        return want
+
+    # camera-like rays over the terrain (unit directions, origin above the ground), coef 0
+    n = 200_000
+    o = np.float32([256, 200, 256]) / np.float32(512) + np.float32(1) + rng.uniform(-0.002, 0.002, (n, 3)).astype(np.float32)
+    d = _unit(np.stack([rng.uniform(-0.8, 0.8, n), rng.uniform(-0.45, 0.45, n), np.ones(n)], 1))
+    prim = check(t9, 9, o, d, 0.0, unit=True, label="camera")
+    assert 0.2 < prim["hit"].mean() < 0.9
+    # secondary rays from the hits: sun-like shadow rays (coef 0) and tangent cone rays (coef 0.5), both from just above the surface
+    m = prim["hit"] != 0
+    so = (prim["position"][m] + prim["normal"][m] * np.float32(1.0 / 512 * 0.001)).astype(np.float32)
+    light = np.float32([-200, -1000, -300]) / np.float32(512) + np.float32(1)
+    check(t9, 9, so, _unit(light - so), 0.0, unit=True, label="shadow")
+    go = (prim["position"][m] + prim["normal"][m] * np.float32(1.0 / 512 / 64)).astype(np.float32)
+    gd = _unit(prim["normal"][m] + rng.uniform(-1000, 1000, (int(m.sum()), 3)).astype(np.float32) * (prim["normal"][m] == 0))
+    cone = check(t9, 9, go, gd, 0.5, unit=True, label="gi")
+    assert cone["hit"].mean() > 0.3
+    # random rays through the cube, un-normalised directions (no fmaf), both coefficients
+    o = rng.uniform(0.9, 2.1, (200_000, 3)).astype(np.float32)
+    d = (rng.standard_normal((200_000, 3)) * rng.choice([1e-3, 1.0, 50.0], (200_000, 1))).astype(np.float32)
+    check(t9, 9, o, d, 0.0, label="random")
+    check(t9, 9, o, d, 0.5, label="random cone")
+    # the random voxel set at depth 6: reference guard (6), a guard that binds (17 = 23 - 6: the walk stops above the voxels), lifted
+    o = rng.uniform(0.95, 2.05, (100_000, 3)).astype(np.float32)
+    d = rng.standard_normal((100_000, 3)).astype(np.float32)
+    for guard in (None, 17, 18, 21, 22, -1):
+        check(r6, 6, o, d, 0.0, guard=guard, label="depth 6 guard %s" % guard)
+        check(r6, 6, o, _unit(d), 0.5, guard=guard, unit=True, label="depth 6 cone guard %s" % guard)
+    # degenerate rays: origins on cell planes / inside solid voxels / outside, axis-parallel and zero components, extreme magnitudes
+    vox = g6["voxels"].astype(np.float32)
+    planes = (rng.integers(0, 65, (20_000, 3)) / np.float32(64) + np.float32(1)).astype(np.float32)
+    inside = ((vox[rng.integers(0, len(vox), 20_000)] + rng.uniform(0, 1, (20_000, 3)).astype(np.float32)) / np.float32(64) + np.float32(1)).astype(np.float32)
+    o = np.concatenate([planes, inside, rng.uniform(-1, 4, (20_000, 3)).astype(np.float32)])
+    axis = np.zeros((len(o), 3), np.float32)
+    axis[np.arange(len(o)), rng.integers(0, 3, len(o))] = rng.choice([-1.0, 1.0], len(o))
+    two = rng.standard_normal((len(o), 3)).astype(np.float32)
+    two[np.arange(len(o)), rng.integers(0, 3, len(o))] = 0.0
+    for d in (axis, two, (two * np.float32(1e30)).astype(np.float32), (two * np.float32(1e-30)).astype(np.float32)):
+        check(r6, 6, o, d, 0.0, label="degenerate")
+        check(r6, 6, o, d, 0.5, label="degenerate cone")
+    bad = np.float32([[np.nan, 1, 1], [1.5, np.inf, 1.5], [1.5, 1.5, 1.5]])
+    check(r6, 6, bad, np.float32([[0, 0, 1], [0, 1, 0], [np.nan, 0, 1]]), 0.0, label="non-finite")
+
+
 def test_grid_dda(port):
     g = golden("grid_random5.npz")
     hits, steps = port.grid_cast(g["occ"], g["origin"], g["dir"])
