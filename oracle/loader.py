@@ -91,6 +91,8 @@ class Port:
                                                 C.c_uint64, C.c_void_p, C.c_int]
         L.vo_grid_cast.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64,
                                    C.c_void_p, C.c_void_p, C.c_int]
+        L.vo_grid_miss_test.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
         L.vo_svo_cast.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p,
                                   C.c_int]
         L.vo_render.argtypes = [C.c_void_p, C.POINTER(PortRenderParams), C.c_void_p, C.c_void_p, C.c_void_p,
@@ -145,6 +147,31 @@ class Port:
         X, Y, Z = cells.shape
         self.lib.vo_grid_cast(_p(cells), X, Y, Z, _p(o), _p(d), len(o), _p(out), _p(steps), threads)
         return out, steps
+
+    def grid_miss_test(self, cells, shift, origin, direction, threads=1):
+        """Prototype (port.c grid_miss_one): 1 where a ray certainly misses the dense grid, judged on the OR-pyramid level `shift`
+        dilated by two cubes; 0 = has to be walked."""
+        cells = np.ascontiguousarray(cells, np.uint8)
+        X, Y, Z = cells.shape
+        k = 1 << shift
+        assert X % k == 0 and Y % k == 0 and Z % k == 0
+        coarse = cells.reshape(X // k, k, Y // k, k, Z // k, k).max(axis=(1, 3, 5)) != 0
+        dil = coarse.copy()
+        for axis in range(3):                                   # box dilation by two cubes, axis by axis
+            acc = dil.copy()
+            for s in (1, 2):
+                a = np.zeros_like(dil); b = np.zeros_like(dil)
+                sl_to = [slice(None)] * 3; sl_from = [slice(None)] * 3
+                sl_to[axis], sl_from[axis] = slice(s, None), slice(None, -s)
+                a[tuple(sl_to)] = dil[tuple(sl_from)]
+                b[tuple(sl_from)] = dil[tuple(sl_to)]
+                acc |= a | b
+            dil = acc
+        dil = np.ascontiguousarray(dil, np.uint8)
+        o, d = _f32(origin), _f32(direction)
+        out = np.zeros(len(o), np.uint8)
+        self.lib.vo_grid_miss_test(_p(dil), dil.shape[0], dil.shape[1], dil.shape[2], shift, X, Y, Z, _p(o), _p(d), len(o), _p(out), threads)
+        return out
 
     def svo_cast(self, occ, depth, origin, direction, max_iter=1 << 30, threads=1):
         occ = np.ascontiguousarray(occ, np.uint8)

@@ -593,6 +593,49 @@ void vo_grid_cast(const uint8_t* cells, int X, int Y, int Z, const float* origin
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* A conservative miss test for Grid3D::castRay on a coarse, dilated occupancy (what a pyramid CAN do for
+ * the dense grids without changing a record).  `coarse` holds one byte per cube of 2^shift cells: non-zero when the cube, or
+ * any cube within two cubes of it on every axis, holds a solid cell.  The EXACT ray (double precision) is marched through the
+ * coarse grid; if it meets no marked cube the reference's fp DDA — whose cells stay within one cell per axis of the exact ray's
+ * cell, see the argument in DESIGN.md — cannot meet a solid cell either.  Returns 1 = certainly a miss, 0 = unknown (walk it).
+ * Prototype and cross-check only (tests/test_oracle_golden.py); the product does not use it yet. */
+static int grid_miss_one(const uint8_t* coarse, int CX, int CY, int CZ, int shift, int X, int Y, int Z, const float o[3],
+                         const float d[3]) {
+    const int dim[3] = {X, Y, Z}, cdim[3] = {CX, CY, CZ};
+    double tm[3], td[3];
+    int c[3], st[3];
+    for (int a = 0; a < 3; ++a) {
+        if (!(o[a] * 0.0f == 0.0f) || !(d[a] * 0.0f == 0.0f) || d[a] == 0.0f) return 0;   /* the fp walk of such a ray is not the ray */
+        if (!(fabsf(o[a]) < 1.0e9f)) return 0;                                         /* (int)o would overflow */
+        const int cell = (int)o[a];                                                    /* :58-60 */
+        if (cell < 0 || cell >= dim[a] || o[a] < 0.0f) return (o[a] < 0.0f && cell == 0) ? 0 : 1;   /* starts outside: no trip, a miss */
+        c[a] = cell >> shift;
+        st[a] = d[a] < 0 ? -1 : 1;
+        const double edge = (double)((c[a] + (st[a] > 0 ? 1 : 0)) << shift);
+        td[a] = fabs((double)(1 << shift) / (double)d[a]);
+        tm[a] = (edge - (double)o[a]) / (double)d[a];
+    }
+    for (;;) {
+        if (coarse[((size_t)c[0] * (size_t)cdim[1] + (size_t)c[1]) * (size_t)cdim[2] + (size_t)c[2]]) return 0;
+        const int side = tm[0] < tm[1] ? (tm[0] < tm[2] ? 0 : 2) : (tm[1] < tm[2] ? 1 : 2);
+        tm[side] += td[side];
+        c[side] += st[side];
+        if (c[side] < 0 || c[side] >= cdim[side]) return 1;
+    }
+}
+typedef struct { const uint8_t* coarse; int CX, CY, CZ, shift, X, Y, Z; const float *o, *d; uint8_t* out; } gmiss_ctx;
+static void gmiss_range(void* c_, uint64_t b, uint64_t e) {
+    gmiss_ctx* c = (gmiss_ctx*)c_;
+    for (uint64_t i = b; i < e; ++i)
+        c->out[i] = (uint8_t)grid_miss_one(c->coarse, c->CX, c->CY, c->CZ, c->shift, c->X, c->Y, c->Z, c->o + 3 * i, c->d + 3 * i);
+}
+void vo_grid_miss_test(const uint8_t* coarse, int CX, int CY, int CZ, int shift, int X, int Y, int Z, const float* origin,
+                       const float* dir, uint64_t n, uint8_t* out, int threads) {
+    gmiss_ctx c = {coarse, CX, CY, CZ, shift, X, Y, Z, origin, dir, out};
+    par_for(gmiss_range, &c, n, 4096, threads);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* SVO<N>::castRay with the hit fill restored, include/svo.hpp:62-70,116-194; Ray volumetric.hpp:25-52 */
 /* ------------------------------------------------------------------------------------------ */
 typedef struct svo_ray {

@@ -61,6 +61,12 @@ void vo_lsvo_cast_restructured(const vo_lnode* nodes, int depth, int guard, cons
 void vo_grid_cast(const uint8_t* cells, int X, int Y, int Z, const float* origin, const float* dir,
                   uint64_t n, vo_hit* out, uint32_t* steps, int threads);
 
+/* Conservative miss test for Grid3D::castRay on a coarse occupancy dilated by two cubes (one byte per cube of 2^shift cells,
+ * coarse[(x*CY+y)*CZ+z]): out[i] = 1 when ray i certainly misses, 0 when it has to be walked.  A prototype of what the pyramid
+ * can do for dense grids without changing a record; pinned to vo_grid_cast by tests/test_oracle_golden.py. */
+void vo_grid_miss_test(const uint8_t* coarse, int CX, int CY, int CZ, int shift, int X, int Y, int Z, const float* origin,
+                       const float* dir, uint64_t n, uint8_t* out, int threads);
+
 /* SVO<depth>::castRay with fillHitResult's commented body restored ("intended SVO"),
  * include/svo.hpp:62-70,116-194, over a dense occupancy occ[(x*S+y)*S+z]. */
 void vo_svo_cast(const uint8_t* occ, int depth, const float* origin, const float* dir, uint32_t max_iter,
